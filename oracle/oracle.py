@@ -1,0 +1,297 @@
+"""oracle/oracle.py — ctypes access to the CPU oracle and to the compiled reference.
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / `--impl reference` legs of bench.py.  The product package (ggml_b200) must never
+import this module (tests/test_product_isolation.py enforces it).
+
+Two objects:
+  * `Oracle` — liboracle_quants.so, this repo's plain-C restatement (oracle/quants_oracle.c).
+  * `Ref`    — oracle/_ref/libggml_probe.so, a thin shim over the UNMODIFIED reference's public API
+               (oracle/ref_probe.cpp) compiled from /root/reference by oracle/Makefile.  The
+               `native` CPU-backend variant is used when the host CPU has every ISA extension it
+               was compiled for (oracle/_ref/native/REQUIRED_FLAGS), else the x86-64-v3 build.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF_DIR = HERE / "_ref"
+
+# enum ggml_type ids (reference include/ggml.h:351-390)
+F32, F16, Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q8_1 = 0, 1, 2, 3, 6, 7, 8, 9
+Q2_K, Q3_K, Q4_K, Q5_K, Q6_K, Q8_K = 10, 11, 12, 13, 14, 15
+TYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q4_1: "q4_1", Q5_0: "q5_0", Q5_1: "q5_1", Q8_0: "q8_0",
+              Q2_K: "q2_K", Q3_K: "q3_K", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K"}
+HOT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
+
+
+def build(ref: bool = True) -> None:
+    """(Re)build liboracle_quants.so and, where /root/reference exists, oracle/_ref."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-s", "-j8", "-C", str(HERE)] + targets, check=True)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Oracle:
+    def __init__(self):
+        so = HERE / "liboracle_quants.so"
+        if not so.exists():
+            build(ref=False)
+        L = self.lib = C.CDLL(str(so))
+        L.oq_fp16_to_fp32.restype = C.c_float
+        L.oq_fp16_to_fp32.argtypes = [C.c_uint16]
+        L.oq_fp32_to_fp16.restype = C.c_uint16
+        L.oq_fp32_to_fp16.argtypes = [C.c_float]
+        L.oq_row_size.restype = C.c_size_t
+        L.oq_row_size.argtypes = [C.c_int, C.c_int64]
+        L.oq_blck_size.restype = C.c_int64
+        L.oq_blck_size.argtypes = [C.c_int]
+        L.oq_type_size.restype = C.c_size_t
+        L.oq_type_size.argtypes = [C.c_int]
+        L.oq_dequantize_row.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.oq_quantize_row_ref.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.oq_quantize_row_q8_0_simd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.oq_quantize_row_q8_0_simd.restype = None
+        L.oq_vec_dot.restype = C.c_float
+        L.oq_vec_dot.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.oq_vec_dot_type.argtypes = [C.c_int]
+        L.oq_mul_mat.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+        L.oq_mul_mat_f64.argtypes = L.oq_mul_mat.argtypes
+        L.oq_mul_mat_id.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int64] * 6
+
+    def row_size(self, t, k):
+        return int(self.lib.oq_row_size(t, k))
+
+    def blck_size(self, t):
+        return int(self.lib.oq_blck_size(t))
+
+    def dequantize(self, t, blocks: np.ndarray, n: int) -> np.ndarray:
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+        out = np.empty(n, dtype=np.float32)
+        rc = self.lib.oq_dequantize_row(t, _p(blocks), _p(out), n)
+        assert rc == 0, f"oracle cannot dequantize type {t}"
+        return out
+
+    def quantize(self, t, x, simd_q8_0: bool = False) -> np.ndarray:
+        x = _f32(x).ravel()
+        out = np.zeros(self.row_size(t, x.size), dtype=np.uint8)
+        if simd_q8_0:
+            assert t == Q8_0
+            self.lib.oq_quantize_row_q8_0_simd(_p(x), _p(out), x.size)
+        else:
+            assert self.lib.oq_quantize_row_ref(t, _p(x), _p(out), x.size) == 0
+        return out
+
+    def vec_dot(self, t, k, wrow: np.ndarray, yq: np.ndarray) -> float:
+        return float(self.lib.oq_vec_dot(t, k, _p(np.ascontiguousarray(wrow)), _p(np.ascontiguousarray(yq))))
+
+    def vec_dot_type(self, t):
+        return int(self.lib.oq_vec_dot_type(t))
+
+    def mul_mat(self, t, W: np.ndarray, X, M, N, K, f64: bool = False) -> np.ndarray:
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        assert W.size == self.row_size(t, K) * M and X.size == N * K
+        Y = np.empty((N, M), dtype=np.float32)
+        fn = self.lib.oq_mul_mat_f64 if f64 else self.lib.oq_mul_mat
+        assert fn(t, _p(W), _p(X), _p(Y), M, N, K) == 0
+        return Y
+
+    def mul_mat_id(self, t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok) -> np.ndarray:
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        assert ids.shape == (n_tok, ids.shape[1]) and ids.shape[1] >= n_used
+        Y = np.empty((n_tok, n_used, M), dtype=np.float32)
+        rc = self.lib.oq_mul_mat_id(t, _p(W), _p(X), _p(ids), ids.shape[1], _p(Y), M, K, n_expert, n_used, nb1, n_tok)
+        assert rc == 0, rc
+        return Y
+
+
+def _host_has_native_isa() -> bool:
+    req = REF_DIR / "native" / "REQUIRED_FLAGS"
+    so = REF_DIR / "native" / "libggml-cpu.so"
+    if not (req.exists() and so.exists()):
+        return False
+    try:
+        flags = set(re.search(r"^flags\s*:\s*(.*)$", Path("/proc/cpuinfo").read_text(), re.M).group(1).split())
+    except Exception:
+        return False
+    need = re.findall(r"__([A-Z0-9_]+?)__ 1", req.read_text())
+    ren = {"AVX512VNNI": "avx512_vnni", "AVX512VBMI2": "avx512_vbmi2", "AVX512BF16": "avx512_bf16",
+           "AVX512FP16": "avx512_fp16", "AVX512BITALG": "avx512_bitalg", "AVX512VPOPCNTDQ": "avx512_vpopcntdq",
+           "AVXVNNI": "avx_vnni", "AVX512VP2INTERSECT": "avx512_vp2intersect"}
+    for n in need:
+        if ren.get(n, n.lower()) not in flags:
+            return False
+    return True
+
+
+def ref_available() -> bool:
+    return (REF_DIR / "libggml_probe.so").exists()
+
+
+def ref_env(native: bool | None = None) -> dict:
+    """Environment for running oracle/_ref binaries (test-backend-ops, gpt-2-*)."""
+    if native is None:
+        native = _host_has_native_isa()
+    env = dict(os.environ)
+    paths = ([str(REF_DIR / "native")] if native else []) + [str(REF_DIR)]
+    env["LD_LIBRARY_PATH"] = ":".join(paths + [env.get("LD_LIBRARY_PATH", "")]).rstrip(":")
+    return env
+
+
+class Ref:
+    """The unmodified reference, through oracle/_ref/libggml_probe.so."""
+
+    _loaded = None
+
+    def __init__(self, native: bool | None = None):
+        if not ref_available():
+            build(ref=True)
+        if native is None:
+            native = _host_has_native_isa()
+        if Ref._loaded is None:
+            C.CDLL(str(REF_DIR / "libggml-base.so"), mode=C.RTLD_GLOBAL)
+            C.CDLL(str(REF_DIR / ("native" if native else ".") / "libggml-cpu.so"), mode=C.RTLD_GLOBAL)
+            C.CDLL(str(REF_DIR / "libggml.so"), mode=C.RTLD_GLOBAL)
+            Ref._loaded = (C.CDLL(str(REF_DIR / "libggml_probe.so")), native)
+        L, self.native = Ref._loaded
+        self.lib = L
+        L.probe_load_backend.argtypes = [C.c_char_p]
+        L.probe_dev_name.restype = C.c_char_p
+        L.probe_dev_name.argtypes = [C.c_int]
+        L.probe_dev_desc.restype = C.c_char_p
+        L.probe_dev_desc.argtypes = [C.c_int]
+        L.probe_row_size.restype = C.c_size_t
+        L.probe_row_size.argtypes = [C.c_int, C.c_int64]
+        L.probe_quantize.restype = C.c_size_t
+        L.probe_quantize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.probe_quantize_row_ref.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.probe_quantize_row_ref.restype = None
+        L.probe_dequantize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.probe_dequantize.restype = None
+        L.probe_cpu_from_float.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.probe_cpu_from_float.restype = None
+        L.probe_cpu_vec_dot.restype = C.c_float
+        L.probe_cpu_vec_dot.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.probe_mul_mat.restype = C.c_double
+        L.probe_mul_mat.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 7 + [C.c_int] * 5
+        L.probe_mul_mat_id.restype = C.c_double
+        L.probe_mul_mat_id.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_int] * 2
+
+    # --- formats
+    def row_size(self, t, k):
+        return int(self.lib.probe_row_size(t, k))
+
+    def quantize(self, t, x, nrows, k) -> np.ndarray:
+        """ggml_quantize_chunk(type, x, …, imatrix=NULL)"""
+        x = _f32(x)
+        out = np.zeros(self.row_size(t, k) * nrows, dtype=np.uint8)
+        n = self.lib.probe_quantize(t, _p(x), _p(out), nrows, k)
+        assert n == out.size
+        return out
+
+    def quantize_row_ref(self, t, x) -> np.ndarray:
+        x = _f32(x).ravel()
+        out = np.zeros(self.row_size(t, x.size), dtype=np.uint8)
+        self.lib.probe_quantize_row_ref(t, _p(x), _p(out), x.size)
+        return out
+
+    def dequantize(self, t, blocks, n) -> np.ndarray:
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+        out = np.empty(n, dtype=np.float32)
+        self.lib.probe_dequantize(t, _p(blocks), _p(out), n)
+        return out
+
+    def cpu_from_float(self, t, x) -> np.ndarray:
+        x = _f32(x).ravel()
+        out = np.zeros(self.row_size(t, x.size), dtype=np.uint8)
+        self.lib.probe_cpu_from_float(t, _p(x), _p(out), x.size)
+        return out
+
+    def cpu_vec_dot(self, t, k, wrow, yq) -> float:
+        return float(self.lib.probe_cpu_vec_dot(t, k, _p(np.ascontiguousarray(wrow)), _p(np.ascontiguousarray(yq))))
+
+    # --- backends
+    def load_backend(self, path) -> bool:
+        return bool(self.lib.probe_load_backend(str(path).encode()))
+
+    def devices(self):
+        return [self.lib.probe_dev_name(i).decode() for i in range(self.lib.probe_dev_count())]
+
+    def hw_threads(self):
+        return int(self.lib.probe_hw_threads())
+
+    def mul_mat(self, t, W, X, M, N, K, dev="CPU", batch=(1, 1, 1, 1), threads=0, repeat=1, iters=1, warmup=0,
+                e2e=False):
+        """returns (Y[ne3b, ne2b, N, M], seconds per mul_mat)"""
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        ne2a, ne3a, ne2b, ne3b = batch
+        assert W.size == self.row_size(t, K) * M * ne2a * ne3a, (W.size, self.row_size(t, K) * M * ne2a * ne3a)
+        assert X.size == K * N * ne2b * ne3b
+        Y = np.empty((ne3b, ne2b, N, M), dtype=np.float32)
+        s = self.lib.probe_mul_mat(dev.encode(), t, _p(W), _p(X), _p(Y), M, N, K, ne2a, ne3a, ne2b, ne3b,
+                                   threads, repeat, iters, warmup, int(e2e))
+        if s < 0:
+            raise RuntimeError(f"probe_mul_mat({dev}) failed: {s}")
+        return Y, float(s)
+
+    def mul_mat_id(self, t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok, dev="CPU", threads=0, iters=1):
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        assert ids.shape == (n_tok, n_used)
+        Y = np.empty((n_tok, n_used, M), dtype=np.float32)
+        s = self.lib.probe_mul_mat_id(dev.encode(), t, _p(W), _p(X), _p(ids), _p(Y), M, K, n_expert, n_used, nb1, n_tok,
+                                      threads, iters)
+        if s < 0:
+            raise RuntimeError(f"probe_mul_mat_id({dev}) failed: {s}")
+        return Y, float(s)
+
+
+def random_blocks(t: int, nblocks: int, rng: np.random.Generator, scale: float = 0.05) -> np.ndarray:
+    """Arbitrary-but-valid packed blocks: uniformly random code bytes (every nibble / 6-bit scale /
+    high-bit pattern occurs) with finite fp16 scales of magnitude ~`scale`."""
+    ts = {Q4_0: 18, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210}[t]
+    b = rng.integers(0, 256, size=(nblocks, ts), dtype=np.uint8)
+
+    def put_half(col, vals):
+        h = vals.astype(np.float16).view(np.uint16)
+        b[:, col] = (h & 0xFF).astype(np.uint8)
+        b[:, col + 1] = (h >> 8).astype(np.uint8)
+
+    if t in (Q4_0, Q8_0):
+        put_half(0, rng.uniform(-scale, scale, nblocks))
+    elif t in (Q4_K, Q5_K):
+        put_half(0, rng.uniform(0, scale / 32, nblocks))
+        put_half(2, rng.uniform(0, scale / 32, nblocks))
+    elif t == Q6_K:
+        put_half(208, rng.uniform(-scale / 64, scale / 64, nblocks))
+    return b.reshape(-1)
+
+
+def nmse(a: np.ndarray, b: np.ndarray) -> float:
+    """normalized mean squared error = mse(a, b) / mse(a, 0), exactly as tests/test-backend-ops.cpp:174-188
+    (a = the backend under test, b = the CPU reference)"""
+    a = np.asarray(a, dtype=np.float32).ravel()
+    b = np.asarray(b, dtype=np.float32).ravel()
+    diff = (a - b).astype(np.float32)
+    num = float(np.sum((diff * diff).astype(np.float64)))
+    den = float(np.sum((a * a).astype(np.float64)))
+    return num / den if den > 0 else num

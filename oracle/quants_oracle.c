@@ -1,0 +1,444 @@
+/* oracle/quants_oracle.c — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement (written for this repo, not copied) of the reference's algorithm
+ * for the hot path GGML_OP_MUL_MAT / GGML_OP_MUL_MAT_ID over block-quantized weights.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it; the
+ * product path (ggml_b200/csrc) never does.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function here
+ * against the unmodified reference compiled from /root/reference into oracle/_ref (bit-exact
+ * for dequantize / quantize, <= 1e-5 relative for the dot products whose float summation
+ * order is unspecified by the reference), and tests/golden/ holds vectors produced by that
+ * reference (tests/golden/make_golden.py) for boxes where oracle/_ref cannot be rebuilt.
+ *
+ * Algorithms restated (reference @ 9a4acb37, paths relative to /root/reference):
+ *   block layouts ............ src/ggml-common.h:161-166 (q4_0) 203-208 (q8_0) 279-290 (q4_K)
+ *                              296-308 (q5_K) 314-320 (q6_K) 323-328 (q8_K)
+ *   dequantize_row_q4_0 ...... src/ggml-quants.c:255-273     dequantize_row_q8_0 .. :349-363
+ *   dequantize_row_q4_K ...... src/ggml-quants.c:1280-1302   get_scale_min_k4 ..... :631-638
+ *   dequantize_row_q5_K ...... src/ggml-quants.c:1482-1507   dequantize_row_q6_K .. :1690-1719
+ *   quantize_row_q4_0_ref .... src/ggml-quants.c:31-66       quantize_row_q8_0_ref  :194-217
+ *   quantize_row_q8_K_ref .... src/ggml-quants.c:2479-2516   nearest_int .......... :372-377
+ *   quantize_row_q8_0 (AVX2) . src/ggml-cpu/ggml-cpu-quants.c:778-835
+ *   vec_dot q4_0.q8_0 ........ src/ggml-cpu/ggml-cpu-quants.c:2294-2311 (scalar tail)
+ *   vec_dot q8_0.q8_0 ........ src/ggml-cpu/ggml-cpu-quants.c:3335 ff.
+ *   vec_dot q4_K.q8_K ........ src/ggml-cpu/ggml-cpu-quants.c:6137-6193 (scalar)
+ *   vec_dot q5_K / q6_K ...... src/ggml-cpu/ggml-cpu-quants.c:6196 ff. / 6833 ff.
+ *   mul_mat driver ........... src/ggml-cpu/ggml-cpu.c:7428-7605 (quantize src1 rows to vec_dot_type,
+ *                              then one vec_dot per (row of src0, column of src1))
+ *   mul_mat_id driver ........ src/ggml-cpu/ggml-cpu.c:7609-7784
+ *
+ * Compiled with -ffp-contract=off: the reference's ggml-base is built without FMA, so
+ * `d*q - m` is a rounded multiply followed by a rounded subtract.
+ */
+#include "quants_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------------------------------------------------------------- fp16 */
+
+float oq_fp16_to_fp32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    const uint32_t exp  = (h >> 10) & 0x1Fu;
+    uint32_t man = h & 0x3FFu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else { /* subnormal: renormalise */
+            int e = -1;
+            do { man <<= 1; ++e; } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7F800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 112u) << 23) | (man << 13);
+    }
+    float f; memcpy(&f, &bits, 4); return f;
+}
+
+/* IEEE round-to-nearest-even, the behaviour of F16C / _cvtss_sh(…, 0) used by the reference build */
+uint16_t oq_fp32_to_fp16(float f) {
+    uint32_t x; memcpy(&x, &f, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (x > 0x7F800000u ? 0x200u : 0u));
+    if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);          /* rounds to inf */
+    if (x < 0x33000001u)  return sign;                                  /* rounds to zero (<= 2^-25) */
+    int e = (int)(x >> 23) - 127;
+    uint32_t m = (x & 0x7FFFFFu) | 0x800000u;
+    int shift;
+    uint32_t he;
+    if (e < -14) { shift = 13 + (-14 - e); he = 0; }                    /* subnormal half */
+    else         { shift = 13;             he = (uint32_t)(e + 15); }
+    uint32_t hm = m >> shift;
+    const uint32_t rem  = m & ((1u << shift) - 1u);
+    const uint32_t half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (hm & 1u))) hm++;
+    uint32_t out;
+    if (he == 0) out = hm;                      /* may carry into exponent 1: correct by construction */
+    else         out = ((he - 1) << 10) + hm;   /* hm includes the implicit bit (0x400) */
+    return (uint16_t)(sign | out);
+}
+
+/* ---------------------------------------------------------------- sizes */
+
+int64_t oq_blck_size(int type) {
+    switch (type) {
+        case OQ_F32: case OQ_F16: return 1;
+        case OQ_Q4_0: case OQ_Q8_0: return 32;
+        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: return 256;
+        default: return 0;
+    }
+}
+size_t oq_type_size(int type) {
+    switch (type) {
+        case OQ_F32: return 4;   case OQ_F16: return 2;
+        case OQ_Q4_0: return 18; case OQ_Q8_0: return 34;
+        case OQ_Q4_K: return 144; case OQ_Q5_K: return 176; case OQ_Q6_K: return 210; case OQ_Q8_K: return 292;
+        default: return 0;
+    }
+}
+size_t oq_row_size(int type, int64_t k) { return (size_t)(k / oq_blck_size(type)) * oq_type_size(type); }
+
+static inline uint16_t rd16(const uint8_t * p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static inline void wr16(uint8_t * p, uint16_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+
+/* the 12-byte packing of eight 6-bit (scale, min) pairs used by Q4_K and Q5_K */
+static void k4_scale_min(int j, const uint8_t * s, int * sc, int * mn) {
+    if (j < 4) { *sc = s[j] & 63;  *mn = s[j + 4] & 63; }
+    else       { *sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4);
+                 *mn = (s[j + 4] >> 4)   | ((s[j]     >> 6) << 4); }
+}
+
+/* ---------------------------------------------------------------- dequantize */
+
+static void deq_q4_0(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, b += 18, y += 32) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int j = 0; j < 16; ++j) {
+            y[j]      = (float)((b[2 + j] & 0x0F) - 8) * d;
+            y[j + 16] = (float)((b[2 + j] >> 4)   - 8) * d;
+        }
+    }
+}
+static void deq_q8_0(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, b += 34, y += 32) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int j = 0; j < 32; ++j) y[j] = (float)(int8_t)b[2 + j] * d;
+    }
+}
+static void deq_q4_K(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 144) {
+        const float d = oq_fp16_to_fp32(rd16(b)), dmin = oq_fp16_to_fp32(rd16(b + 2));
+        const uint8_t * sc = b + 4, * q = b + 16;
+        for (int c = 0; c < 4; ++c, q += 32) {
+            int s0, m0, s1, m1;
+            k4_scale_min(2 * c, sc, &s0, &m0); k4_scale_min(2 * c + 1, sc, &s1, &m1);
+            const float d0 = d * (float)s0, mm0 = dmin * (float)m0;
+            const float d1 = d * (float)s1, mm1 = dmin * (float)m1;
+            for (int l = 0; l < 32; ++l) *y++ = d0 * (float)(q[l] & 0x0F) - mm0;
+            for (int l = 0; l < 32; ++l) *y++ = d1 * (float)(q[l] >> 4)   - mm1;
+        }
+    }
+}
+static void deq_q5_K(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 176) {
+        const float d = oq_fp16_to_fp32(rd16(b)), dmin = oq_fp16_to_fp32(rd16(b + 2));
+        const uint8_t * sc = b + 4, * qh = b + 16, * q = b + 48;
+        for (int c = 0; c < 4; ++c, q += 32) {
+            int s0, m0, s1, m1;
+            k4_scale_min(2 * c, sc, &s0, &m0); k4_scale_min(2 * c + 1, sc, &s1, &m1);
+            const float d0 = d * (float)s0, mm0 = dmin * (float)m0;
+            const float d1 = d * (float)s1, mm1 = dmin * (float)m1;
+            for (int l = 0; l < 32; ++l) *y++ = d0 * (float)((q[l] & 0x0F) + (((qh[l] >> (2 * c))     & 1) << 4)) - mm0;
+            for (int l = 0; l < 32; ++l) *y++ = d1 * (float)((q[l] >> 4)   + (((qh[l] >> (2 * c + 1)) & 1) << 4)) - mm1;
+        }
+    }
+}
+static void deq_q6_K(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 210) {
+        const float d = oq_fp16_to_fp32(rd16(b + 208));
+        for (int h = 0; h < 2; ++h) {
+            const uint8_t * ql = b + 64 * h, * qh = b + 128 + 32 * h;
+            const int8_t  * sc = (const int8_t *)(b + 192 + 8 * h);
+            for (int l = 0; l < 32; ++l) {
+                const int g = l / 16;
+                const int q1 = (int)((ql[l]      & 0x0F) | (((qh[l] >> 0) & 3) << 4)) - 32;
+                const int q2 = (int)((ql[l + 32] & 0x0F) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                const int q3 = (int)((ql[l]      >> 4)   | (((qh[l] >> 4) & 3) << 4)) - 32;
+                const int q4 = (int)((ql[l + 32] >> 4)   | (((qh[l] >> 6) & 3) << 4)) - 32;
+                y[128 * h + l]      = d * (float)sc[g]     * (float)q1;
+                y[128 * h + l + 32] = d * (float)sc[g + 2] * (float)q2;
+                y[128 * h + l + 64] = d * (float)sc[g + 4] * (float)q3;
+                y[128 * h + l + 96] = d * (float)sc[g + 6] * (float)q4;
+            }
+        }
+        y += 256;
+    }
+}
+static void deq_q8_K(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 292, y += 256) {
+        float d; memcpy(&d, b, 4);
+        for (int j = 0; j < 256; ++j) y[j] = d * (float)(int8_t)b[4 + j];
+    }
+}
+
+int oq_dequantize_row(int type, const void * src, float * dst, int64_t k) {
+    const uint8_t * b = (const uint8_t *)src;
+    switch (type) {
+        case OQ_F32:  memcpy(dst, src, (size_t)k * 4); return 0;
+        case OQ_F16:  for (int64_t i = 0; i < k; ++i) dst[i] = oq_fp16_to_fp32(rd16(b + 2 * i)); return 0;
+        case OQ_Q4_0: deq_q4_0(b, dst, k); return 0;
+        case OQ_Q8_0: deq_q8_0(b, dst, k); return 0;
+        case OQ_Q4_K: deq_q4_K(b, dst, k); return 0;
+        case OQ_Q5_K: deq_q5_K(b, dst, k); return 0;
+        case OQ_Q6_K: deq_q6_K(b, dst, k); return 0;
+        case OQ_Q8_K: deq_q8_K(b, dst, k); return 0;
+        default: return -1;
+    }
+}
+
+/* ---------------------------------------------------------------- quantize */
+
+/* round-to-nearest-even through the 1.5*2^23 magic constant (valid for |v| <= 4194303) */
+static inline int rne_int(float v) {
+    float t = v + 12582912.0f;
+    int32_t i; memcpy(&i, &t, 4);
+    return (i & 0x007FFFFF) - 0x00400000;
+}
+
+static void quant_q4_0(const float * x, uint8_t * b, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, x += 32, b += 18) {
+        float amax = 0.0f, vmax = 0.0f;
+        for (int j = 0; j < 32; ++j) if (fabsf(x[j]) > amax) { amax = fabsf(x[j]); vmax = x[j]; }
+        const float d  = vmax / -8.0f;
+        const float id = d != 0.0f ? 1.0f / d : 0.0f;
+        wr16(b, oq_fp32_to_fp16(d));
+        for (int j = 0; j < 16; ++j) {
+            int lo = (int)(int8_t)(x[j] * id + 8.5f);       /* truncation toward zero, as the C cast does */
+            int hi = (int)(int8_t)(x[j + 16] * id + 8.5f);
+            if (lo > 15) lo = 15;
+            if (hi > 15) hi = 15;
+            b[2 + j] = (uint8_t)((lo & 0xFF) | (hi << 4));
+        }
+    }
+}
+static void quant_q8_0(const float * x, uint8_t * b, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, x += 32, b += 34) {
+        float amax = 0.0f;
+        for (int j = 0; j < 32; ++j) if (fabsf(x[j]) > amax) amax = fabsf(x[j]);
+        const float d  = amax / 127.0f;
+        const float id = d != 0.0f ? 1.0f / d : 0.0f;
+        wr16(b, oq_fp32_to_fp16(d));
+        for (int j = 0; j < 32; ++j) b[2 + j] = (uint8_t)(int8_t)roundf(x[j] * id);   /* ties away from zero */
+    }
+}
+void oq_quantize_row_q8_0_simd(const float * x, void * dst, int64_t k) {
+    uint8_t * b = (uint8_t *)dst;
+    for (int64_t i = 0; i < k / 32; ++i, x += 32, b += 34) {
+        float amax = 0.0f;
+        for (int j = 0; j < 32; ++j) if (fabsf(x[j]) > amax) amax = fabsf(x[j]);
+        wr16(b, oq_fp32_to_fp16(amax / 127.0f));
+        const float id = amax != 0.0f ? 127.0f / amax : 0.0f;
+        for (int j = 0; j < 32; ++j) b[2 + j] = (uint8_t)(int8_t)nearbyintf(x[j] * id); /* ties to even (vroundps) */
+    }
+}
+static void quant_q8_K(const float * x, uint8_t * b, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, x += 256, b += 292) {
+        float amax = 0.0f, vmax = 0.0f;
+        for (int j = 0; j < 256; ++j) if (fabsf(x[j]) > amax) { amax = fabsf(x[j]); vmax = x[j]; }
+        if (amax == 0.0f) { memset(b, 0, 292); continue; }   /* bsums are left untouched by the reference; zero here */
+        const float iscale = -127.0f / vmax;
+        int8_t * q = (int8_t *)(b + 4);
+        for (int j = 0; j < 256; ++j) { int v = rne_int(iscale * x[j]); q[j] = (int8_t)(v > 127 ? 127 : v); }
+        for (int g = 0; g < 16; ++g) {
+            int s = 0;
+            for (int j = 0; j < 16; ++j) s += q[16 * g + j];
+            wr16(b + 260 + 2 * g, (uint16_t)(int16_t)s);
+        }
+        const float d = 1.0f / iscale;
+        memcpy(b, &d, 4);
+    }
+}
+
+int oq_quantize_row_ref(int type, const float * src, void * dst, int64_t k) {
+    switch (type) {
+        case OQ_Q4_0: quant_q4_0(src, (uint8_t *)dst, k); return 0;
+        case OQ_Q8_0: quant_q8_0(src, (uint8_t *)dst, k); return 0;
+        case OQ_Q8_K: quant_q8_K(src, (uint8_t *)dst, k); return 0;
+        default: return -1;
+    }
+}
+
+/* ---------------------------------------------------------------- dot products */
+
+int oq_vec_dot_type(int type) {
+    switch (type) {
+        case OQ_Q4_0: case OQ_Q8_0: return OQ_Q8_0;
+        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: return OQ_Q8_K;
+        default: return -1;
+    }
+}
+
+static float dot_q4_0_q8_0(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 32; ++i, w += 18, y += 34) {
+        int s = 0;
+        for (int j = 0; j < 16; ++j) {
+            s += ((int)(w[2 + j] & 0x0F) - 8) * (int)(int8_t)y[2 + j];
+            s += ((int)(w[2 + j] >> 4)   - 8) * (int)(int8_t)y[2 + j + 16];
+        }
+        acc += (float)s * oq_fp16_to_fp32(rd16(w)) * oq_fp16_to_fp32(rd16(y));
+    }
+    return acc;
+}
+static float dot_q8_0_q8_0(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 32; ++i, w += 34, y += 34) {
+        int s = 0;
+        for (int j = 0; j < 32; ++j) s += (int)(int8_t)w[2 + j] * (int)(int8_t)y[2 + j];
+        acc += (float)s * (oq_fp16_to_fp32(rd16(w)) * oq_fp16_to_fp32(rd16(y)));
+    }
+    return acc;
+}
+/* Q4_K and Q5_K share everything but the code extraction: sum_j sc_j*(q.y)_j scaled by d*yd, minus dmin*yd*sum_j m_j*bsum_j */
+static float dot_q45_K_q8_K(int five, int64_t k, const uint8_t * w, const uint8_t * y) {
+    const size_t wb = five ? 176 : 144;
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += wb, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        const float d = oq_fp16_to_fp32(rd16(w)) * yd, dmin = oq_fp16_to_fp32(rd16(w + 2)) * yd;
+        const uint8_t * sc = w + 4, * qh = w + 16, * q = w + (five ? 48 : 16);
+        int32_t sum_sc = 0, sum_mn = 0;
+        for (int c = 0; c < 4; ++c) {
+            int s0, m0, s1, m1;
+            k4_scale_min(2 * c, sc, &s0, &m0); k4_scale_min(2 * c + 1, sc, &s1, &m1);
+            int p0 = 0, p1 = 0, b0 = 0, b1 = 0;
+            for (int l = 0; l < 32; ++l) {
+                int lo = q[32 * c + l] & 0x0F, hi = q[32 * c + l] >> 4;
+                if (five) { lo += ((qh[l] >> (2 * c)) & 1) << 4; hi += ((qh[l] >> (2 * c + 1)) & 1) << 4; }
+                p0 += lo * q8[64 * c + l];      b0 += q8[64 * c + l];
+                p1 += hi * q8[64 * c + 32 + l]; b1 += q8[64 * c + 32 + l];
+            }
+            sum_sc += s0 * p0 + s1 * p1;
+            sum_mn += m0 * b0 + m1 * b1;
+        }
+        acc += d * (float)sum_sc - dmin * (float)sum_mn;
+    }
+    return acc;
+}
+static float dot_q6_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 210, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        const float d = oq_fp16_to_fp32(rd16(w + 208)) * yd;
+        int32_t total = 0;
+        for (int h = 0; h < 2; ++h) {
+            const uint8_t * ql = w + 64 * h, * qh = w + 128 + 32 * h;
+            const int8_t  * sc = (const int8_t *)(w + 192 + 8 * h);
+            const int8_t  * yy = q8 + 128 * h;
+            int part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int l = 0; l < 32; ++l) {
+                const int g = l / 16;
+                const int q1 = (int)((ql[l]      & 0x0F) | (((qh[l] >> 0) & 3) << 4)) - 32;
+                const int q2 = (int)((ql[l + 32] & 0x0F) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                const int q3 = (int)((ql[l]      >> 4)   | (((qh[l] >> 4) & 3) << 4)) - 32;
+                const int q4 = (int)((ql[l + 32] >> 4)   | (((qh[l] >> 6) & 3) << 4)) - 32;
+                part[g]     += q1 * yy[l];
+                part[g + 2] += q2 * yy[l + 32];
+                part[g + 4] += q3 * yy[l + 64];
+                part[g + 6] += q4 * yy[l + 96];
+            }
+            for (int g = 0; g < 8; ++g) total += (int)sc[g] * part[g];
+        }
+        acc += d * (float)total;
+    }
+    return acc;
+}
+
+float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
+    const uint8_t * w = (const uint8_t *)wrow, * y = (const uint8_t *)yq;
+    switch (type) {
+        case OQ_Q4_0: return dot_q4_0_q8_0(k, w, y);
+        case OQ_Q8_0: return dot_q8_0_q8_0(k, w, y);
+        case OQ_Q4_K: return dot_q45_K_q8_K(0, k, w, y);
+        case OQ_Q5_K: return dot_q45_K_q8_K(1, k, w, y);
+        case OQ_Q6_K: return dot_q6_K_q8_K(k, w, y);
+        default: return NAN;
+    }
+}
+
+/* ---------------------------------------------------------------- mat-mul drivers */
+
+static uint8_t * quantize_activations(int vdt, const float * X, int64_t rows, int64_t K, size_t * row_bytes) {
+    const size_t rb = oq_row_size(vdt, K);
+    uint8_t * q = (uint8_t *)malloc(rb * (size_t)rows + 16);
+    if (!q) return NULL;
+    #pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < rows; ++r) {
+        if (vdt == OQ_Q8_0) oq_quantize_row_q8_0_simd(X + r * K, q + rb * r, K);
+        else                quant_q8_K(X + r * K, q + rb * r, K);
+    }
+    *row_bytes = rb;
+    return q;
+}
+
+int oq_mul_mat(int type, const void * W, const float * X, float * Y, int64_t M, int64_t N, int64_t K) {
+    const int vdt = oq_vec_dot_type(type);
+    if (vdt < 0 || K % oq_blck_size(type) != 0) return -1;
+    size_t yrb; uint8_t * yq = quantize_activations(vdt, X, N, K, &yrb);
+    if (!yq) return -2;
+    const size_t wrb = oq_row_size(type, K);
+    #pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m)
+        for (int64_t n = 0; n < N; ++n)
+            Y[n * M + m] = oq_vec_dot(type, K, (const uint8_t *)W + wrb * m, yq + yrb * n);
+    free(yq);
+    return 0;
+}
+
+int oq_mul_mat_f64(int type, const void * W, const float * X, float * Y, int64_t M, int64_t N, int64_t K) {
+    if (K % oq_blck_size(type) != 0) return -1;
+    const size_t wrb = oq_row_size(type, K);
+    int err = 0;
+    #pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+        float * wf = (float *)malloc((size_t)K * 4);
+        if (!wf || oq_dequantize_row(type, (const uint8_t *)W + wrb * m, wf, K) != 0) { err = 1; free(wf); continue; }
+        for (int64_t n = 0; n < N; ++n) {
+            double s = 0.0;
+            for (int64_t k = 0; k < K; ++k) s += (double)wf[k] * (double)X[n * K + k];
+            Y[n * M + m] = (float)s;
+        }
+        free(wf);
+    }
+    return err ? -2 : 0;
+}
+
+int oq_mul_mat_id(int type, const void * W, const float * X, const int32_t * ids, int64_t ids_stride, float * Y,
+                  int64_t M, int64_t K, int64_t n_expert, int64_t n_used, int64_t nb1, int64_t n_tok) {
+    const int vdt = oq_vec_dot_type(type);
+    if (vdt < 0 || K % oq_blck_size(type) != 0) return -1;
+    size_t yrb; uint8_t * yq = quantize_activations(vdt, X, nb1 * n_tok, K, &yrb);
+    if (!yq) return -2;
+    const size_t wrb = oq_row_size(type, K);
+    int bad = 0;
+    #pragma omp parallel for schedule(static) collapse(2)
+    for (int64_t t = 0; t < n_tok; ++t)
+        for (int64_t e = 0; e < n_used; ++e) {
+            const int32_t x = ids[t * ids_stride + e];
+            if (x < 0 || x >= n_expert) { bad = 1; continue; }
+            const uint8_t * w = (const uint8_t *)W + wrb * (size_t)M * (size_t)x;
+            const uint8_t * y = yq + yrb * (size_t)(t * nb1 + (e % nb1));
+            float * out = Y + (t * n_used + e) * M;
+            for (int64_t m = 0; m < M; ++m) out[m] = oq_vec_dot(type, K, w + wrb * m, y);
+        }
+    free(yq);
+    return bad ? -3 : 0;
+}
