@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — GGML_OP_MUL_MAT over block-quantized weights on B200 (contract: see the task statement / DESIGN.md §4).
+
+Headline workload (BASELINE.json configs[1]): Q4_K 4096 -> 11008 mat-vec, n_batch = 1 (Llama-7B FFN shape).
+  step            one sweep over NBUF distinct weight matrices (NBUF x 25.4 MB > 2 x the 126 MB L2, so every
+                  mat-vec streams its weights from HBM), i.e. NBUF mat-vecs
+  value           GB/s of quantized weight bytes processed, whole job (all ranks), inputs resident in HBM,
+                  CUDA-event timed on the launching stream, max over ranks
+  e2e             the same metric through the C ABI with HOST buffers (ggml_b200_mul_mat_host): every mat-vec
+                  copies the activation vector from pinned host memory and the result back, synchronously
+  roofline        algorithmic bytes (weights + x + y) / mean device time per launch, vs the measured HBM peak
+  cpu_baseline    the unmodified reference's ggml-cpu backend (oracle/_ref) on this box's host cores, same shape
+  --impl reference  the reference arm: ggml-cpu via its own public API, same metric/config
+N > 1: weak scaling — every rank owns one row-shard (M rows) of an (N*M) x K matrix and the output slices are
+exchanged with an NCCL all-gather (the path's only exchange step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WL = {"type": "q4_K", "type_id": 12, "K": 4096, "M": 11008, "N": 1}
+METRIC = "mul_mat_q4_K_4096x11008_n1_weight_throughput"
+UNIT = "GB/s"
+
+
+def weight_bytes(K, M):
+    return (K // 256) * 144 * M
+
+
+def algorithmic_bytes(K, M, N):
+    return weight_bytes(K, M) + K * N * 4 + M * N * 4
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_weights(torch, nbuf, K, M, seed):
+    """NBUF distinct packed Q4_K matrices: arbitrary code bytes, finite small fp16 d/dmin per superblock."""
+    rb = (K // 256) * 144
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    out = []
+    for _ in range(nbuf):
+        w = torch.randint(0, 256, (M * (K // 256), 144), dtype=torch.uint8, device="cuda", generator=gen)
+        d = (torch.rand((M * (K // 256), 2), device="cuda", generator=gen) * 2e-3 + 1e-4).to(torch.float16).view(torch.uint8)
+        w[:, 0:4] = d.reshape(-1, 4)
+        out.append(w.reshape(-1))
+    assert out[0].numel() == rb * M
+    return out
+
+
+def cpu_baseline(sample_s=12.0):
+    """The reference's ggml-cpu MUL_MAT on the host cores (oracle/_ref), bounded sample of the same workload."""
+    from oracle import oracle as O
+    ref = O.Ref()
+    K, M, N, t = WL["K"], WL["M"], WL["N"], WL["type_id"]
+    rng = np.random.default_rng(1234)
+    W = O.random_blocks(t, M * K // 256, rng)
+    X = np.random.default_rng(5678).uniform(-1, 1, K * N).astype(np.float32)
+    best = None
+    hw = ref.hw_threads()
+    for threads in sorted({hw, max(1, hw // 2)}, reverse=True):
+        _, s = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=64, iters=1, warmup=1)          # probe
+        iters = max(1, int(sample_s / 2 / max(s * 64, 1e-6)))
+        _, s = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=64, iters=iters, warmup=1)
+        if best is None or s < best[0]:
+            best = (s, threads, iters * 64)
+    s, threads, n = best
+    return {"value": weight_bytes(K, M) / s / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{n} MUL_MAT nodes (q4_K {K}x{M}, n=1, node repeated 64x per graph, persistent threadpool), "
+                      f"ggml-cpu {'native' if ref.native else 'x86-64-v3'} build, {s * 1e6:.1f} us per mat-vec",
+            "us_per_matvec": s * 1e6}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, M, N = WL["K"], WL["M"], WL["N"]
+    from oracle import oracle as O
+    ref = O.Ref()
+    t = WL["type_id"]
+    rng = np.random.default_rng(1234)
+    W = O.random_blocks(t, M * K // 256, rng)
+    X = np.random.default_rng(5678).uniform(-1, 1, K * N).astype(np.float32)
+    threads = ref.hw_threads()
+    # one step = one sweep of NBUF mat-vecs like the GPU arm, shrunk if the requested K steps would take > ~90 s
+    nbuf = 13
+    _, s1 = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=nbuf, iters=2, warmup=1)
+    per_step = nbuf
+    if s1 * nbuf * (args.steps + args.warmup) > 90.0:
+        per_step = max(1, int(90.0 / (s1 * (args.steps + args.warmup))))
+    _, s = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=per_step, iters=args.steps, warmup=args.warmup, e2e=True)
+    val = weight_bytes(K, M) / s / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": s * per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 x int4 (q4_K x q8_K), f32 accumulate",
+            "data": "synthetic", "config": {"workload": f"q4_K {K}x{M} mat-vec n_batch=1 (BASELINE.json configs[1])", "mat_vecs_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{per_step} mat-vecs per step through ggml_backend_graph_compute on ggml-cpu ({'native' if ref.native else 'x86-64-v3'} build), tensor_set/get included"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import ggml_b200 as g
+    g.lib()                                    # fail loudly if the CUDA library is missing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    K, M, N, t = WL["K"], WL["M"], WL["N"], WL["type_id"]
+    wb = weight_bytes(K, M)
+    nbuf = 13                                                       # 13 x 25.4 MB = 330 MB > 2 x L2
+    Ws = make_weights(torch, nbuf, K, M, seed=1234 + rank)
+    X = torch.rand(N * K, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5678)) * 2 - 1
+    Yloc = torch.empty((1, 1, N, M), dtype=torch.float32, device="cuda")
+    Yall = torch.empty((world, N * M), dtype=torch.float32, device="cuda") if world > 1 else None
+    assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMV, "headline workload must run on the TMA mat-vec kernel"
+
+    use_graph = (world == 1) and not args.no_graph
+
+    def sweep():
+        for i in range(nbuf):
+            g.mul_mat(t, Ws[i], X, M, N, K, out=Yloc)
+            if world > 1:
+                dist.all_gather_into_tensor(Yall, Yloc.view(-1))
+
+    sweep()                                                          # first-launch setup outside capture
+    torch.cuda.synchronize()
+    graph = None
+    launches_per_step = None
+    if use_graph:
+        c0 = g.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            sweep()
+        launches_per_step = g.launch_count() - c0
+        step = graph.replay
+    else:
+        step = sweep
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c0 = g.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launched = (g.launch_count() - c0) if not use_graph else launches_per_step * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    n_mv = nbuf * args.steps
+    value = world * n_mv * wb / (ms * 1e-3) / 1e9
+    us_per_launch = ms * 1e3 / n_mv
+
+    # ---- e2e: host buffers through the C ABI (rank-local; aggregated like `value`)
+    import ctypes as C
+    xh = torch.empty(N * K, dtype=torch.float32).pin_memory()
+    xh.copy_(X.cpu())
+    yh = torch.empty(N * M, dtype=torch.float32).pin_memory()
+    a = g.mul_mat_args(t, Ws[0], X, Yloc, M, N, K)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    e2e_n = min(n_mv, 2000)
+
+    def e2e_once(i):
+        a.src0 = Ws[i % nbuf].data_ptr()
+        g.check(g.lib().ggml_b200_mul_mat_host(C.byref(a), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), stream), "ggml_b200_mul_mat_host")
+
+    for i in range(20):
+        e2e_once(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_n):
+        e2e_once(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_val = world * e2e_n * wb / e2e_s / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    achieved = algorithmic_bytes(K, M, N) / (us_per_launch * 1e-6) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "r01_gemv_q4k_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 x int4 (q4_K weights x q8_K activations, dp4a), f32 accumulate", "data": "synthetic",
+        "config": {"workload": f"q4_K {K}x{M} mat-vec n_batch=1 (BASELINE.json configs[1])", "mat_vecs_per_step": nbuf,
+                   "l2_policy": f"inputs larger than L2: {nbuf} distinct weight matrices ({nbuf * wb / 1e6:.0f} MB) visited round-robin",
+                   "launch": "CUDA-graph replay of one sweep" if use_graph else "plain stream launches",
+                   "parallelism": f"row-shard x{world} + NCCL all-gather of output slices" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": K * N * 4 * nbuf, "d2h_bytes_per_step": M * N * 4 * nbuf,
+                "us_per_matvec": e2e_s / e2e_n * 1e6, "api": "ggml_b200_mul_mat_host (pinned host x -> device, kernel, y -> host, stream sync)"},
+        "gpu_launches": int(launched),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "mmvq_tma_kernel<Q4_K,1,4>", "us_per_launch": us_per_launch,
+                     "algorithmic_bytes_per_launch": algorithmic_bytes(K, M, N), "peak_source": peak_src},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as e:                                     # the baseline is a report, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+"""ggml_b200 — B200-native (sm_100a) kernels for ggml's block-quantized MUL_MAT / MUL_MAT_ID hot path.
+
+The product is native code: `libggml-b200-kernels.so` (hand-written CUDA behind the C ABI of
+include/ggml-b200.h) and `libggml-b200.so` (the ggml backend plug-in built on it).  This Python module is only
+a ctypes mirror of that C ABI for tests and benchmarks; PyTorch supplies device memory and streams.
+There is no CPU fallback: importing works anywhere, but every compute entry point raises if the CUDA library
+is missing or reports an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+KERNELS_SO = PKG / "libggml-b200-kernels.so"
+BACKEND_SO = PKG / "libggml-b200.so"
+
+# enum ggml_type ids (reference include/ggml.h:351-390)
+F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 8, 12, 13, 14
+QUANT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
+TYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K"}
+
+MM_AUTO, MM_GENERIC, MM_GEMV, MM_GEMM = 0, 1, 2, 4
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class MulMatArgs(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_int32),
+                ("K", C.c_int64), ("M", C.c_int64), ("N", C.c_int64),
+                ("ne02", C.c_int64), ("ne03", C.c_int64), ("ne12", C.c_int64), ("ne13", C.c_int64),
+                ("nb01", C.c_size_t), ("nb02", C.c_size_t), ("nb03", C.c_size_t),
+                ("nb11", C.c_size_t), ("nb12", C.c_size_t), ("nb13", C.c_size_t),
+                ("src0", C.c_void_p), ("src1", C.c_void_p), ("dst", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_size", C.c_size_t)]
+
+
+class MulMatIdArgs(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_int32),
+                ("K", C.c_int64), ("M", C.c_int64), ("n_expert", C.c_int64), ("n_used", C.c_int64),
+                ("nb1cols", C.c_int64), ("n_tok", C.c_int64),
+                ("nb01", C.c_size_t), ("nb02", C.c_size_t), ("nb11", C.c_size_t), ("nb12", C.c_size_t),
+                ("ids_nb1", C.c_size_t),
+                ("src0", C.c_void_p), ("src1", C.c_void_p), ("ids", C.c_void_p), ("dst", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_size", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The kernel-launch shim.  Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not KERNELS_SO.exists():
+            raise B200Error(f"{KERNELS_SO} is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(str(KERNELS_SO))
+        L.ggml_b200_last_error.restype = C.c_char_p
+        L.ggml_b200_version.restype = C.c_char_p
+        L.ggml_b200_launch_count.restype = C.c_uint64
+        L.ggml_b200_row_size.restype = C.c_size_t
+        L.ggml_b200_row_size.argtypes = [C.c_int32, C.c_int64]
+        L.ggml_b200_act_record_size.restype = C.c_size_t
+        L.ggml_b200_act_record_size.argtypes = [C.c_int32, C.c_int64]
+        L.ggml_b200_quantize_activations.argtypes = [C.c_int32, C.c_void_p, C.c_size_t, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.ggml_b200_mul_mat_workspace_size.restype = C.c_size_t
+        L.ggml_b200_mul_mat_workspace_size.argtypes = [C.POINTER(MulMatArgs)]
+        L.ggml_b200_mul_mat_plan.argtypes = [C.POINTER(MulMatArgs)]
+        L.ggml_b200_mul_mat.argtypes = [C.POINTER(MulMatArgs), C.c_void_p]
+        L.ggml_b200_mul_mat_host.argtypes = [C.POINTER(MulMatArgs), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ggml_b200_mul_mat_id_workspace_size.restype = C.c_size_t
+        L.ggml_b200_mul_mat_id_workspace_size.argtypes = [C.POINTER(MulMatIdArgs)]
+        L.ggml_b200_mul_mat_id.argtypes = [C.POINTER(MulMatIdArgs), C.c_void_p]
+        L.ggml_b200_dequantize.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+        L.ggml_b200_quantize.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise B200Error(f"{what} failed ({rc}): {lib().ggml_b200_last_error().decode()}")
+
+
+def row_size(t: int, k: int) -> int:
+    return int(lib().ggml_b200_row_size(t, k))
+
+
+def launch_count() -> int:
+    return int(lib().ggml_b200_launch_count())
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Workspace:
+    """Grow-only device scratch (a torch uint8 tensor) handed to the C ABI."""
+
+    def __init__(self):
+        self.t = None
+
+    def get(self, nbytes: int):
+        import torch
+        if self.t is None or self.t.numel() < nbytes:
+            self.t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device="cuda")
+        return self.t
+
+
+_ws = Workspace()
+
+
+def mul_mat_args(t, W, X, Y, M, N, K, batch=(1, 1, 1, 1), flags=MM_AUTO, nb=None) -> MulMatArgs:
+    """W: cuda uint8 tensor of packed blocks; X: cuda float32; Y: cuda float32 [ne13, ne12, N, M]."""
+    ne02, ne03, ne12, ne13 = batch
+    rb = row_size(t, K)
+    a = MulMatArgs()
+    a.type, a.flags, a.K, a.M, a.N = t, flags, K, M, N
+    a.ne02, a.ne03, a.ne12, a.ne13 = ne02, ne03, ne12, ne13
+    if nb is None:
+        a.nb01, a.nb02, a.nb03 = rb, rb * M, rb * M * ne02
+        a.nb11, a.nb12, a.nb13 = K * 4, K * 4 * N, K * 4 * N * ne12
+    else:
+        a.nb01, a.nb02, a.nb03, a.nb11, a.nb12, a.nb13 = nb
+    a.src0, a.src1, a.dst = W.data_ptr(), X.data_ptr(), Y.data_ptr()
+    need = int(lib().ggml_b200_mul_mat_workspace_size(C.byref(a)))
+    ws = _ws.get(need)
+    a.workspace, a.workspace_size = ws.data_ptr(), ws.numel()
+    return a
+
+
+def mul_mat(t, W, X, M, N, K, batch=(1, 1, 1, 1), flags=MM_AUTO, out=None, nb=None):
+    """GGML_OP_MUL_MAT on the current CUDA stream.  Returns Y[ne13, ne12, N, M] (float32, cuda)."""
+    import torch
+    ne02, ne03, ne12, ne13 = batch
+    Y = out if out is not None else torch.empty((ne13, ne12, N, M), dtype=torch.float32, device="cuda")
+    a = mul_mat_args(t, W, X, Y, M, N, K, batch, flags, nb)
+    check(lib().ggml_b200_mul_mat(C.byref(a), _stream()), "ggml_b200_mul_mat")
+    return Y
+
+
+def mul_mat_plan(t, M, N, K, flags=MM_AUTO) -> int:
+    import torch
+    a = MulMatArgs()
+    a.type, a.flags, a.K, a.M, a.N = t, flags, K, M, N
+    a.ne02 = a.ne03 = a.ne12 = a.ne13 = 1
+    rb = row_size(t, K)
+    a.nb01, a.nb02, a.nb03, a.nb11, a.nb12, a.nb13 = rb, rb * M, rb * M, K * 4, K * 4 * N, K * 4 * N
+    a.src0 = a.src1 = a.dst = 256      # aligned dummies: plan() never dereferences
+    return int(lib().ggml_b200_mul_mat_plan(C.byref(a)))
+
+
+def mul_mat_id(t, W, X, ids, M, K, n_expert, n_used, nb1cols, n_tok):
+    """GGML_OP_MUL_MAT_ID.  W: packed [n_expert, M, row]; X: f32 [n_tok, nb1cols, K]; ids: int32 [n_tok, >= n_used]."""
+    import torch
+    Y = torch.empty((n_tok, n_used, M), dtype=torch.float32, device="cuda")
+    rb = row_size(t, K)
+    a = MulMatIdArgs()
+    a.type, a.flags, a.K, a.M = t, 0, K, M
+    a.n_expert, a.n_used, a.nb1cols, a.n_tok = n_expert, n_used, nb1cols, n_tok
+    a.nb01, a.nb02, a.nb11, a.nb12 = rb, rb * M, K * 4, K * 4 * nb1cols
+    a.ids_nb1 = ids.stride(0) * 4
+    a.src0, a.src1, a.ids, a.dst = W.data_ptr(), X.data_ptr(), ids.data_ptr(), Y.data_ptr()
+    need = int(lib().ggml_b200_mul_mat_id_workspace_size(C.byref(a)))
+    ws = _ws.get(need)
+    a.workspace, a.workspace_size = ws.data_ptr(), ws.numel()
+    check(lib().ggml_b200_mul_mat_id(C.byref(a), _stream()), "ggml_b200_mul_mat_id")
+    return Y
+
+
+def dequantize(t, blocks, n, dtype=None):
+    import torch
+    dtype = dtype or torch.float32
+    out = torch.empty(n, dtype=dtype, device="cuda")
+    check(lib().ggml_b200_dequantize(t, blocks.data_ptr(), out.data_ptr(), F32 if dtype == torch.float32 else F16, n, _stream()),
+          "ggml_b200_dequantize")
+    return out
+
+
+def quantize(t, x):
+    import torch
+    x = x.contiguous()
+    out = torch.empty(row_size(t, x.numel()), dtype=torch.uint8, device="cuda")
+    check(lib().ggml_b200_quantize(t, x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ggml_b200_quantize")
+    return out
+
+
+def quantize_activations(weight_type, x):
+    """x: f32 cuda [rows, K] -> uint8 [rows, record_size] (q | bsums | d), as the mat-vec kernels consume it."""
+    import torch
+    rows, K = x.shape
+    rs = int(lib().ggml_b200_act_record_size(weight_type, K))
+    out = torch.zeros((rows, rs), dtype=torch.uint8, device="cuda")
+    check(lib().ggml_b200_quantize_activations(weight_type, x.data_ptr(), x.stride(0) * 4, rows, K, out.data_ptr(), _stream()),
+          "ggml_b200_quantize_activations")
+    return out

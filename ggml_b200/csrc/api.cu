@@ -1,0 +1,131 @@
+// api.cu — extern "C" kernel-launch shim (include/ggml-b200.h, layer 1): argument validation, kernel-family
+// selection, workspace accounting.  No CPU fallback anywhere: unsupported combinations return an error code.
+#include "b200_internal.h"
+#include "b200_quants.cuh"
+
+#include <cstdarg>
+#include <mutex>
+
+namespace b200 {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char * fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static int validate(const ggml_b200_mul_mat_args * a) {
+    if (!a) { set_error("mul_mat: NULL args"); return GGML_B200_EINVAL; }
+    if (type_bytes(a->type) == 0) { set_error("mul_mat: unsupported weight type %d", a->type); return GGML_B200_EUNSUPPORTED; }
+    if (a->K <= 0 || a->M < 0 || a->N < 0 || a->ne02 < 1 || a->ne03 < 1 || a->ne12 < 1 || a->ne13 < 1) { set_error("mul_mat: bad shape"); return GGML_B200_EINVAL; }
+    if (a->K % type_qk(a->type) != 0) { set_error("mul_mat: K=%lld is not a multiple of the block size %d", (long long)a->K, type_qk(a->type)); return GGML_B200_EINVAL; }
+    if (a->ne12 % a->ne02 != 0 || a->ne13 % a->ne03 != 0) { set_error("mul_mat: batch dims do not broadcast"); return GGML_B200_EINVAL; }
+    if (a->M > 0 && a->N > 0 && (!a->src0 || !a->src1 || !a->dst)) { set_error("mul_mat: NULL tensor pointer"); return GGML_B200_EINVAL; }
+    if (a->nb01 < row_bytes(a->type, a->K) || (a->nb01 & 1) || (a->nb02 & 1) || (a->nb03 & 1) || ((uintptr_t)a->src0 & 1)) { set_error("mul_mat: bad src0 strides/alignment"); return GGML_B200_EINVAL; }
+    if ((a->nb11 & 3) || (a->nb12 & 3) || (a->nb13 & 3) || ((uintptr_t)a->src1 & 3)) { set_error("mul_mat: src1 must be 4-byte aligned"); return GGML_B200_EINVAL; }
+    // Q4_K / Q5_K headers are read as 16-byte vectors
+    if ((a->type == T_Q4_K || a->type == T_Q5_K) && (((uintptr_t)a->src0 | a->nb01 | a->nb02 | a->nb03) & 15)) { set_error("mul_mat: Q4_K/Q5_K rows must be 16-byte aligned"); return GGML_B200_EINVAL; }
+    return GGML_B200_OK;
+}
+
+static int plan(const ggml_b200_mul_mat_args & a) {
+    if (a.flags & GGML_B200_MM_FORCE_GENERIC) return GGML_B200_MM_FORCE_GENERIC;
+    if (a.flags & GGML_B200_MM_FORCE_GEMV) return mmvq_tma_eligible(a) ? GGML_B200_MM_FORCE_GEMV : GGML_B200_EUNSUPPORTED;
+    if (a.flags & GGML_B200_MM_FORCE_GEMM) return mmq_tc_eligible(a) ? GGML_B200_MM_FORCE_GEMM : GGML_B200_EUNSUPPORTED;
+    if (a.N <= 8 && mmvq_tma_eligible(a)) return GGML_B200_MM_FORCE_GEMV;
+    if (a.N > 8 && mmq_tc_eligible(a)) return GGML_B200_MM_FORCE_GEMM;
+    return GGML_B200_MM_FORCE_GENERIC;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char * ggml_b200_last_error(void) { return g_err; }
+const char * ggml_b200_version(void) { return "ggml-b200 0.1 (sm_100a)"; }
+uint64_t ggml_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int ggml_b200_sm_count(void) { return sm_count(); }
+int ggml_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+size_t ggml_b200_row_size(int32_t type, int64_t k) {
+    if (type == T_F32) return (size_t)k * 4;
+    if (type == T_F16) return (size_t)k * 2;
+    return row_bytes(type, k);
+}
+
+size_t ggml_b200_act_record_size(int32_t weight_type, int64_t K) {
+    return (size_t)make_act_layout(K, type_is_kquant(weight_type)).bytes;
+}
+
+int ggml_b200_quantize_activations(int32_t weight_type, const float * src, size_t row_stride_bytes, int64_t nrows, int64_t K,
+                                   void * dst_records, void * stream) {
+    if (type_bytes(weight_type) == 0 || K <= 0 || K % type_qk(weight_type) != 0 || nrows < 0 || (row_stride_bytes & 3)) { set_error("quantize_activations: bad arguments"); return GGML_B200_EINVAL; }
+    return launch_quantize_activations(weight_type, src, K, nrows, 1, 1, row_stride_bytes, 0, 0, dst_records, (cudaStream_t)stream);
+}
+
+int ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args) {
+    const int rc = validate(args);
+    if (rc != GGML_B200_OK) return rc;
+    return plan(*args);
+}
+
+size_t ggml_b200_mul_mat_workspace_size(const ggml_b200_mul_mat_args * args) {
+    if (validate(args) != GGML_B200_OK) return 0;
+    switch (plan(*args)) {
+        case GGML_B200_MM_FORCE_GEMV: return 0;
+        case GGML_B200_MM_FORCE_GEMM: return mmq_tc_workspace(*args);
+        default: return mmvq_generic_workspace(*args);
+    }
+}
+
+int ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream) {
+    int rc = validate(args);
+    if (rc != GGML_B200_OK) return rc;
+    if (args->M == 0 || args->N == 0) return GGML_B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (plan(*args)) {
+        case GGML_B200_MM_FORCE_GEMV:    return launch_mmvq_tma(*args, st);
+        case GGML_B200_MM_FORCE_GEMM:    return launch_mmq_tc(*args, st);
+        case GGML_B200_MM_FORCE_GENERIC: return launch_mmvq_generic(*args, st);
+        default: set_error("mul_mat: the forced kernel family cannot run this shape"); return GGML_B200_EUNSUPPORTED;
+    }
+}
+
+int ggml_b200_mul_mat_host(const ggml_b200_mul_mat_args * args, const float * host_src1, float * host_dst, void * stream) {
+    int rc = validate(args);
+    if (rc != GGML_B200_OK) return rc;
+    if (!host_src1 || !host_dst) { set_error("mul_mat_host: NULL host pointer"); return GGML_B200_EINVAL; }
+    if (args->nb11 != (size_t)args->K * 4 || args->nb12 != args->nb11 * (size_t)args->N || args->nb13 != args->nb12 * (size_t)args->ne12) { set_error("mul_mat_host: device staging for src1 must be contiguous"); return GGML_B200_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t xin = (size_t)args->K * args->N * args->ne12 * args->ne13 * 4, yout = (size_t)args->M * args->N * args->ne12 * args->ne13 * 4;
+    B200_CUDA_TRY(cudaMemcpyAsync((void *)args->src1, host_src1, xin, cudaMemcpyHostToDevice, st));
+    rc = ggml_b200_mul_mat(args, stream);
+    if (rc != GGML_B200_OK) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(host_dst, args->dst, yout, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return GGML_B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,46 @@
+// b200_internal.h — host-side plumbing shared by the kernel translation units (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/ggml-b200.h"
+
+namespace b200 {
+
+extern std::atomic<uint64_t> g_launches;
+void set_error(const char * fmt, ...);
+int  sm_count();
+
+#define B200_CUDA_TRY(expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            ::b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return GGML_B200_ECUDA;                                                                 \
+        }                                                                                           \
+    } while (0)
+
+#define B200_LAUNCH_CHECK()                                                                          \
+    do {                                                                                            \
+        ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+        B200_CUDA_TRY(cudaGetLastError());                                                          \
+    } while (0)
+
+// mmvq.cu
+int    launch_quantize_activations(int type, const float * x, int64_t K, int64_t n11, int64_t n12, int64_t n13,
+                                   size_t nb11, size_t nb12, size_t nb13, void * recs, cudaStream_t st);
+int    launch_mmvq_generic(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+bool   mmvq_tma_eligible(const ggml_b200_mul_mat_args & a);
+int    launch_mmvq_tma(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+size_t mmvq_generic_workspace(const ggml_b200_mul_mat_args & a);
+
+// mmq_tc.cu (tcgen05 GEMM)
+bool   mmq_tc_eligible(const ggml_b200_mul_mat_args & a);
+size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a);
+int    launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+
+} // namespace b200

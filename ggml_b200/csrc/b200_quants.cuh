@@ -1,0 +1,310 @@
+// b200_quants.cuh — packed block formats and the 64-element "unit" integer dot product (sm_100a).
+//
+// Weights stay in the reference's packed block_q* layout in HBM (consumed as-is, never repacked):
+//   Q4_0 18 B / 32   (reference src/ggml-common.h:161-166)   Q8_0 34 B / 32   (:203-208)
+//   Q4_K 144 B / 256 (:279-290)   Q5_K 176 B / 256 (:296-308)   Q6_K 210 B / 256 (:314-320)
+// Activations are quantized on the fly to int8 exactly as the reference CPU backend does before its
+// vec_dot (src/ggml-cpu/ggml-cpu.c:7490-7509): Q8_0-style (per 32, fp16-rounded scale; AVX2 flavour
+// src/ggml-cpu/ggml-cpu-quants.c:778-835) for Q4_0/Q8_0 weights, Q8_K-style (per 256, f32 scale;
+// src/ggml-quants.c:2479-2516) for the K-quants, so results match ggml-cpu up to f32 summation order.
+//
+// Work decomposition shared by every mat-vec kernel: a row is a sequence of UNITS of 64 weights.
+//   Q4_0 / Q8_0 : unit u = blocks 2u, 2u+1               (36 B / 68 B, 4-byte aligned when K % 64 == 0)
+//   Q4_K / Q5_K : unit u = superblock u/4, 64-chunk u%4  (32 B of qs [+ 32 B qh] + the 16 B header)
+//   Q6_K        : unit u = superblock u/4, half (u/2)%2, l-range 16*(u%2): 4 groups of 16 weights
+// A unit's activations are 4 pieces of 16 int8: contiguous for all formats but Q6_K (stride 32).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// enum ggml_type ids (reference include/ggml.h:351-390)
+enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
+
+template <int T> struct fmt;
+template <> struct fmt<T_Q4_0> { static constexpr int QK = 32,  BYTES = 18,  ACT_K = 0; };
+template <> struct fmt<T_Q8_0> { static constexpr int QK = 32,  BYTES = 34,  ACT_K = 0; };
+template <> struct fmt<T_Q4_K> { static constexpr int QK = 256, BYTES = 144, ACT_K = 1; };
+template <> struct fmt<T_Q5_K> { static constexpr int QK = 256, BYTES = 176, ACT_K = 1; };
+template <> struct fmt<T_Q6_K> { static constexpr int QK = 256, BYTES = 210, ACT_K = 1; };
+
+__host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 ? 32 : 256; }
+__host__ __device__ inline int    type_bytes(int t) { return t == T_Q4_0 ? 18 : t == T_Q8_0 ? 34 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : 0; }
+__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K; }
+__host__ __device__ inline size_t row_bytes(int t, int64_t k) { return (size_t)(k / type_qk(t)) * type_bytes(t); }
+
+// ------------------------------------------------------------------ quantized activation record
+// One record per activation row (K values), the same for both families:
+//   q   : int8[K]
+//   bs  : int16[K/16]   sums of q over groups of 16 (block_q8_K.bsums; also gives Q4_0's "-8" term)
+//   d   : float[K/32] (fp16-rounded, Q8_0 family) or float[K/256] (Q8_K family)
+// laid out q | bs | d, each part 16-byte aligned.
+struct act_layout {
+    int32_t off_bs, off_d, bytes;
+};
+__host__ __device__ inline act_layout make_act_layout(int64_t K, bool kq) {
+    act_layout L;
+    L.off_bs = (int32_t)((K + 15) & ~(int64_t)15);
+    L.off_d  = L.off_bs + (int32_t)(((K / 16) * 2 + 15) & ~(int64_t)15);
+    L.bytes  = L.off_d + (int32_t)((((kq ? K / 256 : K / 32)) * 4 + 15) & ~(int64_t)15);
+    return L;
+}
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ float h2f(uint32_t bits16) { return __half2float(__ushort_as_half((unsigned short)bits16)); }
+
+// n consecutive 32-bit words starting at a 2-byte aligned address (generic/global/shared)
+template <int N> __device__ __forceinline__ void load_words_a2(const uint8_t * p, uint32_t (&w)[N]) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t * q = (const uint32_t *)(a & ~(uintptr_t)3);
+    if (a & 2) {
+        uint32_t prev = q[0];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const uint32_t nxt = q[i + 1]; w[i] = __funnelshift_r(prev, nxt, 16); prev = nxt; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = q[i];
+    }
+}
+__device__ __forceinline__ uint32_t load_u16(const uint8_t * p) { return *(const uint16_t *)p; }
+
+// activations of one unit, shared by every weight row processed against it
+struct unit_act {
+    int   q[16];   // 64 int8
+    int   bs[4];   // sums of the four groups of 16
+    float d[2];    // Q8_0 family: scales of the two 32-blocks; Q8_K family: d[0] = superblock scale
+};
+
+// k offset of 16-piece g of unit u
+template <int T> __device__ __forceinline__ int unit_piece_k(int u, int g) {
+    if constexpr (T == T_Q6_K) return (u >> 2) * 256 + ((u >> 1) & 1) * 128 + (u & 1) * 16 + g * 32;
+    else                       return u * 64 + g * 16;
+}
+
+template <int T> __device__ __forceinline__ void load_unit_act(const uint8_t * rec, const act_layout & L, int u, unit_act & A) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int k = unit_piece_k<T>(u, g);
+        const int4 v = *(const int4 *)(rec + k);
+        A.q[4 * g + 0] = v.x; A.q[4 * g + 1] = v.y; A.q[4 * g + 2] = v.z; A.q[4 * g + 3] = v.w;
+        A.bs[g] = *(const int16_t *)(rec + L.off_bs + (k >> 4) * 2);
+    }
+    const float * d = (const float *)(rec + L.off_d);
+    if constexpr (fmt<T>::ACT_K) { A.d[0] = d[u >> 2]; A.d[1] = 0.0f; }
+    else                        { A.d[0] = d[2 * u]; A.d[1] = d[2 * u + 1]; }
+}
+
+// ------------------------------------------------------------------ unit dot products
+// `row` points at the first byte of a weight row (2-byte aligned; 16-byte aligned for Q4_K/Q5_K).
+// Returns this unit's contribution to dot(row, activation) in f32.
+
+__device__ __forceinline__ int dp4a_s(int a, int b, int c) { return __dp4a(a, b, c); }
+
+// Q4_K / Q5_K: 6-bit (scale, min) pair j of the 12-byte packing (reference get_scale_min_k4, ggml-quants.c:631-638)
+__device__ __forceinline__ void k4_scale_min(const uint32_t (&s)[3], int j, int & sc, int & mn) {
+    // s[0] = bytes 0..3, s[1] = bytes 4..7, s[2] = bytes 8..11
+    if (j < 4) {
+        sc = (s[0] >> (8 * j)) & 63;
+        mn = (s[1] >> (8 * j)) & 63;
+    } else {
+        const int jj = j - 4;
+        const uint32_t b8 = (s[2] >> (8 * jj)) & 0xFF;
+        sc = (b8 & 0x0F) | (((s[0] >> (8 * jj + 6)) & 3) << 4);
+        mn = (b8 >> 4)   | (((s[1] >> (8 * jj + 6)) & 3) << 4);
+    }
+}
+
+template <int T> __device__ __forceinline__ float unit_dot(const uint8_t * row, int u, const unit_act & A);
+
+template <> __device__ __forceinline__ float unit_dot<T_Q4_0>(const uint8_t * row, int u, const unit_act & A) {
+    uint32_t w[9];
+    load_words_a2<9>(row + 36 * u, w);
+    // block 0: d = w0[15:0], qs = bytes 2..17 ; block 1: d = w4[31:16], qs = w5..w8
+    uint32_t qa[4], qb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qa[i] = __funnelshift_r(w[i], w[i + 1], 16); qb[i] = w[5 + i]; }
+    int s0 = 0, s1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s0 = dp4a_s(qa[i] & 0x0F0F0F0F,        A.q[i],      s0);
+        s0 = dp4a_s((qa[i] >> 4) & 0x0F0F0F0F, A.q[4 + i],  s0);
+        s1 = dp4a_s(qb[i] & 0x0F0F0F0F,        A.q[8 + i],  s1);
+        s1 = dp4a_s((qb[i] >> 4) & 0x0F0F0F0F, A.q[12 + i], s1);
+    }
+    s0 -= 8 * (A.bs[0] + A.bs[1]);
+    s1 -= 8 * (A.bs[2] + A.bs[3]);
+    const float d0 = h2f(w[0] & 0xFFFF), d1 = h2f(w[4] >> 16);
+    return (float)s0 * d0 * A.d[0] + (float)s1 * d1 * A.d[1];
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q8_0>(const uint8_t * row, int u, const unit_act & A) {
+    uint32_t w[17];
+    load_words_a2<17>(row + 68 * u, w);
+    int s0 = 0, s1 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s0 = dp4a_s((int)__funnelshift_r(w[i], w[i + 1], 16), A.q[i], s0);
+        s1 = dp4a_s((int)w[9 + i], A.q[8 + i], s1);
+    }
+    const float d0 = h2f(w[0] & 0xFFFF), d1 = h2f(w[8] >> 16);
+    return (float)s0 * (d0 * A.d[0]) + (float)s1 * (d1 * A.d[1]);
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q4_K>(const uint8_t * row, int u, const unit_act & A) {
+    const uint8_t * sb = row + 144 * (u >> 2);
+    const int c = u & 3;
+    const uint4 hdr = *(const uint4 *)sb;                   // d | dmin | scales[12]
+    const uint4 qa = *(const uint4 *)(sb + 16 + 32 * c), qb = *(const uint4 *)(sb + 32 + 32 * c);
+    const uint32_t q[8] = { qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w };
+    int p0 = 0, p1 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        p0 = dp4a_s(q[i] & 0x0F0F0F0F,        A.q[i],     p0);
+        p1 = dp4a_s((q[i] >> 4) & 0x0F0F0F0F, A.q[8 + i], p1);
+    }
+    const uint32_t s[3] = { hdr.y, hdr.z, hdr.w };
+    int sc0, m0, sc1, m1;
+    k4_scale_min(s, 2 * c, sc0, m0);
+    k4_scale_min(s, 2 * c + 1, sc1, m1);
+    const float d = h2f(hdr.x & 0xFFFF) * A.d[0], dmin = h2f(hdr.x >> 16) * A.d[0];
+    return d * (float)(sc0 * p0 + sc1 * p1) - dmin * (float)(m0 * (A.bs[0] + A.bs[1]) + m1 * (A.bs[2] + A.bs[3]));
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q5_K>(const uint8_t * row, int u, const unit_act & A) {
+    const uint8_t * sb = row + 176 * (u >> 2);
+    const int c = u & 3;
+    const uint4 hdr = *(const uint4 *)sb;                   // d | dmin | scales[12]
+    const uint4 ha = *(const uint4 *)(sb + 16), hb = *(const uint4 *)(sb + 32);      // qh[32]
+    const uint4 qa = *(const uint4 *)(sb + 48 + 32 * c), qb = *(const uint4 *)(sb + 64 + 32 * c);
+    const uint32_t q[8] = { qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w };
+    const uint32_t h[8] = { ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w };
+    int p0 = 0, p1 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t hi = h[i] >> (2 * c);
+        p0 = dp4a_s((q[i] & 0x0F0F0F0F)        | ((hi & 0x01010101) << 4), A.q[i],     p0);
+        p1 = dp4a_s(((q[i] >> 4) & 0x0F0F0F0F) | ((hi & 0x02020202) << 3), A.q[8 + i], p1);
+    }
+    const uint32_t s[3] = { hdr.y, hdr.z, hdr.w };
+    int sc0, m0, sc1, m1;
+    k4_scale_min(s, 2 * c, sc0, m0);
+    k4_scale_min(s, 2 * c + 1, sc1, m1);
+    const float d = h2f(hdr.x & 0xFFFF) * A.d[0], dmin = h2f(hdr.x >> 16) * A.d[0];
+    return d * (float)(sc0 * p0 + sc1 * p1) - dmin * (float)(m0 * (A.bs[0] + A.bs[1]) + m1 * (A.bs[2] + A.bs[3]));
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q6_K>(const uint8_t * row, int u, const unit_act & A) {
+    const uint8_t * sb = row + 210 * (u >> 2);
+    const int h = (u >> 1) & 1, j = u & 1;
+    uint32_t la[4], lb[4], qh[4], sw[2];
+    load_words_a2<4>(sb + 64 * h + 16 * j, la);             // ql[64h + l],      l = 16j .. 16j+15
+    load_words_a2<4>(sb + 64 * h + 32 + 16 * j, lb);        // ql[64h + 32 + l]
+    load_words_a2<4>(sb + 128 + 32 * h + 16 * j, qh);       // qh[32h + l]
+    load_words_a2<2>(sb + 192 + 8 * h, sw);                 // scales[8h .. 8h+7]
+    int p[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        p[0] = dp4a_s((la[i] & 0x0F0F0F0F)        | ((qh[i] << 4) & 0x30303030), A.q[i],      p[0]);
+        p[1] = dp4a_s((lb[i] & 0x0F0F0F0F)        | ((qh[i] << 2) & 0x30303030), A.q[4 + i],  p[1]);
+        p[2] = dp4a_s(((la[i] >> 4) & 0x0F0F0F0F) | ( qh[i]       & 0x30303030), A.q[8 + i],  p[2]);
+        p[3] = dp4a_s(((lb[i] >> 4) & 0x0F0F0F0F) | ((qh[i] >> 2) & 0x30303030), A.q[12 + i], p[3]);
+    }
+    int tot = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int idx = j + 2 * g;                                            // scales[8h + j + 2g]
+        const int sc = (int)(int8_t)((sw[idx >> 2] >> (8 * (idx & 3))) & 0xFF);
+        tot += sc * (p[g] - 32 * A.bs[g]);
+    }
+    const float d = h2f(load_u16(sb + 208)) * A.d[0];
+    return d * (float)tot;
+}
+
+// ------------------------------------------------------------------ activation quantizers (device)
+__device__ __forceinline__ float4 load_f4(const float * p) {
+    if (((uintptr_t)p & 15) == 0) return *(const float4 *)p;
+    return make_float4(p[0], p[1], p[2], p[3]);
+}
+
+// One warp quantizes 256 consecutive activations x[0..255] (a Q8_K superblock, or eight Q8_0 blocks):
+// lane l holds x[4l..4l+3] and x[128+4l..128+4l+3].  `kvalid` = number of valid elements (multiple of 32).
+
+// Q8_0 family, AVX2 flavour: d = fp16(amax/127), q = rne(x * (127/amax))
+__device__ __forceinline__ void warp_quantize_q8_0_x256(const float * x, int kvalid, uint8_t * rec, const act_layout & L, int k0) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int k = half * 128 + 4 * lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < kvalid) v = load_f4(x + k);
+        float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+        const int q0 = __float2int_rn(v.x * id), q1 = __float2int_rn(v.y * id), q2 = __float2int_rn(v.z * id), q3 = __float2int_rn(v.w * id);
+        int s = q0 + q1 + q2 + q3;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);      // sum over 16 elements (4 lanes)
+        if (k < kvalid) {
+            *(uint32_t *)(rec + k0 + k) = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+            if ((lane & 3) == 0) *(int16_t *)(rec + L.off_bs + ((k0 + k) >> 4) * 2) = (int16_t)s;
+            if ((lane & 7) == 0) ((float *)(rec + L.off_d))[(k0 + k) >> 5] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
+        }
+    }
+}
+
+// Q8_K family: iscale = -127/max (max = the first element of largest magnitude), q = min(127, rne(iscale*x)), d = 1/iscale
+__device__ __forceinline__ void warp_quantize_q8_K_x256(const float * x, uint8_t * rec, const act_layout & L, int k0) {
+    const int lane = threadIdx.x & 31;
+    const float4 a = load_f4(x + 4 * lane), b = load_f4(x + 128 + 4 * lane);
+    const float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+    float amax = 0.0f, vmax = 0.0f; int imax = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = (i < 4 ? 4 * lane + i : 128 + 4 * lane + (i - 4));
+        const float ax = fabsf(v[i]);
+        if (ax > amax || (ax == amax && ax != 0.0f && idx < imax)) { amax = ax; vmax = v[i]; imax = idx; }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, amax, o), ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+        const int   oi = __shfl_xor_sync(0xffffffffu, imax, o);
+        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; vmax = ov; imax = oi; }
+    }
+    int q[8];
+    float d = 0.0f;
+    if (amax != 0.0f) {
+        const float iscale = __fdiv_rn(-127.0f, vmax);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = min(127, __float2int_rn(iscale * v[i]));
+        d = __fdiv_rn(1.0f, iscale);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = 0;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int k = half * 128 + 4 * lane;
+        const int * qq = q + 4 * half;
+        *(uint32_t *)(rec + k0 + k) = (uint32_t)(qq[0] & 0xFF) | ((uint32_t)(qq[1] & 0xFF) << 8) | ((uint32_t)(qq[2] & 0xFF) << 16) | ((uint32_t)(qq[3] & 0xFF) << 24);
+        int s = qq[0] + qq[1] + qq[2] + qq[3];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if ((lane & 3) == 0) *(int16_t *)(rec + L.off_bs + ((k0 + k) >> 4) * 2) = (int16_t)s;
+    }
+    if (lane == 0) ((float *)(rec + L.off_d))[k0 >> 8] = d;
+}
+
+// all warps of the CTA quantize one activation row x[0..K) into `rec` (shared or global)
+template <bool KQ> __device__ __forceinline__ void cta_quantize_row(const float * x, int64_t K, uint8_t * rec, const act_layout & L) {
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int64_t k0 = (int64_t)warp * 256; k0 < K; k0 += (int64_t)nwarp * 256) {
+        if constexpr (KQ) warp_quantize_q8_K_x256(x + k0, rec, L, (int)k0);
+        else              warp_quantize_q8_0_x256(x + k0, (int)min((int64_t)256, K - k0), rec, L, (int)k0);
+    }
+}
+
+} // namespace b200

@@ -1,0 +1,553 @@
+// ggml-b200.cpp — the ggml backend plug-in (include/ggml-b200.h, layer 2).
+//
+// Implements the reference's backend SPI (src/ggml-backend-impl.h:17-207) for NVIDIA B200:
+//   ggml_backend_reg_i          -> "B200" registry entry, one device per visible GPU
+//   ggml_backend_device_i       -> B200<i>: memory, props, supports_op / supports_buft / offload_op, events
+//   ggml_backend_buffer_type_i  -> device memory (cudaMalloc), alignment 128; pinned host buffer type
+//   ggml_backend_buffer_i       -> set/get/memset/cpy/clear with synchronous semantics
+//   ggml_backend_i              -> one CUDA stream; graph_compute walks cgraph->nodes and launches the kernels
+//                                  of libggml-b200-kernels.so through its extern "C" shim
+// so that ggml_backend_sched, tests/test-backend-ops and examples/gpt-2 drive it unmodified.  This file is what
+// would live in src/ggml-b200/ of the ggml tree; it is host-side C++ only (no kernels) and is compiled against
+// the reference's headers.  It replaces the vtable glue of src/ggml-cuda/ggml-cuda.cu:480-3438.
+//
+// supports_op is exact: anything it accepts is executed on the device, there is no CPU fallback in here
+// (unsupported nodes reaching graph_compute abort, as in the reference, ggml-cuda.cu:2655-2659).
+
+#include "ggml.h"
+#include "ggml-backend.h"
+#include "ggml-backend-impl.h"
+#include "ggml-impl.h"
+#include "ggml-cuda.h"          // the C ABI we additionally provide for programs built with -DGGML_USE_CUDA
+
+#include "ggml-b200.h"
+#include "ggml-b200-backend.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define B200_MAX_DEVICES 16
+
+#define CUDA_OK(expr)                                                                                          \
+    do {                                                                                                       \
+        cudaError_t err_ = (expr);                                                                             \
+        if (err_ != cudaSuccess) {                                                                             \
+            GGML_LOG_ERROR("ggml-b200: %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(err_), __FILE__, __LINE__); \
+            GGML_ABORT("CUDA error");                                                                          \
+        }                                                                                                      \
+    } while (0)
+
+#define SHIM_OK(expr)                                                                                          \
+    do {                                                                                                       \
+        int rc_ = (expr);                                                                                      \
+        if (rc_ != GGML_B200_OK) {                                                                             \
+            GGML_LOG_ERROR("ggml-b200: %s failed (%d): %s\n", #expr, rc_, ggml_b200_last_error());             \
+            GGML_ABORT("kernel shim error");                                                                   \
+        }                                                                                                      \
+    } while (0)
+
+namespace {
+
+struct device_ctx {
+    int         index = 0;
+    std::string name;          // "B2000", "B2001", ...
+    std::string description;   // cudaDeviceProp.name
+    ggml_backend_buffer_type buft{};        // device memory
+    std::string buft_name;
+};
+
+struct backend_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    void *       workspace = nullptr;   // stream-ordered scratch for the kernel shim
+    size_t       workspace_size = 0;
+    std::string  name;
+
+    void * scratch(size_t need) {
+        if (need <= workspace_size) return workspace;
+        if (workspace) CUDA_OK(cudaFreeAsync(workspace, stream));
+        size_t sz = need + need / 4;
+        sz = (sz + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+        CUDA_OK(cudaMallocAsync(&workspace, sz, stream));
+        workspace_size = sz;
+        return workspace;
+    }
+};
+
+struct buffer_ctx {
+    int    device = 0;
+    void * base = nullptr;
+};
+
+struct scoped_device {
+    int prev = -1;
+    explicit scoped_device(int dev) {
+        CUDA_OK(cudaGetDevice(&prev));
+        if (prev != dev) CUDA_OK(cudaSetDevice(dev)); else prev = -1;
+    }
+    ~scoped_device() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+ggml_backend_reg_t b200_reg();
+ggml_guid_t b200_guid() {
+    static ggml_guid guid = { 0xb2, 0x00, 0x5a, 0x10, 0x0a, 0x67, 0x67, 0x6d, 0x6c, 0x2d, 0x62, 0x32, 0x30, 0x30, 0x01, 0x00 };
+    return &guid;
+}
+
+// ------------------------------------------------------------------------------------------ buffers
+bool buft_is_b200(ggml_backend_buffer_type_t buft);
+bool buffer_is_b200(ggml_backend_buffer_t buffer);
+
+void buffer_free(ggml_backend_buffer_t buffer) {
+    buffer_ctx * ctx = (buffer_ctx *) buffer->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaFree(ctx->base));
+    delete ctx;
+}
+void * buffer_get_base(ggml_backend_buffer_t buffer) { return ((buffer_ctx *) buffer->context)->base; }
+
+void buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, uint8_t value, size_t offset, size_t size) {
+    buffer_ctx * ctx = (buffer_ctx *) buffer->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaMemsetAsync((char *) tensor->data + offset, value, size, cudaStreamPerThread));
+    CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+}
+void buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
+    buffer_ctx * ctx = (buffer_ctx *) buffer->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaMemcpyAsync((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+}
+void buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
+    buffer_ctx * ctx = (buffer_ctx *) buffer->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaMemcpyAsync(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+}
+bool buffer_cpy_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * src, ggml_tensor * dst) {
+    ggml_backend_buffer_t sbuf = src->view_src ? src->view_src->buffer : src->buffer;
+    if (!sbuf || !buffer_is_b200(sbuf)) return false;
+    buffer_ctx * sctx = (buffer_ctx *) sbuf->context;
+    buffer_ctx * dctx = (buffer_ctx *) buffer->context;
+    scoped_device sd(dctx->device);
+    if (sctx->device == dctx->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, cudaStreamPerThread));
+    else                              CUDA_OK(cudaMemcpyPeerAsync(dst->data, dctx->device, src->data, sctx->device, ggml_nbytes(src), cudaStreamPerThread));
+    CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+    return true;
+}
+void buffer_clear(ggml_backend_buffer_t buffer, uint8_t value) {
+    buffer_ctx * ctx = (buffer_ctx *) buffer->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemset(ctx->base, value, buffer->size));
+    CUDA_OK(cudaDeviceSynchronize());
+}
+
+const ggml_backend_buffer_i k_buffer_iface = {
+    /* .free_buffer   = */ buffer_free,
+    /* .get_base      = */ buffer_get_base,
+    /* .init_tensor   = */ nullptr,
+    /* .memset_tensor = */ buffer_memset_tensor,
+    /* .set_tensor    = */ buffer_set_tensor,
+    /* .get_tensor    = */ buffer_get_tensor,
+    /* .cpy_tensor    = */ buffer_cpy_tensor,
+    /* .clear         = */ buffer_clear,
+    /* .reset         = */ nullptr,
+};
+
+const char * buft_get_name(ggml_backend_buffer_type_t buft) { return ((device_ctx *) buft->device->context)->buft_name.c_str(); }
+ggml_backend_buffer_t buft_alloc_buffer(ggml_backend_buffer_type_t buft, size_t size) {
+    device_ctx * dctx = (device_ctx *) buft->device->context;
+    scoped_device sd(dctx->index);
+    void * ptr = nullptr;
+    // +256: the mat-vec kernels read packed 2-byte-aligned blocks through aligned 32-bit words, which may touch
+    // up to 2 bytes past the last block of the last tensor
+    cudaError_t err = cudaMalloc(&ptr, size + 256);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        GGML_LOG_ERROR("ggml-b200: allocating %.2f MiB on device %d failed: %s\n", size / 1048576.0, dctx->index, cudaGetErrorString(err));
+        return nullptr;
+    }
+    buffer_ctx * ctx = new buffer_ctx{ dctx->index, ptr };
+    return ggml_backend_buffer_init(buft, k_buffer_iface, ctx, size);
+}
+size_t buft_get_alignment(ggml_backend_buffer_type_t) { return 128; }
+size_t buft_get_alloc_size(ggml_backend_buffer_type_t, const ggml_tensor * tensor) { return ggml_nbytes(tensor); }
+
+const ggml_backend_buffer_type_i k_buft_iface = {
+    /* .get_name       = */ buft_get_name,
+    /* .alloc_buffer   = */ buft_alloc_buffer,
+    /* .get_alignment  = */ buft_get_alignment,
+    /* .get_max_size   = */ nullptr,
+    /* .get_alloc_size = */ buft_get_alloc_size,
+    /* .is_host        = */ nullptr,
+};
+
+bool buft_is_b200(ggml_backend_buffer_type_t buft) { return buft && buft->iface.get_name == buft_get_name; }
+bool buffer_is_b200(ggml_backend_buffer_t buffer) { return buffer && buft_is_b200(buffer->buft); }
+
+// pinned host buffers: a CPU buffer (so the CPU backend can use it) whose memory is cudaMallocHost'ed
+const char * host_buft_get_name(ggml_backend_buffer_type_t) { return "B200_Host"; }
+void host_buffer_free(ggml_backend_buffer_t buffer) { CUDA_OK(cudaFreeHost(buffer->context)); }
+ggml_backend_buffer_t host_buft_alloc_buffer(ggml_backend_buffer_type_t buft, size_t size) {
+    void * ptr = nullptr;
+    if (cudaMallocHost(&ptr, size) != cudaSuccess) {
+        cudaGetLastError();
+        GGML_LOG_WARN("ggml-b200: failed to allocate %.2f MiB of pinned memory, using pageable memory\n", size / 1048576.0);
+        return ggml_backend_buft_alloc_buffer(ggml_backend_cpu_buffer_type(), size);
+    }
+    ggml_backend_buffer_t buffer = ggml_backend_cpu_buffer_from_ptr(ptr, size);
+    buffer->buft = buft;
+    buffer->iface.free_buffer = host_buffer_free;
+    return buffer;
+}
+size_t host_buft_get_alignment(ggml_backend_buffer_type_t) { return 64; }
+bool   host_buft_is_host(ggml_backend_buffer_type_t) { return true; }
+
+ggml_backend_buffer_type_t host_buffer_type() {
+    static ggml_backend_buffer_type buft = {
+        /* .iface   = */ { host_buft_get_name, host_buft_alloc_buffer, host_buft_get_alignment, nullptr, nullptr, host_buft_is_host },
+        /* .device  = */ ggml_backend_reg_dev_get(b200_reg(), 0),
+        /* .context = */ nullptr,
+    };
+    return &buft;
+}
+
+// ------------------------------------------------------------------------------------------ op support
+bool is_b200_weight_type(ggml_type t) {
+    return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K;
+}
+
+bool tensor_on_device(const ggml_tensor * t, int device) {
+    ggml_backend_buffer_t buf = t->view_src ? t->view_src->buffer : t->buffer;
+    if (!buf) return true;                       // not allocated yet: the scheduler decides placement
+    if (!buffer_is_b200(buf)) return false;
+    return ((buffer_ctx *) buf->context)->device == device;
+}
+
+bool supports_mul_mat(const ggml_tensor * op) {
+    const ggml_tensor * a = op->src[0], * b = op->src[1];
+    if (!is_b200_weight_type(a->type) || b->type != GGML_TYPE_F32 || op->type != GGML_TYPE_F32) return false;
+    if (a->nb[0] != ggml_type_size(a->type) || b->nb[0] != sizeof(float)) return false;   // K is the contiguous dim
+    if (!ggml_is_contiguous(op)) return false;
+    if ((a->type == GGML_TYPE_Q4_K || a->type == GGML_TYPE_Q5_K) && ((a->nb[1] | a->nb[2] | a->nb[3]) & 15)) return false;
+    if ((b->nb[1] | b->nb[2] | b->nb[3]) & 3) return false;
+    return true;
+}
+
+bool supports_mul_mat_id(const ggml_tensor * op) {
+    const ggml_tensor * as = op->src[0], * b = op->src[1], * ids = op->src[2];
+    if (!is_b200_weight_type(as->type) || b->type != GGML_TYPE_F32 || ids->type != GGML_TYPE_I32 || op->type != GGML_TYPE_F32) return false;
+    if (as->nb[0] != ggml_type_size(as->type) || b->nb[0] != sizeof(float) || ids->nb[0] != sizeof(int32_t)) return false;
+    if (as->ne[3] != 1 || b->ne[3] != 1 || !ggml_is_contiguous(op)) return false;
+    if ((as->type == GGML_TYPE_Q4_K || as->type == GGML_TYPE_Q5_K) && ((as->nb[1] | as->nb[2]) & 15)) return false;
+    return true;
+}
+
+bool device_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
+    const int device = ((device_ctx *) dev->context)->index;
+    for (int i = 0; i < GGML_MAX_SRC; ++i)
+        if (op->src[i] && !tensor_on_device(op->src[i], device)) return false;
+    switch (op->op) {
+        case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
+            return true;
+        case GGML_OP_MUL_MAT:    return supports_mul_mat(op);
+        case GGML_OP_MUL_MAT_ID: return supports_mul_mat_id(op);
+        default: return false;
+    }
+}
+
+bool device_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_type_t buft) {
+    if (buft_is_b200(buft)) return buft->device == dev;
+    return false;
+}
+
+// the scheduler asks whether an op whose weights live in host memory is worth shipping over (ggml-cuda.cu:3241-3247)
+bool device_offload_op(ggml_backend_dev_t, const ggml_tensor * op) {
+    const int min_batch = 32;
+    return (op->op == GGML_OP_MUL_MAT && op->ne[1] >= min_batch) || (op->op == GGML_OP_MUL_MAT_ID && op->ne[2] >= min_batch);
+}
+
+// ------------------------------------------------------------------------------------------ compute
+void compute_mul_mat(backend_ctx * ctx, const ggml_tensor * dst) {
+    const ggml_tensor * a = dst->src[0], * b = dst->src[1];
+    ggml_b200_mul_mat_args args{};
+    args.type = (int32_t) a->type;
+    args.flags = GGML_B200_MM_AUTO;
+    args.K = a->ne[0]; args.M = a->ne[1]; args.N = b->ne[1];
+    args.ne02 = a->ne[2]; args.ne03 = a->ne[3]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
+    args.nb01 = a->nb[1]; args.nb02 = a->nb[2]; args.nb03 = a->nb[3];
+    args.nb11 = b->nb[1]; args.nb12 = b->nb[2]; args.nb13 = b->nb[3];
+    args.src0 = a->data; args.src1 = (const float *) b->data; args.dst = (float *) dst->data;
+    const size_t need = ggml_b200_mul_mat_workspace_size(&args);
+    args.workspace = ctx->scratch(need);
+    args.workspace_size = ctx->workspace_size;
+    SHIM_OK(ggml_b200_mul_mat(&args, ctx->stream));
+}
+
+void compute_mul_mat_id(backend_ctx * ctx, const ggml_tensor * dst) {
+    const ggml_tensor * as = dst->src[0], * b = dst->src[1], * ids = dst->src[2];
+    ggml_b200_mul_mat_id_args args{};
+    args.type = (int32_t) as->type;
+    args.K = as->ne[0]; args.M = as->ne[1]; args.n_expert = as->ne[2];
+    args.n_used = ids->ne[0]; args.nb1cols = b->ne[1]; args.n_tok = b->ne[2];
+    args.nb01 = as->nb[1]; args.nb02 = as->nb[2];
+    args.nb11 = b->nb[1]; args.nb12 = b->nb[2];
+    args.ids_nb1 = ids->nb[1];
+    args.src0 = as->data; args.src1 = (const float *) b->data; args.ids = (const int32_t *) ids->data; args.dst = (float *) dst->data;
+    const size_t need = ggml_b200_mul_mat_id_workspace_size(&args);
+    args.workspace = ctx->scratch(need);
+    args.workspace_size = ctx->workspace_size;
+    SHIM_OK(ggml_b200_mul_mat_id(&args, ctx->stream));
+}
+
+// ------------------------------------------------------------------------------------------ backend (stream)
+const char * backend_get_name(ggml_backend_t backend) { return ((backend_ctx *) backend->context)->name.c_str(); }
+
+void backend_free(ggml_backend_t backend) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    {
+        scoped_device sd(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->workspace) cudaFreeAsync(ctx->workspace, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    delete backend;
+}
+
+void backend_set_tensor_async(ggml_backend_t backend, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaMemcpyAsync((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice, ctx->stream));
+}
+void backend_get_tensor_async(ggml_backend_t backend, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaMemcpyAsync(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost, ctx->stream));
+}
+void backend_synchronize(ggml_backend_t backend) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+}
+
+ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        ggml_tensor * node = cgraph->nodes[i];
+        if (ggml_is_empty(node)) continue;
+        switch (node->op) {
+            case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
+                break;
+            case GGML_OP_MUL_MAT:    compute_mul_mat(ctx, node);    break;
+            case GGML_OP_MUL_MAT_ID: compute_mul_mat_id(ctx, node); break;
+            default:
+                GGML_LOG_ERROR("ggml-b200: op %s is not supported (supports_op must have declined it)\n", ggml_op_desc(node));
+                GGML_ABORT("unsupported op");
+        }
+    }
+    return GGML_STATUS_SUCCESS;
+}
+
+void backend_event_record(ggml_backend_t backend, ggml_backend_event_t event) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaEventRecord((cudaEvent_t) event->context, ctx->stream));
+}
+void backend_event_wait(ggml_backend_t backend, ggml_backend_event_t event) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    CUDA_OK(cudaStreamWaitEvent(ctx->stream, (cudaEvent_t) event->context, 0));
+}
+
+const ggml_backend_i k_backend_iface = {
+    /* .get_name           = */ backend_get_name,
+    /* .free               = */ backend_free,
+    /* .set_tensor_async   = */ backend_set_tensor_async,
+    /* .get_tensor_async   = */ backend_get_tensor_async,
+    /* .cpy_tensor_async   = */ nullptr,
+    /* .synchronize        = */ backend_synchronize,
+    /* .graph_plan_create  = */ nullptr,
+    /* .graph_plan_free    = */ nullptr,
+    /* .graph_plan_update  = */ nullptr,
+    /* .graph_plan_compute = */ nullptr,
+    /* .graph_compute      = */ backend_graph_compute,
+    /* .event_record       = */ backend_event_record,
+    /* .event_wait         = */ backend_event_wait,
+};
+
+// ------------------------------------------------------------------------------------------ device
+const char * device_get_name(ggml_backend_dev_t dev) { return ((device_ctx *) dev->context)->name.c_str(); }
+const char * device_get_description(ggml_backend_dev_t dev) { return ((device_ctx *) dev->context)->description.c_str(); }
+void device_get_memory(ggml_backend_dev_t dev, size_t * free, size_t * total) {
+    scoped_device sd(((device_ctx *) dev->context)->index);
+    CUDA_OK(cudaMemGetInfo(free, total));
+}
+enum ggml_backend_dev_type device_get_type(ggml_backend_dev_t) { return GGML_BACKEND_DEVICE_TYPE_GPU; }
+void device_get_props(ggml_backend_dev_t dev, ggml_backend_dev_props * props) {
+    props->name = device_get_name(dev);
+    props->description = device_get_description(dev);
+    props->type = GGML_BACKEND_DEVICE_TYPE_GPU;
+    device_get_memory(dev, &props->memory_free, &props->memory_total);
+    props->caps = { /* .async = */ true, /* .host_buffer = */ true, /* .buffer_from_host_ptr = */ false, /* .events = */ true };
+}
+ggml_backend_t device_init_backend(ggml_backend_dev_t dev, const char *) {
+    return ggml_backend_b200_init(((device_ctx *) dev->context)->index);
+}
+ggml_backend_buffer_type_t device_get_buffer_type(ggml_backend_dev_t dev) { return &((device_ctx *) dev->context)->buft; }
+ggml_backend_buffer_type_t device_get_host_buffer_type(ggml_backend_dev_t) { return host_buffer_type(); }
+
+ggml_backend_event_t device_event_new(ggml_backend_dev_t dev) {
+    scoped_device sd(((device_ctx *) dev->context)->index);
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    return new ggml_backend_event{ dev, ev };
+}
+void device_event_free(ggml_backend_dev_t, ggml_backend_event_t event) {
+    CUDA_OK(cudaEventDestroy((cudaEvent_t) event->context));
+    delete event;
+}
+void device_event_synchronize(ggml_backend_dev_t, ggml_backend_event_t event) { CUDA_OK(cudaEventSynchronize((cudaEvent_t) event->context)); }
+
+const ggml_backend_device_i k_device_iface = {
+    /* .get_name             = */ device_get_name,
+    /* .get_description      = */ device_get_description,
+    /* .get_memory           = */ device_get_memory,
+    /* .get_type             = */ device_get_type,
+    /* .get_props            = */ device_get_props,
+    /* .init_backend         = */ device_init_backend,
+    /* .get_buffer_type      = */ device_get_buffer_type,
+    /* .get_host_buffer_type = */ device_get_host_buffer_type,
+    /* .buffer_from_host_ptr = */ nullptr,
+    /* .supports_op          = */ device_supports_op,
+    /* .supports_buft        = */ device_supports_buft,
+    /* .offload_op           = */ device_offload_op,
+    /* .event_new            = */ device_event_new,
+    /* .event_free           = */ device_event_free,
+    /* .event_synchronize    = */ device_event_synchronize,
+};
+
+// ------------------------------------------------------------------------------------------ registry
+struct reg_ctx {
+    std::vector<ggml_backend_device *> devices;
+};
+
+const char * reg_get_name(ggml_backend_reg_t) { return "B200"; }
+size_t reg_get_device_count(ggml_backend_reg_t reg) { return ((reg_ctx *) reg->context)->devices.size(); }
+ggml_backend_dev_t reg_get_device(ggml_backend_reg_t reg, size_t index) {
+    reg_ctx * ctx = (reg_ctx *) reg->context;
+    GGML_ASSERT(index < ctx->devices.size());
+    return ctx->devices[index];
+}
+void * reg_get_proc_address(ggml_backend_reg_t, const char * name) {
+    if (strcmp(name, "ggml_backend_b200_launch_count") == 0) return (void *) ggml_b200_launch_count;
+    return nullptr;
+}
+
+ggml_backend_reg_t b200_reg() {
+    static ggml_backend_reg reg;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        reg_ctx * ctx = new reg_ctx;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        if (n > B200_MAX_DEVICES) n = B200_MAX_DEVICES;
+        for (int i = 0; i < n; ++i) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, i) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (prop.major != 10) {   // sm_100a binaries only load on Blackwell data-centre parts
+                GGML_LOG_WARN("ggml-b200: skipping device %d (%s, sm_%d%d): kernels are built for sm_100a\n", i, prop.name, prop.major, prop.minor);
+                continue;
+            }
+            device_ctx * dctx = new device_ctx;
+            dctx->index = i;
+            dctx->name = "B200" + std::to_string(i);
+            dctx->description = prop.name;
+            dctx->buft_name = dctx->name;
+            ggml_backend_device * dev = new ggml_backend_device{ k_device_iface, &reg, dctx };
+            dctx->buft = ggml_backend_buffer_type{ k_buft_iface, dev, nullptr };
+            ctx->devices.push_back(dev);
+        }
+        reg = ggml_backend_reg{ GGML_BACKEND_API_VERSION, { reg_get_name, reg_get_device_count, reg_get_device, reg_get_proc_address }, ctx };
+    });
+    return &reg;
+}
+
+} // namespace
+
+// ============================================================================================ exported C ABI
+extern "C" {
+
+GGML_B200_API ggml_backend_reg_t ggml_backend_b200_reg(void) { return b200_reg(); }
+
+GGML_B200_API ggml_backend_t ggml_backend_b200_init(int device) {
+    ggml_backend_reg_t reg = b200_reg();
+    reg_ctx * rctx = (reg_ctx *) reg->context;
+    ggml_backend_device * dev = nullptr;
+    for (auto * d : rctx->devices) if (((device_ctx *) d->context)->index == device) dev = d;
+    if (!dev) {
+        GGML_LOG_ERROR("ggml-b200: invalid device %d\n", device);
+        return nullptr;
+    }
+    backend_ctx * ctx = new backend_ctx;
+    ctx->device = device;
+    ctx->name = ((device_ctx *) dev->context)->name;
+    {
+        scoped_device sd(device);
+        CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    }
+    return new ggml_backend{ b200_guid(), k_backend_iface, dev, ctx };
+}
+
+GGML_B200_API bool ggml_backend_is_b200(ggml_backend_t backend) { return backend != nullptr && ggml_guid_matches(backend->guid, b200_guid()); }
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_b200_buffer_type(int device) {
+    reg_ctx * rctx = (reg_ctx *) b200_reg()->context;
+    for (auto * d : rctx->devices) if (((device_ctx *) d->context)->index == device) return &((device_ctx *) d->context)->buft;
+    return nullptr;
+}
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_b200_host_buffer_type(void) { return host_buffer_type(); }
+GGML_B200_API int ggml_backend_b200_get_device_count(void) { return (int) ((reg_ctx *) b200_reg()->context)->devices.size(); }
+
+// dynamic loading (src/ggml-backend-reg.cpp:220-263): ggml_backend_load(path) / $GGML_BACKEND_PATH
+GGML_B200_API ggml_backend_reg_t ggml_backend_init(void) { return b200_reg(); }
+GGML_B200_API int ggml_backend_score(void) { return ggml_backend_b200_get_device_count() > 0 ? 100 : 0; }
+
+// include/ggml-cuda.h:23-45 — the symbols the examples bind when compiled with -DGGML_USE_CUDA
+// (examples/gpt-2/main-backend.cpp:203-211, main-sched.cpp:115-123, tests/test-mul-mat.cpp:50-58)
+GGML_B200_API ggml_backend_t ggml_backend_cuda_init(int device) { return ggml_backend_b200_init(device); }
+GGML_B200_API bool ggml_backend_is_cuda(ggml_backend_t backend) { return ggml_backend_is_b200(backend); }
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_buffer_type(int device) { return ggml_backend_b200_buffer_type(device); }
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_split_buffer_type(int, const float *) {
+    GGML_LOG_ERROR("ggml-b200: split buffers are provided by ggml_backend_b200_split_buffer_type (row shards + NVLink gather)\n");
+    return nullptr;
+}
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_host_buffer_type(void) { return host_buffer_type(); }
+GGML_B200_API int ggml_backend_cuda_get_device_count(void) { return ggml_backend_b200_get_device_count(); }
+GGML_B200_API void ggml_backend_cuda_get_device_description(int device, char * description, size_t description_size) {
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    snprintf(description, description_size, "%s", prop.name);
+}
+GGML_B200_API void ggml_backend_cuda_get_device_memory(int device, size_t * free, size_t * total) {
+    scoped_device sd(device);
+    CUDA_OK(cudaMemGetInfo(free, total));
+}
+GGML_B200_API bool ggml_backend_cuda_register_host_buffer(void * buffer, size_t size) {
+    if (cudaHostRegister(buffer, size, cudaHostRegisterPortable | cudaHostRegisterReadOnly) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+GGML_B200_API void ggml_backend_cuda_unregister_host_buffer(void * buffer) {
+    if (cudaHostUnregister(buffer) != cudaSuccess) cudaGetLastError();
+}
+GGML_B200_API ggml_backend_reg_t ggml_backend_cuda_reg(void) { return b200_reg(); }
+
+} // extern "C"

@@ -1,0 +1,149 @@
+/* ggml-b200.h — the C ABI of the B200-native ggml backend.
+ *
+ * Two layers, both plain C (pointers, sizes, an opaque stream handle; no torch / ggml C++ types):
+ *
+ *  (1) KERNEL-LAUNCH SHIM  — libggml-b200-kernels.so.  Hand-written sm_100a kernels for the hot path
+ *      GGML_OP_MUL_MAT / GGML_OP_MUL_MAT_ID over block-quantized weights + their dequantize family.
+ *      Replaces, in the reference (paths relative to the ggml tree @ 9a4acb37):
+ *        ggml_cuda_op_mul_mat_vec_q   src/ggml-cuda/mmvq.cu:338      (quantized GEMV, n <= 8)
+ *        ggml_cuda_op_mul_mat_q       src/ggml-cuda/mmq.cu:3         (quantized GEMM)
+ *        quantize_row_q8_1_cuda       src/ggml-cuda/quantize.cu:129  (activation quantizer)
+ *        ggml_cuda_mul_mat_id         src/ggml-cuda/ggml-cuda.cu:1955
+ *        dequantize_row_*_cuda        src/ggml-cuda/convert.cu:500-640
+ *      and computes what the CPU backend's ggml_compute_forward_mul_mat (src/ggml-cpu/ggml-cpu.c:7428)
+ *      and ggml_compute_forward_mul_mat_id (:7609) compute.
+ *
+ *  (2) BACKEND PLUG-IN     — libggml-b200.so.  The reference's own backend SPI
+ *      (src/ggml-backend-impl.h: ggml_backend_reg_i / _device_i / _buffer_type_i / _buffer_i / ggml_backend_i)
+ *      implemented on top of (1), so ggml_backend_sched, tests/test-backend-ops and examples/gpt-2 run
+ *      unmodified.  Entry points: ggml_backend_init / ggml_backend_score (dynamic loading,
+ *      src/ggml-backend-reg.cpp:220-263), ggml_backend_b200_reg / ggml_backend_b200_init, and the
+ *      include/ggml-cuda.h:23-45 facade (ggml_backend_cuda_init …) for programs compiled with -DGGML_USE_CUDA.
+ *
+ * All device pointers are CUDA device pointers on the current device; `stream` is a cudaStream_t
+ * (CUstream) cast to void*; functions are asynchronous on that stream unless stated otherwise.
+ * Return value: 0 on success, a negative GGML_B200_E* code otherwise (never a silent CPU fallback).
+ */
+#ifndef GGML_B200_H
+#define GGML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#  define GGML_B200_API __declspec(dllexport)
+#else
+#  define GGML_B200_API __attribute__((visibility("default")))
+#endif
+
+enum ggml_b200_status {
+    GGML_B200_OK            =  0,
+    GGML_B200_EUNSUPPORTED  = -1,  /* type / shape combination not implemented */
+    GGML_B200_EINVAL        = -2,  /* malformed arguments (K not a multiple of the block size, NULL pointers, …) */
+    GGML_B200_EWORKSPACE    = -3,  /* workspace too small: call ggml_b200_mul_mat_workspace_size */
+    GGML_B200_ECUDA         = -4,  /* CUDA runtime error, see ggml_b200_last_error */
+};
+
+/* numeric ids are the reference's enum ggml_type (include/ggml.h:351-390) */
+enum ggml_b200_type {
+    GGML_B200_TYPE_F32  = 0,  GGML_B200_TYPE_F16  = 1,
+    GGML_B200_TYPE_Q4_0 = 2,  GGML_B200_TYPE_Q8_0 = 8,
+    GGML_B200_TYPE_Q4_K = 12, GGML_B200_TYPE_Q5_K = 13, GGML_B200_TYPE_Q6_K = 14,
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * MUL_MAT:  dst[i3][i2][n][m] = sum_k src0[i3/r3][i2/r2][m][k] * src1[i3][i2][n][k]
+ * with ggml's shapes/strides (src/ggml.c:2686-2709): src0 = W[ne00=K, ne01=M, ne02, ne03] in a
+ * block-quantized type (rows contiguous along K, strides nb01/nb02/nb03 in BYTES), src1 = X[K, N, ne12, ne13]
+ * f32 (element stride 4 B along K, nb11/nb12/nb13 in bytes), dst = Y[M, N, ne12, ne13] f32 contiguous.
+ * Broadcast: ne12 % ne02 == 0, ne13 % ne03 == 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ggml_b200_mul_mat_args {
+    int32_t      type;                    /* enum ggml_b200_type of src0 */
+    int32_t      flags;                   /* GGML_B200_MM_* */
+    int64_t      K, M, N;                 /* ne00, ne01, ne11 */
+    int64_t      ne02, ne03, ne12, ne13;  /* batch dims (>= 1) */
+    size_t       nb01, nb02, nb03;        /* src0 strides, bytes */
+    size_t       nb11, nb12, nb13;        /* src1 strides, bytes */
+    const void * src0;                    /* device, packed blocks */
+    const float* src1;                    /* device */
+    float *      dst;                     /* device, contiguous [ne13][ne12][N][M] */
+    void *       workspace;               /* device scratch, >= ggml_b200_mul_mat_workspace_size() */
+    size_t       workspace_size;
+} ggml_b200_mul_mat_args;
+
+enum {
+    GGML_B200_MM_AUTO        = 0,
+    GGML_B200_MM_FORCE_GENERIC = 1,   /* strided one-warp-per-output kernel (any shape) */
+    GGML_B200_MM_FORCE_GEMV  = 2,     /* TMA-staged bandwidth kernel (N <= 8) */
+    GGML_B200_MM_FORCE_GEMM  = 4,     /* tcgen05 tensor-core kernel */
+};
+
+GGML_B200_API size_t ggml_b200_mul_mat_workspace_size(const ggml_b200_mul_mat_args * args);
+GGML_B200_API int    ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream);
+/* which kernel family AUTO would pick: 1 generic, 2 gemv, 4 gemm, <0 error */
+GGML_B200_API int    ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args);
+
+/* MUL_MAT with HOST activations / results: copies src1 (host, contiguous [N][K]) to the device, runs
+ * ggml_b200_mul_mat and copies dst back, all on `stream`, then synchronizes it.  src0 stays device-resident
+ * (weights are uploaded once at model load, like the reference's buffer.set_tensor).  Used for the
+ * end-to-end measurement; `args->src1` / `args->dst` must point at device staging buffers. */
+GGML_B200_API int    ggml_b200_mul_mat_host(const ggml_b200_mul_mat_args * args, const float * host_src1, float * host_dst, void * stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MUL_MAT_ID (src/ggml.c:2735-2762): as[K, M, n_expert] quantized, b[K, nb1cols, n_tok] f32,
+ * ids[n_used, n_tok] i32 (row stride ids_nb1 bytes) -> dst[M, n_used, n_tok] f32 contiguous:
+ *   dst[t][e][:] = as[ids[t][e]] . b[t][e % nb1cols]
+ * Expert routing is resolved on the device (no host synchronisation).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ggml_b200_mul_mat_id_args {
+    int32_t      type;
+    int32_t      flags;
+    int64_t      K, M, n_expert, n_used, nb1cols, n_tok;
+    size_t       nb01, nb02;              /* expert matrices: row stride, matrix stride (bytes) */
+    size_t       nb11, nb12;              /* b: column stride, token stride (bytes) */
+    size_t       ids_nb1;                 /* ids: token stride (bytes) */
+    const void * src0;
+    const float* src1;
+    const int32_t * ids;
+    float *      dst;
+    void *       workspace;
+    size_t       workspace_size;
+} ggml_b200_mul_mat_id_args;
+
+GGML_B200_API size_t ggml_b200_mul_mat_id_workspace_size(const ggml_b200_mul_mat_id_args * args);
+GGML_B200_API int    ggml_b200_mul_mat_id(const ggml_b200_mul_mat_id_args * args, void * stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Block formats (src/ggml-common.h, src/ggml-quants.c) — bit-exact with the reference's
+ * dequantize_row_* / quantize_row_*_ref.
+ * ------------------------------------------------------------------------------------------- */
+GGML_B200_API size_t ggml_b200_row_size(int32_t type, int64_t k);                 /* = ggml_row_size */
+/* dst[n] (f32 or f16 per dst_type) = dequantize(src blocks); n % block size == 0 */
+GGML_B200_API int    ggml_b200_dequantize(int32_t type, const void * src, void * dst, int32_t dst_type, int64_t n, void * stream);
+/* f32 -> Q8_0 / Q4_0 blocks (quantize_row_q8_0_ref / quantize_row_q4_0_ref), n % 32 == 0 */
+GGML_B200_API int    ggml_b200_quantize(int32_t type, const float * src, void * dst, int64_t n, void * stream);
+/* activation quantizer exactly as the CPU backend applies it before vec_dot: rows of K f32 -> int8 records
+ * (debug/verification entry point; layout: ggml_b200_act_record_size bytes per row: q[K] | bsums int16[K/16] | d f32[]) */
+GGML_B200_API size_t ggml_b200_act_record_size(int32_t weight_type, int64_t K);
+GGML_B200_API int    ggml_b200_quantize_activations(int32_t weight_type, const float * src, size_t row_stride_bytes,
+                                                    int64_t nrows, int64_t K, void * dst_records, void * stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Introspection
+ * ------------------------------------------------------------------------------------------- */
+GGML_B200_API const char * ggml_b200_last_error(void);
+GGML_B200_API int          ggml_b200_device_count(void);
+GGML_B200_API int          ggml_b200_sm_count(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+GGML_B200_API uint64_t     ggml_b200_launch_count(void);
+GGML_B200_API const char * ggml_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_H */

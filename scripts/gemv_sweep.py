@@ -1,0 +1,65 @@
+"""Developer sweep (not the bench contract): device-time of the mat-vec kernels over shapes / tunables.
+Usage: python scripts/gemv_sweep.py [--types q4_K,q8_0] [--n 1]   (env GGML_B200_GEMV_* select tunables)"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import ggml_b200 as g  # noqa: E402
+
+NAMES = {v: k for k, v in g.TYPE_NAMES.items()}
+
+
+def time_mm(t, M, N, K, flags, reps=200):
+    rb = g.row_size(t, K)
+    nbuf = max(2, int(np.ceil(300e6 / (rb * M))))           # rotate > 2x L2 worth of weights
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    Ws = []
+    for i in range(nbuf):
+        w = torch.randint(0, 256, (M * rb,), dtype=torch.uint8, device="cuda", generator=gen)
+        # sane fp16 scales: clear exponent top bits of every block's d so values stay finite
+        Ws.append(w)
+    X = torch.rand(N * K, device="cuda") * 2 - 1
+    Y = torch.empty((1, 1, N, M), device="cuda")
+    for i in range(3):
+        g.mul_mat(t, Ws[i % nbuf], X, M, N, K, flags=flags, out=Y)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(reps):
+        g.mul_mat(t, Ws[i % nbuf], X, M, N, K, flags=flags, out=Y)
+    ev1.record()
+    torch.cuda.synchronize()
+    us = ev0.elapsed_time(ev1) * 1000 / reps
+    return us, rb * M
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--types", default="q4_0,q8_0,q4_K,q5_K,q6_K")
+    ap.add_argument("--n", default="1")
+    ap.add_argument("--shapes", default="4096x4096,11008x4096,4096x11008,32000x4096")
+    ap.add_argument("--generic", action="store_true")
+    a = ap.parse_args()
+    tun = {k: v for k, v in os.environ.items() if k.startswith("GGML_B200_")}
+    for tn in a.types.split(","):
+        t = NAMES[tn]
+        for sh in a.shapes.split(","):
+            M, K = (int(v) for v in sh.split("x"))
+            K = K // 256 * 256
+            for n in (int(v) for v in a.n.split(",")):
+                for flags in ([g.MM_GEMV] + ([g.MM_GENERIC] if a.generic else [])):
+                    if flags == g.MM_GEMV and g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
+                        continue
+                    us, wb = time_mm(t, M, n, K, flags)
+                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": "gemv" if flags == g.MM_GEMV else "generic",
+                                      "us": round(us, 2), "GBps": round(wb / us / 1e3, 1), "tun": tun}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
