@@ -46,9 +46,9 @@ static int validate(const ggml_b200_mul_mat_args * a) {
 
 static int plan(const ggml_b200_mul_mat_args & a) {
     if (a.flags & GGML_B200_MM_FORCE_GENERIC) return GGML_B200_MM_FORCE_GENERIC;
-    if (a.flags & GGML_B200_MM_FORCE_GEMV) return mmvq_tma_eligible(a) ? GGML_B200_MM_FORCE_GEMV : GGML_B200_EUNSUPPORTED;
+    if (a.flags & GGML_B200_MM_FORCE_GEMV) return (mmvq_sb_eligible(a) || mmvq_tma_eligible(a)) ? GGML_B200_MM_FORCE_GEMV : GGML_B200_EUNSUPPORTED;
     if (a.flags & GGML_B200_MM_FORCE_GEMM) return mmq_tc_eligible(a) ? GGML_B200_MM_FORCE_GEMM : GGML_B200_EUNSUPPORTED;
-    if (a.N <= 8 && mmvq_tma_eligible(a)) return GGML_B200_MM_FORCE_GEMV;
+    if (a.N <= 8 && (mmvq_sb_eligible(a) || mmvq_tma_eligible(a))) return GGML_B200_MM_FORCE_GEMV;
     if (a.N > 8 && mmq_tc_eligible(a)) return GGML_B200_MM_FORCE_GEMM;
     return GGML_B200_MM_FORCE_GENERIC;
 }
@@ -106,7 +106,10 @@ int ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream) {
     if (args->M == 0 || args->N == 0) return GGML_B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (plan(*args)) {
-        case GGML_B200_MM_FORCE_GEMV:    return launch_mmvq_tma(*args, st);
+        case GGML_B200_MM_FORCE_GEMV:
+            // n = 1: one-lane-per-256-weights kernel (mmvq_sb.cu); 2..8 columns: unit kernel (mmvq.cu)
+            if (!(args->flags & GGML_B200_MM_GEMV_V1) && mmvq_sb_eligible(*args)) return launch_mmvq_sb(*args, st);
+            return launch_mmvq_tma(*args, st);
         case GGML_B200_MM_FORCE_GEMM:    return launch_mmq_tc(*args, st);
         case GGML_B200_MM_FORCE_GENERIC: return launch_mmvq_generic(*args, st);
         default: set_error("mul_mat: the forced kernel family cannot run this shape"); return GGML_B200_EUNSUPPORTED;

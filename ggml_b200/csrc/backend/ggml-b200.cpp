@@ -250,6 +250,45 @@ bool supports_mul_mat_id(const ggml_tensor * op) {
     return true;
 }
 
+bool is_f32_contig(const ggml_tensor * t) { return t->type == GGML_TYPE_F32 && ggml_is_contiguous(t); }
+
+bool supports_mul_mat_float(const ggml_tensor * op) {
+    const ggml_tensor * a = op->src[0], * b = op->src[1];
+    return (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16) && b->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32;
+}
+
+bool supports_small_op(const ggml_tensor * op) {
+    const ggml_tensor * a = op->src[0], * b = op->src[1];
+    switch (op->op) {
+        case GGML_OP_GET_ROWS:
+            return op->type == GGML_TYPE_F32 && b->type == GGML_TYPE_I32 && op->nb[0] == sizeof(float) &&
+                   (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16 || is_b200_weight_type(a->type)) && a->nb[0] == ggml_type_size(a->type);
+        case GGML_OP_ADD: case GGML_OP_MUL: case GGML_OP_SUB: case GGML_OP_DIV:
+            return a->type == GGML_TYPE_F32 && b->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && ggml_can_repeat(b, a);
+        case GGML_OP_NORM: case GGML_OP_RMS_NORM:
+            return a->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && a->nb[0] == sizeof(float) && op->nb[0] == sizeof(float);
+        case GGML_OP_SCALE: case GGML_OP_DIAG_MASK_INF:
+            return is_f32_contig(a) && is_f32_contig(op);
+        case GGML_OP_SOFT_MAX:
+            return is_f32_contig(a) && is_f32_contig(op) && (!b || ((b->type == GGML_TYPE_F32 || b->type == GGML_TYPE_F16) && ggml_is_contiguous(b)));
+        case GGML_OP_UNARY:
+            switch (ggml_get_unary_op(op)) {
+                case GGML_UNARY_OP_GELU: case GGML_UNARY_OP_SILU: case GGML_UNARY_OP_RELU: case GGML_UNARY_OP_TANH: case GGML_UNARY_OP_NEG:
+                case GGML_UNARY_OP_ABS: case GGML_UNARY_OP_GELU_QUICK: case GGML_UNARY_OP_SIGMOID: case GGML_UNARY_OP_EXP:
+                    return is_f32_contig(a) && is_f32_contig(op);
+                default: return false;
+            }
+        case GGML_OP_CPY: case GGML_OP_CONT: case GGML_OP_DUP: {
+            const ggml_tensor * d = op->op == GGML_OP_CPY ? b : op;
+            const bool sf = a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16, df = d->type == GGML_TYPE_F32 || d->type == GGML_TYPE_F16;
+            if (sf && df) return true;
+            return a->type == GGML_TYPE_F32 && (d->type == GGML_TYPE_Q8_0 || d->type == GGML_TYPE_Q4_0) && a->nb[0] == sizeof(float) &&
+                   a->ne[0] % 32 == 0 && d->ne[0] % 32 == 0 && d->nb[0] == ggml_type_size(d->type) && ggml_is_contiguous(d);
+        }
+        default: return false;
+    }
+}
+
 bool device_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
     const int device = ((device_ctx *) dev->context)->index;
     for (int i = 0; i < GGML_MAX_SRC; ++i)
@@ -257,9 +296,9 @@ bool device_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
     switch (op->op) {
         case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
             return true;
-        case GGML_OP_MUL_MAT:    return supports_mul_mat(op);
+        case GGML_OP_MUL_MAT:    return supports_mul_mat(op) || supports_mul_mat_float(op);
         case GGML_OP_MUL_MAT_ID: return supports_mul_mat_id(op);
-        default: return false;
+        default: return supports_small_op(op);
     }
 }
 
@@ -307,6 +346,57 @@ void compute_mul_mat_id(backend_ctx * ctx, const ggml_tensor * dst) {
     SHIM_OK(ggml_b200_mul_mat_id(&args, ctx->stream));
 }
 
+ggml_b200_tensor desc(const ggml_tensor * t) {
+    ggml_b200_tensor d;
+    d.data = t->data; d.type = (int32_t) t->type;
+    for (int i = 0; i < 4; ++i) { d.ne[i] = t->ne[i]; d.nb[i] = t->nb[i]; }
+    return d;
+}
+
+void compute_small_op(backend_ctx * ctx, ggml_tensor * node) {
+    const ggml_tensor * a = node->src[0], * b = node->src[1];
+    void * st = ctx->stream;
+    switch (node->op) {
+        case GGML_OP_GET_ROWS: { auto s = desc(a), i = desc(b), d = desc(node); SHIM_OK(ggml_b200_op_get_rows(&s, &i, &d, st)); } break;
+        case GGML_OP_ADD: case GGML_OP_MUL: case GGML_OP_SUB: case GGML_OP_DIV: {
+            const int op = node->op == GGML_OP_ADD ? 0 : node->op == GGML_OP_MUL ? 1 : node->op == GGML_OP_SUB ? 2 : 3;
+            auto x = desc(a), y = desc(b), d = desc(node);
+            SHIM_OK(ggml_b200_op_bin_bcast(op, &x, &y, &d, st));
+        } break;
+        case GGML_OP_NORM: case GGML_OP_RMS_NORM: {
+            auto s = desc(a), d = desc(node);
+            SHIM_OK(ggml_b200_op_norm(node->op == GGML_OP_RMS_NORM, &s, &d, ggml_get_op_params_f32(node, 0), st));
+        } break;
+        case GGML_OP_SCALE:
+            SHIM_OK(ggml_b200_op_scale((const float *) a->data, (float *) node->data, ggml_get_op_params_f32(node, 0), ggml_nelements(node), st));
+            break;
+        case GGML_OP_DIAG_MASK_INF:
+            SHIM_OK(ggml_b200_op_diag_mask_inf((const float *) a->data, (float *) node->data, node->ne[0], node->ne[1], ggml_nelements(node), ggml_get_op_params_i32(node, 0), st));
+            break;
+        case GGML_OP_SOFT_MAX:
+            SHIM_OK(ggml_b200_op_soft_max((const float *) a->data, b ? b->data : nullptr, b ? (int32_t) b->type : 0, (float *) node->data,
+                                          node->ne[0], node->ne[1], node->ne[2], node->ne[3], ggml_get_op_params_f32(node, 0), ggml_get_op_params_f32(node, 1), st));
+            break;
+        case GGML_OP_UNARY: {
+            int u = -1;
+            switch (ggml_get_unary_op(node)) {
+                case GGML_UNARY_OP_GELU: u = GGML_B200_UNARY_GELU; break;          case GGML_UNARY_OP_SILU: u = GGML_B200_UNARY_SILU; break;
+                case GGML_UNARY_OP_RELU: u = GGML_B200_UNARY_RELU; break;          case GGML_UNARY_OP_TANH: u = GGML_B200_UNARY_TANH; break;
+                case GGML_UNARY_OP_NEG:  u = GGML_B200_UNARY_NEG; break;           case GGML_UNARY_OP_ABS:  u = GGML_B200_UNARY_ABS; break;
+                case GGML_UNARY_OP_GELU_QUICK: u = GGML_B200_UNARY_GELU_QUICK; break; case GGML_UNARY_OP_SIGMOID: u = GGML_B200_UNARY_SIGMOID; break;
+                case GGML_UNARY_OP_EXP:  u = GGML_B200_UNARY_EXP; break;
+                default: GGML_ABORT("unsupported unary op");
+            }
+            SHIM_OK(ggml_b200_op_unary(u, (const float *) a->data, (float *) node->data, ggml_nelements(node), st));
+        } break;
+        case GGML_OP_CPY:  { auto s = desc(a), d = desc(b);    SHIM_OK(ggml_b200_op_cpy(&s, &d, st)); } break;
+        case GGML_OP_CONT: case GGML_OP_DUP: { auto s = desc(a), d = desc(node); SHIM_OK(ggml_b200_op_cpy(&s, &d, st)); } break;
+        default:
+            GGML_LOG_ERROR("ggml-b200: op %s is not supported (supports_op must have declined it)\n", ggml_op_desc(node));
+            GGML_ABORT("unsupported op");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ backend (stream)
 const char * backend_get_name(ggml_backend_t backend) { return ((backend_ctx *) backend->context)->name.c_str(); }
 
@@ -348,11 +438,12 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
         switch (node->op) {
             case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
                 break;
-            case GGML_OP_MUL_MAT:    compute_mul_mat(ctx, node);    break;
+            case GGML_OP_MUL_MAT:
+                if (is_b200_weight_type(node->src[0]->type)) compute_mul_mat(ctx, node);
+                else { auto x = desc(node->src[0]), y = desc(node->src[1]), d = desc(node); SHIM_OK(ggml_b200_op_mul_mat_f(&x, &y, &d, ctx->stream)); }
+                break;
             case GGML_OP_MUL_MAT_ID: compute_mul_mat_id(ctx, node); break;
-            default:
-                GGML_LOG_ERROR("ggml-b200: op %s is not supported (supports_op must have declined it)\n", ggml_op_desc(node));
-                GGML_ABORT("unsupported op");
+            default: compute_small_op(ctx, node); break;
         }
     }
     return GGML_STATUS_SUCCESS;

@@ -1,0 +1,392 @@
+// ops.cu — the small device ops either side of the quantized mat-mul in the examples/gpt-2 graph
+// (SURVEY.md §8f-1): GET_ROWS, ADD/MUL/SUB/DIV with broadcast, NORM / RMS_NORM, SCALE, DIAG_MASK_INF, SOFT_MAX,
+// unary GELU/SILU/RELU/…, CPY/CONT/DUP (strided, f32/f16 and f32 -> Q8_0/Q4_0), and the float (f32/f16 x f32)
+// batched strided MUL_MAT used for KQ and KQV.  They exist so that `gpt-2-backend` runs entirely on the device
+// (it has no scheduler to fall back to the CPU).  Semantics follow the CPU backend (src/ggml-cpu/ggml-cpu.c):
+//   get_rows :8560-8760   add/mul bcast :4660-5560   norm :8915-8975   rms_norm :8990-9050   scale :8300-8345
+//   diag_mask :9745-9805  soft_max :9810-9925        gelu :6520-6570 (+ fp16 table, ggml-cpu.c:1355)   dup/cpy :3220-4300
+// They replace the reference's getrows.cu, binbcast.cu, norm.cu, scale.cu, diagmask.cu, softmax.cu, unary.cu, cpy.cu, mmv.cu.
+#include "b200_internal.h"
+#include "b200_quants.cuh"
+
+#include <cfloat>
+
+namespace b200 {
+
+struct tdesc {      // device-side copy of ggml_b200_tensor
+    uint8_t * data; int32_t type; int64_t ne[4]; size_t nb[4];
+};
+static inline tdesc T(const ggml_b200_tensor * t) {
+    tdesc d; d.data = (uint8_t *)t->data; d.type = t->type;
+    for (int i = 0; i < 4; ++i) { d.ne[i] = t->ne[i]; d.nb[i] = t->nb[i]; }
+    return d;
+}
+static inline int64_t nelem(const tdesc & t) { return t.ne[0] * t.ne[1] * t.ne[2] * t.ne[3]; }
+static inline int64_t nrows(const tdesc & t) { return t.ne[1] * t.ne[2] * t.ne[3]; }
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide reduce (blockDim multiple of 32, <= 1024); result broadcast to all threads
+template <bool MAX> __device__ __forceinline__ float block_reduce(float v, float * sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = MAX ? warp_max_f(v) : warp_sum_f(v);
+    if (nw == 1) return v;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = lane < nw ? sh[lane] : (MAX ? -INFINITY : 0.0f);
+    r = MAX ? warp_max_f(r) : warp_sum_f(r);
+    return r;
+}
+
+// ------------------------------------------------------------------ dequantize one element (bit-exact, as dequant.cu)
+__device__ __forceinline__ float load_elem(const uint8_t * row, int type, int64_t i) {
+    switch (type) {
+        case T_F32: return ((const float *)row)[i];
+        case T_F16: return __half2float(((const __half *)row)[i]);
+        case T_Q4_0: {
+            const uint8_t * b = row + (i / 32) * 18; const int j = (int)(i % 32);
+            const int q = j < 16 ? (b[2 + j] & 0x0F) : (b[2 + j - 16] >> 4);
+            return __fmul_rn((float)(q - 8), h2f(load_u16(b)));
+        }
+        case T_Q8_0: {
+            const uint8_t * b = row + (i / 32) * 34;
+            return __fmul_rn((float)(int8_t)b[2 + (i % 32)], h2f(load_u16(b)));
+        }
+        case T_Q4_K: case T_Q5_K: {
+            const int BY = type == T_Q4_K ? 144 : 176;
+            const uint8_t * b = row + (i / 256) * BY;
+            const int w = (int)(i % 256), c = w / 64, l = w % 32, hi = (w % 64) / 32, j = 2 * c + hi;
+            const uint8_t * s = b + 4;
+            int sc, mn;
+            if (j < 4) { sc = s[j] & 63; mn = s[j + 4] & 63; }
+            else       { sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4); mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4); }
+            const uint8_t qb = b[(type == T_Q5_K ? 48 : 16) + 32 * c + l];
+            int v = hi ? (qb >> 4) : (qb & 0x0F);
+            if (type == T_Q5_K) v += ((b[16 + l] >> j) & 1) << 4;
+            return __fsub_rn(__fmul_rn(__fmul_rn(h2f(load_u16(b)), (float)sc), (float)v), __fmul_rn(h2f(load_u16(b + 2)), (float)mn));
+        }
+        case T_Q6_K: {
+            const uint8_t * b = row + (i / 256) * 210;
+            const int w = (int)(i % 256), h = w / 128, pos = (w % 128) / 32, l = w % 32;
+            const uint8_t ql = b[64 * h + (pos & 1) * 32 + l], qh = b[128 + 32 * h + l];
+            const int lo = pos >= 2 ? (ql >> 4) : (ql & 0x0F);
+            const int v = (int)(int8_t)(lo | (((qh >> (2 * pos)) & 3) << 4)) - 32;
+            const int sc = (int)(int8_t)b[192 + 8 * h + l / 16 + 2 * pos];
+            return __fmul_rn(__fmul_rn(h2f(load_u16(b + 208)), (float)sc), (float)v);
+        }
+        default: return 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------ GET_ROWS
+__global__ void get_rows_kernel(tdesc src, tdesc ids, tdesc dst) {
+    // one CTA per destination row (i10, i11, i12)
+    const int64_t r = blockIdx.x;
+    const int64_t i10 = r % ids.ne[0], i11 = (r / ids.ne[0]) % ids.ne[1], i12 = r / (ids.ne[0] * ids.ne[1]);
+    const int32_t i01 = *(const int32_t *)(ids.data + i10 * ids.nb[0] + i11 * ids.nb[1] + i12 * ids.nb[2]);
+    const uint8_t * srow = src.data + (int64_t)i01 * src.nb[1] + i11 * src.nb[2] + i12 * src.nb[3];
+    float * drow = (float *)(dst.data + i10 * dst.nb[1] + i11 * dst.nb[2] + i12 * dst.nb[3]);
+    for (int64_t i = threadIdx.x; i < src.ne[0]; i += blockDim.x) drow[i] = load_elem(srow, src.type, i);
+}
+
+// ------------------------------------------------------------------ binary ops with broadcast (f32)
+template <int OP> __device__ __forceinline__ float bin_op(float a, float b) {
+    if (OP == 0) return a + b;
+    if (OP == 1) return a * b;
+    if (OP == 2) return a - b;
+    return a / b;
+}
+template <int OP> __global__ void bin_bcast_kernel(tdesc a, tdesc b, tdesc d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t i0 = i % d.ne[0], i1 = (i / d.ne[0]) % d.ne[1], i2 = (i / (d.ne[0] * d.ne[1])) % d.ne[2], i3 = i / (d.ne[0] * d.ne[1] * d.ne[2]);
+    const float x = *(const float *)(a.data + i0 * a.nb[0] + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+    const float y = *(const float *)(b.data + (i0 % b.ne[0]) * b.nb[0] + (i1 % b.ne[1]) * b.nb[1] + (i2 % b.ne[2]) * b.nb[2] + (i3 % b.ne[3]) * b.nb[3]);
+    *(float *)(d.data + i0 * d.nb[0] + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]) = bin_op<OP>(x, y);
+}
+
+// ------------------------------------------------------------------ NORM / RMS_NORM (rows contiguous along dim 0)
+template <bool RMS> __global__ void norm_kernel(tdesc s, tdesc d, float eps) {
+    __shared__ float sh[32];
+    const int64_t r = blockIdx.x;
+    const int64_t i1 = r % s.ne[1], i2 = (r / s.ne[1]) % s.ne[2], i3 = r / (s.ne[1] * s.ne[2]);
+    const float * x = (const float *)(s.data + i1 * s.nb[1] + i2 * s.nb[2] + i3 * s.nb[3]);
+    float * y = (float *)(d.data + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]);
+    const int64_t n = s.ne[0];
+    float mean = 0.0f;
+    if (!RMS) {
+        float sum = 0.0f;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) sum += x[i];
+        mean = block_reduce<false>(sum, sh) / (float)n;
+    }
+    float sq = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i] - mean; sq += v * v; }
+    const float var = block_reduce<false>(sq, sh) / (float)n;
+    const float scale = 1.0f / sqrtf(var + eps);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = (x[i] - mean) * scale;
+}
+
+// ------------------------------------------------------------------ SCALE, DIAG_MASK_INF, unary
+__global__ void scale_kernel(const float * x, float * y, float s, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] * s;
+}
+__global__ void diag_mask_inf_kernel(const float * x, float * y, int64_t ne0, int64_t ne1, int n_past, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t c = i % ne0, r = (i / ne0) % ne1;
+    y[i] = c > n_past + r ? -INFINITY : x[i];
+}
+enum { U_GELU = 0, U_SILU = 1, U_RELU = 2, U_TANH = 3, U_NEG = 4, U_ABS = 5, U_GELU_QUICK = 6, U_SIGMOID = 7, U_EXP = 8, U_SQR = 9, U_SQRT = 10 };
+__global__ void unary_kernel(int uop, const float * x, float * y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    float r;
+    switch (uop) {
+        case U_GELU: {
+            // the CPU path evaluates GELU through an fp16 -> fp16 table (ggml_vec_gelu_f32, ggml-cpu.c:1355 ff.)
+            if (v <= -10.0f) r = 0.0f;
+            else if (v >= 10.0f) r = v;
+            else {
+                const float xh = __half2float(__float2half_rn(v));
+                const float g = 0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh)));
+                r = __half2float(__float2half_rn(g));
+            }
+        } break;
+        case U_SILU: r = v / (1.0f + expf(-v)); break;
+        case U_RELU: r = fmaxf(v, 0.0f); break;
+        case U_TANH: r = tanhf(v); break;
+        case U_NEG: r = -v; break;
+        case U_ABS: r = fabsf(v); break;
+        case U_GELU_QUICK: r = v * (1.0f / (1.0f + expf(-1.702f * v))); break;
+        case U_SIGMOID: r = 1.0f / (1.0f + expf(-v)); break;
+        case U_EXP: r = expf(v); break;
+        case U_SQR: r = v * v; break;
+        default: r = sqrtf(v); break;
+    }
+    y[i] = r;
+}
+
+// ------------------------------------------------------------------ SOFT_MAX (rows contiguous): softmax(x*scale + mask*slope)
+__global__ void soft_max_kernel(const float * x, const uint8_t * mask, int mask_type, float * y, int64_t ne0, int64_t ne1, int64_t ne2,
+                                float scale, float max_bias, float m0, float m1, uint32_t n_head_log2) {
+    __shared__ float sh[32];
+    const int64_t r = blockIdx.x;                 // row = i1 + ne1 * (i2 + ne2 * i3)
+    const int64_t i1 = r % ne1;
+    const float * xr = x + r * ne0;
+    float * yr = y + r * ne0;
+    float slope = 1.0f;
+    if (max_bias > 0.0f) {
+        const uint32_t h = (uint32_t)((r / ne1) % ne2);
+        slope = h < n_head_log2 ? powf(m0, (float)(h + 1)) : powf(m1, (float)(2 * (h - n_head_log2) + 1));
+    }
+    const uint8_t * mr = mask ? mask + (size_t)i1 * ne0 * (mask_type == T_F16 ? 2 : 4) : nullptr;
+    auto val = [&](int64_t i) {
+        float v = xr[i] * scale;
+        if (mr) v += slope * (mask_type == T_F16 ? __half2float(((const __half *)mr)[i]) : ((const float *)mr)[i]);
+        return v;
+    };
+    float mx = -INFINITY;
+    for (int64_t i = threadIdx.x; i < ne0; i += blockDim.x) mx = fmaxf(mx, val(i));
+    mx = block_reduce<true>(mx, sh);
+    float sum = 0.0f;
+    for (int64_t i = threadIdx.x; i < ne0; i += blockDim.x) { const float e = expf(val(i) - mx); yr[i] = e; sum += e; }
+    sum = block_reduce<false>(sum, sh);
+    const float inv = 1.0f / sum;
+    for (int64_t i = threadIdx.x; i < ne0; i += blockDim.x) yr[i] *= inv;
+}
+
+// ------------------------------------------------------------------ CPY / CONT / DUP (same element count, any strides)
+__device__ __forceinline__ size_t offset_of(const tdesc & t, int64_t i) {    // i = linear element index in t's logical order
+    const int64_t i0 = i % t.ne[0], i1 = (i / t.ne[0]) % t.ne[1], i2 = (i / (t.ne[0] * t.ne[1])) % t.ne[2], i3 = i / (t.ne[0] * t.ne[1] * t.ne[2]);
+    return i0 * t.nb[0] + i1 * t.nb[1] + i2 * t.nb[2] + i3 * t.nb[3];
+}
+__global__ void cpy_kernel(tdesc s, tdesc d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t * sp = s.data + offset_of(s, i);
+    uint8_t * dp = d.data + offset_of(d, i);
+    const float v = s.type == T_F32 ? *(const float *)sp : __half2float(*(const __half *)sp);
+    if (d.type == T_F32) *(float *)dp = v;
+    else if (s.type == T_F16) *(__half *)dp = *(const __half *)sp;
+    else *(__half *)dp = __float2half_rn(v);
+}
+// f32 (strided, dim-0 contiguous) -> Q8_0 / Q4_0 rows (dst rows contiguous blocks); one thread per 32-block
+template <int QT> __global__ void cpy_f32_q_kernel(tdesc s, tdesc d, int64_t nblocks) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const int64_t e = b * 32;                                   // linear element index of the block start
+    const float * x = (const float *)(s.data + offset_of(s, e));
+    const int64_t bpr = d.ne[0] / 32;                           // dst blocks per row
+    const int64_t drow = b / bpr, dblk = b % bpr;
+    const int64_t i1 = drow % d.ne[1], i2 = (drow / d.ne[1]) % d.ne[2], i3 = drow / (d.ne[1] * d.ne[2]);
+    uint8_t * o = d.data + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3] + dblk * (QT == T_Q8_0 ? 34 : 18);
+    float amax = 0.0f, vmax = 0.0f;
+    for (int i = 0; i < 32; ++i) if (amax < fabsf(x[i])) { amax = fabsf(x[i]); vmax = x[i]; }
+    if (QT == T_Q8_0) {
+        const float dd = __fdiv_rn(amax, 127.0f), id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
+        *(__half *)o = __float2half_rn(dd);
+        for (int i = 0; i < 32; ++i) o[2 + i] = (uint8_t)(int8_t)roundf(__fmul_rn(x[i], id));
+    } else {
+        const float dd = __fdiv_rn(vmax, -8.0f), id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
+        *(__half *)o = __float2half_rn(dd);
+        for (int i = 0; i < 16; ++i) {
+            const int lo = min(15, (int)(int8_t)(int)__fadd_rn(__fmul_rn(x[i], id), 8.5f));
+            const int hi = min(15, (int)(int8_t)(int)__fadd_rn(__fmul_rn(x[i + 16], id), 8.5f));
+            o[2 + i] = (uint8_t)((lo & 0xFF) | (hi << 4));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ float MUL_MAT (f32 / f16 weights x f32), batched + strided
+// one warp per output element; the CPU rounds src1 to f16 when src0 is f16 (vec_dot_type, ggml-cpu.c:262-268)
+__global__ void __launch_bounds__(128) mul_mat_f_kernel(tdesc a, tdesc b, tdesc d, int64_t nout) {
+    const int lane = threadIdx.x & 31;
+    const int64_t o = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (o >= nout) return;
+    const int64_t m = o % d.ne[0], n = (o / d.ne[0]) % d.ne[1], i12 = (o / (d.ne[0] * d.ne[1])) % d.ne[2], i13 = o / (d.ne[0] * d.ne[1] * d.ne[2]);
+    const int64_t i02 = i12 / (b.ne[2] / a.ne[2]), i03 = i13 / (b.ne[3] / a.ne[3]);
+    const uint8_t * ar = a.data + m * a.nb[1] + i02 * a.nb[2] + i03 * a.nb[3];
+    const uint8_t * br = b.data + n * b.nb[1] + i12 * b.nb[2] + i13 * b.nb[3];
+    float acc = 0.0f;
+    if (a.type == T_F32) {
+        for (int64_t k = lane; k < a.ne[0]; k += 32) acc += *(const float *)(ar + k * a.nb[0]) * *(const float *)(br + k * b.nb[0]);
+    } else {
+        for (int64_t k = lane; k < a.ne[0]; k += 32)
+            acc += __half2float(*(const __half *)(ar + k * a.nb[0])) * __half2float(__float2half_rn(*(const float *)(br + k * b.nb[0])));
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) *(float *)(d.data + m * d.nb[0] + n * d.nb[1] + i12 * d.nb[2] + i13 * d.nb[3]) = acc;
+}
+
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+} // namespace b200
+
+using namespace b200;
+
+#define REQUIRE(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return GGML_B200_EUNSUPPORTED; } } while (0)
+
+extern "C" {
+
+int ggml_b200_op_get_rows(const ggml_b200_tensor * src0, const ggml_b200_tensor * ids, const ggml_b200_tensor * dst, void * stream) {
+    const tdesc s = T(src0), i = T(ids), d = T(dst);
+    REQUIRE(d.type == T_F32 && i.type == 26 /* GGML_TYPE_I32 */, "dst must be f32, ids i32");
+    REQUIRE(s.type == T_F32 || s.type == T_F16 || type_bytes(s.type) != 0, "unsupported row type");
+    REQUIRE(d.nb[0] == 4, "dst rows must be contiguous");
+    const int64_t rows = i.ne[0] * i.ne[1] * i.ne[2];
+    if (rows == 0 || s.ne[0] == 0) return GGML_B200_OK;
+    get_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(s, i, d);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_bin_bcast(int32_t op, const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream) {
+    const tdesc a = T(src0), b = T(src1), d = T(dst);
+    REQUIRE(a.type == T_F32 && b.type == T_F32 && d.type == T_F32, "f32 only");
+    const int64_t n = nelem(d);
+    if (n == 0) return GGML_B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = blocks_for(n, 256);
+    switch (op) {
+        case 0: bin_bcast_kernel<0><<<g, 256, 0, st>>>(a, b, d, n); break;
+        case 1: bin_bcast_kernel<1><<<g, 256, 0, st>>>(a, b, d, n); break;
+        case 2: bin_bcast_kernel<2><<<g, 256, 0, st>>>(a, b, d, n); break;
+        case 3: bin_bcast_kernel<3><<<g, 256, 0, st>>>(a, b, d, n); break;
+        default: set_error("bin_bcast: bad op %d", op); return GGML_B200_EINVAL;
+    }
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_norm(int32_t rms, const ggml_b200_tensor * src, const ggml_b200_tensor * dst, float eps, void * stream) {
+    const tdesc s = T(src), d = T(dst);
+    REQUIRE(s.type == T_F32 && d.type == T_F32 && s.nb[0] == 4 && d.nb[0] == 4, "f32 rows contiguous along dim 0");
+    const int64_t rows = nrows(s);
+    if (rows == 0 || s.ne[0] == 0) return GGML_B200_OK;
+    const int threads = s.ne[0] >= 1024 ? 256 : s.ne[0] >= 256 ? 128 : 32;
+    if (rms) norm_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d, eps);
+    else     norm_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d, eps);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_scale(const float * src, float * dst, float s, int64_t n, void * stream) {
+    if (n <= 0) return GGML_B200_OK;
+    scale_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, s, n);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_diag_mask_inf(const float * src, float * dst, int64_t ne0, int64_t ne1, int64_t n, int32_t n_past, void * stream) {
+    if (n <= 0) return GGML_B200_OK;
+    diag_mask_inf_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, ne0, ne1, n_past, n);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_unary(int32_t uop, const float * src, float * dst, int64_t n, void * stream) {
+    if (n <= 0) return GGML_B200_OK;
+    if (uop < 0 || uop > U_SQRT) { set_error("unary: bad op %d", uop); return GGML_B200_EINVAL; }
+    unary_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(uop, src, dst, n);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_soft_max(const float * src, const void * mask, int32_t mask_type, float * dst, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+                          float scale, float max_bias, void * stream) {
+    const int64_t rows = ne1 * ne2 * ne3;
+    if (rows == 0 || ne0 == 0) return GGML_B200_OK;
+    const uint32_t n_head = (uint32_t)ne2;
+    uint32_t n_head_log2 = 1; while (n_head_log2 * 2 <= n_head) n_head_log2 *= 2;
+    const float m0 = powf(2.0f, -(max_bias) / n_head_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / n_head_log2);
+    const int threads = ne0 >= 1024 ? 256 : ne0 >= 128 ? 128 : 32;
+    soft_max_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const uint8_t *)mask, mask_type, dst, ne0, ne1, ne2, scale, max_bias, m0, m1, n_head_log2);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_cpy(const ggml_b200_tensor * src, const ggml_b200_tensor * dst, void * stream) {
+    const tdesc s = T(src), d = T(dst);
+    const int64_t n = nelem(s);
+    REQUIRE(n == nelem(d), "element counts differ");
+    if (n == 0) return GGML_B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((s.type == T_F32 || s.type == T_F16) && (d.type == T_F32 || d.type == T_F16)) {
+        cpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, d, n);
+    } else if (s.type == T_F32 && (d.type == T_Q8_0 || d.type == T_Q4_0)) {
+        REQUIRE(s.nb[0] == 4 && s.ne[0] % 32 == 0 && d.ne[0] % 32 == 0, "f32 -> q needs dim-0 contiguous rows of whole blocks");
+        const int64_t nb = n / 32;
+        if (d.type == T_Q8_0) cpy_f32_q_kernel<T_Q8_0><<<blocks_for(nb, 128), 128, 0, st>>>(s, d, nb);
+        else                  cpy_f32_q_kernel<T_Q4_0><<<blocks_for(nb, 128), 128, 0, st>>>(s, d, nb);
+    } else {
+        set_error("cpy: unsupported type pair %d -> %d", s.type, d.type);
+        return GGML_B200_EUNSUPPORTED;
+    }
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_mul_mat_f(const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream) {
+    const tdesc a = T(src0), b = T(src1), d = T(dst);
+    REQUIRE((a.type == T_F32 || a.type == T_F16) && b.type == T_F32 && d.type == T_F32, "f32/f16 x f32 -> f32");
+    REQUIRE(a.ne[0] == b.ne[0] && d.ne[0] == a.ne[1] && d.ne[1] == b.ne[1] && d.ne[2] == b.ne[2] && d.ne[3] == b.ne[3], "shape mismatch");
+    REQUIRE(b.ne[2] % a.ne[2] == 0 && b.ne[3] % a.ne[3] == 0, "batch dims do not broadcast");
+    const int64_t nout = nelem(d);
+    if (nout == 0) return GGML_B200_OK;
+    mul_mat_f_kernel<<<blocks_for(nout, 4), 128, 0, (cudaStream_t)stream>>>(a, b, d, nout);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+} // extern "C"

@@ -81,6 +81,7 @@ enum {
     GGML_B200_MM_FORCE_GENERIC = 1,   /* strided one-warp-per-output kernel (any shape) */
     GGML_B200_MM_FORCE_GEMV  = 2,     /* TMA-staged bandwidth kernel (N <= 8) */
     GGML_B200_MM_FORCE_GEMM  = 4,     /* tcgen05 tensor-core kernel */
+    GGML_B200_MM_GEMV_V1     = 8,     /* with FORCE_GEMV: the first-generation 64-weight-unit kernel (mmvq.cu) even for n = 1 */
 };
 
 GGML_B200_API size_t ggml_b200_mul_mat_workspace_size(const ggml_b200_mul_mat_args * args);
@@ -132,6 +133,36 @@ GGML_B200_API int    ggml_b200_quantize(int32_t type, const float * src, void * 
 GGML_B200_API size_t ggml_b200_act_record_size(int32_t weight_type, int64_t K);
 GGML_B200_API int    ggml_b200_quantize_activations(int32_t weight_type, const float * src, size_t row_stride_bytes,
                                                     int64_t nrows, int64_t K, void * dst_records, void * stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The small ops either side of the mat-mul in the examples/gpt-2 graph, so that a whole
+ * token graph runs on the device.  Tensors are described like ggml tensors: ne[] in elements, nb[] in bytes.
+ * Replaces src/ggml-cuda/{getrows,binbcast,norm,scale,diagmask,softmax,unary,cpy,mmv}.cu; semantics follow the
+ * CPU backend (src/ggml-cpu/ggml-cpu.c), see ggml_b200/csrc/ops.cu for line references.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ggml_b200_tensor {
+    void *  data;      /* device */
+    int32_t type;      /* enum ggml_type id: 0 f32, 1 f16, 26 i32, or a block-quantized type */
+    int64_t ne[4];
+    size_t  nb[4];
+} ggml_b200_tensor;
+
+enum ggml_b200_unary { GGML_B200_UNARY_GELU = 0, GGML_B200_UNARY_SILU = 1, GGML_B200_UNARY_RELU = 2, GGML_B200_UNARY_TANH = 3,
+                       GGML_B200_UNARY_NEG = 4, GGML_B200_UNARY_ABS = 5, GGML_B200_UNARY_GELU_QUICK = 6, GGML_B200_UNARY_SIGMOID = 7,
+                       GGML_B200_UNARY_EXP = 8, GGML_B200_UNARY_SQR = 9, GGML_B200_UNARY_SQRT = 10 };
+
+GGML_B200_API int ggml_b200_op_get_rows(const ggml_b200_tensor * src0, const ggml_b200_tensor * ids, const ggml_b200_tensor * dst, void * stream);
+/* op: 0 add, 1 mul, 2 sub, 3 div; src1 broadcasts into dst's shape; dst may alias src0 */
+GGML_B200_API int ggml_b200_op_bin_bcast(int32_t op, const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream);
+GGML_B200_API int ggml_b200_op_norm(int32_t rms, const ggml_b200_tensor * src, const ggml_b200_tensor * dst, float eps, void * stream);
+GGML_B200_API int ggml_b200_op_scale(const float * src, float * dst, float s, int64_t n, void * stream);
+GGML_B200_API int ggml_b200_op_diag_mask_inf(const float * src, float * dst, int64_t ne0, int64_t ne1, int64_t n, int32_t n_past, void * stream);
+GGML_B200_API int ggml_b200_op_unary(int32_t uop, const float * src, float * dst, int64_t n, void * stream);
+GGML_B200_API int ggml_b200_op_soft_max(const float * src, const void * mask, int32_t mask_type, float * dst, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+                                        float scale, float max_bias, void * stream);
+GGML_B200_API int ggml_b200_op_cpy(const ggml_b200_tensor * src, const ggml_b200_tensor * dst, void * stream);
+/* float mat-mul: src0 f32/f16 [K, M, ne02, ne03] (any strides) x src1 f32 [K, N, ne12, ne13] -> dst f32 */
+GGML_B200_API int ggml_b200_op_mul_mat_f(const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Introspection

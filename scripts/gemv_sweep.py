@@ -15,7 +15,7 @@ import ggml_b200 as g  # noqa: E402
 NAMES = {v: k for k, v in g.TYPE_NAMES.items()}
 
 
-def time_mm(t, M, N, K, flags, reps=200):
+def time_mm(t, M, N, K, flags, reps=400):
     rb = g.row_size(t, K)
     nbuf = max(2, int(np.ceil(300e6 / (rb * M))))           # rotate > 2x L2 worth of weights
     gen = torch.Generator(device="cuda").manual_seed(1)
@@ -26,16 +26,25 @@ def time_mm(t, M, N, K, flags, reps=200):
         Ws.append(w)
     X = torch.rand(N * K, device="cuda") * 2 - 1
     Y = torch.empty((1, 1, N, M), device="cuda")
-    for i in range(3):
-        g.mul_mat(t, Ws[i % nbuf], X, M, N, K, flags=flags, out=Y)
+    for i in range(nbuf):
+        g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Y)
     torch.cuda.synchronize()
+    # python/ctypes launch overhead (~10 us) exceeds the kernel time: replay a CUDA graph of one sweep instead
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(nbuf):
+            g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Y)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    sweeps = max(3, reps // nbuf)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(reps):
-        g.mul_mat(t, Ws[i % nbuf], X, M, N, K, flags=flags, out=Y)
+    for _ in range(sweeps):
+        graph.replay()
     ev1.record()
     torch.cuda.synchronize()
-    us = ev0.elapsed_time(ev1) * 1000 / reps
+    us = ev0.elapsed_time(ev1) * 1000 / (sweeps * nbuf)
     return us, rb * M
 
 
@@ -45,6 +54,7 @@ def main():
     ap.add_argument("--n", default="1")
     ap.add_argument("--shapes", default="4096x4096,11008x4096,4096x11008,32000x4096")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--v1", action="store_true")
     a = ap.parse_args()
     tun = {k: v for k, v in os.environ.items() if k.startswith("GGML_B200_")}
     for tn in a.types.split(","):
@@ -53,11 +63,11 @@ def main():
             M, K = (int(v) for v in sh.split("x"))
             K = K // 256 * 256
             for n in (int(v) for v in a.n.split(",")):
-                for flags in ([g.MM_GEMV] + ([g.MM_GENERIC] if a.generic else [])):
-                    if flags == g.MM_GEMV and g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
+                for flags in ([g.MM_GEMV] + ([g.MM_GEMV | g.MM_GEMV_V1] if a.v1 else []) + ([g.MM_GENERIC] if a.generic else [])):
+                    if flags != g.MM_GENERIC and g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
                         continue
                     us, wb = time_mm(t, M, n, K, flags)
-                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": "gemv" if flags == g.MM_GEMV else "generic",
+                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": {g.MM_GEMV: "gemv", g.MM_GEMV | g.MM_GEMV_V1: "gemv_v1"}.get(flags, "generic"),
                                       "us": round(us, 2), "GBps": round(wb / us / 1e3, 1), "tun": tun}), flush=True)
 
 

@@ -117,15 +117,17 @@ def test_mul_mat_golden(t, g):
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8])
 def test_gemv_vs_oracle(t, n, g, oracle):
     # shapes chosen to hit: K-parts 1..8, partial last stage, tiny M, rows-per-stage granules
-    for (M, K) in [(1000, 4096), (257, 1024), (64, 11008 // 256 * 256), (24, 256), (4096, 768 if t in (O.Q4_0, O.Q8_0) else 2048)]:
+    for (M, K) in [(1000, 4096), (257, 1024), (64, 11008 // 256 * 256), (24, 256), (4096, 768 if t in (O.Q4_0, O.Q8_0) else 2048), (3000, 2048), (136, 8192)]:
         if g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
             continue
         W = weights(oracle, t, M, K, seed=M + K + t)
         X = np.random.default_rng(5678).uniform(-1, 1, n * K).astype(np.float32)
-        Y = g.mul_mat(t, dev(W), dev(X), M, n, K, flags=g.MM_GEMV).cpu().numpy()[0, 0]
         want = oracle.mul_mat(t, W, X, M, n, K)
-        assert O.nmse(Y, want) < TOL, (M, K, n)
-        assert np.isfinite(Y).all()
+        # n = 1 has two kernels: the one-lane-per-256-weights kernel (default) and the 64-weight-unit kernel (V1)
+        for flags in ((g.MM_GEMV, g.MM_GEMV | g.MM_GEMV_V1) if n == 1 else (g.MM_GEMV,)):
+            Y = g.mul_mat(t, dev(W), dev(X), M, n, K, flags=flags).cpu().numpy()[0, 0]
+            assert O.nmse(Y, want) < TOL, (M, K, n, flags)
+            assert np.isfinite(Y).all()
 
 
 @pytest.mark.parametrize("t", TYPES, ids=IDS)
