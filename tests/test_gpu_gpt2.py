@@ -1,0 +1,53 @@
+"""GPU: the reference's examples/gpt-2 programs, compiled UNMODIFIED, running a synthetic GPT-2 117M (Q4_0) on the
+B200 backend (BASELINE.json configs[3]).  `gpt-2-backend-b200` = main-backend.cpp built with -DGGML_USE_CUDA and linked
+against libggml-b200.so (which exports the ggml-cuda.h ABI), so every node of the token graph runs on the device
+(no scheduler, no CPU fallback).  Greedy decoding (--top_k 1) must produce the same tokens as the CPU backend."""
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+TMP = Path("/tmp/ggml_b200_gpt2")
+
+
+@pytest.fixture(scope="module")
+def model():
+    for exe in ("gpt-2-backend", "gpt-2-backend-b200", "gpt-2-sched-b200", "gpt-2-quantize"):
+        if not (O.REF_DIR / exe).exists():
+            pytest.fail(f"oracle/_ref/{exe} missing (make -C oracle ref b200bins in the build container)")
+    TMP.mkdir(exist_ok=True)
+    f16, q40 = TMP / "gpt2_f16.bin", TMP / "gpt2_q4_0.bin"
+    if not q40.exists():
+        subprocess.run([sys.executable, str(ROOT / "scripts" / "make_gpt2_synth.py"), str(f16)], check=True)
+        subprocess.run([str(O.REF_DIR / "gpt-2-quantize"), str(f16), str(q40), "2"], check=True, env=O.ref_env(), capture_output=True)
+    return q40
+
+
+def run(exe, model, n=24, extra=()):
+    cmd = [str(O.REF_DIR / exe), "-m", str(model), "-s", "1234", "-n", str(n), "-t", "8", "--ignore-eos", "--top_k", "1", "-p", "a b c", *extra]
+    p = subprocess.run(cmd, env=O.ref_env(), capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-2000:]
+    text = [l for l in p.stdout.splitlines() if l.startswith("a b c")]
+    ms = re.search(r"predict time =\s*([\d.]+) ms /\s*([\d.]+) ms per token", out)
+    return text[0] if text else "", float(ms.group(2)) if ms else None, out
+
+
+def test_gpt2_backend_tokens_match_cpu(model):
+    cpu_text, cpu_ms, _ = run("gpt-2-backend", model)
+    gpu_text, gpu_ms, out = run("gpt-2-backend-b200", model)
+    assert "using CUDA backend" in out, out[-1500:]
+    assert cpu_text and gpu_text == cpu_text, f"\ncpu: {cpu_text}\ngpu: {gpu_text}"
+    print(f"gpt-2 117M q4_0: cpu {cpu_ms} ms/token, b200 {gpu_ms} ms/token")
+
+
+def test_gpt2_sched_full_offload(model):
+    cpu_text, _, _ = run("gpt-2-backend", model)
+    gpu_text, gpu_ms, out = run("gpt-2-sched-b200", model, extra=("-ngl", "99"))
+    assert gpu_text == cpu_text, f"\ncpu: {cpu_text}\ngpu: {gpu_text}\n{out[-1500:]}"

@@ -209,3 +209,48 @@ def test_full_size_properties(t, M, K, g, oracle):
     # generic kernel agrees bit-for-bit?  No (different summation order) -- but to round-off
     Yg = g.mul_mat(t, Wd, Xd, M, 1, K, flags=g.MM_GENERIC).cpu().numpy()[0, 0, 0]
     assert O.nmse(Yg, Y) < TOL
+
+
+GEMM_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K]
+
+
+@pytest.mark.parametrize("t", GEMM_TYPES, ids=[O.TYPE_NAMES[t] for t in GEMM_TYPES])
+def test_gemm_tcgen05_vs_oracle(t, g, oracle):
+    """tcgen05 path (bf16 operands, f32 TMEM accumulation).  Tolerances, stated: NMSE <= 1e-4 against the oracle (which
+    itself carries the int8 activation-quantization noise), <= 2e-5 against the exact f64 product of the dequantized
+    weights; the reference's own gate is 5e-4 (tests/test-backend-ops.cpp:1915-1917)."""
+    for (M, N, K) in [(128, 16, 256), (256, 32, 512), (1000, 100, 1024), (384, 512, 2048), (130, 257, 768)]:
+        if g.mul_mat_plan(t, M, N, K, g.MM_GEMM) != g.MM_GEMM:
+            continue
+        W = weights(oracle, t, M, K, seed=3 * M + N + K)
+        X = np.random.default_rng(N + K).uniform(-1, 1, N * K).astype(np.float32)
+        Y = g.mul_mat(t, dev(W), dev(X), M, N, K, flags=g.MM_GEMM).cpu().numpy()[0, 0]
+        assert np.isfinite(Y).all(), (M, N, K)
+        assert O.nmse(Y, oracle.mul_mat(t, W, X, M, N, K)) < 1e-4, (M, N, K)
+        assert O.nmse(Y, oracle.mul_mat(t, W, X, M, N, K, f64=True)) < 2e-5, (M, N, K)
+
+
+@pytest.mark.parametrize("t", [O.Q8_0, O.Q4_K], ids=["q8_0", "q4_K"])
+def test_gemm_full_size_properties(t, g, oracle):
+    """BASELINE.json configs[2] (Q8_0 4096x4096, n_batch = 512) and its Q4_K twin: sampled rows against the oracle,
+    and exact size-independent properties (column permutation equivariance, power-of-two scaling, repeatability)."""
+    import torch
+    M, N, K = 4096, 512, 4096
+    W = weights(oracle, t, M, K, seed=77, rng_blocks=True)
+    X = np.random.default_rng(5678).uniform(-1, 1, (N, K)).astype(np.float32)
+    Wd, Xd = dev(W), dev(X)
+    assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMM
+    Y = g.mul_mat(t, Wd, Xd, M, N, K).cpu().numpy()[0, 0]
+    assert np.isfinite(Y).all()
+    rows = np.random.default_rng(2).choice(M, 24, replace=False)
+    rb = oracle.row_size(t, K)
+    Wsub = np.concatenate([W[r * rb:(r + 1) * rb] for r in rows])
+    want = oracle.mul_mat(t, Wsub, X.reshape(-1), len(rows), N, K, f64=True)
+    assert O.nmse(Y[:, rows], want) < 2e-5
+    Y2 = g.mul_mat(t, Wd, Xd, M, N, K).cpu().numpy()[0, 0]
+    assert np.array_equal(Y, Y2)                                               # split-K hand-off is ordered: bitwise repeatable
+    perm = np.random.default_rng(3).permutation(N)
+    Yp = g.mul_mat(t, Wd, dev(X[perm]), M, N, K).cpu().numpy()[0, 0]
+    assert np.array_equal(Yp, Y[perm])                                         # activation rows are independent
+    Y4 = g.mul_mat(t, Wd, dev(X * 0.25), M, N, K).cpu().numpy()[0, 0]
+    assert np.array_equal(Y4, Y * 0.25)                                        # power-of-two scaling commutes with bf16 rounding
