@@ -20,7 +20,7 @@ F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 8, 12, 13, 14
 QUANT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
 TYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K"}
 
-MM_AUTO, MM_GENERIC, MM_GEMV, MM_GEMM, MM_GEMV_V1 = 0, 1, 2, 4, 8
+MM_AUTO, MM_GENERIC, MM_GEMV, MM_GEMM, MM_GEMV_V1, MM_SRC0_STATIC = 0, 1, 2, 4, 8, 16
 
 
 class B200Error(RuntimeError):

@@ -46,7 +46,10 @@ static int validate(const ggml_b200_mul_mat_args * a) {
 
 static int plan(const ggml_b200_mul_mat_args & a) {
     if (a.flags & GGML_B200_MM_FORCE_GENERIC) return GGML_B200_MM_FORCE_GENERIC;
-    if (a.flags & GGML_B200_MM_FORCE_GEMV) return (mmvq_sb_eligible(a) || mmvq_tma_eligible(a)) ? GGML_B200_MM_FORCE_GEMV : GGML_B200_EUNSUPPORTED;
+    if (a.flags & GGML_B200_MM_FORCE_GEMV) {
+        const bool ok = (a.flags & GGML_B200_MM_GEMV_V1) ? mmvq_tma_eligible(a) : (mmvq_sb_eligible(a) || mmvq_tma_eligible(a));
+        return ok ? GGML_B200_MM_FORCE_GEMV : GGML_B200_EUNSUPPORTED;
+    }
     if (a.flags & GGML_B200_MM_FORCE_GEMM) return mmq_tc_eligible(a) ? GGML_B200_MM_FORCE_GEMM : GGML_B200_EUNSUPPORTED;
     if (a.N <= 8 && (mmvq_sb_eligible(a) || mmvq_tma_eligible(a))) return GGML_B200_MM_FORCE_GEMV;
     if (a.N > 8 && mmq_tc_eligible(a)) return GGML_B200_MM_FORCE_GEMM;

@@ -318,7 +318,8 @@ void compute_mul_mat(backend_ctx * ctx, const ggml_tensor * dst) {
     const ggml_tensor * a = dst->src[0], * b = dst->src[1];
     ggml_b200_mul_mat_args args{};
     args.type = (int32_t) a->type;
-    args.flags = GGML_B200_MM_AUTO;
+    // weights (graph leaves, uploaded with set_tensor before graph_compute) may be prefetched ahead of the previous node
+    args.flags = (a->op == GGML_OP_NONE && a->view_src == nullptr) ? GGML_B200_MM_SRC0_STATIC : GGML_B200_MM_AUTO;
     args.K = a->ne[0]; args.M = a->ne[1]; args.N = b->ne[1];
     args.ne02 = a->ne[2]; args.ne03 = a->ne[3]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
     args.nb01 = a->nb[1]; args.nb02 = a->nb[2]; args.nb03 = a->nb[3];

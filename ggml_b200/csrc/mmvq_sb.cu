@@ -351,6 +351,7 @@ struct sb_params {
     int64_t M, K;
     int32_t row_bytes, rows_per_chunk, nchunks, stage_bytes, nstages, ntasks_row;
     unsigned int * counters;      // [0] next chunk, [1] finished CTAs (both return to 0 at kernel end)
+    int32_t src0_static;          // weights are not produced by the preceding kernel: prefetch them before griddepcontrol.wait
     sb_act A;
 };
 
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
     if (warp == SB_CONSUMER_WARPS) {
         // ===== producer warp: weights do not depend on the previous kernel, start streaming immediately
         if (lane == 0) {
+            if (!p.src0_static) pdl_wait();
             issue(0, (int)blockIdx.x);                            // first chunk is static
             pdl_wait();                                           // the chunk counter belongs to the previous launch until it completes
             int it = 1;
@@ -423,13 +425,17 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
         const int64_t row0 = (int64_t)chunk * p.rows_per_chunk;
         const int rows = (int)min((int64_t)p.rows_per_chunk, p.M - row0);
         const uint8_t * st = stages + (size_t)s * p.stage_bytes;
-        for (int r = warp * RPW + sub; r < rows; r += SB_CONSUMER_WARPS * RPW) {
-            const uint8_t * row = st + (size_t)r * p.row_bytes;
+        // the row loop is warp-uniform (both half-warps iterate together): the shuffles below use the full mask
+        for (int r0 = warp * RPW; r0 < rows; r0 += SB_CONSUMER_WARPS * RPW) {
+            const int r = r0 + sub;
             float acc = 0.0f;
-            for (int t = l; t < p.ntasks_row; t += LPR) acc += task_dot<T>(row + (size_t)t * F::TASK_B, rec, p.A, t);
+            if (r < rows) {
+                const uint8_t * row = st + (size_t)r * p.row_bytes;
+                for (int t = l; t < p.ntasks_row; t += LPR) acc += task_dot<T>(row + (size_t)t * F::TASK_B, rec, p.A, t);
+            }
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (l == 0) p.y[row0 + r] = acc;
+            if (l == 0 && r < rows) p.y[row0 + r] = acc;
         }
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
@@ -458,7 +464,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     if ((a.M * rb) % 16 != 0) return false;
     static const int env_stage_kb = getenv("GGML_B200_SB_STAGE_KB") ? atoi(getenv("GGML_B200_SB_STAGE_KB")) : 36;
     static const int env_stages   = getenv("GGML_B200_SB_STAGES")   ? atoi(getenv("GGML_B200_SB_STAGES"))   : 2;
-    static const int env_ctas     = getenv("GGML_B200_SB_CTAS")     ? atoi(getenv("GGML_B200_SB_CTAS"))     : 2;
+    static const int env_ctas     = getenv("GGML_B200_SB_CTAS")     ? atoi(getenv("GGML_B200_SB_CTAS"))     : 1;
     constexpr int RPW = 32 / F::LPR;
     int granule = 1; while ((granule * rb) % 16 != 0) granule *= 2;
     int step = SB_CONSUMER_WARPS * RPW; while (step % granule != 0) step *= 2;
@@ -475,6 +481,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     p.ntasks_row = (int)(a.K / F::TASK_W);
     p.A = make_sb_act(a.K);
     p.counters = sb_counters();
+    p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     if (!p.counters) return false;
     auto smem_of = [&]() { return p.nstages * p.stage_bytes + p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
     int ctas = env_ctas < 1 ? 1 : env_ctas > 2 ? 2 : env_ctas;

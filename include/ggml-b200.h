@@ -81,6 +81,8 @@ enum {
     GGML_B200_MM_FORCE_GENERIC = 1,   /* strided one-warp-per-output kernel (any shape) */
     GGML_B200_MM_FORCE_GEMV  = 2,     /* TMA-staged bandwidth kernel (N <= 8) */
     GGML_B200_MM_FORCE_GEMM  = 4,     /* tcgen05 tensor-core kernel */
+    GGML_B200_MM_SRC0_STATIC = 16,    /* src0 is not written by the preceding kernel on this stream (model weights): the mat-vec may
+                                         prefetch it before waiting for that kernel (programmatic dependent launch) */
     GGML_B200_MM_GEMV_V1     = 8,     /* with FORCE_GEMV: the first-generation 64-weight-unit kernel (mmvq.cu) even for n = 1 */
 };
 
