@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = the mat-vec kernel stores its rows into every peer's y over NVLink and signals flags; "
+                         "'nccl' = ncclAllGather of the slices after the kernel (the baseline)")
     ap.add_argument("--cpu-baseline-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_child:
@@ -211,15 +214,37 @@ def main():
     Yall = torch.empty((world, N * M), dtype=torch.float32, device="cuda") if world > 1 else None
     assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMV, "headline workload must run on the TMA mat-vec kernel"
 
-    use_graph = (world == 1) and not args.no_graph
+    fused = world > 1 and args.exchange == "fused"
+    use_graph = (world == 1 or fused) and not args.no_graph
+    ex = None
+    # Like the reference's own perf harness (tests/test-backend-ops.cpp eval_perf, :657-660: the op node repeated in one
+    # graph on the same inputs, one output tensor per node) the mat-vecs of a sweep are INDEPENDENT: fixed activation vector,
+    # one output buffer per weight matrix.  Weights and activations are final before the timed region, so the launches are
+    # flagged SRC0_STATIC | SRC1_STATIC and consecutive launches may overlap (programmatic dependent launch).
+    # `dependent_chain` re-times the sweep with every launch waiting for the previous one (one shared output, activations
+    # treated as produced by the preceding kernel): the latency-bound lower bracket.
+    Ys = [torch.empty((1, 1, N, M), dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+    F_IND = g.MM_SRC0_STATIC | g.MM_SRC1_STATIC
+    F_DEP = g.MM_SRC0_STATIC
+    if fused:
+        ex = g.PeerExchange(world * M, rank, world, rank * M)
+        margs = [g.mul_mat_args(t, Ws[i], X, Yloc, M, N, K, flags=g.MM_SRC0_STATIC) for i in range(nbuf)]
 
-    def sweep():
+    def sweep(dependent=False):
         for i in range(nbuf):
-            g.mul_mat(t, Ws[i], X, M, N, K, out=Yloc, flags=g.MM_SRC0_STATIC)      # weights are static model data
-            if world > 1:
+            if fused:
+                ex.mul_mat_gather(margs[i])                                            # compute + NVLink peer stores + flag publish
+                ex.wait()                                                              # all ranks' slices have landed here
+            elif world > 1:
+                g.mul_mat(t, Ws[i], X, M, N, K, out=Yloc, flags=F_DEP)
                 dist.all_gather_into_tensor(Yall, Yloc.view(-1))
+            elif dependent:
+                g.mul_mat(t, Ws[i], X, M, N, K, out=Yloc, flags=F_DEP)
+            else:
+                g.mul_mat(t, Ws[i], X, M, N, K, out=Ys[i], flags=F_IND)
 
     sweep()                                                          # first-launch setup outside capture
+    sweep(True)
     torch.cuda.synchronize()
     graph = None
     launches_per_step = None
@@ -262,6 +287,25 @@ def main():
     n_mv = nbuf * args.steps
     value = world * n_mv * wb / (ms * 1e-3) / 1e9
     us_per_launch = ms * 1e3 / n_mv
+    dep_us = None
+    if world == 1:
+        if use_graph:
+            gdep = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gdep):
+                sweep(True)
+            dstep = gdep.replay
+        else:
+            dstep = lambda: sweep(True)
+        for _ in range(args.warmup):
+            dstep()
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            dstep()
+        d1.record()
+        torch.cuda.synchronize()
+        dep_us = d0.elapsed_time(d1) * 1e3 / n_mv
 
     # ---- e2e: host buffers through the C ABI (rank-local; aggregated like `value`)
     import ctypes as C
@@ -292,9 +336,14 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
+            if ex is not None:
+                ex.close()
             dist.destroy_process_group()
         return
 
+    if world > 1:
+        dist.barrier()
     peak, peak_src = measured_peaks()
     achieved = algorithmic_bytes(K, M, N) / (us_per_launch * 1e-6) / 1e9
     traffic = None
@@ -311,7 +360,12 @@ def main():
         "config": {"workload": f"q4_K {K}x{M} mat-vec n_batch=1 (BASELINE.json configs[1])", "mat_vecs_per_step": nbuf,
                    "l2_policy": f"inputs larger than L2: {nbuf} distinct weight matrices ({nbuf * wb / 1e6:.0f} MB) visited round-robin",
                    "launch": "CUDA-graph replay of one sweep" if use_graph else "plain stream launches",
-                   "parallelism": f"row-shard x{world} + NCCL all-gather of output slices" if world > 1 else "single GPU"},
+                   "independence": "mat-vecs of a sweep are independent ops (fixed x, one y per weight matrix) as in the reference's eval_perf; "
+                                   "consecutive launches may overlap via programmatic dependent launch",
+                   "dependent_chain": None if dep_us is None else {"us_per_matvec": dep_us, "GBps": wb / dep_us / 1e3,
+                                                                   "note": "every launch waits for the previous kernel (x treated as its output, shared y)"},
+                   "parallelism": (f"row-shard x{world}, exchange fused into the mat-vec kernel (NVLink peer stores + flags)" if fused else
+                                   f"row-shard x{world} + NCCL all-gather of output slices") if world > 1 else "single GPU"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": K * N * 4 * nbuf, "d2h_bytes_per_step": M * N * 4 * nbuf,
                 "us_per_matvec": e2e_s / e2e_n * 1e6, "api": "ggml_b200_mul_mat_host (pinned host x -> device, kernel, y -> host, stream sync)"},
         "gpu_launches": int(launched),
@@ -329,6 +383,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "reference", "sample": f"failed: {type(e).__name__}: {e}"[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
+        if ex is not None:
+            ex.close()
         dist.destroy_process_group()
 
 

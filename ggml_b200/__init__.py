@@ -20,7 +20,7 @@ F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 8, 12, 13, 14
 QUANT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
 TYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K"}
 
-MM_AUTO, MM_GENERIC, MM_GEMV, MM_GEMM, MM_GEMV_V1, MM_SRC0_STATIC = 0, 1, 2, 4, 8, 16
+MM_AUTO, MM_GENERIC, MM_GEMV, MM_GEMM, MM_GEMV_V1, MM_SRC0_STATIC, MM_SRC1_STATIC = 0, 1, 2, 4, 8, 16, 32
 
 
 class B200Error(RuntimeError):
@@ -197,3 +197,70 @@ def quantize_activations(weight_type, x):
     check(lib().ggml_b200_quantize_activations(weight_type, x.data_ptr(), x.stride(0) * 4, rows, K, out.data_ptr(), _stream()),
           "ggml_b200_quantize_activations")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row-sharded multi-GPU mat-vec with the exchange fused into the kernel (peer stores over NVLink, CUDA IPC buffers)
+class Gather(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("row_offset", C.c_int64), ("epoch", C.c_uint32),
+                ("y_peers", C.c_void_p * 8), ("flag_peers", C.c_void_p * 8)]
+
+
+class PeerExchange:
+    """Per-rank full-length y + flag array, visible to every peer.  `group` is a torch.distributed group (NCCL)."""
+
+    def __init__(self, m_total: int, rank: int, world: int, row_offset: int):
+        import torch.distributed as dist
+        L = lib()
+        L.ggml_b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+        L.ggml_b200_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ggml_b200_ipc_close.argtypes = [C.c_void_p]
+        L.ggml_b200_ipc_free.argtypes = [C.c_void_p]
+        L.ggml_b200_mul_mat_gather.argtypes = [C.POINTER(MulMatArgs), C.POINTER(Gather), C.c_void_p]
+        L.ggml_b200_gather_wait.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p]
+        assert 1 <= world <= 8
+        self.rank, self.world, self.m_total = rank, world, m_total
+        self.y_ptr, self.f_ptr = C.c_void_p(), C.c_void_p()
+        hy, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+        check(L.ggml_b200_ipc_alloc(m_total * 4, C.byref(self.y_ptr), hy), "ipc_alloc(y)")
+        check(L.ggml_b200_ipc_alloc(256, C.byref(self.f_ptr), hf), "ipc_alloc(flags)")
+        handles = [None] * world
+        dist.all_gather_object(handles, (hy.raw, hf.raw))
+        self.ga = Gather()
+        self.ga.world, self.ga.rank, self.ga.row_offset, self.ga.epoch = world, rank, row_offset, 0
+        self._opened = []
+        for q, (hyq, hfq) in enumerate(handles):
+            if q == rank:
+                py, pf = self.y_ptr, self.f_ptr
+            else:
+                py, pf = C.c_void_p(), C.c_void_p()
+                check(L.ggml_b200_ipc_open(C.create_string_buffer(hyq, 64), C.byref(py)), "ipc_open(y)")
+                check(L.ggml_b200_ipc_open(C.create_string_buffer(hfq, 64), C.byref(pf)), "ipc_open(flags)")
+                self._opened += [py, pf]
+            self.ga.y_peers[q] = py.value
+            self.ga.flag_peers[q] = pf.value
+        dist.barrier()
+
+    def mul_mat_gather(self, args: MulMatArgs):
+        check(lib().ggml_b200_mul_mat_gather(C.byref(args), C.byref(self.ga), _stream()), "ggml_b200_mul_mat_gather")
+
+    def wait(self):
+        check(lib().ggml_b200_gather_wait(self.f_ptr, self.world, 0, _stream()), "ggml_b200_gather_wait")
+
+    def y_full(self):
+        """the gathered full-length y of this rank as a torch tensor (copy)"""
+        import torch
+        out = torch.empty(self.m_total, dtype=torch.float32, device="cuda")
+        cudart = torch.cuda.cudart()
+        torch.cuda.synchronize()
+        rc = cudart.cudaMemcpy(out.data_ptr(), self.y_ptr.value, self.m_total * 4, 3)      # cudaMemcpyDeviceToDevice
+        assert int(rc) == 0, rc
+        return out
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for p in self._opened:
+            lib().ggml_b200_ipc_close(p)
+        lib().ggml_b200_ipc_free(self.y_ptr)
+        lib().ggml_b200_ipc_free(self.f_ptr)

@@ -4,6 +4,7 @@
 #include "b200_quants.cuh"
 
 #include <cstdarg>
+#include <cstring>
 #include <mutex>
 
 namespace b200 {
@@ -118,6 +119,41 @@ int ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream) {
         default: set_error("mul_mat: the forced kernel family cannot run this shape"); return GGML_B200_EUNSUPPORTED;
     }
 }
+
+int ggml_b200_mul_mat_gather(const ggml_b200_mul_mat_args * args, const ggml_b200_gather * ga, void * stream) {
+    int rc = validate(args);
+    if (rc != GGML_B200_OK) return rc;
+    if (!ga || ga->world < 1 || ga->world > 8 || ga->rank < 0 || ga->rank >= ga->world) { set_error("mul_mat_gather: bad gather descriptor"); return GGML_B200_EINVAL; }
+    for (int q = 0; q < ga->world; ++q) if (!ga->y_peers[q] || !ga->flag_peers[q]) { set_error("mul_mat_gather: NULL peer pointer"); return GGML_B200_EINVAL; }
+    if (!mmvq_sb_eligible(*args)) { set_error("mul_mat_gather: only the n = 1 mat-vec path supports the fused gather"); return GGML_B200_EUNSUPPORTED; }
+    return launch_mmvq_sb(*args, (cudaStream_t)stream, ga);
+}
+
+int ggml_b200_debug_trace(unsigned long long * out256) { return debug_read_trace(out256); }
+
+int ggml_b200_gather_wait(const uint32_t * flags_local, int32_t world, uint32_t epoch, void * stream) {
+    if (!flags_local || world < 1 || world > 8) { set_error("gather_wait: bad arguments"); return GGML_B200_EINVAL; }
+    return launch_gather_wait(flags_local, world, epoch, (cudaStream_t)stream);
+}
+
+int ggml_b200_ipc_alloc(size_t bytes, void ** dev_ptr, void * handle64) {
+    if (!dev_ptr || !handle64 || bytes == 0) { set_error("ipc_alloc: bad arguments"); return GGML_B200_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    B200_CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+    B200_CUDA_TRY(cudaMemset(*dev_ptr, 0, bytes));
+    B200_CUDA_TRY(cudaDeviceSynchronize());
+    B200_CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, *dev_ptr));
+    return GGML_B200_OK;
+}
+int ggml_b200_ipc_free(void * dev_ptr) { B200_CUDA_TRY(cudaFree(dev_ptr)); return GGML_B200_OK; }
+int ggml_b200_ipc_open(const void * handle64, void ** dev_ptr) {
+    if (!dev_ptr || !handle64) { set_error("ipc_open: bad arguments"); return GGML_B200_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    B200_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GGML_B200_OK;
+}
+int ggml_b200_ipc_close(void * dev_ptr) { B200_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr)); return GGML_B200_OK; }
 
 int ggml_b200_mul_mat_host(const ggml_b200_mul_mat_args * args, const float * host_src1, float * host_dst, void * stream) {
     int rc = validate(args);

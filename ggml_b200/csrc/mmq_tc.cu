@@ -299,19 +299,26 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
         // ===================== epilogue
         tc_wait(acc_full, 0);
         tc_fence_after();
-        const int lg = warp & 3, chalf = dwarp >> 2;          // TMEM lane quarter of this warp, column half
+        // each warp owns its TMEM lane quarter (warp % 4) and, when the tile is >= 64 columns wide, one column half
+        const int lg = warp & 3;
+        const bool split_cols = p.BN >= 64;
+        const int chalf = split_cols ? (dwarp >> 2) : 0;
+        const int ncol = split_cols ? p.BN / 2 : p.BN;        // multiple of 32
+        const bool active = split_cols || (dwarp >> 2) == 0;
         const int64_t m = (int64_t)tm * TC_BM + lg * 32 + lane;
-        const int ncol_half = p.BN / 2;
-        const int64_t n_base = (int64_t)tn * p.BN + chalf * ncol_half;
+        const int col0 = chalf * ncol;
+        const int64_t n_base = (int64_t)tn * p.BN + col0;
         float * part = p.partials ? p.partials + ((size_t)tile * (p.splitk - 1)) * (size_t)(p.BN * TC_BM) : nullptr;
         if (ks > 0) {
             // split-K partial: [ks-1][n_local][m_local]
             float * dst = part + (size_t)(ks - 1) * (p.BN * TC_BM);
-            for (int c0 = 0; c0 < ncol_half; c0 += 32) {
-                float v[32];
-                tc_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(chalf * ncol_half + c0), v);
+            if (active) {
+                for (int c0 = 0; c0 < ncol; c0 += 32) {
+                    float v[32];
+                    tc_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(col0 + c0), v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dst[(size_t)(chalf * ncol_half + c0 + i) * TC_BM + lg * 32 + lane] = v[i];
+                    for (int i = 0; i < 32; ++i) dst[(size_t)(col0 + c0 + i) * TC_BM + lg * 32 + lane] = v[i];
+                }
             }
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(TC_DQ_WARPS * 32) : "memory");
@@ -321,20 +328,25 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
                 if (dq == 0) { while (atomicAdd(&p.flags[tile], 0u) < (unsigned)(p.splitk - 1)) __nanosleep(64); __threadfence(); }
                 asm volatile("bar.sync 1, %0;" ::"n"(TC_DQ_WARPS * 32) : "memory");
             }
-            for (int c0 = 0; c0 < ncol_half; c0 += 32) {
-                float v[32];
-                tc_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(chalf * ncol_half + c0), v);
-                for (int j = 1; j < p.splitk; ++j) {
-                    const float * src = part + (size_t)(j - 1) * (p.BN * TC_BM);
+            if (active) {
+                for (int c0 = 0; c0 < ncol; c0 += 32) {
+                    float v[32];
+                    tc_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(col0 + c0), v);
+                    for (int j = 1; j < p.splitk; ++j) {
+                        const float * src = part + (size_t)(j - 1) * (p.BN * TC_BM);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __ldcg(&src[(size_t)(chalf * ncol_half + c0 + i) * TC_BM + lg * 32 + lane]);
-                }
-                if (m < p.M) {
+                        for (int i = 0; i < 32; ++i) v[i] += __ldcg(&src[(size_t)(col0 + c0 + i) * TC_BM + lg * 32 + lane]);
+                    }
+                    if (m < p.M) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { const int64_t n = n_base + c0 + i; if (n < p.N) p.y[(size_t)n * p.M + m] = v[i]; }
+                        for (int i = 0; i < 32; ++i) { const int64_t n = n_base + c0 + i; if (n < p.N) p.y[(size_t)n * p.M + m] = v[i]; }
+                    }
                 }
             }
-            if (p.splitk > 1 && dq == 0) p.flags[tile] = 0;     // leave the flag clean for the next launch
+            if (p.splitk > 1) {
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_DQ_WARPS * 32) : "memory");
+                if (dq == 0) p.flags[tile] = 0;                 // leave the flag clean for the next launch
+            }
         }
         tc_fence_before();
     }

@@ -20,6 +20,7 @@
 #include "b200_internal.h"
 #include "b200_quants.cuh"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace b200 {
@@ -54,6 +55,7 @@ __device__ __forceinline__ void sb_tma_g2s(void * dst_smem, const void * src_gme
 // programmatic dependent launch: let the next kernel's prologue start / wait for the previous kernel's results
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // mixed-sign dp4a: bytes of a are unsigned, bytes of b signed
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
@@ -91,9 +93,8 @@ __host__ __device__ inline sb_act make_sb_act(int64_t K) {
 }
 
 // one warp quantizes act-task t (256 values) into the interleaved record
-template <bool KQ> __device__ __forceinline__ void sb_quantize_task(const float * x, uint8_t * rec, const sb_act & A, int t) {
+template <bool KQ> __device__ __forceinline__ void sb_quantize_task(const float4 a, const float4 b, uint8_t * rec, const sb_act & A, int t) {
     const int lane = threadIdx.x & 31;
-    const float4 a = load_f4(x + 4 * lane), b = load_f4(x + 128 + 4 * lane);
     const float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
     int q[8];
     if constexpr (KQ) {
@@ -350,8 +351,17 @@ struct sb_params {
     const uint8_t * w; const float * x; float * y;
     int64_t M, K;
     int32_t row_bytes, rows_per_chunk, nchunks, stage_bytes, nstages, ntasks_row;
-    unsigned int * counters;      // [0] next chunk, [1] finished CTAs (both return to 0 at kernel end)
+    unsigned int * counters;      // this launch's scheduling slot: [0] next chunk, [1] finished producers, [2] finished CTAs (all return to 0)
+    unsigned int * ctl;           // device-global control words: [0] exchange epoch, [1] trace launch index
+    int32_t src1_static;          // activations are not produced by the preceding kernel either: never wait for it (independent ops overlap)
     int32_t src0_static;          // weights are not produced by the preceding kernel: prefetch them before griddepcontrol.wait
+    // row-sharded multi-GPU: every result is stored straight into each peer's full-length y over NVLink (world == 0: off)
+    unsigned long long * dbg;     // optional %globaltimer trace (GGML_B200_SB_DEBUG=1): 32 launches x 8 stamps
+    int32_t world, rank;
+    int64_t row_offset;
+    uint32_t epoch;
+    float *    y_peers[8];
+    uint32_t * flag_peers[8];
     sb_act A;
 };
 
@@ -368,6 +378,14 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
+    unsigned long long * dbg = nullptr;
+    if (p.dbg && blockIdx.x == 0) {
+        __shared__ unsigned int dbg_slot;
+        if (tid == 0) dbg_slot = atomicAdd(&p.ctl[1], 1u) % 32u;
+        __syncthreads();
+        dbg = p.dbg + dbg_slot * 8;
+        if (tid == 0) dbg[0] = gtime();                          // CTA 0 entry
+    }
 
     if (tid == 0) {
         for (int s = 0; s < p.nstages; ++s) { sb_mbar_init(&full[s], 1); sb_mbar_init(&empty[s], SB_CONSUMER_WARPS); }
@@ -393,7 +411,9 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
         if (lane == 0) {
             if (!p.src0_static) pdl_wait();
             issue(0, (int)blockIdx.x);                            // first chunk is static
-            pdl_wait();                                           // the chunk counter belongs to the previous launch until it completes
+            if (dbg) dbg[1] = gtime();                            // first TMA issued
+            // (the scheduling counters are per launch slot, so the producer never has to wait for the previous grid on their account)
+            if (dbg) dbg[2] = gtime();                            // producer past griddepcontrol.wait                                           // the chunk counter belongs to the previous launch until it completes
             int it = 1;
             bool done = (int)blockIdx.x >= p.nchunks;
             while (!done) {
@@ -412,16 +432,28 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
     }
 
     // ===== consumers: quantize the activation vector (needs the previous kernel's output)
-    pdl_wait();
-    for (int t = warp; t < p.A.ntask; t += SB_CONSUMER_WARPS) sb_quantize_task<F::KQ != 0>(p.x + (size_t)t * 256, rec, p.A, t);
+    if (!p.src1_static) pdl_wait();
+    if (dbg && tid == 0) dbg[3] = gtime();                       // consumers past griddepcontrol.wait
+    // two act-tasks per warp per round, both loads in flight before either is processed (this phase is on the critical
+    // path of a dependent launch: it can only start once the previous kernel's output is visible)
+    for (int t0 = warp; t0 < p.A.ntask; t0 += 2 * SB_CONSUMER_WARPS) {
+        const int t1 = t0 + SB_CONSUMER_WARPS;
+        const float * x0 = p.x + (size_t)t0 * 256, * x1 = p.x + (size_t)t1 * 256;
+        const float4 a0 = load_f4(x0 + 4 * lane), b0 = load_f4(x0 + 128 + 4 * lane);
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+        if (t1 < p.A.ntask) { a1 = load_f4(x1 + 4 * lane); b1 = load_f4(x1 + 128 + 4 * lane); }
+        sb_quantize_task<F::KQ != 0>(a0, b0, rec, p.A, t0);
+        if (t1 < p.A.ntask) sb_quantize_task<F::KQ != 0>(a1, b1, rec, p.A, t1);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");        // consumers only
 
     const int sub = lane / LPR, l = lane % LPR;
     for (int it = 0;; ++it) {
         const int s = it % p.nstages;
         sb_mbar_wait(&full[s], (uint32_t)(it / p.nstages) & 1u);
+        if (dbg && tid == 0 && it == 0) dbg[4] = gtime();        // first stage landed
         const int chunk = chunk_of[s];
-        if (chunk < 0) break;
+        if (chunk < 0) { if (dbg && tid == 0) dbg[5] = gtime(); break; }   // last stage done
         const int64_t row0 = (int64_t)chunk * p.rows_per_chunk;
         const int rows = (int)min((int64_t)p.rows_per_chunk, p.M - row0);
         const uint8_t * st = stages + (size_t)s * p.stage_bytes;
@@ -435,22 +467,59 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
             }
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (l == 0 && r < rows) p.y[row0 + r] = acc;
+            if (l == 0 && r < rows) {
+                if (p.world == 0) p.y[row0 + r] = acc;
+                else {
+#pragma unroll 1
+                    for (int q = 0; q < p.world; ++q) p.y_peers[q][p.row_offset + row0 + r] = acc;      // peer stores (NVLink)
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
     }
+    if (p.world > 0) {
+        // fused gather: when the last CTA has stored its rows, publish this rank's epoch in every peer's flag array
+        asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
+        if (tid == 0) {
+            __threadfence_system();
+            if (atomicAdd(&p.counters[2], 1u) == gridDim.x - 1) {
+                p.counters[2] = 0;
+                // the exchange epoch lives on the device (ctl[0]) so that a CUDA graph can replay the launch
+                const uint32_t e = p.epoch ? p.epoch : p.ctl[0] + 1;
+                p.ctl[0] = e;
+                __threadfence_system();
+                for (int q = 0; q < p.world; ++q)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_peers[q] + p.rank), "r"(e) : "memory");
+            }
+        }
+    }
+}
+
+// wait until every rank has published `epoch` in this rank's flag array (one warp)
+__global__ void gather_wait_kernel(const uint32_t * flags, int world, uint32_t epoch, const unsigned int * ctl) {
+    const int q = threadIdx.x;
+    if (epoch == 0) epoch = ctl[0];          // the epoch this rank published with its last fused mat-vec
+    if (q < world) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
+        } while ((int32_t)(v - epoch) < 0);
+    }
+    __syncwarp();
+    __threadfence_system();
 }
 
 struct sb_plan { sb_params p; int grid, smem; };
 
+// device control block: [0,64) global control words, [64, 64 + 64*8) 64 per-launch scheduling slots, byte 4096.. trace
 static unsigned int * sb_counters() {
     static unsigned int * ptr[64] = { nullptr };
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!ptr[dev]) {
-        if (cudaMalloc(&ptr[dev], 256) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        cudaMemset(ptr[dev], 0, 256);
+        if (cudaMalloc(&ptr[dev], 8192) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(ptr[dev], 0, 8192);
     }
     return ptr[dev];
 }
@@ -463,7 +532,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     if (a.nb01 != rb || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0) return false;
     if ((a.M * rb) % 16 != 0) return false;
     static const int env_stage_kb = getenv("GGML_B200_SB_STAGE_KB") ? atoi(getenv("GGML_B200_SB_STAGE_KB")) : 36;
-    static const int env_stages   = getenv("GGML_B200_SB_STAGES")   ? atoi(getenv("GGML_B200_SB_STAGES"))   : 2;
+    static const int env_stages   = getenv("GGML_B200_SB_STAGES")   ? atoi(getenv("GGML_B200_SB_STAGES"))   : 0;
     static const int env_ctas     = getenv("GGML_B200_SB_CTAS")     ? atoi(getenv("GGML_B200_SB_CTAS"))     : 1;
     constexpr int RPW = 32 / F::LPR;
     int granule = 1; while ((granule * rb) % 16 != 0) granule *= 2;
@@ -477,14 +546,29 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     p.w = (const uint8_t *)a.src0; p.x = a.src1; p.y = a.dst; p.M = a.M; p.K = a.K;
     p.row_bytes = (int)rb; p.rows_per_chunk = rpc; p.nchunks = (int)((a.M + rpc - 1) / rpc);
     p.stage_bytes = (int)(((size_t)rpc * rb + 127) & ~(size_t)127);
-    p.nstages = env_stages < 2 ? 2 : env_stages > SB_MAX_STAGES ? SB_MAX_STAGES : env_stages;
+    p.nstages = env_stages;       // 0 = automatic (below)
     p.ntasks_row = (int)(a.K / F::TASK_W);
     p.A = make_sb_act(a.K);
-    p.counters = sb_counters();
+    p.ctl = sb_counters();
+    static std::atomic<unsigned> seq{0};
+    p.counters = p.ctl ? p.ctl + 64 + (seq.fetch_add(1) % 64u) * 8 : nullptr;
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
+    p.world = 0; p.rank = 0; p.row_offset = 0; p.epoch = 0;
+    static const bool env_dbg = getenv("GGML_B200_SB_DEBUG") && atoi(getenv("GGML_B200_SB_DEBUG")) != 0;
+    p.dbg = (env_dbg && p.ctl) ? (unsigned long long *)(p.ctl + 1024) : nullptr;
+    p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
+    for (int q = 0; q < 8; ++q) { p.y_peers[q] = nullptr; p.flag_peers[q] = nullptr; }
     if (!p.counters) return false;
     auto smem_of = [&]() { return p.nstages * p.stage_bytes + p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
     int ctas = env_ctas < 1 ? 1 : env_ctas > 2 ? 2 : env_ctas;
+    if (p.nstages <= 0) {
+        // deepest ring that still lets TWO launches be co-resident on an SM (<= 113 KB each), so that programmatic dependent
+        // launch can overlap the next mat-vec's prologue and first TMA round trip with this one's tail
+        p.nstages = 4;
+        while (p.nstages > 2 && smem_of() > 113 * 1024) p.nstages--;
+    }
+    if (p.nstages < 2) p.nstages = 2;
+    if (p.nstages > SB_MAX_STAGES) p.nstages = SB_MAX_STAGES;
     while (smem_of() * ctas > 222 * 1024 && p.nstages > 2) p.nstages--;
     if (smem_of() * ctas > 222 * 1024) ctas = 1;
     if (smem_of() > 222 * 1024) return false;
@@ -494,13 +578,17 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     return true;
 }
 
-template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const ggml_b200_gather * ga, cudaStream_t st) {
     sb_plan pl;
     if (!make_sb_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the superblock mat-vec kernel"); return GGML_B200_EUNSUPPORTED; }
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         attr_set = true;
+    }
+    if (ga) {
+        pl.p.world = ga->world; pl.p.rank = ga->rank; pl.p.row_offset = ga->row_offset; pl.p.epoch = ga->epoch;
+        for (int q = 0; q < ga->world; ++q) { pl.p.y_peers[q] = ga->y_peers[q]; pl.p.flag_peers[q] = ga->flag_peers[q]; }
     }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
     cudaLaunchConfig_t cfg = {};
@@ -526,15 +614,29 @@ bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {
     }
 }
 
-int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml_b200_gather * ga) {
     switch (a.type) {
-        case T_Q4_0: return launch_sb<T_Q4_0>(a, st);
-        case T_Q8_0: return launch_sb<T_Q8_0>(a, st);
-        case T_Q4_K: return launch_sb<T_Q4_K>(a, st);
-        case T_Q5_K: return launch_sb<T_Q5_K>(a, st);
-        case T_Q6_K: return launch_sb<T_Q6_K>(a, st);
+        case T_Q4_0: return launch_sb<T_Q4_0>(a, ga, st);
+        case T_Q8_0: return launch_sb<T_Q8_0>(a, ga, st);
+        case T_Q4_K: return launch_sb<T_Q4_K>(a, ga, st);
+        case T_Q5_K: return launch_sb<T_Q5_K>(a, ga, st);
+        case T_Q6_K: return launch_sb<T_Q6_K>(a, ga, st);
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;
     }
+}
+
+int debug_read_trace(unsigned long long * out) {
+    unsigned int * c = sb_counters();
+    if (!c) return GGML_B200_ECUDA;
+    B200_CUDA_TRY(cudaDeviceSynchronize());
+    B200_CUDA_TRY(cudaMemcpy(out, c + 1024, 32 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return GGML_B200_OK;
+}
+
+int launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cudaStream_t st) {
+    gather_wait_kernel<<<1, 32, 0, st>>>(flags, world, epoch, sb_counters());
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
 }
 
 } // namespace b200

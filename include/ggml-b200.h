@@ -83,6 +83,9 @@ enum {
     GGML_B200_MM_FORCE_GEMM  = 4,     /* tcgen05 tensor-core kernel */
     GGML_B200_MM_SRC0_STATIC = 16,    /* src0 is not written by the preceding kernel on this stream (model weights): the mat-vec may
                                          prefetch it before waiting for that kernel (programmatic dependent launch) */
+    GGML_B200_MM_SRC1_STATIC = 32,    /* src1 is not written by the preceding kernel either (e.g. Q/K/V or gate/up projections that share
+                                         one input, or a perf harness repeating an op): the launch never waits for it, so independent
+                                         mat-vecs overlap; dst must not alias the preceding kernel's dst */
     GGML_B200_MM_GEMV_V1     = 8,     /* with FORCE_GEMV: the first-generation 64-weight-unit kernel (mmvq.cu) even for n = 1 */
 };
 
@@ -96,6 +99,29 @@ GGML_B200_API int    ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args)
  * (weights are uploaded once at model load, like the reference's buffer.set_tensor).  Used for the
  * end-to-end measurement; `args->src1` / `args->dst` must point at device staging buffers. */
 GGML_B200_API int    ggml_b200_mul_mat_host(const ggml_b200_mul_mat_args * args, const float * host_src1, float * host_dst, void * stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded MUL_MAT across GPUs (one process per GPU), fused with the exchange: rank r computes rows
+ * [row_offset, row_offset + M) of the full product and the mat-vec kernel stores every result directly into each
+ * peer's full-length y over NVLink (peer pointers from CUDA IPC), then publishes `epoch` in every peer's flag array;
+ * ggml_b200_gather_wait makes the stream wait until all ranks have published.  Replaces the reference's split-buffer
+ * gather (cudaMemcpy3DPeerAsync + events, src/ggml-cuda/ggml-cuda.cu:1333-1351, 1621-1647).  n = 1 mat-vec path only.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ggml_b200_gather {
+    int32_t    world, rank;          /* <= 8 */
+    int64_t    row_offset;           /* first row of this rank's shard in the full y */
+    uint32_t   epoch;                /* 0: device-managed counter (CUDA-graph replayable), else an explicit increasing value */
+    float *    y_peers[8];           /* full-length y of every rank (own entry included) */
+    uint32_t * flag_peers[8];        /* flag array (>= world uint32, zero-initialised) of every rank */
+} ggml_b200_gather;
+
+GGML_B200_API int ggml_b200_mul_mat_gather(const ggml_b200_mul_mat_args * args, const ggml_b200_gather * gather, void * stream);
+GGML_B200_API int ggml_b200_gather_wait(const uint32_t * flags_local, int32_t world, uint32_t epoch, void * stream);
+/* CUDA-IPC plumbing for the peer buffers: allocate (zeroed) + export a 64-byte handle; open / close a peer's handle */
+GGML_B200_API int ggml_b200_ipc_alloc(size_t bytes, void ** dev_ptr, void * handle64);
+GGML_B200_API int ggml_b200_ipc_free(void * dev_ptr);
+GGML_B200_API int ggml_b200_ipc_open(const void * handle64, void ** dev_ptr);
+GGML_B200_API int ggml_b200_ipc_close(void * dev_ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * MUL_MAT_ID (src/ggml.c:2735-2762): as[K, M, n_expert] quantized, b[K, nb1cols, n_tok] f32,
@@ -175,6 +201,8 @@ GGML_B200_API int          ggml_b200_sm_count(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 GGML_B200_API uint64_t     ggml_b200_launch_count(void);
 GGML_B200_API const char * ggml_b200_version(void);
+/* developer aid (GGML_B200_SB_DEBUG=1): %globaltimer stamps of CTA 0 for the last 32 mat-vec launches, 8 per launch */
+GGML_B200_API int          ggml_b200_debug_trace(unsigned long long * out256);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,9 @@ import ggml_b200 as g  # noqa: E402
 NAMES = {v: k for k, v in g.TYPE_NAMES.items()}
 
 
+IND = False
+
+
 def time_mm(t, M, N, K, flags, reps=400):
     rb = g.row_size(t, K)
     nbuf = max(2, int(np.ceil(300e6 / (rb * M))))           # rotate > 2x L2 worth of weights
@@ -26,14 +29,17 @@ def time_mm(t, M, N, K, flags, reps=400):
         Ws.append(w)
     X = torch.rand(N * K, device="cuda") * 2 - 1
     Y = torch.empty((1, 1, N, M), device="cuda")
+    Ys = [torch.empty((1, 1, N, M), device="cuda") for _ in range(nbuf)] if IND else [Y] * nbuf
+    if IND and flags == g.MM_GEMV:
+        flags = flags | g.MM_SRC0_STATIC | g.MM_SRC1_STATIC
     for i in range(nbuf):
-        g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Y)
+        g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Ys[i])
     torch.cuda.synchronize()
     # python/ctypes launch overhead (~10 us) exceeds the kernel time: replay a CUDA graph of one sweep instead
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         for i in range(nbuf):
-            g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Y)
+            g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Ys[i])
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize()
@@ -55,7 +61,10 @@ def main():
     ap.add_argument("--shapes", default="4096x4096,11008x4096,4096x11008,32000x4096")
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--v1", action="store_true")
+    ap.add_argument("--independent", action="store_true", help="flag launches SRC0_STATIC|SRC1_STATIC and give each its own output")
     a = ap.parse_args()
+    global IND
+    IND = a.independent
     tun = {k: v for k, v in os.environ.items() if k.startswith("GGML_B200_")}
     for tn in a.types.split(","):
         t = NAMES[tn]
@@ -67,7 +76,7 @@ def main():
                     if flags != g.MM_GENERIC and g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
                         continue
                     us, wb = time_mm(t, M, n, K, flags)
-                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": {g.MM_GEMV: "gemv", g.MM_GEMV | g.MM_GEMV_V1: "gemv_v1"}.get(flags, "generic"),
+                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": {g.MM_GEMV: "gemv_ind" if IND else "gemv", g.MM_GEMV | g.MM_GEMV_V1: "gemv_v1"}.get(flags, "generic"),
                                       "us": round(us, 2), "GBps": round(wb / us / 1e3, 1), "tun": tun}), flush=True)
 
 

@@ -43,9 +43,10 @@ def main():
             f.write(data.tobytes())
 
         tensor("model/ln_f/g", [n_embd], "f32"); tensor("model/ln_f/b", [n_embd], "f32")
+        # lm_head must precede wte: the loaders alias lm_head to wte when wte is seen first (main-sched.cpp:504-513)
+        tensor("model/lm_head", [n_embd, n_vocab], "f16")
         tensor("model/wte", [n_embd, n_vocab], "f16")
         tensor("model/wpe", [n_embd, n_ctx], "f32")
-        tensor("model/lm_head", [n_embd, n_vocab], "f16")
         for i in range(n_layer):
             p = f"model/h{i}/"
             tensor(p + "ln_1/g", [n_embd], "f32"); tensor(p + "ln_1/b", [n_embd], "f32")

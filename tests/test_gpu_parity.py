@@ -110,7 +110,9 @@ def test_mul_mat_golden(t, g):
         M, N, K = (int(v) for v in z[f"shape{ci}"])
         for flags in (g.MM_AUTO, g.MM_GENERIC):
             Y = g.mul_mat(t, dev(z[f"W{ci}"]), dev(z[f"X{ci}"]), M, N, K, flags=flags).cpu().numpy()[0, 0]
-            assert O.nmse(Y, z[f"Y{ci}"]) < TOL, (ci, M, N, K, flags)
+            # the tcgen05 path (n >= 16) computes with bf16 operands: stated tolerance 1e-4 (reference gate 5e-4); int8 paths 1e-10
+            tol = 1e-4 if g.mul_mat_plan(t, M, N, K, flags) == g.MM_GEMM else TOL
+            assert O.nmse(Y, z[f"Y{ci}"]) < tol, (ci, M, N, K, flags)
 
 
 @pytest.mark.parametrize("t", TYPES, ids=IDS)
