@@ -227,14 +227,17 @@ def main():
     F_IND = g.MM_SRC0_STATIC | g.MM_SRC1_STATIC
     F_DEP = g.MM_SRC0_STATIC
     if fused:
-        ex = g.PeerExchange(world * M, rank, world, rank * M)
-        margs = [g.mul_mat_args(t, Ws[i], X, Yloc, M, N, K, flags=g.MM_SRC0_STATIC) for i in range(nbuf)]
+        # same independence rules as N = 1: every op of the sweep has its own gathered-y slot on every rank; the peer stores
+        # and flag publication of op i overlap the streaming of op i+1; one stream-wait at the end of the sweep
+        ex = g.PeerExchange(world * M, rank, world, rank * M, slots=nbuf)
+        margs = [g.mul_mat_args(t, Ws[i], X, Yloc, M, N, K, flags=F_IND) for i in range(nbuf)]
 
     def sweep(dependent=False):
         for i in range(nbuf):
             if fused:
-                ex.mul_mat_gather(margs[i])                                            # compute + NVLink peer stores + flag publish
-                ex.wait()                                                              # all ranks' slices have landed here
+                ex.mul_mat_gather(margs[i], slot=i)                                    # compute + NVLink peer stores + flag publish
+                if i == nbuf - 1:
+                    ex.wait()                                                          # every rank's slices of the whole sweep have landed
             elif world > 1:
                 g.mul_mat(t, Ws[i], X, M, N, K, out=Yloc, flags=F_DEP)
                 dist.all_gather_into_tensor(Yall, Yloc.view(-1))

@@ -207,9 +207,9 @@ class Gather(C.Structure):
 
 
 class PeerExchange:
-    """Per-rank full-length y + flag array, visible to every peer.  `group` is a torch.distributed group (NCCL)."""
+    """Per-rank gathered-y buffers (`slots` full-length vectors) + flag array, visible to every peer through CUDA IPC."""
 
-    def __init__(self, m_total: int, rank: int, world: int, row_offset: int):
+    def __init__(self, m_total: int, rank: int, world: int, row_offset: int, slots: int = 1):
         import torch.distributed as dist
         L = lib()
         L.ggml_b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
@@ -219,16 +219,15 @@ class PeerExchange:
         L.ggml_b200_mul_mat_gather.argtypes = [C.POINTER(MulMatArgs), C.POINTER(Gather), C.c_void_p]
         L.ggml_b200_gather_wait.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p]
         assert 1 <= world <= 8
-        self.rank, self.world, self.m_total = rank, world, m_total
+        self.rank, self.world, self.m_total, self.slots = rank, world, m_total, slots
         self.y_ptr, self.f_ptr = C.c_void_p(), C.c_void_p()
         hy, hf = C.create_string_buffer(64), C.create_string_buffer(64)
-        check(L.ggml_b200_ipc_alloc(m_total * 4, C.byref(self.y_ptr), hy), "ipc_alloc(y)")
+        check(L.ggml_b200_ipc_alloc(slots * m_total * 4, C.byref(self.y_ptr), hy), "ipc_alloc(y)")
         check(L.ggml_b200_ipc_alloc(256, C.byref(self.f_ptr), hf), "ipc_alloc(flags)")
         handles = [None] * world
         dist.all_gather_object(handles, (hy.raw, hf.raw))
-        self.ga = Gather()
-        self.ga.world, self.ga.rank, self.ga.row_offset, self.ga.epoch = world, rank, row_offset, 0
         self._opened = []
+        ys, fs = [], []
         for q, (hyq, hfq) in enumerate(handles):
             if q == rank:
                 py, pf = self.y_ptr, self.f_ptr
@@ -237,25 +236,34 @@ class PeerExchange:
                 check(L.ggml_b200_ipc_open(C.create_string_buffer(hyq, 64), C.byref(py)), "ipc_open(y)")
                 check(L.ggml_b200_ipc_open(C.create_string_buffer(hfq, 64), C.byref(pf)), "ipc_open(flags)")
                 self._opened += [py, pf]
-            self.ga.y_peers[q] = py.value
-            self.ga.flag_peers[q] = pf.value
+            ys.append(py.value); fs.append(pf.value)
+        self.ga = []
+        for sl in range(slots):
+            ga = Gather()
+            ga.world, ga.rank, ga.row_offset, ga.epoch = world, rank, sl * m_total + row_offset, 0
+            for q in range(world):
+                ga.y_peers[q] = ys[q]; ga.flag_peers[q] = fs[q]
+            self.ga.append(ga)
         dist.barrier()
 
-    def mul_mat_gather(self, args: MulMatArgs):
-        check(lib().ggml_b200_mul_mat_gather(C.byref(args), C.byref(self.ga), _stream()), "ggml_b200_mul_mat_gather")
+    def mul_mat_gather(self, args: MulMatArgs, slot: int = 0):
+        """compute this rank's rows and store them into every peer's gathered y (slot); publishes one exchange epoch"""
+        check(lib().ggml_b200_mul_mat_gather(C.byref(args), C.byref(self.ga[slot]), _stream()), "ggml_b200_mul_mat_gather")
 
     def wait(self):
+        """stream-wait until every rank has published as many exchanges as this rank has"""
         check(lib().ggml_b200_gather_wait(self.f_ptr, self.world, 0, _stream()), "ggml_b200_gather_wait")
 
-    def y_full(self):
-        """the gathered full-length y of this rank as a torch tensor (copy)"""
+    def y_full(self, slot: int = 0):
+        """zero-copy torch view of this rank's gathered y (slot)"""
         import torch
-        out = torch.empty(self.m_total, dtype=torch.float32, device="cuda")
-        cudart = torch.cuda.cudart()
-        torch.cuda.synchronize()
-        rc = cudart.cudaMemcpy(out.data_ptr(), self.y_ptr.value, self.m_total * 4, 3)      # cudaMemcpyDeviceToDevice
-        assert int(rc) == 0, rc
-        return out
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.m_total,), "typestr": "<f4", "version": 2,
+                                      "data": (self.y_ptr.value + slot * self.m_total * 4, False)}
+        return torch.as_tensor(v, device="cuda")
 
     def close(self):
         import torch

@@ -4,6 +4,7 @@
 #include "b200_quants.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -46,6 +47,8 @@ static int validate(const ggml_b200_mul_mat_args * a) {
 }
 
 static int plan(const ggml_b200_mul_mat_args & a) {
+    static const bool env_generic = getenv("GGML_B200_FORCE_GENERIC") && atoi(getenv("GGML_B200_FORCE_GENERIC")) != 0;   // debugging aid
+    if (env_generic) return GGML_B200_MM_FORCE_GENERIC;
     if (a.flags & GGML_B200_MM_FORCE_GENERIC) return GGML_B200_MM_FORCE_GENERIC;
     if (a.flags & GGML_B200_MM_FORCE_GEMV) {
         const bool ok = (a.flags & GGML_B200_MM_GEMV_V1) ? mmvq_tma_eligible(a) : (mmvq_sb_eligible(a) || mmvq_tma_eligible(a));

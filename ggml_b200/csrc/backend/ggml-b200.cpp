@@ -68,9 +68,15 @@ struct backend_ctx {
     void *       workspace = nullptr;   // stream-ordered scratch for the kernel shim
     size_t       workspace_size = 0;
     std::string  name;
+    // CUDA-graph replay of whole ggml graphs (like the reference, src/ggml-cuda/ggml-cuda.cu:2696-2767): the node loop is
+    // stream-captured, the executable graph is updated in place (cudaGraphExecUpdate) and launched once per graph_compute
+    cudaGraphExec_t graph_exec = nullptr;
+    int             graph_calls = 0;      // the first graph_compute runs eagerly (one-time attribute / allocation work)
+    bool            capturing = false;
 
     void * scratch(size_t need) {
         if (need <= workspace_size) return workspace;
+        GGML_ASSERT(!capturing && "scratch must be sized before stream capture");
         if (workspace) CUDA_OK(cudaFreeAsync(workspace, stream));
         size_t sz = need + need / 4;
         sz = (sz + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
@@ -406,6 +412,7 @@ void backend_free(ggml_backend_t backend) {
     {
         scoped_device sd(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
         if (ctx->workspace) cudaFreeAsync(ctx->workspace, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
@@ -430,9 +437,29 @@ void backend_synchronize(ggml_backend_t backend) {
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 }
 
-ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
-    backend_ctx * ctx = (backend_ctx *) backend->context;
-    scoped_device sd(ctx->device);
+size_t node_scratch_need(const ggml_tensor * node) {
+    if (node->op == GGML_OP_MUL_MAT && is_b200_weight_type(node->src[0]->type)) {
+        const ggml_tensor * a = node->src[0], * b = node->src[1];
+        ggml_b200_mul_mat_args args{};
+        args.type = (int32_t) a->type;
+        args.K = a->ne[0]; args.M = a->ne[1]; args.N = b->ne[1];
+        args.ne02 = a->ne[2]; args.ne03 = a->ne[3]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
+        args.nb01 = a->nb[1]; args.nb02 = a->nb[2]; args.nb03 = a->nb[3];
+        args.nb11 = b->nb[1]; args.nb12 = b->nb[2]; args.nb13 = b->nb[3];
+        args.src0 = a->data; args.src1 = (const float *) b->data; args.dst = (float *) node->data;
+        return ggml_b200_mul_mat_workspace_size(&args);
+    }
+    if (node->op == GGML_OP_MUL_MAT_ID) {
+        const ggml_tensor * as = node->src[0], * b = node->src[1];
+        ggml_b200_mul_mat_id_args args{};
+        args.type = (int32_t) as->type; args.K = as->ne[0]; args.M = as->ne[1]; args.n_expert = as->ne[2];
+        args.n_used = node->src[2]->ne[0]; args.nb1cols = b->ne[1]; args.n_tok = b->ne[2];
+        return ggml_b200_mul_mat_id_workspace_size(&args);
+    }
+    return 0;
+}
+
+void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (ggml_is_empty(node)) continue;
@@ -447,6 +474,43 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
             default: compute_small_op(ctx, node); break;
         }
     }
+}
+
+ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    static const bool graphs_off = getenv("GGML_B200_DISABLE_GRAPHS") && atoi(getenv("GGML_B200_DISABLE_GRAPHS")) != 0;
+    int n_real = 0;
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        const ggml_op op = cgraph->nodes[i]->op;
+        n_real += !(op == GGML_OP_NONE || op == GGML_OP_RESHAPE || op == GGML_OP_VIEW || op == GGML_OP_PERMUTE || op == GGML_OP_TRANSPOSE);
+    }
+    const bool use_graph = !graphs_off && n_real >= 8 && ctx->graph_calls++ > 0;
+    if (!use_graph) {
+        compute_nodes(ctx, cgraph);
+        return GGML_STATUS_SUCCESS;
+    }
+    // size the scratch pool before capturing (allocation is not part of the graph)
+    size_t need = 0;
+    for (int i = 0; i < cgraph->n_nodes; ++i) { const size_t n = node_scratch_need(cgraph->nodes[i]); if (n > need) need = n; }
+    ctx->scratch(need);
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    compute_nodes(ctx, cgraph);
+    ctx->capturing = false;
+    CUDA_OK(cudaStreamEndCapture(ctx->stream, &graph));
+    if (ctx->graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(ctx->graph_exec, graph, &info) != cudaSuccess) {      // topology changed: re-instantiate
+            cudaGetLastError();
+            CUDA_OK(cudaGraphExecDestroy(ctx->graph_exec));
+            ctx->graph_exec = nullptr;
+        }
+    }
+    if (!ctx->graph_exec) CUDA_OK(cudaGraphInstantiate(&ctx->graph_exec, graph, 0));
+    CUDA_OK(cudaGraphDestroy(graph));
+    CUDA_OK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
     return GGML_STATUS_SUCCESS;
 }
 

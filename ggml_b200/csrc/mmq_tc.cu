@@ -201,6 +201,35 @@ struct tc_params {
     int32_t BN, m_tiles, n_tiles, splitk, chunks_total, nstages, raw_words_per_chunk;   // raw_words_per_chunk: row advance per chunk in 4-byte elements
 };
 
+// dequantizer main loop of one thread: row `row` of the tile, K-steps 2*KH and 2*KH+1 of every chunk.  KH is a template
+// parameter so that the code paths never have to be merged through register moves.
+template <int T, int KH>
+__device__ __forceinline__ void tc_dequant_loop(const tc_params & p, int nchunks, int row, int lane, uint8_t * a_ring, int a_bytes, const uint8_t * raw,
+                                                uint64_t * full, uint64_t * empty, uint64_t * raw_full, uint64_t * raw_empty) {
+    constexpr int RAW = tcfmt<T>::RAW;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const int a_row_off = (row >> 3) * 1024 + (row & 7) * 128;
+    for (int c = 0; c < nchunks; ++c) {
+        const int rs = c & 1;
+        tc_wait(&raw_full[rs], (uint32_t)(c >> 1) & 1u);
+        const uint8_t * rr = raw + rs * TC_BM * RAW + row * RAW;
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            uint4 v[8];
+            if (qq == 0) dq64<T, 2 * KH>(rr, v); else dq64<T, 2 * KH + 1>(rr, v);
+            if (qq == 1) { __syncwarp(); if (lane == 0) tc_arrive(&raw_empty[rs]); }     // raw bytes are in registers now
+            const int step = 4 * c + 2 * KH + qq, s = step % p.nstages;
+            if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
+            uint8_t * a_row = a_ring + s * a_bytes + a_row_off;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) *(uint4 *)(a_row + (((uint32_t)ch ^ sw) << 4)) = v[ch];
+            tc_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc_arrive(&full[s]);
+        }
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const tc_params p) {
@@ -270,41 +299,20 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
             __syncwarp();
         }
     } else {
-        // ===================== dequantizers: thread -> (row, pair of K-steps)
-        const int dq = tid - 64, row = dq & 127, kh = dq >> 7, dwarp = dq >> 5;
-        uint8_t * a_row_base = nullptr;
-        const uint32_t sw = (uint32_t)(row & 7);
-        for (int c = 0; c < nchunks; ++c) {
-            const int rs = c & 1;
-            tc_wait(&raw_full[rs], (uint32_t)(c >> 1) & 1u);
-            const uint8_t * rr = raw + rs * TC_BM * RAW + row * RAW;
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-                const int q = 2 * kh + qq;                     // K-step inside the chunk
-                const int step = 4 * c + q, s = step % p.nstages;
-                uint4 v[8];
-                if (kh == 0) { if (qq == 0) dq64<T, 0>(rr, v); else dq64<T, 1>(rr, v); }
-                else         { if (qq == 0) dq64<T, 2>(rr, v); else dq64<T, 3>(rr, v); }
-                if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
-                a_row_base = a_ring + s * a_bytes + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) *(uint4 *)(a_row_base + (((uint32_t)ch ^ sw) << 4)) = v[ch];
-                tc_fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tc_arrive(&full[s]);
-            }
-            __syncwarp();
-            if (lane == 0) tc_arrive(&raw_empty[rs]);
-        }
+        // ===================== dequantizers: thread -> (row, pair of K-steps of the chunk); 4 warps per pair
+        const int dq = tid - 64, row = dq & 127, ksel = dq >> 7, dwarp = dq >> 5;
+        if (ksel == 0) tc_dequant_loop<T, 0>(p, nchunks, row, lane, a_ring, a_bytes, raw, full, empty, raw_full, raw_empty);
+        else           tc_dequant_loop<T, 1>(p, nchunks, row, lane, a_ring, a_bytes, raw, full, empty, raw_full, raw_empty);
         // ===================== epilogue
         tc_wait(acc_full, 0);
         tc_fence_after();
-        // each warp owns its TMEM lane quarter (warp % 4) and, when the tile is >= 64 columns wide, one column half
+        // each warp owns its TMEM lane quarter (warp % 4) and one of up to four column groups (multiples of 32 columns)
         const int lg = warp & 3;
-        const bool split_cols = p.BN >= 64;
-        const int chalf = split_cols ? (dwarp >> 2) : 0;
-        const int ncol = split_cols ? p.BN / 2 : p.BN;        // multiple of 32
-        const bool active = split_cols || (dwarp >> 2) == 0;
+        const int ngroups = p.BN >= 64 * (TC_DQ_WARPS / 4) / 2 && TC_DQ_WARPS >= 16 ? 4 : p.BN >= 64 ? 2 : 1;
+        const int cgrp = dwarp >> 2;
+        const bool active = cgrp < ngroups;
+        const int ncol = p.BN / ngroups;
+        const int chalf = active ? cgrp : 0;
         const int64_t m = (int64_t)tm * TC_BM + lg * 32 + lane;
         const int col0 = chalf * ncol;
         const int64_t n_base = (int64_t)tn * p.BN + col0;

@@ -469,28 +469,43 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (l == 0 && r < rows) {
                 if (p.world == 0) p.y[row0 + r] = acc;
-                else {
-#pragma unroll 1
-                    for (int q = 0; q < p.world; ++q) p.y_peers[q][p.row_offset + row0 + r] = acc;      // peer stores (NVLink)
-                }
+                else p.y_peers[p.rank][p.row_offset + row0 + r] = acc;       // own slot of the gathered y; pushed to the peers below
             }
         }
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
     }
     if (p.world > 0) {
-        // fused gather: when the last CTA has stored its rows, publish this rank's epoch in every peer's flag array
+        // fused gather: the CTA that finishes last pushes this rank's slice to every peer's gathered y with coalesced 16-byte
+        // stores over NVLink (one CTA -> one system-scope fence covers all the remote stores), then raises this rank's epoch in
+        // every peer's flag array.  The other SMs are already free for the next (overlapping) launch.
+        __shared__ int s_last;
+        __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
         if (tid == 0) {
+            s_last = atomicAdd(&p.counters[2], 1u) == gridDim.x - 1;
+            if (s_last) { p.counters[2] = 0; __threadfence(); }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
+        if (s_last) {
+            const float * src = p.y_peers[p.rank] + p.row_offset;
+            const int64_t n = p.M;
+            const bool vec = ((p.row_offset | n) & 3) == 0;
+            for (int q = 0; q < p.world; ++q) {
+                if (q == p.rank) continue;
+                float * dst = p.y_peers[q] + p.row_offset;
+                if (vec) { for (int64_t i = tid; i < n / 4; i += SB_CONSUMER_WARPS * 32) ((float4 *)dst)[i] = __ldcg((const float4 *)src + i); }
+                else     { for (int64_t i = tid; i < n; i += SB_CONSUMER_WARPS * 32) dst[i] = __ldcg(src + i); }
+            }
             __threadfence_system();
-            if (atomicAdd(&p.counters[2], 1u) == gridDim.x - 1) {
-                p.counters[2] = 0;
+            asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
+            if (tid == 0) {
                 // the exchange epoch lives on the device (ctl[0]) so that a CUDA graph can replay the launch
-                const uint32_t e = p.epoch ? p.epoch : p.ctl[0] + 1;
-                p.ctl[0] = e;
+                // (atomic: independent launches overlap, two grids may finish together; the flags only ever grow)
+                const uint32_t e = p.epoch ? p.epoch : atomicAdd(&p.ctl[0], 1u) + 1u;
                 __threadfence_system();
                 for (int q = 0; q < p.world; ++q)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_peers[q] + p.rank), "r"(e) : "memory");
+                    asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(p.flag_peers[q] + p.rank), "r"(e) : "memory");
             }
         }
     }

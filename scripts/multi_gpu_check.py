@@ -26,6 +26,7 @@ Yl = torch.empty((1, 1, 1, hi - lo), device="cuda")
 a = g.mul_mat_args(t, Wd, Xd, Yl, hi - lo, 1, K)
 for it in range(3):
     ex.mul_mat_gather(a); ex.wait()
+torch.cuda.synchronize()
 y = ex.y_full().cpu().numpy()
 want = orc.mul_mat(t, W, X, M_total, 1, K)[0]
 err = O.nmse(y, want)
