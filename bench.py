@@ -310,31 +310,47 @@ def main():
         torch.cuda.synchronize()
         dep_us = d0.elapsed_time(d1) * 1e3 / n_mv
 
-    # ---- e2e: host buffers through the C ABI (rank-local; aggregated like `value`)
+    # ---- e2e: host buffers through the C ABI (rank-local; aggregated like `value`).  One step = one call of
+    # ggml_b200_mul_mat_host_batch: upload the step's input x from pinned host memory, the sweep's NBUF mat-vecs, download the
+    # NBUF results into pinned host memory, synchronise.  (The per-op variant ggml_b200_mul_mat_host is timed too.)
     import ctypes as C
+    L = g.lib()
+    L.ggml_b200_mul_mat_host_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     xh = torch.empty(N * K, dtype=torch.float32).pin_memory()
     xh.copy_(X.cpu())
-    yh = torch.empty(N * M, dtype=torch.float32).pin_memory()
-    a = g.mul_mat_args(t, Ws[0], X, Yloc, M, N, K, flags=g.MM_SRC0_STATIC)
+    yh = torch.empty((nbuf, N * M), dtype=torch.float32).pin_memory()
+    arr = (g.MulMatArgs * nbuf)()
+    for i in range(nbuf):
+        ai = g.mul_mat_args(t, Ws[i], X, Ys[i], M, N, K, flags=F_IND)
+        C.memmove(C.addressof(arr[i]), C.addressof(ai), C.sizeof(g.MulMatArgs))
+    hdst = (C.c_void_p * nbuf)(*[yh[i].data_ptr() for i in range(nbuf)])
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    e2e_n = min(n_mv, 2000)
 
-    def e2e_once(i):
-        a.src0 = Ws[i % nbuf].data_ptr()
-        g.check(g.lib().ggml_b200_mul_mat_host(C.byref(a), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), stream), "ggml_b200_mul_mat_host")
+    def e2e_step():
+        g.check(L.ggml_b200_mul_mat_host_batch(arr, nbuf, C.c_void_p(xh.data_ptr()), hdst, stream), "ggml_b200_mul_mat_host_batch")
 
-    for i in range(20):
-        e2e_once(i)
+    for _ in range(5):
+        e2e_step()
     barrier()
+    e2e_steps = max(20, min(args.steps, 300))
     t0 = time.perf_counter()
-    for i in range(e2e_n):
-        e2e_once(i)
+    for _ in range(e2e_steps):
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    a1 = g.mul_mat_args(t, Ws[0], X, Yloc, M, N, K, flags=g.MM_SRC0_STATIC)
+    for i in range(10):
+        g.check(L.ggml_b200_mul_mat_host(C.byref(a1), C.c_void_p(xh.data_ptr()), C.c_void_p(yh[0].data_ptr()), stream), "ggml_b200_mul_mat_host")
+    t1 = time.perf_counter()
+    for i in range(200):
+        a1.src0 = Ws[i % nbuf].data_ptr()
+        g.check(L.ggml_b200_mul_mat_host(C.byref(a1), C.c_void_p(xh.data_ptr()), C.c_void_p(yh[0].data_ptr()), stream), "ggml_b200_mul_mat_host")
+    per_op_us = (time.perf_counter() - t1) / 200 * 1e6
     if world > 1:
         tt = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
+    e2e_n = e2e_steps * nbuf
     e2e_val = world * e2e_n * wb / e2e_s / 1e9
 
     if rank != 0:
@@ -369,12 +385,14 @@ def main():
                                                                    "note": "every launch waits for the previous kernel (x treated as its output, shared y)"},
                    "parallelism": (f"row-shard x{world}, exchange fused into the mat-vec kernel (NVLink peer stores + flags)" if fused else
                                    f"row-shard x{world} + NCCL all-gather of output slices") if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": K * N * 4 * nbuf, "d2h_bytes_per_step": M * N * 4 * nbuf,
-                "us_per_matvec": e2e_s / e2e_n * 1e6, "api": "ggml_b200_mul_mat_host (pinned host x -> device, kernel, y -> host, stream sync)"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": K * N * 4, "d2h_bytes_per_step": M * N * 4 * nbuf,
+                "us_per_step": e2e_s / e2e_steps * 1e6, "us_per_matvec": e2e_s / e2e_n * 1e6,
+                "api": "ggml_b200_mul_mat_host_batch: per step, pinned host x -> device, the sweep's 13 mat-vecs, 13 results -> pinned host, stream sync",
+                "per_op_call_us": per_op_us, "per_op_api": "ggml_b200_mul_mat_host (upload, one mat-vec, download, sync per op)"},
         "gpu_launches": int(launched),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "mmvq_tma_kernel<Q4_K,1,4>", "us_per_launch": us_per_launch,
+                     "kernel": "mmvq_sb_kernel<Q4_K>", "us_per_launch": us_per_launch,
                      "algorithmic_bytes_per_launch": algorithmic_bytes(K, M, N), "peak_source": peak_src},
     }
     if world == 1 and not args.no_cpu_baseline:

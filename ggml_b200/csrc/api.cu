@@ -173,4 +173,24 @@ int ggml_b200_mul_mat_host(const ggml_b200_mul_mat_args * args, const float * ho
     return GGML_B200_OK;
 }
 
+int ggml_b200_mul_mat_host_batch(const ggml_b200_mul_mat_args * args, int32_t n, const float * host_src1, float * const * host_dst, void * stream) {
+    if (!args || n < 1 || !host_src1 || !host_dst) { set_error("mul_mat_host_batch: bad arguments"); return GGML_B200_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n; ++i) {
+        int rc = validate(&args[i]);
+        if (rc != GGML_B200_OK) return rc;
+        if (args[i].src1 != args[0].src1 || args[i].K != args[0].K || args[i].N != args[0].N || args[i].ne12 != 1 || args[i].ne13 != 1 ||
+            args[i].nb11 != (size_t)args[i].K * 4) { set_error("mul_mat_host_batch: all ops must share one contiguous src1 staging buffer"); return GGML_B200_EINVAL; }
+    }
+    B200_CUDA_TRY(cudaMemcpyAsync((void *)args[0].src1, host_src1, (size_t)args[0].K * args[0].N * 4, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n; ++i) {
+        int rc = ggml_b200_mul_mat(&args[i], stream);
+        if (rc != GGML_B200_OK) return rc;
+    }
+    for (int i = 0; i < n; ++i)
+        B200_CUDA_TRY(cudaMemcpyAsync(host_dst[i], args[i].dst, (size_t)args[i].M * args[i].N * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return GGML_B200_OK;
+}
+
 } // extern "C"

@@ -99,6 +99,9 @@ GGML_B200_API int    ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args)
  * (weights are uploaded once at model load, like the reference's buffer.set_tensor).  Used for the
  * end-to-end measurement; `args->src1` / `args->dst` must point at device staging buffers. */
 GGML_B200_API int    ggml_b200_mul_mat_host(const ggml_b200_mul_mat_args * args, const float * host_src1, float * host_dst, void * stream);
+/* n MUL_MATs that consume the same HOST activations (e.g. the projections of one layer, or a perf sweep): one upload of src1 into the
+ * shared device staging buffer args[0].src1, n launches, n downloads into host_dst[i], one synchronisation. */
+GGML_B200_API int    ggml_b200_mul_mat_host_batch(const ggml_b200_mul_mat_args * args, int32_t n, const float * host_src1, float * const * host_dst, void * stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-sharded MUL_MAT across GPUs (one process per GPU), fused with the exchange: rank r computes rows
