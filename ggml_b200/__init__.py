@@ -272,3 +272,75 @@ class PeerExchange:
             lib().ggml_b200_ipc_close(p)
         lib().ggml_b200_ipc_free(self.y_ptr)
         lib().ggml_b200_ipc_free(self.f_ptr)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused epilogue / small ops used by the backend's graph-level fusion (thin ctypes mirrors, for the tests)
+class Epilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("dst_bias", C.c_void_p), ("unary", C.c_int32), ("dst_unary", C.c_void_p)]
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("type", C.c_int32), ("ne", C.c_int64 * 4), ("nb", C.c_size_t * 4)]
+
+
+def tensor_desc(t) -> TensorDesc:
+    """descriptor of a contiguous torch tensor in ggml order (ne[0] = last torch dim)"""
+    import torch
+    d = TensorDesc()
+    d.data = t.data_ptr()
+    d.type = {torch.float32: F32, torch.float16: F16, torch.int32: 26}[t.dtype]
+    shape = list(t.shape)[::-1] + [1] * (4 - t.dim())
+    es = t.element_size()
+    nb = es
+    for i in range(4):
+        d.ne[i] = shape[i]
+        d.nb[i] = nb
+        nb *= shape[i]
+    return d
+
+
+def mul_mat_fused(t, W, X, M, K, bias, gelu: bool):
+    """y = W.x ; y2 = y + bias ; y3 = gelu(y2) in one launch (n = 1).  Returns (y, y2, y3 or None)."""
+    import torch
+    L = lib()
+    L.ggml_b200_mul_mat_fused.argtypes = [C.POINTER(MulMatArgs), C.POINTER(Epilogue), C.c_void_p]
+    Y = torch.empty((1, 1, 1, M), dtype=torch.float32, device="cuda")
+    Y2 = torch.empty(M, dtype=torch.float32, device="cuda")
+    Y3 = torch.empty(M, dtype=torch.float32, device="cuda") if gelu else None
+    a = mul_mat_args(t, W, X, Y, M, 1, K)
+    ep = Epilogue()
+    ep.bias, ep.dst_bias, ep.unary, ep.dst_unary = bias.data_ptr(), Y2.data_ptr(), 1 if gelu else 0, (Y3.data_ptr() if gelu else None)
+    check(L.ggml_b200_mul_mat_fused(C.byref(a), C.byref(ep), _stream()), "ggml_b200_mul_mat_fused")
+    return Y.view(-1), Y2, Y3
+
+
+def op_unary(uop: int, x):
+    import torch
+    L = lib()
+    L.ggml_b200_op_unary.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    y = torch.empty_like(x)
+    check(L.ggml_b200_op_unary(uop, x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "ggml_b200_op_unary")
+    return y
+
+
+def op_norm(x, eps: float, rms: bool = False):
+    import torch
+    L = lib()
+    L.ggml_b200_op_norm.argtypes = [C.c_int32, C.POINTER(TensorDesc), C.POINTER(TensorDesc), C.c_float, C.c_void_p]
+    y = torch.empty_like(x)
+    s, d = tensor_desc(x), tensor_desc(y)
+    check(L.ggml_b200_op_norm(int(rms), C.byref(s), C.byref(d), eps, _stream()), "ggml_b200_op_norm")
+    return y
+
+
+def op_norm_affine(x, gain, bias, eps: float, rms: bool = False):
+    import torch
+    L = lib()
+    L.ggml_b200_op_norm_affine.argtypes = [C.c_int32, C.POINTER(TensorDesc), C.POINTER(TensorDesc), C.c_void_p, C.POINTER(TensorDesc),
+                                           C.c_void_p, C.POINTER(TensorDesc), C.c_float, C.c_void_p]
+    y1, y2, y3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    s, d1, d2, d3 = tensor_desc(x), tensor_desc(y1), tensor_desc(y2), tensor_desc(y3)
+    check(L.ggml_b200_op_norm_affine(int(rms), C.byref(s), C.byref(d1), gain.data_ptr(), C.byref(d2), bias.data_ptr(), C.byref(d3), eps, _stream()),
+          "ggml_b200_op_norm_affine")
+    return y1, y2, y3

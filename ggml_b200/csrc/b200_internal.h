@@ -39,7 +39,7 @@ int    launch_mmvq_tma(const ggml_b200_mul_mat_args & a, cudaStream_t st);
 size_t mmvq_generic_workspace(const ggml_b200_mul_mat_args & a);
 // mmvq_sb.cu (n = 1 bandwidth path)
 bool   mmvq_sb_eligible(const ggml_b200_mul_mat_args & a);
-int    launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml_b200_gather * ga = nullptr);
+int    launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml_b200_gather * ga = nullptr, const ggml_b200_epilogue * ep = nullptr);
 int    debug_read_trace(unsigned long long * out);
 int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cudaStream_t st);
 

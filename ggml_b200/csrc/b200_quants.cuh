@@ -54,6 +54,14 @@ __host__ __device__ inline act_layout make_act_layout(int64_t K, bool kq) {
 }
 
 // ------------------------------------------------------------------ small helpers
+// GELU exactly as the CPU backend evaluates it: through an fp16 -> fp16 table (ggml_vec_gelu_f32, src/ggml-cpu/ggml-cpu.c:1355 ff.)
+__device__ __forceinline__ float gelu_ggml(float v) {
+    if (v <= -10.0f) return 0.0f;
+    if (v >= 10.0f) return v;
+    const float xh = __half2float(__float2half_rn(v));
+    const float g = 0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh)));
+    return __half2float(__float2half_rn(g));
+}
 __device__ __forceinline__ float h2f(uint32_t bits16) { return __half2float(__ushort_as_half((unsigned short)bits16)); }
 
 // n consecutive 32-bit words starting at a 2-byte aligned address (generic/global/shared)

@@ -459,7 +459,57 @@ size_t node_scratch_need(const ggml_tensor * node) {
     return 0;
 }
 
+bool is_row_vector_f32(const ggml_tensor * t, int64_t n) {      // a contiguous f32 [n] (bias / gain) tensor
+    return t && t->type == GGML_TYPE_F32 && t->ne[0] == n && ggml_nelements(t) == n && t->nb[0] == sizeof(float);
+}
+
+// MUL_MAT (n = 1, quantized) [+ ADD bias [+ GELU]] -> one launch; returns the number of extra nodes consumed (0 = not fused)
+int try_fuse_mul_mat(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
+    ggml_tensor * mm = cgraph->nodes[i];
+    if (i + 1 >= cgraph->n_nodes || mm->src[1]->ne[1] != 1 || ggml_nelements(mm) != mm->ne[0]) return 0;
+    ggml_tensor * add = cgraph->nodes[i + 1];
+    if (add->op != GGML_OP_ADD || add->src[0] != mm || !is_row_vector_f32(add->src[1], mm->ne[0]) || !is_f32_contig(add) || !ggml_are_same_shape(add, mm)) return 0;
+    ggml_b200_epilogue ep{};
+    ep.bias = (const float *) add->src[1]->data; ep.dst_bias = (float *) add->data;
+    int consumed = 1;
+    if (i + 2 < cgraph->n_nodes) {
+        ggml_tensor * un = cgraph->nodes[i + 2];
+        if (un->op == GGML_OP_UNARY && ggml_get_unary_op(un) == GGML_UNARY_OP_GELU && un->src[0] == add && is_f32_contig(un)) {
+            ep.unary = 1; ep.dst_unary = (float *) un->data; consumed = 2;
+        }
+    }
+    const ggml_tensor * a = mm->src[0], * b = mm->src[1];
+    ggml_b200_mul_mat_args args{};
+    args.type = (int32_t) a->type;
+    args.flags = (a->op == GGML_OP_NONE && a->view_src == nullptr) ? GGML_B200_MM_SRC0_STATIC : GGML_B200_MM_AUTO;
+    args.K = a->ne[0]; args.M = a->ne[1]; args.N = 1;
+    args.ne02 = a->ne[2]; args.ne03 = a->ne[3]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
+    args.nb01 = a->nb[1]; args.nb02 = a->nb[2]; args.nb03 = a->nb[3];
+    args.nb11 = b->nb[1]; args.nb12 = b->nb[2]; args.nb13 = b->nb[3];
+    args.src0 = a->data; args.src1 = (const float *) b->data; args.dst = (float *) mm->data;
+    const int rc = ggml_b200_mul_mat_fused(&args, &ep, ctx->stream);
+    if (rc == GGML_B200_EUNSUPPORTED) return 0;              // shape not on the mat-vec kernel: run the nodes one by one
+    SHIM_OK(rc);
+    return consumed;
+}
+
+// NORM / RMS_NORM -> MUL(gain) -> ADD(bias) -> one launch
+int try_fuse_norm(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
+    ggml_tensor * nm = cgraph->nodes[i];
+    if (i + 2 >= cgraph->n_nodes) return 0;
+    ggml_tensor * mul = cgraph->nodes[i + 1], * add = cgraph->nodes[i + 2];
+    const int64_t n = nm->ne[0];
+    if (mul->op != GGML_OP_MUL || mul->src[0] != nm || !is_row_vector_f32(mul->src[1], n) || !ggml_are_same_shape(mul, nm)) return 0;
+    if (add->op != GGML_OP_ADD || add->src[0] != mul || !is_row_vector_f32(add->src[1], n) || !ggml_are_same_shape(add, nm)) return 0;
+    if (mul->type != GGML_TYPE_F32 || add->type != GGML_TYPE_F32 || mul->nb[0] != sizeof(float) || add->nb[0] != sizeof(float)) return 0;
+    auto s = desc(nm->src[0]), d1 = desc(nm), d2 = desc(mul), d3 = desc(add);
+    SHIM_OK(ggml_b200_op_norm_affine(nm->op == GGML_OP_RMS_NORM, &s, &d1, (const float *) mul->src[1]->data, &d2, (const float *) add->src[1]->data, &d3,
+                                     ggml_get_op_params_f32(nm, 0), ctx->stream));
+    return 2;
+}
+
 void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
+    static const bool fuse = !(getenv("GGML_B200_DISABLE_FUSION") && atoi(getenv("GGML_B200_DISABLE_FUSION")) != 0);
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (ggml_is_empty(node)) continue;
@@ -467,10 +517,16 @@ void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
             case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
                 break;
             case GGML_OP_MUL_MAT:
-                if (is_b200_weight_type(node->src[0]->type)) compute_mul_mat(ctx, node);
-                else { auto x = desc(node->src[0]), y = desc(node->src[1]), d = desc(node); SHIM_OK(ggml_b200_op_mul_mat_f(&x, &y, &d, ctx->stream)); }
+                if (is_b200_weight_type(node->src[0]->type)) {
+                    const int extra = fuse ? try_fuse_mul_mat(ctx, cgraph, i) : 0;
+                    if (extra > 0) i += extra; else compute_mul_mat(ctx, node);
+                } else { auto x = desc(node->src[0]), y = desc(node->src[1]), d = desc(node); SHIM_OK(ggml_b200_op_mul_mat_f(&x, &y, &d, ctx->stream)); }
                 break;
             case GGML_OP_MUL_MAT_ID: compute_mul_mat_id(ctx, node); break;
+            case GGML_OP_NORM: case GGML_OP_RMS_NORM: {
+                const int extra = fuse ? try_fuse_norm(ctx, cgraph, i) : 0;
+                if (extra > 0) i += extra; else compute_small_op(ctx, node);
+            } break;
             default: compute_small_op(ctx, node); break;
         }
     }

@@ -356,6 +356,8 @@ struct sb_params {
     int32_t src1_static;          // activations are not produced by the preceding kernel either: never wait for it (independent ops overlap)
     int32_t src0_static;          // weights are not produced by the preceding kernel: prefetch them before griddepcontrol.wait
     // row-sharded multi-GPU: every result is stored straight into each peer's full-length y over NVLink (world == 0: off)
+    // fused epilogue (bias add and GELU of the following ggml nodes): y2 = y + bias, y3 = gelu(y2); null = off
+    const float * ep_bias; float * ep_y2; float * ep_y3;
     unsigned long long * dbg;     // optional %globaltimer trace (GGML_B200_SB_DEBUG=1): 32 launches x 8 stamps
     int32_t world, rank;
     int64_t row_offset;
@@ -468,7 +470,14 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (l == 0 && r < rows) {
-                if (p.world == 0) p.y[row0 + r] = acc;
+                if (p.world == 0) {
+                    p.y[row0 + r] = acc;
+                    if (p.ep_bias) {
+                        const float v2 = acc + p.ep_bias[row0 + r];
+                        p.ep_y2[row0 + r] = v2;
+                        if (p.ep_y3) p.ep_y3[row0 + r] = gelu_ggml(v2);
+                    }
+                }
                 else p.y_peers[p.rank][p.row_offset + row0 + r] = acc;       // own slot of the gathered y; pushed to the peers below
             }
         }
@@ -569,6 +578,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     p.counters = p.ctl ? p.ctl + 64 + (seq.fetch_add(1) % 64u) * 8 : nullptr;
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     p.world = 0; p.rank = 0; p.row_offset = 0; p.epoch = 0;
+    p.ep_bias = nullptr; p.ep_y2 = nullptr; p.ep_y3 = nullptr;
     static const bool env_dbg = getenv("GGML_B200_SB_DEBUG") && atoi(getenv("GGML_B200_SB_DEBUG")) != 0;
     p.dbg = (env_dbg && p.ctl) ? (unsigned long long *)(p.ctl + 1024) : nullptr;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
@@ -593,7 +603,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     return true;
 }
 
-template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const ggml_b200_gather * ga, cudaStream_t st) {
+template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const ggml_b200_gather * ga, cudaStream_t st, const ggml_b200_epilogue * ep = nullptr) {
     sb_plan pl;
     if (!make_sb_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the superblock mat-vec kernel"); return GGML_B200_EUNSUPPORTED; }
     static bool attr_set = false;
@@ -601,6 +611,7 @@ template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const gg
         B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         attr_set = true;
     }
+    if (ep && ep->bias) { pl.p.ep_bias = ep->bias; pl.p.ep_y2 = ep->dst_bias; pl.p.ep_y3 = ep->unary == 1 ? ep->dst_unary : nullptr; }
     if (ga) {
         pl.p.world = ga->world; pl.p.rank = ga->rank; pl.p.row_offset = ga->row_offset; pl.p.epoch = ga->epoch;
         for (int q = 0; q < ga->world; ++q) { pl.p.y_peers[q] = ga->y_peers[q]; pl.p.flag_peers[q] = ga->flag_peers[q]; }
@@ -629,13 +640,13 @@ bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {
     }
 }
 
-int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml_b200_gather * ga) {
+int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml_b200_gather * ga, const ggml_b200_epilogue * ep) {
     switch (a.type) {
-        case T_Q4_0: return launch_sb<T_Q4_0>(a, ga, st);
-        case T_Q8_0: return launch_sb<T_Q8_0>(a, ga, st);
-        case T_Q4_K: return launch_sb<T_Q4_K>(a, ga, st);
-        case T_Q5_K: return launch_sb<T_Q5_K>(a, ga, st);
-        case T_Q6_K: return launch_sb<T_Q6_K>(a, ga, st);
+        case T_Q4_0: return launch_sb<T_Q4_0>(a, ga, st, ep);
+        case T_Q8_0: return launch_sb<T_Q8_0>(a, ga, st, ep);
+        case T_Q4_K: return launch_sb<T_Q4_K>(a, ga, st, ep);
+        case T_Q5_K: return launch_sb<T_Q5_K>(a, ga, st, ep);
+        case T_Q6_K: return launch_sb<T_Q6_K>(a, ga, st, ep);
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }

@@ -135,6 +135,32 @@ template <bool RMS> __global__ void norm_kernel(tdesc s, tdesc d, float eps) {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = (x[i] - mean) * scale;
 }
 
+// NORM -> MUL(gain) -> ADD(bias) in one pass; every intermediate tensor of the three ggml nodes is still written
+template <bool RMS> __global__ void norm_affine_kernel(tdesc s, tdesc d1, const float * gain, tdesc d2, const float * bias, tdesc d3, float eps) {
+    __shared__ float sh[32];
+    const int64_t r = blockIdx.x;
+    const int64_t i1 = r % s.ne[1], i2 = (r / s.ne[1]) % s.ne[2], i3 = r / (s.ne[1] * s.ne[2]);
+    const float * x = (const float *)(s.data + i1 * s.nb[1] + i2 * s.nb[2] + i3 * s.nb[3]);
+    float * y1 = (float *)(d1.data + i1 * d1.nb[1] + i2 * d1.nb[2] + i3 * d1.nb[3]);
+    float * y2 = (float *)(d2.data + i1 * d2.nb[1] + i2 * d2.nb[2] + i3 * d2.nb[3]);
+    float * y3 = (float *)(d3.data + i1 * d3.nb[1] + i2 * d3.nb[2] + i3 * d3.nb[3]);
+    const int64_t n = s.ne[0];
+    float mean = 0.0f;
+    if (!RMS) {
+        float sum = 0.0f;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) sum += x[i];
+        mean = block_reduce<false>(sum, sh) / (float)n;
+    }
+    float sq = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i] - mean; sq += v * v; }
+    const float var = block_reduce<false>(sq, sh) / (float)n;
+    const float scale = 1.0f / sqrtf(var + eps);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float a = (x[i] - mean) * scale, b = a * gain[i], c = b + bias[i];
+        y1[i] = a; y2[i] = b; y3[i] = c;
+    }
+}
+
 // ------------------------------------------------------------------ SCALE, DIAG_MASK_INF, unary
 __global__ void scale_kernel(const float * x, float * y, float s, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,16 +179,7 @@ __global__ void unary_kernel(int uop, const float * x, float * y, int64_t n) {
     const float v = x[i];
     float r;
     switch (uop) {
-        case U_GELU: {
-            // the CPU path evaluates GELU through an fp16 -> fp16 table (ggml_vec_gelu_f32, ggml-cpu.c:1355 ff.)
-            if (v <= -10.0f) r = 0.0f;
-            else if (v >= 10.0f) r = v;
-            else {
-                const float xh = __half2float(__float2half_rn(v));
-                const float g = 0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh)));
-                r = __half2float(__float2half_rn(g));
-            }
-        } break;
+        case U_GELU: r = gelu_ggml(v); break;
         case U_SILU: r = v / (1.0f + expf(-v)); break;
         case U_RELU: r = fmaxf(v, 0.0f); break;
         case U_TANH: r = tanhf(v); break;
@@ -317,6 +334,20 @@ int ggml_b200_op_norm(int32_t rms, const ggml_b200_tensor * src, const ggml_b200
     const int threads = s.ne[0] >= 1024 ? 256 : s.ne[0] >= 256 ? 128 : 32;
     if (rms) norm_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d, eps);
     else     norm_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d, eps);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_norm_affine(int32_t rms, const ggml_b200_tensor * src, const ggml_b200_tensor * dst_norm, const float * gain, const ggml_b200_tensor * dst_mul,
+                             const float * bias, const ggml_b200_tensor * dst_add, float eps, void * stream) {
+    const tdesc s = T(src), d1 = T(dst_norm), d2 = T(dst_mul), d3 = T(dst_add);
+    REQUIRE(s.type == T_F32 && d1.type == T_F32 && d2.type == T_F32 && d3.type == T_F32, "f32 only");
+    REQUIRE(s.nb[0] == 4 && d1.nb[0] == 4 && d2.nb[0] == 4 && d3.nb[0] == 4 && gain && bias, "rows contiguous along dim 0");
+    const int64_t rows = nrows(s);
+    if (rows == 0 || s.ne[0] == 0) return GGML_B200_OK;
+    const int threads = s.ne[0] >= 1024 ? 256 : s.ne[0] >= 256 ? 128 : 32;
+    if (rms) norm_affine_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d1, gain, d2, bias, d3, eps);
+    else     norm_affine_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d1, gain, d2, bias, d3, eps);
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }

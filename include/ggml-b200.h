@@ -94,6 +94,18 @@ GGML_B200_API int    ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void
 /* which kernel family AUTO would pick: 1 generic, 2 gemv, 4 gemm, <0 error */
 GGML_B200_API int    ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args);
 
+/* MUL_MAT whose two following ggml nodes are folded into the kernel's epilogue: dst_bias = dst + bias (GGML_OP_ADD with a [M] f32
+ * bias) and, if unary == 1, dst_unary = GELU(dst_bias) (GGML_UNARY_OP_GELU); all three tensors are written, so the graph's other
+ * readers still see them.  Returns GGML_B200_EUNSUPPORTED when the shape does not run on the n = 1 mat-vec kernel (caller falls back
+ * to separate ops). */
+typedef struct ggml_b200_epilogue {
+    const float * bias;       /* [M] */
+    float *       dst_bias;   /* [M] */
+    int32_t       unary;      /* 0 none, 1 GELU */
+    float *       dst_unary;  /* [M] or NULL */
+} ggml_b200_epilogue;
+GGML_B200_API int    ggml_b200_mul_mat_fused(const ggml_b200_mul_mat_args * args, const ggml_b200_epilogue * epilogue, void * stream);
+
 /* MUL_MAT with HOST activations / results: copies src1 (host, contiguous [N][K]) to the device, runs
  * ggml_b200_mul_mat and copies dst back, all on `stream`, then synchronizes it.  src0 stays device-resident
  * (weights are uploaded once at model load, like the reference's buffer.set_tensor).  Used for the
@@ -186,6 +198,9 @@ GGML_B200_API int ggml_b200_op_get_rows(const ggml_b200_tensor * src0, const ggm
 /* op: 0 add, 1 mul, 2 sub, 3 div; src1 broadcasts into dst's shape; dst may alias src0 */
 GGML_B200_API int ggml_b200_op_bin_bcast(int32_t op, const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream);
 GGML_B200_API int ggml_b200_op_norm(int32_t rms, const ggml_b200_tensor * src, const ggml_b200_tensor * dst, float eps, void * stream);
+/* NORM / RMS_NORM followed by MUL(gain[ne0]) and ADD(bias[ne0]) in one pass; the three ggml nodes' outputs are all written */
+GGML_B200_API int ggml_b200_op_norm_affine(int32_t rms, const ggml_b200_tensor * src, const ggml_b200_tensor * dst_norm, const float * gain, const ggml_b200_tensor * dst_mul,
+                                           const float * bias, const ggml_b200_tensor * dst_add, float eps, void * stream);
 GGML_B200_API int ggml_b200_op_scale(const float * src, float * dst, float s, int64_t n, void * stream);
 GGML_B200_API int ggml_b200_op_diag_mask_inf(const float * src, float * dst, int64_t ne0, int64_t ne1, int64_t n, int32_t n_past, void * stream);
 GGML_B200_API int ggml_b200_op_unary(int32_t uop, const float * src, float * dst, int64_t n, void * stream);

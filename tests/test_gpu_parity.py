@@ -258,3 +258,36 @@ def test_gemm_full_size_properties(t, g, oracle):
     assert np.array_equal(Yp, Y[perm])                                         # activation rows are independent
     Y4 = g.mul_mat(t, Wd, dev(X * 0.25), M, N, K).cpu().numpy()[0, 0]
     assert np.array_equal(Y4, Y * 0.25)                                        # power-of-two scaling commutes with bf16 rounding
+
+
+@pytest.mark.parametrize("t", [O.Q4_0, O.Q4_K, O.Q8_0], ids=["q4_0", "q4_K", "q8_0"])
+def test_fused_epilogue_matches_separate_ops(t, g, oracle):
+    """graph-level fusion used for the gpt-2 graph: MUL_MAT + ADD(bias) + GELU in one launch must write exactly what the
+    three separate device ops write (which are themselves pinned by the reference's test-backend-ops)"""
+    import torch
+    M, K = 3072, 768 if t != O.Q4_K else 1024
+    W = weights(oracle, t, M, K, seed=5)
+    rng = np.random.default_rng(9)
+    X = rng.uniform(-1, 1, K).astype(np.float32)
+    bias = torch.from_numpy(rng.uniform(-0.5, 0.5, M).astype(np.float32)).cuda()
+    Wd, Xd = dev(W), dev(X)
+    y, y2, y3 = g.mul_mat_fused(t, Wd, Xd, M, K, bias, gelu=True)
+    y_ref = g.mul_mat(t, Wd, Xd, M, 1, K).view(-1)
+    assert torch.equal(y, y_ref)
+    assert torch.equal(y2, y_ref + bias)
+    assert torch.equal(y3, g.op_unary(0, y_ref + bias))
+    assert O.nmse(y.cpu().numpy(), oracle.mul_mat(t, W, X, M, 1, K)[0]) < TOL
+
+
+def test_fused_norm_affine_matches_separate_ops(g):
+    import torch
+    x = torch.randn(7, 768, device="cuda") * 3 + 0.5
+    gain = torch.randn(768, device="cuda") * 0.02 + 1
+    bias = torch.randn(768, device="cuda") * 0.02
+    for rms in (False, True):
+        y1, y2, y3 = g.op_norm_affine(x, gain, bias, 1e-5, rms=rms)
+        n = g.op_norm(x, 1e-5, rms=rms)
+        assert torch.equal(y1, n) and torch.equal(y2, n * gain) and torch.equal(y3, n * gain + bias)
+        xd = x.double()
+        ref = (xd / torch.sqrt((xd * xd).mean(-1, keepdim=True) + 1e-5)) if rms else ((xd - xd.mean(-1, keepdim=True)) / torch.sqrt(xd.var(-1, unbiased=False, keepdim=True) + 1e-5))
+        assert O.nmse(y1.cpu().numpy(), ref.float().cpu().numpy()) < 1e-10
