@@ -156,7 +156,7 @@ template <bool RMS> __global__ void norm_affine_kernel(tdesc s, tdesc d1, const 
     const float var = block_reduce<false>(sq, sh) / (float)n;
     const float scale = 1.0f / sqrtf(var + eps);
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const float a = (x[i] - mean) * scale, b = a * gain[i], c = b + bias[i];
+        const float a = (x[i] - mean) * scale, b = __fmul_rn(a, gain[i]), c = __fadd_rn(b, bias[i]);   // separately rounded, like the three ggml ops
         y1[i] = a; y2[i] = b; y3[i] = c;
     }
 }
