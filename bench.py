@@ -103,6 +103,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+NBUF = 13          # distinct weight matrices per step: 13 x 25.4 MB = 330 MB > 2 x the 126 MB L2 (and > the host's last-level cache)
+
+
 def make_weights(torch, nbuf, K, M, seed):
     """NBUF distinct packed Q4_K matrices: arbitrary code bytes, finite small fp16 d/dmin per superblock."""
     rb = (K // 256) * 144
@@ -127,15 +130,16 @@ def cpu_baseline(sample_s=12.0):
     X = np.random.default_rng(5678).uniform(-1, 1, K * N).astype(np.float32)
     best = None
     hw = ref.hw_threads()
-    for threads in sorted({hw, max(1, hw // 2)}, reverse=True):
-        _, s = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=64, iters=1, warmup=1)          # probe
-        iters = max(1, int(sample_s / 2 / max(s * 64, 1e-6)))
-        _, s = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=64, iters=iters, warmup=1)
+    nw = NBUF                                   # same sweep as the GPU arm: 13 distinct matrices (330 MB), larger than the host's LLC
+    for threads in sorted({hw, max(1, hw // 2), max(1, hw // 4)}, reverse=True):
+        _, s = ref.mul_mat_sweep(t, W, X, M, N, K, nw, threads=threads, iters=2, warmup=1)          # probe
+        iters = max(1, int(sample_s / 3 / max(s * nw, 1e-6)))
+        _, s = ref.mul_mat_sweep(t, W, X, M, N, K, nw, threads=threads, iters=iters, warmup=1)
         if best is None or s < best[0]:
-            best = (s, threads, iters * 64)
+            best = (s, threads, iters * nw)
     s, threads, n = best
     return {"value": weight_bytes(K, M) / s / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": f"{n} MUL_MAT nodes (q4_K {K}x{M}, n=1, node repeated 64x per graph, persistent threadpool), "
+            "sample": f"{n} MUL_MAT nodes (q4_K {K}x{M}, n=1; {nw} distinct weight tensors per graph = 330 MB sweep, persistent threadpool), "
                       f"ggml-cpu {'native' if ref.native else 'x86-64-v3'} build, {s * 1e6:.1f} us per mat-vec",
             "us_per_matvec": s * 1e6}
 
@@ -155,23 +159,24 @@ def run_reference_arm(args):
     # physical core: oversubscribing the SMT siblings of a 2-socket host slows ggml-cpu's spin barriers down by several x)
     hw = ref.hw_threads()
     best_s, threads = None, hw
+    nbuf = NBUF
     for th in sorted({hw, max(1, hw // 2), max(1, hw // 4)}, reverse=True):
-        _, sp = ref.mul_mat(t, W, X, M, N, K, threads=th, repeat=13, iters=3, warmup=1)
+        _, sp = ref.mul_mat_sweep(t, W, X, M, N, K, nbuf, threads=th, iters=3, warmup=1)
         if best_s is None or sp < best_s:
             best_s, threads = sp, th
-    # one step = one sweep of NBUF mat-vecs like the GPU arm, shrunk if the requested K steps would take > ~90 s
-    nbuf = 13
-    s1 = best_s
+    # one step = one sweep of NBUF mat-vecs over NBUF distinct weight tensors (330 MB > the host's last-level cache), like the GPU arm;
+    # fewer timed steps if the requested K would take > ~90 s
     per_step = nbuf
-    if s1 * nbuf * (args.steps + args.warmup) > 90.0:
-        per_step = max(1, int(90.0 / (s1 * (args.steps + args.warmup))))
-    _, s = ref.mul_mat(t, W, X, M, N, K, threads=threads, repeat=per_step, iters=args.steps, warmup=args.warmup, e2e=True)
+    steps = args.steps
+    if best_s * nbuf * (steps + args.warmup) > 90.0:
+        steps = max(1, int(90.0 / (best_s * nbuf)) - args.warmup)
+    _, s = ref.mul_mat_sweep(t, W, X, M, N, K, nbuf, threads=threads, iters=steps, warmup=args.warmup, e2e=True)
     val = weight_bytes(K, M) / s / 1e9
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": s * per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 x int4 (q4_K x q8_K), f32 accumulate",
             "data": "synthetic", "config": {"workload": f"q4_K {K}x{M} mat-vec n_batch=1 (BASELINE.json configs[1])", "mat_vecs_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": f"{per_step} mat-vecs per step through ggml_backend_graph_compute on ggml-cpu ({'native' if ref.native else 'x86-64-v3'} build), tensor_set/get included"},
+                             "sample": f"{per_step} mat-vecs over {per_step} distinct weight tensors per step through ggml_backend_graph_compute on ggml-cpu ({'native' if ref.native else 'x86-64-v3'} build), tensor_set/get included"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -214,7 +219,7 @@ def main():
 
     K, M, N, t = WL["K"], WL["M"], WL["N"], WL["type_id"]
     wb = weight_bytes(K, M)
-    nbuf = 13                                                       # 13 x 25.4 MB = 330 MB > 2 x L2
+    nbuf = NBUF                                                     # 13 x 25.4 MB = 330 MB > 2 x L2
     Ws = make_weights(torch, nbuf, K, M, seed=1234 + rank)
     X = torch.rand(N * K, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5678)) * 2 - 1
     Yloc = torch.empty((1, 1, N, M), dtype=torch.float32, device="cuda")

@@ -191,6 +191,8 @@ class Ref:
         L.probe_cpu_vec_dot.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.probe_mul_mat.restype = C.c_double
         L.probe_mul_mat.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 7 + [C.c_int] * 5
+        L.probe_mul_mat_sweep.restype = C.c_double
+        L.probe_mul_mat_sweep.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_int] * 5
         L.probe_mul_mat_id.restype = C.c_double
         L.probe_mul_mat_id.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_int] * 2
 
@@ -250,6 +252,17 @@ class Ref:
                                    threads, repeat, iters, warmup, int(e2e))
         if s < 0:
             raise RuntimeError(f"probe_mul_mat({dev}) failed: {s}")
+        return Y, float(s)
+
+    def mul_mat_sweep(self, t, W, X, M, N, K, nw, dev="CPU", threads=0, iters=1, warmup=0, e2e=False):
+        """nw distinct weight tensors (same bytes, separate memory), nw MUL_MAT nodes per graph -> (Y[N, M], seconds per mul_mat)"""
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        assert W.size == self.row_size(t, K) * M and X.size == K * N
+        Y = np.empty((N, M), dtype=np.float32)
+        s = self.lib.probe_mul_mat_sweep(dev.encode(), t, _p(W), _p(X), _p(Y), M, N, K, nw, threads, iters, warmup, int(e2e))
+        if s < 0:
+            raise RuntimeError(f"probe_mul_mat_sweep({dev}) failed: {s}")
         return Y, float(s)
 
     def mul_mat_id(self, t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok, dev="CPU", threads=0, iters=1):

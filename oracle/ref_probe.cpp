@@ -142,6 +142,47 @@ double probe_mul_mat(const char * dev, int type_a, const void * W, const float *
     return (t1 - t0) / ((double) (iters > 0 ? iters : 1) * repeat);
 }
 
+// The bench workload on the reference's CPU backend: `nw` DISTINCT weight tensors (each filled with the same W bytes, but separate
+// memory, so a sweep streams nw x the matrix from DRAM like the GPU arm's 13-matrix sweep instead of re-reading one cache-resident
+// matrix), one shared x, nw MUL_MAT nodes in one graph.  Returns seconds per mul_mat node.  e2e: tensor_set(x) before and
+// tensor_get of every y after, inside the timed region.
+double probe_mul_mat_sweep(const char * dev, int type_a, const void * W, const float * X, float * Y,
+                           int64_t M, int64_t N, int64_t K, int nw, int n_threads, int iters, int warmup, int e2e) {
+    backend_holder h;
+    if (!open_backend(h, dev, n_threads)) return -1.0;
+    ggml_init_params ip = { ggml_tensor_overhead() * (size_t)(2 * nw + 8) + ggml_graph_overhead_custom(nw + 8, false), nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * b = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, K, N);
+    std::vector<ggml_tensor *> ws, outs;
+    ggml_cgraph * gf = ggml_new_graph_custom(ctx, nw + 8, false);
+    for (int r = 0; r < nw; ++r) {
+        ggml_tensor * a = ggml_new_tensor_2d(ctx, (ggml_type) type_a, K, M);
+        ggml_tensor * c = ggml_mul_mat(ctx, a, b);
+        ws.push_back(a);
+        outs.push_back(c);
+        ggml_build_forward_expand(gf, c);
+    }
+    if (!ggml_backend_supports_op(h.be, outs[0])) { ggml_free(ctx); return -2.0; }
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, h.be);
+    if (!buf) { ggml_free(ctx); return -3.0; }
+    for (ggml_tensor * a : ws) ggml_backend_tensor_set(a, W, 0, ggml_nbytes(a));
+    ggml_backend_tensor_set(b, X, 0, ggml_nbytes(b));
+    for (int i = 0; i < warmup; ++i) ggml_backend_graph_compute(h.be, gf);
+    ggml_backend_synchronize(h.be);
+    double t0 = now_s();
+    for (int i = 0; i < iters; ++i) {
+        if (e2e) ggml_backend_tensor_set(b, X, 0, ggml_nbytes(b));
+        ggml_backend_graph_compute(h.be, gf);
+        if (e2e) for (ggml_tensor * c : outs) ggml_backend_tensor_get(c, Y, 0, ggml_nbytes(c));
+    }
+    ggml_backend_synchronize(h.be);
+    double t1 = now_s();
+    ggml_backend_tensor_get(outs.back(), Y, 0, ggml_nbytes(outs.back()));
+    ggml_backend_buffer_free(buf);
+    ggml_free(ctx);
+    return (t1 - t0) / ((double) (iters > 0 ? iters : 1) * nw);
+}
+
 // C[M, n_used, n_tok] = MUL_MAT_ID(as[type; K x M x n_expert], b[f32; K x nb1 x n_tok], ids[i32; n_used x n_tok])
 // (src/ggml.c:2735).  ids is given as the dense [n_ids_total x n_tok] array of which the
 // first n_used columns are viewed (as test_mul_mat_id does, test-backend-ops.cpp:2017).
