@@ -55,6 +55,10 @@ __device__ __forceinline__ void sb_tma_g2s(void * dst_smem, const void * src_gme
 // programmatic dependent launch: let the next kernel's prologue start / wait for the previous kernel's results
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// pull a byte range into L2 without occupying shared memory (bulk prefetch; 16-byte aligned address and size)
+__device__ __forceinline__ void sb_prefetch_l2(const void * src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // mixed-sign dp4a: bytes of a are unsigned, bytes of b signed
@@ -73,40 +77,47 @@ template <> struct sbfmt<T_Q6_K> { static constexpr int TASK_W = 256, TASK_B = 2
 template <> struct sbfmt<T_Q4_0> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 136, LPR = 32, KQ = 0; };
 
-// Task-interleaved activation record in shared memory (ntask = K / 256 "act tasks" of 256 values each):
-//   q   : chunk j (16 int8 = values 16j..16j+15 of act-task t) at (j * ntask + t) * 16,           j = 0..15
-//   s32 : eight int32 sums of 32 values of act-task t:  two 16-byte chunks at off_s32 + (jj * ntask + t) * 16
-//   s16 : sixteen int16 sums of 16 values:              two chunks at off_s16 + (jj * ntask + t) * 16
-//   d   : Q8_K family: one float per act-task at off_d + 4 t;  Q8_0 family: eight floats, chunks at off_d + (jj * ntask + t) * 16
-// consecutive lanes (tasks) read consecutive 16-byte chunks -> conflict-free LDS.128, lanes on the other row broadcast.
+// Activation record in shared memory: one SB_REC-byte record per act-task (256 consecutive activations), task t at rec + t * SB_REC:
+//   +0   q    : 256 int8 (chunk j = values 16 j .. 16 j + 15 at +16 j)
+//   +256 s32  : eight int32 sums of 32 values
+//   +288 s16  : sixteen int16 sums of 16 values
+//   +320 h32  : the eight 32-sums again as int16 (operand of dp2a against packed 6-bit mins)
+//   +336 d    : Q8_K family: one float;  Q8_0 family: eight floats (fp16-rounded block scales)
+// SB_REC = 23 x 16: an odd number of 16-byte units, so lanes working on consecutive tasks hit different bank groups with every
+// LDS.128 (conflict-free), and every load address is "task base + immediate" -- no address arithmetic inside the dot products.
+constexpr int SB_REC = 368, SB_OFF_S32 = 256, SB_OFF_S16 = 288, SB_OFF_H32 = 320, SB_OFF_D = 336;
 struct sb_act {
-    int32_t ntask, off_s32, off_s16, off_d, bytes;
+    int32_t ntask, bytes;
 };
 __host__ __device__ inline sb_act make_sb_act(int64_t K) {
     sb_act A;
     A.ntask = (int32_t)(K / 256);
-    A.off_s32 = 16 * A.ntask * 16;
-    A.off_s16 = A.off_s32 + 2 * A.ntask * 16;
-    A.off_d   = A.off_s16 + 2 * A.ntask * 16;
-    A.bytes   = A.off_d + 2 * A.ntask * 16;
+    A.bytes = A.ntask * SB_REC;
     return A;
 }
 
-// one warp quantizes act-task t (256 values) into the interleaved record
-template <bool KQ> __device__ __forceinline__ void sb_quantize_task(const float4 a, const float4 b, uint8_t * rec, const sb_act & A, int t) {
-    const int lane = threadIdx.x & 31;
-    const float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-    int q[8];
+// Half a warp (16 lanes) quantizes act-task t: lane l owns values 16 l .. 16 l + 15 (= chunk l of the record), so the chunk, its
+// 16-sum and most of the amax search are lane-local; 4 shuffle rounds, and two tasks per warp run side by side.
+// Shuffles use xor distances < 16, i.e. they never cross the half-warp; all 32 lanes must call this together.
+// Numerics: exactly ggml-cpu's quantize_row_q8_K (KQ) / AVX2 quantize_row_q8_0 (see b200_quants.cuh).
+template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * rec, int t) {
+    const int l = threadIdx.x & 15;
+    float v[16];
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 f = load_f4(x + (size_t)t * 256 + 16 * l + 4 * i); v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    }
+    uint8_t * rb = rec + (size_t)t * SB_REC;
+    int q[16];
     if constexpr (KQ) {
         float amax = 0.0f, vmax = 0.0f; int imax = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = (i < 4 ? 4 * lane + i : 128 + 4 * lane + (i - 4));
-            const float ax = fabsf(v[i]);
-            if (ax > amax) { amax = ax; vmax = v[i]; imax = idx; }
-        }
+        for (int i = 0; i < 16; ++i) { const float ax = fabsf(v[i]); if (ax > amax) { amax = ax; vmax = v[i]; imax = 16 * l + i; } }
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < 16; o <<= 1) {
             const float oa = __shfl_xor_sync(0xffffffffu, amax, o), ov = __shfl_xor_sync(0xffffffffu, vmax, o);
             const int   oi = __shfl_xor_sync(0xffffffffu, imax, o);
             if (oa > amax || (oa == amax && oi < imax)) { amax = oa; vmax = ov; imax = oi; }
@@ -115,78 +126,70 @@ template <bool KQ> __device__ __forceinline__ void sb_quantize_task(const float4
         if (amax != 0.0f) {
             const float iscale = __fdiv_rn(-127.0f, vmax);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = min(127, __float2int_rn(iscale * v[i]));
+            for (int i = 0; i < 16; ++i) q[i] = min(127, __float2int_rn(iscale * v[i]));
             d = __fdiv_rn(1.0f, iscale);
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = 0;
+            for (int i = 0; i < 16; ++i) q[i] = 0;
         }
-        if (lane == 0) *(float *)(rec + A.off_d + 4 * t) = d;
+        if (l == 0 && valid) *(float *)(rb + SB_OFF_D) = d;
     } else {
+        float amax = 0.0f;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const float * vv = v + 4 * half;
-            float amax = fmaxf(fmaxf(fabsf(vv[0]), fabsf(vv[1])), fmaxf(fabsf(vv[2]), fabsf(vv[3])));
+        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));               // 32-value block = lanes 2b, 2b+1
+        const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-            const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[4 * half + i] = __float2int_rn(vv[i] * id);
-            if ((lane & 7) == 0) {
-                const int blk = 4 * half + (lane >> 3);              // 32-block index inside the act-task
-                *(float *)(rec + A.off_d + ((blk >> 2) * A.ntask + t) * 16 + (blk & 3) * 4) = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
-            }
-        }
+        for (int i = 0; i < 16; ++i) q[i] = __float2int_rn(v[i] * id);
+        if ((l & 1) == 0 && valid) *(float *)(rb + SB_OFF_D + 4 * (l >> 1)) = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
     }
+    int4 pk; int s = 0;
+    int * pw = &pk.x;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int * qq = q + 4 * half;
-        const int w = 32 * half + lane;                              // word index inside the act-task
-        *(uint32_t *)(rec + ((w >> 2) * A.ntask + t) * 16 + (w & 3) * 4) =
-            (uint32_t)(qq[0] & 0xFF) | ((uint32_t)(qq[1] & 0xFF) << 8) | ((uint32_t)(qq[2] & 0xFF) << 16) | ((uint32_t)(qq[3] & 0xFF) << 24);
-        int s = qq[0] + qq[1] + qq[2] + qq[3];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);                     // 16 values
-        if ((lane & 3) == 0) {
-            const int g16 = 8 * half + (lane >> 2);
-            *(int16_t *)(rec + A.off_s16 + ((g16 >> 3) * A.ntask + t) * 16 + (g16 & 7) * 2) = (int16_t)s;
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 4);                     // 32 values
-        if ((lane & 7) == 0) {
-            const int g32 = 4 * half + (lane >> 3);
-            *(int32_t *)(rec + A.off_s32 + ((g32 >> 2) * A.ntask + t) * 16 + (g32 & 3) * 4) = s;
+    for (int w = 0; w < 4; ++w) {
+        pw[w] = (int)((uint32_t)(q[4 * w] & 0xFF) | ((uint32_t)(q[4 * w + 1] & 0xFF) << 8) | ((uint32_t)(q[4 * w + 2] & 0xFF) << 16) | ((uint32_t)(q[4 * w + 3] & 0xFF) << 24));
+        s += q[4 * w] + q[4 * w + 1] + q[4 * w + 2] + q[4 * w + 3];
+    }
+    const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);
+    if (valid) {
+        *(int4 *)(rb + 16 * l) = pk;
+        *(int16_t *)(rb + SB_OFF_S16 + 2 * l) = (int16_t)s;
+        if ((l & 1) == 0) {
+            *(int32_t *)(rb + SB_OFF_S32 + 4 * (l >> 1)) = s2;
+            *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)s2;          // |s2| <= 32 * 127
         }
     }
 }
 
 __device__ __forceinline__ int4 lds128(const uint8_t * p) { return *(const int4 *)p; }
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (lo) / b.byte2, b.byte3 (hi); a halves signed, b bytes unsigned (su) or signed (ss)
+__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_lo_ss(int a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_ss(int a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+template <int B> __device__ __forceinline__ int ubyte(uint32_t x) { return (int)__byte_perm(x, 0, 0x4440 + B); }             // zero-extended byte B
+// sign-extended byte B: PTX prmt in default mode replicates the sign of the selected byte when bit 3 of a selector nibble is set
+// (__byte_perm only honours 3 selector bits, hence the inline PTX)
+template <int B> __device__ __forceinline__ int sbyte(uint32_t x) {
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"((uint32_t)(B | ((8 | B) << 4) | ((8 | B) << 8) | ((8 | B) << 12))));
+    return d;
+}
 
 // ----------------------------------------------------------------------------- task dot products
 // `w` points at the task's first byte in the shared-memory stage, `rec` at the activation record, `t` = task index in the row.
-template <int T> __device__ __forceinline__ float task_dot(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t);
+template <int T> __device__ __forceinline__ float task_dot(const uint8_t * w, const uint8_t * rec, int t);
 
-// 6-bit (scale, min) pair J of the 12-byte pack, J compile-time
-template <int J> __device__ __forceinline__ void k4_sm(uint32_t s0, uint32_t s1, uint32_t s2, int & sc, int & mn) {
-    if constexpr (J < 4) {
-        sc = (s0 >> (8 * J)) & 63;
-        mn = (s1 >> (8 * J)) & 63;
-    } else {
-        constexpr int jj = J - 4;
-        sc = ((s2 >> (8 * jj)) & 0x0F) | (((s0 >> (8 * jj + 6)) & 3) << 4);
-        mn = ((s2 >> (8 * jj + 4)) & 0x0F) | (((s1 >> (8 * jj + 6)) & 3) << 4);
-    }
-}
-
+// one 64-weight chunk C of a Q4_K / Q5_K superblock: sub-block 2C in the low nibbles (scale sc0), 2C+1 in the high ones (sc1)
 template <int C, bool FIVE>
-__device__ __forceinline__ void q45_chunk(const uint8_t * qs, const uint32_t (&qh)[8], const uint8_t * rec, const sb_act & A, int t,
-                                           uint32_t s0, uint32_t s1, uint32_t s2, const int (&s32)[8], int & acc_s, int & acc_m) {
+__device__ __forceinline__ void q45_chunk(const uint8_t * qs, const uint32_t (&qh)[8], const uint8_t * a, int sc0, int sc1, int & acc_s) {
     const int4 qa = lds128(qs + 32 * C), qb = lds128(qs + 32 * C + 16);
     const uint32_t q[8] = { (uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w, (uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w };
     int p0 = 0, p1 = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int4 ylo = lds128(rec + ((4 * C + h) * A.ntask + t) * 16);          // values 64C + 16h ..   (sub-block 2C)
-        const int4 yhi = lds128(rec + ((4 * C + 2 + h) * A.ntask + t) * 16);      // values 64C + 32 + 16h (sub-block 2C+1)
+        const int4 ylo = lds128(a + (4 * C + h) * 16);                              // values 64C + 16h ..   (sub-block 2C)
+        const int4 yhi = lds128(a + (4 * C + 2 + h) * 16);                          // values 64C + 32 + 16h (sub-block 2C+1)
         const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -202,52 +205,56 @@ __device__ __forceinline__ void q45_chunk(const uint8_t * qs, const uint32_t (&q
         }
     }
     if constexpr (!FIVE) p1 >>= 4;                                                  // exact: a multiple of 16
-    int sc0, m0, sc1, m1;
-    k4_sm<2 * C>(s0, s1, s2, sc0, m0);
-    k4_sm<2 * C + 1>(s0, s1, s2, sc1, m1);
     acc_s += sc0 * p0 + sc1 * p1;
-    acc_m += m0 * s32[2 * C] + m1 * s32[2 * C + 1];
 }
 
-template <bool FIVE> __device__ __forceinline__ float q45_task(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t) {
+template <bool FIVE> __device__ __forceinline__ float q45_task(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
     const int4 hdr = lds128(w);                                     // d | dmin | scales[12]
-    const int4 sa = lds128(rec + A.off_s32 + t * 16), sb = lds128(rec + A.off_s32 + (A.ntask + t) * 16);
-    const int s32[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+    const int4 h32 = lds128(a + SB_OFF_H32);                        // eight 32-sums, int16
     uint32_t qh[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     if constexpr (FIVE) {
         const int4 ha = lds128(w + 16), hb = lds128(w + 32);
         qh[0] = ha.x; qh[1] = ha.y; qh[2] = ha.z; qh[3] = ha.w; qh[4] = hb.x; qh[5] = hb.y; qh[6] = hb.z; qh[7] = hb.w;
     }
     const uint8_t * qs = w + (FIVE ? 48 : 16);
+    // the 6-bit (scale, min) pairs of get_scale_min_k4, four sub-blocks per word
     const uint32_t s0 = hdr.y, s1 = hdr.z, s2 = hdr.w;
-    int acc_s = 0, acc_m = 0;
-    q45_chunk<0, FIVE>(qs, qh, rec, A, t, s0, s1, s2, s32, acc_s, acc_m);
-    q45_chunk<1, FIVE>(qs, qh, rec, A, t, s0, s1, s2, s32, acc_s, acc_m);
-    q45_chunk<2, FIVE>(qs, qh, rec, A, t, s0, s1, s2, s32, acc_s, acc_m);
-    q45_chunk<3, FIVE>(qs, qh, rec, A, t, s0, s1, s2, s32, acc_s, acc_m);
-    const float yd = *(const float *)(rec + A.off_d + 4 * t);
+    const uint32_t sc_lo = s0 & 0x3F3F3F3Fu, mn_lo = s1 & 0x3F3F3F3Fu;                                   // sub-blocks 0..3
+    const uint32_t sc_hi = (s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u);                               // sub-blocks 4..7
+    const uint32_t mn_hi = ((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u);
+    int acc_m = dp2a_lo_su(h32.x, mn_lo, 0);                        // sum_j min_j * (sum of the 32 activations of sub-block j)
+    acc_m = dp2a_hi_su(h32.y, mn_lo, acc_m);
+    acc_m = dp2a_lo_su(h32.z, mn_hi, acc_m);
+    acc_m = dp2a_hi_su(h32.w, mn_hi, acc_m);
+    int acc_s = 0;
+    q45_chunk<0, FIVE>(qs, qh, a, ubyte<0>(sc_lo), ubyte<1>(sc_lo), acc_s);
+    q45_chunk<1, FIVE>(qs, qh, a, ubyte<2>(sc_lo), ubyte<3>(sc_lo), acc_s);
+    q45_chunk<2, FIVE>(qs, qh, a, ubyte<0>(sc_hi), ubyte<1>(sc_hi), acc_s);
+    q45_chunk<3, FIVE>(qs, qh, a, ubyte<2>(sc_hi), ubyte<3>(sc_hi), acc_s);
+    const float yd = *(const float *)(a + SB_OFF_D);
     const float d = h2f((uint32_t)hdr.x & 0xFFFF) * yd, dmin = h2f((uint32_t)hdr.x >> 16) * yd;
     return d * (float)acc_s - dmin * (float)acc_m;
 }
-template <> __device__ __forceinline__ float task_dot<T_Q4_K>(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t) { return q45_task<false>(w, rec, A, t); }
-template <> __device__ __forceinline__ float task_dot<T_Q5_K>(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t) { return q45_task<true>(w, rec, A, t); }
+template <> __device__ __forceinline__ float task_dot<T_Q4_K>(const uint8_t * w, const uint8_t * rec, int t) { return q45_task<false>(w, rec, t); }
+template <> __device__ __forceinline__ float task_dot<T_Q5_K>(const uint8_t * w, const uint8_t * rec, int t) { return q45_task<true>(w, rec, t); }
 
 // Q4_0: task = 8 blocks of 18 bytes = 144 bytes (16-byte aligned), act-task == task
-template <> __device__ __forceinline__ float task_dot<T_Q4_0>(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t) {
+template <> __device__ __forceinline__ float task_dot<T_Q4_0>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
     uint32_t ww[37];
 #pragma unroll
     for (int i = 0; i < 9; ++i) { const int4 v = lds128(w + 16 * i); ww[4 * i] = v.x; ww[4 * i + 1] = v.y; ww[4 * i + 2] = v.z; ww[4 * i + 3] = v.w; }
     ww[36] = 0;
-    const int4 sa = lds128(rec + A.off_s32 + t * 16), sb = lds128(rec + A.off_s32 + (A.ntask + t) * 16);
+    const int4 sa = lds128(a + SB_OFF_S32), sb = lds128(a + SB_OFF_S32 + 16);
     const int s32[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-    const int4 da = lds128(rec + A.off_d + t * 16), db = lds128(rec + A.off_d + (A.ntask + t) * 16);
+    const int4 da = lds128(a + SB_OFF_D), db = lds128(a + SB_OFF_D + 16);
     const float yd[8] = { __int_as_float(da.x), __int_as_float(da.y), __int_as_float(da.z), __int_as_float(da.w),
                           __int_as_float(db.x), __int_as_float(db.y), __int_as_float(db.z), __int_as_float(db.w) };
     float acc = 0.0f;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
         // block b starts at byte 18 b = word 4.5 b: even b word-aligned, odd b half-word shifted (all compile-time)
-        constexpr int dummy = 0; (void)dummy;
         const int w0 = (18 * b) / 4;
         const bool odd = (b & 1) != 0;
         uint32_t q[4];
@@ -261,7 +268,7 @@ template <> __device__ __forceinline__ float task_dot<T_Q4_0>(const uint8_t * w,
 #pragma unroll
             for (int i = 0; i < 4; ++i) q[i] = ww[w0 + 1 + i];
         }
-        const int4 ylo = lds128(rec + ((2 * b) * A.ntask + t) * 16), yhi = lds128(rec + ((2 * b + 1) * A.ntask + t) * 16);
+        const int4 ylo = lds128(a + (2 * b) * 16), yhi = lds128(a + (2 * b + 1) * 16);
         const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
         int p0 = 0, p1 = 0;
 #pragma unroll
@@ -276,13 +283,14 @@ template <> __device__ __forceinline__ float task_dot<T_Q4_0>(const uint8_t * w,
 }
 
 // Q8_0: task = 4 blocks of 34 bytes = 136 bytes (8-byte aligned); two tasks per 256-value act-task
-template <> __device__ __forceinline__ float task_dot<T_Q8_0>(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t) {
+template <> __device__ __forceinline__ float task_dot<T_Q8_0>(const uint8_t * w, const uint8_t * rec, int t) {
     uint32_t ww[35];
 #pragma unroll
     for (int i = 0; i < 17; ++i) { const uint2 v = *(const uint2 *)(w + 8 * i); ww[2 * i] = v.x; ww[2 * i + 1] = v.y; }
     ww[34] = 0;
     const int at = t >> 1, hf = t & 1;                                             // act-task, which half of it
-    const int4 dv = lds128(rec + A.off_d + (hf * A.ntask + at) * 16);
+    const uint8_t * a = rec + (size_t)at * SB_REC + hf * 128;                      // q chunks 8 hf .. 8 hf + 7
+    const int4 dv = lds128(rec + (size_t)at * SB_REC + SB_OFF_D + hf * 16);
     const float yd[4] = { __int_as_float(dv.x), __int_as_float(dv.y), __int_as_float(dv.z), __int_as_float(dv.w) };
     float acc = 0.0f;
 #pragma unroll
@@ -290,7 +298,7 @@ template <> __device__ __forceinline__ float task_dot<T_Q8_0>(const uint8_t * w,
         const int w0 = (34 * b) / 4;
         const bool odd = (b & 1) != 0;                                             // 34 b mod 4 = 2 for odd b
         const uint32_t dbits = odd ? (ww[w0] >> 16) : (ww[w0] & 0xFFFF);
-        const int4 y0 = lds128(rec + ((8 * hf + 2 * b) * A.ntask + at) * 16), y1 = lds128(rec + ((8 * hf + 2 * b + 1) * A.ntask + at) * 16);
+        const int4 y0 = lds128(a + (2 * b) * 16), y1 = lds128(a + (2 * b + 1) * 16);
         const int y[8] = { y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w };
         int s = 0;
 #pragma unroll
@@ -304,21 +312,28 @@ template <> __device__ __forceinline__ float task_dot<T_Q8_0>(const uint8_t * w,
 }
 
 // Q6_K: 210-byte superblocks are only 2-byte aligned: aligned words + one run-time funnel shift (0 or 16 bits)
-template <> __device__ __forceinline__ float task_dot<T_Q6_K>(const uint8_t * w, const uint8_t * rec, const sb_act & A, int t) {
+template <> __device__ __forceinline__ float task_dot<T_Q6_K>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
     const uint32_t sh = ((uint32_t)(uintptr_t)w & 2) * 8;
     const uint32_t * wa = (const uint32_t *)((uintptr_t)w & ~(uintptr_t)3);
     auto word = [&](int i) { return __funnelshift_r(wa[i], wa[i + 1], sh); };     // 32-bit word i of the superblock
-    const int4 sa = lds128(rec + A.off_s16 + t * 16), sb = lds128(rec + A.off_s16 + (A.ntask + t) * 16);
-    const uint32_t s16w[8] = { (uint32_t)sa.x, (uint32_t)sa.y, (uint32_t)sa.z, (uint32_t)sa.w, (uint32_t)sb.x, (uint32_t)sb.y, (uint32_t)sb.z, (uint32_t)sb.w };
+    const int4 sa = lds128(a + SB_OFF_S16), sb = lds128(a + SB_OFF_S16 + 16);
+    const int s16w[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };       // sixteen 16-sums, int16 pairs
     int tot = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const uint32_t scw0 = word(48 + 2 * h), scw1 = word(48 + 2 * h + 1);       // scales[8h .. 8h+7]
+        const uint32_t scw0 = word(48 + 2 * h), scw1 = word(48 + 2 * h + 1);       // int8 scales[8h .. 8h+7]
+        // value = d * sc * (q - 32): the "- 32" part is sum_g sc_g * (16-sum)_g, two groups per dp2a
+        int off = dp2a_lo_ss(s16w[4 * h], scw0, 0);
+        off = dp2a_hi_ss(s16w[4 * h + 1], scw0, off);
+        off = dp2a_lo_ss(s16w[4 * h + 2], scw1, off);
+        off = dp2a_hi_ss(s16w[4 * h + 3], scw1, off);
+        tot -= 32 * off;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                                              // l-range 16 j .. 16 j + 15
             int p[4] = { 0, 0, 0, 0 };
-            const int4 yv0 = lds128(rec + ((8 * h + j) * A.ntask + t) * 16), yv1 = lds128(rec + ((8 * h + j + 2) * A.ntask + t) * 16);
-            const int4 yv2 = lds128(rec + ((8 * h + j + 4) * A.ntask + t) * 16), yv3 = lds128(rec + ((8 * h + j + 6) * A.ntask + t) * 16);
+            const int4 yv0 = lds128(a + (8 * h + j) * 16), yv1 = lds128(a + (8 * h + j + 2) * 16);
+            const int4 yv2 = lds128(a + (8 * h + j + 4) * 16), yv3 = lds128(a + (8 * h + j + 6) * 16);
             const int ya[4] = { yv0.x, yv0.y, yv0.z, yv0.w }, yb[4] = { yv1.x, yv1.y, yv1.z, yv1.w };
             const int yc[4] = { yv2.x, yv2.y, yv2.z, yv2.w }, yd4[4] = { yv3.x, yv3.y, yv3.z, yv3.w };
 #pragma unroll
@@ -329,22 +344,16 @@ template <> __device__ __forceinline__ float task_dot<T_Q6_K>(const uint8_t * w,
                 p[2] = __dp4a((int)(((la >> 4) & 0x0F0F0F0F) | ( qh       & 0x30303030)), yc[i], p[2]);
                 p[3] = __dp4a((int)(((lb >> 4) & 0x0F0F0F0F) | ((qh >> 2) & 0x30303030)), yd4[i], p[3]);
             }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int idx = j + 2 * g;                                          // scales[8h + j + 2g]
-                const int sc = (int)(int8_t)(((idx < 4 ? scw0 : scw1) >> (8 * (idx & 3))) & 0xFF);
-                const int g16 = 8 * h + j + 2 * g;                                  // 16-group index in the superblock
-                const int bs = (int)(int16_t)((s16w[g16 >> 1] >> (16 * (g16 & 1))) & 0xFFFF);
-                tot += sc * (p[g] - 32 * bs);
-            }
+            // scales[8h + j + 2g] multiplies p[g]
+            if (j == 0) tot += sbyte<0>(scw0) * p[0] + sbyte<2>(scw0) * p[1] + sbyte<0>(scw1) * p[2] + sbyte<2>(scw1) * p[3];
+            else        tot += sbyte<1>(scw0) * p[0] + sbyte<3>(scw0) * p[1] + sbyte<1>(scw1) * p[2] + sbyte<3>(scw1) * p[3];
         }
     }
-    const float d = h2f(word(52) & 0xFFFF) * *(const float *)(rec + A.off_d + 4 * t);
+    const float d = h2f(word(52) & 0xFFFF) * *(const float *)(a + SB_OFF_D);
     return d * (float)tot;
 }
 
 // ----------------------------------------------------------------------------- kernel
-constexpr int SB_CONSUMER_WARPS = 8;
 constexpr int SB_MAX_STAGES = 6;
 
 struct sb_params {
@@ -355,6 +364,7 @@ struct sb_params {
     unsigned int * ctl;           // device-global control words: [0] exchange epoch, [1] trace launch index
     int32_t src1_static;          // activations are not produced by the preceding kernel either: never wait for it (independent ops overlap)
     int32_t src0_static;          // weights are not produced by the preceding kernel: prefetch them before griddepcontrol.wait
+    int64_t l2_prefetch_bytes;    // dependent launches: bytes of W every CTA's share of which is pulled into L2 while the previous kernel still runs (0 = off)
     // row-sharded multi-GPU: every result is stored straight into each peer's full-length y over NVLink (world == 0: off)
     // fused epilogue (bias add and GELU of the following ggml nodes): y2 = y + bias, y3 = gelu(y2); null = off
     const float * ep_bias; float * ep_y2; float * ep_y3;
@@ -367,9 +377,10 @@ struct sb_params {
     sb_act A;
 };
 
-template <int T>
-__global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kernel(const sb_params p) {
+template <int T, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, NW == 8 ? 2 : 4) mmvq_sb_kernel(const sb_params p) {
     using F = sbfmt<T>;
+    constexpr int SB_CONSUMER_WARPS = NW;
     constexpr int LPR = F::LPR, RPW = 32 / LPR;                 // rows per warp pass
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t * stages = smem;
@@ -380,12 +391,11 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
-    unsigned long long * dbg = nullptr;
+    // trace slot of this launch (host-chosen): CTA 0 stamps [0..5]; every CTA folds its own times into [6] (latest exit) and
+    // [7] (latest consumer release from griddepcontrol.wait)
+    unsigned long long * dbg = nullptr, * dbg_all = p.dbg;
     if (p.dbg && blockIdx.x == 0) {
-        __shared__ unsigned int dbg_slot;
-        if (tid == 0) dbg_slot = atomicAdd(&p.ctl[1], 1u) % 32u;
-        __syncthreads();
-        dbg = p.dbg + dbg_slot * 8;
+        dbg = p.dbg;
         if (tid == 0) dbg[0] = gtime();                          // CTA 0 entry
     }
 
@@ -413,15 +423,25 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
         if (lane == 0) {
             if (!p.src0_static) pdl_wait();
             issue(0, (int)blockIdx.x);                            // first chunk is static
+            if (p.l2_prefetch_bytes > 0) {
+                // this launch cannot consume before the previous kernel's output is visible, but HBM need not idle meanwhile:
+                // CTA b pulls slice b of the matrix into L2 (whoever ends up consuming it), the ring then streams from L2
+                const int64_t per = ((p.l2_prefetch_bytes + gridDim.x - 1) / gridDim.x + 15) & ~(int64_t)15;
+                const int64_t lo = (int64_t)blockIdx.x * per;
+                const int64_t hi = min(lo + per, p.l2_prefetch_bytes & ~(int64_t)15);
+                for (int64_t o = lo; o < hi; o += 32768) sb_prefetch_l2(p.w + o, (uint32_t)min((int64_t)32768, hi - o));
+            }
             if (dbg) dbg[1] = gtime();                            // first TMA issued
             // (the scheduling counters are per launch slot, so the producer never has to wait for the previous grid on their account)
             if (dbg) dbg[2] = gtime();                            // producer past griddepcontrol.wait                                           // the chunk counter belongs to the previous launch until it completes
+            // the next chunk index is fetched (one global atomic round trip) BEFORE waiting for a free stage, so the atomic's
+            // latency overlaps the consumers' work instead of delaying the refill
             int it = 1;
             bool done = (int)blockIdx.x >= p.nchunks;
             while (!done) {
                 const int s = it % p.nstages;
-                if (it >= p.nstages) sb_mbar_wait(&empty[s], (uint32_t)((it / p.nstages) - 1) & 1u);
                 const int chunk = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
+                if (it >= p.nstages) sb_mbar_wait(&empty[s], (uint32_t)((it / p.nstages) - 1) & 1u);
                 issue(s, chunk);
                 done = chunk >= p.nchunks;
                 ++it;
@@ -436,16 +456,12 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
     // ===== consumers: quantize the activation vector (needs the previous kernel's output)
     if (!p.src1_static) pdl_wait();
     if (dbg && tid == 0) dbg[3] = gtime();                       // consumers past griddepcontrol.wait
-    // two act-tasks per warp per round, both loads in flight before either is processed (this phase is on the critical
-    // path of a dependent launch: it can only start once the previous kernel's output is visible)
-    for (int t0 = warp; t0 < p.A.ntask; t0 += 2 * SB_CONSUMER_WARPS) {
-        const int t1 = t0 + SB_CONSUMER_WARPS;
-        const float * x0 = p.x + (size_t)t0 * 256, * x1 = p.x + (size_t)t1 * 256;
-        const float4 a0 = load_f4(x0 + 4 * lane), b0 = load_f4(x0 + 128 + 4 * lane);
-        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
-        if (t1 < p.A.ntask) { a1 = load_f4(x1 + 4 * lane); b1 = load_f4(x1 + 128 + 4 * lane); }
-        sb_quantize_task<F::KQ != 0>(a0, b0, rec, p.A, t0);
-        if (t1 < p.A.ntask) sb_quantize_task<F::KQ != 0>(a1, b1, rec, p.A, t1);
+    if (dbg_all && tid == 0) atomicMax(dbg_all + 7, gtime());
+    // one act-task per half-warp per round (this phase is on the critical path of a dependent launch: it can only start once
+    // the previous kernel's output is visible)
+    for (int t0 = 2 * warp; t0 < p.A.ntask; t0 += 2 * SB_CONSUMER_WARPS) {
+        const int t = t0 + (lane >> 4);
+        sb_quantize_task_h<F::KQ != 0>(p.x, t < p.A.ntask, rec, t);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");        // consumers only
 
@@ -455,7 +471,7 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
         sb_mbar_wait(&full[s], (uint32_t)(it / p.nstages) & 1u);
         if (dbg && tid == 0 && it == 0) dbg[4] = gtime();        // first stage landed
         const int chunk = chunk_of[s];
-        if (chunk < 0) { if (dbg && tid == 0) dbg[5] = gtime(); break; }   // last stage done
+        if (chunk < 0) { if (dbg && tid == 0) dbg[5] = gtime(); if (dbg_all && tid == 0) atomicMax(dbg_all + 6, gtime()); break; }   // last stage done
         const int64_t row0 = (int64_t)chunk * p.rows_per_chunk;
         const int rows = (int)min((int64_t)p.rows_per_chunk, p.M - row0);
         const uint8_t * st = stages + (size_t)s * p.stage_bytes;
@@ -465,7 +481,7 @@ __global__ void __launch_bounds__((SB_CONSUMER_WARPS + 1) * 32, 2) mmvq_sb_kerne
             float acc = 0.0f;
             if (r < rows) {
                 const uint8_t * row = st + (size_t)r * p.row_bytes;
-                for (int t = l; t < p.ntasks_row; t += LPR) acc += task_dot<T>(row + (size_t)t * F::TASK_B, rec, p.A, t);
+                for (int t = l; t < p.ntasks_row; t += LPR) acc += task_dot<T>(row + (size_t)t * F::TASK_B, rec, t);
             }
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -534,7 +550,7 @@ __global__ void gather_wait_kernel(const uint32_t * flags, int world, uint32_t e
     __threadfence_system();
 }
 
-struct sb_plan { sb_params p; int grid, smem; };
+struct sb_plan { sb_params p; int grid, smem, nw; };
 
 // device control block: [0,64) global control words, [64, 64 + 64*8) 64 per-launch scheduling slots, byte 4096.. trace
 static unsigned int * sb_counters() {
@@ -555,9 +571,21 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     const size_t rb = row_bytes(a.type, a.K);
     if (a.nb01 != rb || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0) return false;
     if ((a.M * rb) % 16 != 0) return false;
-    static const int env_stage_kb = getenv("GGML_B200_SB_STAGE_KB") ? atoi(getenv("GGML_B200_SB_STAGE_KB")) : 36;
-    static const int env_stages   = getenv("GGML_B200_SB_STAGES")   ? atoi(getenv("GGML_B200_SB_STAGES"))   : 0;
-    static const int env_ctas     = getenv("GGML_B200_SB_CTAS")     ? atoi(getenv("GGML_B200_SB_CTAS"))     : 1;
+    // Two operating points (profiles/r01_gemv_q4k_final.md): launches flagged independent of their predecessor (SRC1_STATIC) run as
+    // small CTAs (4 consumer warps, 18 KB stages) of which four launches share an SM, a deep pipeline ACROSS launches; a dependent
+    // launch wants its prologue short and its prefetch deep: 8 consumer warps, 36 KB stages, two launches per SM, W pulled into L2.
+    const bool ind = (a.flags & GGML_B200_MM_SRC1_STATIC) != 0;
+    static const int e_stage_kb = getenv("GGML_B200_SB_STAGE_KB") ? atoi(getenv("GGML_B200_SB_STAGE_KB")) : 0;
+    static const int env_stages = getenv("GGML_B200_SB_STAGES")   ? atoi(getenv("GGML_B200_SB_STAGES"))   : 0;
+    static const int env_ctas   = getenv("GGML_B200_SB_CTAS")     ? atoi(getenv("GGML_B200_SB_CTAS"))     : 1;
+    static const int e_warps    = getenv("GGML_B200_SB_WARPS")    ? atoi(getenv("GGML_B200_SB_WARPS"))    : 0;
+    static const int e_resident = getenv("GGML_B200_SB_RESIDENT") ? atoi(getenv("GGML_B200_SB_RESIDENT")) : 0;
+    static const int e_l2_mb    = getenv("GGML_B200_SB_L2_MB")    ? atoi(getenv("GGML_B200_SB_L2_MB"))    : 48;
+    const int env_warps    = e_warps    ? e_warps    : (ind ? 4 : 8);
+    const int env_resident = e_resident ? e_resident : (ind ? 4 : 2);
+    const int env_stage_kb = e_stage_kb ? e_stage_kb : (ind ? 18 : 36);
+    const int SB_CONSUMER_WARPS = env_warps == 4 ? 4 : 8;
+    pl.nw = SB_CONSUMER_WARPS;
     constexpr int RPW = 32 / F::LPR;
     int granule = 1; while ((granule * rb) % 16 != 0) granule *= 2;
     int step = SB_CONSUMER_WARPS * RPW; while (step % granule != 0) step *= 2;
@@ -577,25 +605,29 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     static std::atomic<unsigned> seq{0};
     p.counters = p.ctl ? p.ctl + 64 + (seq.fetch_add(1) % 64u) * 8 : nullptr;
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
+    p.l2_prefetch_bytes = (!ind && p.src0_static && e_l2_mb > 0) ? (int64_t)std::min<size_t>((size_t)a.M * rb, (size_t)e_l2_mb << 20) : 0;
     p.world = 0; p.rank = 0; p.row_offset = 0; p.epoch = 0;
     p.ep_bias = nullptr; p.ep_y2 = nullptr; p.ep_y3 = nullptr;
     static const bool env_dbg = getenv("GGML_B200_SB_DEBUG") && atoi(getenv("GGML_B200_SB_DEBUG")) != 0;
-    p.dbg = (env_dbg && p.ctl) ? (unsigned long long *)(p.ctl + 1024) : nullptr;
+    static std::atomic<unsigned> dbg_seq{0};
+    p.dbg = (env_dbg && p.ctl) ? (unsigned long long *)(p.ctl + 1024) + (dbg_seq.fetch_add(1) % 32u) * 8 : nullptr;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
     for (int q = 0; q < 8; ++q) { p.y_peers[q] = nullptr; p.flag_peers[q] = nullptr; }
     if (!p.counters) return false;
     auto smem_of = [&]() { return p.nstages * p.stage_bytes + p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
-    int ctas = env_ctas < 1 ? 1 : env_ctas > 2 ? 2 : env_ctas;
+    const int max_res = SB_CONSUMER_WARPS == 8 ? 2 : 4;                       // register-limited residency (__launch_bounds__)
+    int ctas = env_ctas < 1 ? 1 : env_ctas > max_res ? max_res : env_ctas;
+    int resident = env_resident < ctas ? ctas : env_resident > max_res ? max_res : env_resident;
     if (p.nstages <= 0) {
-        // deepest ring that still lets TWO launches be co-resident on an SM (<= 113 KB each), so that programmatic dependent
+        // deepest ring that still lets `resident` CTAs (of consecutive launches) share an SM, so that programmatic dependent
         // launch can overlap the next mat-vec's prologue and first TMA round trip with this one's tail
         p.nstages = 4;
-        while (p.nstages > 2 && smem_of() > 113 * 1024) p.nstages--;
+        while (p.nstages > 2 && smem_of() * resident > 226 * 1024) p.nstages--;
     }
     if (p.nstages < 2) p.nstages = 2;
     if (p.nstages > SB_MAX_STAGES) p.nstages = SB_MAX_STAGES;
     while (smem_of() * ctas > 222 * 1024 && p.nstages > 2) p.nstages--;
-    if (smem_of() * ctas > 222 * 1024) ctas = 1;
+    while (smem_of() * ctas > 222 * 1024 && ctas > 1) ctas--;
     if (smem_of() > 222 * 1024) return false;
     pl.smem = smem_of();
     pl.grid = sm_count() * ctas;
@@ -603,29 +635,33 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     return true;
 }
 
+template <int T, int NW> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        attr_set = true;
+    }
+    static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((NW + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<T, NW>, pl.p));
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
 template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const ggml_b200_gather * ga, cudaStream_t st, const ggml_b200_epilogue * ep = nullptr) {
     sb_plan pl;
     if (!make_sb_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the superblock mat-vec kernel"); return GGML_B200_EUNSUPPORTED; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-        attr_set = true;
-    }
     if (ep && ep->bias) { pl.p.ep_bias = ep->bias; pl.p.ep_y2 = ep->dst_bias; pl.p.ep_y3 = ep->unary == 1 ? ep->dst_unary : nullptr; }
     if (ga) {
         pl.p.world = ga->world; pl.p.rank = ga->rank; pl.p.row_offset = ga->row_offset; pl.p.epoch = ga->epoch;
         for (int q = 0; q < ga->world; ++q) { pl.p.y_peers[q] = ga->y_peers[q]; pl.p.flag_peers[q] = ga->flag_peers[q]; }
     }
-    static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((SB_CONSUMER_WARPS + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<T>, pl.p));
-    B200_LAUNCH_CHECK();
-    return GGML_B200_OK;
+    return pl.nw == 4 ? launch_sb_nw<T, 4>(pl, st) : launch_sb_nw<T, 8>(pl, st);
 }
 
 bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {

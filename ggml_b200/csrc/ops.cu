@@ -13,6 +13,10 @@
 
 namespace b200 {
 
+// A quantized mat-vec launched after one of these small ops (with the programmatic-serialization attribute) may start its
+// weight prefetch while the small op still runs; it still waits (griddepcontrol.wait) for this kernel's results before reading them.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct tdesc {      // device-side copy of ggml_b200_tensor
     uint8_t * data; int32_t type; int64_t ne[4]; size_t nb[4];
 };
@@ -89,6 +93,7 @@ __device__ __forceinline__ float load_elem(const uint8_t * row, int type, int64_
 
 // ------------------------------------------------------------------ GET_ROWS
 __global__ void get_rows_kernel(tdesc src, tdesc ids, tdesc dst) {
+    pdl_trigger();
     // one CTA per destination row (i10, i11, i12)
     const int64_t r = blockIdx.x;
     const int64_t i10 = r % ids.ne[0], i11 = (r / ids.ne[0]) % ids.ne[1], i12 = r / (ids.ne[0] * ids.ne[1]);
@@ -106,6 +111,7 @@ template <int OP> __device__ __forceinline__ float bin_op(float a, float b) {
     return a / b;
 }
 template <int OP> __global__ void bin_bcast_kernel(tdesc a, tdesc b, tdesc d, int64_t n) {
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t i0 = i % d.ne[0], i1 = (i / d.ne[0]) % d.ne[1], i2 = (i / (d.ne[0] * d.ne[1])) % d.ne[2], i3 = i / (d.ne[0] * d.ne[1] * d.ne[2]);
@@ -116,6 +122,7 @@ template <int OP> __global__ void bin_bcast_kernel(tdesc a, tdesc b, tdesc d, in
 
 // ------------------------------------------------------------------ NORM / RMS_NORM (rows contiguous along dim 0)
 template <bool RMS> __global__ void norm_kernel(tdesc s, tdesc d, float eps) {
+    pdl_trigger();
     __shared__ float sh[32];
     const int64_t r = blockIdx.x;
     const int64_t i1 = r % s.ne[1], i2 = (r / s.ne[1]) % s.ne[2], i3 = r / (s.ne[1] * s.ne[2]);
@@ -137,6 +144,7 @@ template <bool RMS> __global__ void norm_kernel(tdesc s, tdesc d, float eps) {
 
 // NORM -> MUL(gain) -> ADD(bias) in one pass; every intermediate tensor of the three ggml nodes is still written
 template <bool RMS> __global__ void norm_affine_kernel(tdesc s, tdesc d1, const float * gain, tdesc d2, const float * bias, tdesc d3, float eps) {
+    pdl_trigger();
     __shared__ float sh[32];
     const int64_t r = blockIdx.x;
     const int64_t i1 = r % s.ne[1], i2 = (r / s.ne[1]) % s.ne[2], i3 = r / (s.ne[1] * s.ne[2]);
@@ -163,10 +171,12 @@ template <bool RMS> __global__ void norm_affine_kernel(tdesc s, tdesc d1, const 
 
 // ------------------------------------------------------------------ SCALE, DIAG_MASK_INF, unary
 __global__ void scale_kernel(const float * x, float * y, float s, int64_t n) {
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = x[i] * s;
 }
 __global__ void diag_mask_inf_kernel(const float * x, float * y, int64_t ne0, int64_t ne1, int n_past, int64_t n) {
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t c = i % ne0, r = (i / ne0) % ne1;
@@ -174,6 +184,7 @@ __global__ void diag_mask_inf_kernel(const float * x, float * y, int64_t ne0, in
 }
 enum { U_GELU = 0, U_SILU = 1, U_RELU = 2, U_TANH = 3, U_NEG = 4, U_ABS = 5, U_GELU_QUICK = 6, U_SIGMOID = 7, U_EXP = 8, U_SQR = 9, U_SQRT = 10 };
 __global__ void unary_kernel(int uop, const float * x, float * y, int64_t n) {
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float v = x[i];
@@ -197,6 +208,7 @@ __global__ void unary_kernel(int uop, const float * x, float * y, int64_t n) {
 // ------------------------------------------------------------------ SOFT_MAX (rows contiguous): softmax(x*scale + mask*slope)
 __global__ void soft_max_kernel(const float * x, const uint8_t * mask, int mask_type, float * y, int64_t ne0, int64_t ne1, int64_t ne2,
                                 float scale, float max_bias, float m0, float m1, uint32_t n_head_log2) {
+    pdl_trigger();
     __shared__ float sh[32];
     const int64_t r = blockIdx.x;                 // row = i1 + ne1 * (i2 + ne2 * i3)
     const int64_t i1 = r % ne1;
@@ -229,6 +241,7 @@ __device__ __forceinline__ size_t offset_of(const tdesc & t, int64_t i) {    // 
     return i0 * t.nb[0] + i1 * t.nb[1] + i2 * t.nb[2] + i3 * t.nb[3];
 }
 __global__ void cpy_kernel(tdesc s, tdesc d, int64_t n) {
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t * sp = s.data + offset_of(s, i);
@@ -240,6 +253,7 @@ __global__ void cpy_kernel(tdesc s, tdesc d, int64_t n) {
 }
 // f32 (strided, dim-0 contiguous) -> Q8_0 / Q4_0 rows (dst rows contiguous blocks); one thread per 32-block
 template <int QT> __global__ void cpy_f32_q_kernel(tdesc s, tdesc d, int64_t nblocks) {
+    pdl_trigger();
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const int64_t e = b * 32;                                   // linear element index of the block start
@@ -268,6 +282,7 @@ template <int QT> __global__ void cpy_f32_q_kernel(tdesc s, tdesc d, int64_t nbl
 // ------------------------------------------------------------------ float MUL_MAT (f32 / f16 weights x f32), batched + strided
 // one warp per output element; the CPU rounds src1 to f16 when src0 is f16 (vec_dot_type, ggml-cpu.c:262-268)
 __global__ void __launch_bounds__(128) mul_mat_f_kernel(tdesc a, tdesc b, tdesc d, int64_t nout) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t o = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (o >= nout) return;

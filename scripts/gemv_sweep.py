@@ -32,6 +32,8 @@ def time_mm(t, M, N, K, flags, reps=400):
     Ys = [torch.empty((1, 1, N, M), device="cuda") for _ in range(nbuf)] if IND else [Y] * nbuf
     if IND and flags == g.MM_GEMV:
         flags = flags | g.MM_SRC0_STATIC | g.MM_SRC1_STATIC
+    elif flags == g.MM_GEMV and not os.environ.get("SWEEP_NO_SRC0_STATIC"):
+        flags = flags | g.MM_SRC0_STATIC          # weights are graph leaves (what the backend passes)
     for i in range(nbuf):
         g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Ys[i])
     torch.cuda.synchronize()
@@ -62,9 +64,18 @@ def main():
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--v1", action="store_true")
     ap.add_argument("--independent", action="store_true", help="flag launches SRC0_STATIC|SRC1_STATIC and give each its own output")
+    ap.add_argument("--both", action="store_true", help="time dependent and independent launches")
     a = ap.parse_args()
     global IND
     IND = a.independent
+    if a.both:
+        for IND in (False, True):
+            run(a)
+        return
+    run(a)
+
+
+def run(a):
     tun = {k: v for k, v in os.environ.items() if k.startswith("GGML_B200_")}
     for tn in a.types.split(","):
         t = NAMES[tn]

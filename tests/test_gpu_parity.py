@@ -126,7 +126,8 @@ def test_gemv_vs_oracle(t, n, g, oracle):
         X = np.random.default_rng(5678).uniform(-1, 1, n * K).astype(np.float32)
         want = oracle.mul_mat(t, W, X, M, n, K)
         # n = 1 has two kernels: the one-lane-per-256-weights kernel (default) and the 64-weight-unit kernel (V1)
-        for flags in ((g.MM_GEMV, g.MM_GEMV | g.MM_GEMV_V1) if n == 1 else (g.MM_GEMV,)):
+        # (+ its two operating points: dependent launch = 8-warp CTAs + L2 prefetch of static weights; independent launch = 4-warp CTAs)
+        for flags in ((g.MM_GEMV, g.MM_GEMV | g.MM_GEMV_V1, g.MM_GEMV | g.MM_SRC0_STATIC, g.MM_GEMV | g.MM_SRC0_STATIC | g.MM_SRC1_STATIC) if n == 1 else (g.MM_GEMV,)):
             if g.mul_mat_plan(t, M, n, K, flags) != g.MM_GEMV:
                 continue
             Y = g.mul_mat(t, dev(W), dev(X), M, n, K, flags=flags).cpu().numpy()[0, 0]
