@@ -127,7 +127,7 @@ int ggml_b200_mul_mat_fused(const ggml_b200_mul_mat_args * args, const ggml_b200
     int rc = validate(args);
     if (rc != GGML_B200_OK) return rc;
     if (!ep || !ep->bias || !ep->dst_bias || (ep->unary != 0 && ep->unary != 1) || (ep->unary == 1 && !ep->dst_unary)) { set_error("mul_mat_fused: bad epilogue"); return GGML_B200_EINVAL; }
-    if (plan(*args) != GGML_B200_MM_FORCE_GEMV || !mmvq_sb_eligible(*args)) { set_error("mul_mat_fused: only the n = 1 mat-vec kernel has the fused epilogue"); return GGML_B200_EUNSUPPORTED; }
+    if (args->N != 1 || plan(*args) != GGML_B200_MM_FORCE_GEMV || !mmvq_sb_eligible(*args)) { set_error("mul_mat_fused: only the n = 1 mat-vec kernel has the fused epilogue"); return GGML_B200_EUNSUPPORTED; }
     if (args->M == 0) return GGML_B200_OK;
     return launch_mmvq_sb(*args, (cudaStream_t)stream, nullptr, ep);
 }
@@ -137,7 +137,7 @@ int ggml_b200_mul_mat_gather(const ggml_b200_mul_mat_args * args, const ggml_b20
     if (rc != GGML_B200_OK) return rc;
     if (!ga || ga->world < 1 || ga->world > 8 || ga->rank < 0 || ga->rank >= ga->world) { set_error("mul_mat_gather: bad gather descriptor"); return GGML_B200_EINVAL; }
     for (int q = 0; q < ga->world; ++q) if (!ga->y_peers[q] || !ga->flag_peers[q]) { set_error("mul_mat_gather: NULL peer pointer"); return GGML_B200_EINVAL; }
-    if (!mmvq_sb_eligible(*args)) { set_error("mul_mat_gather: only the n = 1 mat-vec path supports the fused gather"); return GGML_B200_EUNSUPPORTED; }
+    if (args->N != 1 || !mmvq_sb_eligible(*args)) { set_error("mul_mat_gather: only the n = 1 mat-vec path supports the fused gather"); return GGML_B200_EUNSUPPORTED; }
     return launch_mmvq_sb(*args, (cudaStream_t)stream, ga);
 }
 

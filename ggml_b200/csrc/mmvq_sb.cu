@@ -353,6 +353,97 @@ template <> __device__ __forceinline__ float task_dot<T_Q6_K>(const uint8_t * w,
     return d * (float)tot;
 }
 
+// ----------------------------------------------------------------------------- several activation columns (2 <= n <= 8)
+// The weights of a task are decoded once and dotted with every column's record (records of column c at rec + c * rec_stride).
+// Per column the floating-point operations are exactly those of the n = 1 path, so column c of an n-column product is
+// bit-identical to the n = 1 product with that column.
+template <int C, bool FIVE, int NC>
+__device__ __forceinline__ void q45_chunk_nc(const uint8_t * qs, const uint32_t (&qh)[8], const uint8_t * a0, int rec_stride, int ncols, int sc0, int sc1, int (&acc_s)[NC]) {
+    const int4 qa = lds128(qs + 32 * C), qb = lds128(qs + 32 * C + 16);
+    const uint32_t q[8] = { (uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w, (uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w };
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if constexpr (FIVE) {
+            const uint32_t hb = qh[i] >> (2 * C);
+            lo[i] = (q[i] & 0x0F0F0F0F) | ((hb & 0x01010101) << 4);
+            hi[i] = ((q[i] >> 4) & 0x0F0F0F0F) | ((hb & 0x02020202) << 3);
+        } else {
+            lo[i] = q[i] & 0x0F0F0F0F;
+            hi[i] = q[i] & 0xF0F0F0F0u;                                               // 16 x the high nibbles
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (c < ncols) {
+            const uint8_t * a = a0 + c * rec_stride;
+            int p0 = 0, p1 = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int4 ylo = lds128(a + (4 * C + h) * 16), yhi = lds128(a + (4 * C + 2 + h) * 16);
+                const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    p0 = __dp4a((int)lo[4 * h + i], yl[i], p0);
+                    if constexpr (FIVE) p1 = __dp4a((int)hi[4 * h + i], yh[i], p1);
+                    else                p1 = dp4a_us(hi[4 * h + i], yh[i], p1);
+                }
+            }
+            if constexpr (!FIVE) p1 >>= 4;
+            acc_s[c] += sc0 * p0 + sc1 * p1;
+        }
+    }
+}
+
+template <bool FIVE, int NC>
+__device__ __forceinline__ void q45_task_nc(const uint8_t * w, const uint8_t * rec, int rec_stride, int t, int ncols, float (&acc)[NC]) {
+    const uint8_t * a0 = rec + (size_t)t * SB_REC;
+    const int4 hdr = lds128(w);
+    uint32_t qh[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if constexpr (FIVE) {
+        const int4 ha = lds128(w + 16), hb = lds128(w + 32);
+        qh[0] = ha.x; qh[1] = ha.y; qh[2] = ha.z; qh[3] = ha.w; qh[4] = hb.x; qh[5] = hb.y; qh[6] = hb.z; qh[7] = hb.w;
+    }
+    const uint8_t * qs = w + (FIVE ? 48 : 16);
+    const uint32_t s0 = hdr.y, s1 = hdr.z, s2 = hdr.w;
+    const uint32_t sc_lo = s0 & 0x3F3F3F3Fu, mn_lo = s1 & 0x3F3F3F3Fu;
+    const uint32_t sc_hi = (s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u);
+    const uint32_t mn_hi = ((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u);
+    int acc_s[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc_s[c] = 0;
+    q45_chunk_nc<0, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<0>(sc_lo), ubyte<1>(sc_lo), acc_s);
+    q45_chunk_nc<1, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<2>(sc_lo), ubyte<3>(sc_lo), acc_s);
+    q45_chunk_nc<2, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<0>(sc_hi), ubyte<1>(sc_hi), acc_s);
+    q45_chunk_nc<3, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<2>(sc_hi), ubyte<3>(sc_hi), acc_s);
+    const float wd = h2f((uint32_t)hdr.x & 0xFFFF), wm = h2f((uint32_t)hdr.x >> 16);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (c < ncols) {
+            const uint8_t * a = a0 + c * rec_stride;
+            const int4 h32 = lds128(a + SB_OFF_H32);
+            int acc_m = dp2a_lo_su(h32.x, mn_lo, 0);
+            acc_m = dp2a_hi_su(h32.y, mn_lo, acc_m);
+            acc_m = dp2a_lo_su(h32.z, mn_hi, acc_m);
+            acc_m = dp2a_hi_su(h32.w, mn_hi, acc_m);
+            const float yd = *(const float *)(a + SB_OFF_D);
+            const float d = wd * yd, dmin = wm * yd;
+            acc[c] += d * (float)acc_s[c] - dmin * (float)acc_m;
+        }
+    }
+}
+
+template <int T, int NC>
+__device__ __forceinline__ void task_dot_nc(const uint8_t * w, const uint8_t * rec, int rec_stride, int t, int ncols, float (&acc)[NC]) {
+    if constexpr (T == T_Q4_K)      q45_task_nc<false, NC>(w, rec, rec_stride, t, ncols, acc);
+    else if constexpr (T == T_Q5_K) q45_task_nc<true, NC>(w, rec, rec_stride, t, ncols, acc);
+    else {
+        // other formats: the single-column dot product per column (the weight bytes are re-read from shared memory, not from HBM)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (c < ncols) acc[c] += task_dot<T>(w, rec + c * rec_stride, t);
+    }
+}
+
 // ----------------------------------------------------------------------------- kernel
 constexpr int SB_MAX_STAGES = 6;
 
@@ -362,6 +453,7 @@ struct sb_params {
     int32_t row_bytes, rows_per_chunk, nchunks, stage_bytes, nstages, ntasks_row;
     unsigned int * counters;      // this launch's scheduling slot: [0] next chunk, [1] finished producers, [2] finished CTAs (all return to 0)
     unsigned int * ctl;           // device-global control words: [0] exchange epoch, [1] trace launch index
+    int32_t ncols; int64_t x_stride;   // activation columns (1..8) and the distance between them in floats; y is [ncols][M]
     int32_t src1_static;          // activations are not produced by the preceding kernel either: never wait for it (independent ops overlap)
     int32_t src0_static;          // weights are not produced by the preceding kernel: prefetch them before griddepcontrol.wait
     int64_t l2_prefetch_bytes;    // dependent launches: bytes of W every CTA's share of which is pulled into L2 while the previous kernel still runs (0 = off)
@@ -377,15 +469,15 @@ struct sb_params {
     sb_act A;
 };
 
-template <int T, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, NW == 8 ? 2 : 4) mmvq_sb_kernel(const sb_params p) {
+template <int T, int NW, int NC>
+__global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) mmvq_sb_kernel(const sb_params p) {
     using F = sbfmt<T>;
     constexpr int SB_CONSUMER_WARPS = NW;
     constexpr int LPR = F::LPR, RPW = 32 / LPR;                 // rows per warp pass
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t * stages = smem;
     uint8_t * rec    = stages + (size_t)p.nstages * p.stage_bytes;
-    uint64_t * full  = (uint64_t *)(rec + p.A.bytes);
+    uint64_t * full  = (uint64_t *)(rec + NC * p.A.bytes);      // NC activation records (one per column)
     uint64_t * empty = full + SB_MAX_STAGES;
     int * chunk_of   = (int *)(empty + SB_MAX_STAGES);          // chunk id held by each stage (-1 = end)
 
@@ -459,9 +551,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW == 8 ? 2 : 4) mmvq_sb_kernel
     if (dbg_all && tid == 0) atomicMax(dbg_all + 7, gtime());
     // one act-task per half-warp per round (this phase is on the critical path of a dependent launch: it can only start once
     // the previous kernel's output is visible)
-    for (int t0 = 2 * warp; t0 < p.A.ntask; t0 += 2 * SB_CONSUMER_WARPS) {
-        const int t = t0 + (lane >> 4);
-        sb_quantize_task_h<F::KQ != 0>(p.x, t < p.A.ntask, rec, t);
+    for (int i0 = 2 * warp; i0 < p.ncols * p.A.ntask; i0 += 2 * SB_CONSUMER_WARPS) {
+        const int i = i0 + (lane >> 4);
+        const bool ok = i < p.ncols * p.A.ntask;
+        const int c = NC == 1 ? 0 : (ok ? i / p.A.ntask : 0), t = NC == 1 ? i : (ok ? i % p.A.ntask : 0);
+        sb_quantize_task_h<F::KQ != 0>(p.x + (size_t)c * p.x_stride, ok, rec + c * p.A.bytes, t);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");        // consumers only
 
@@ -478,6 +572,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW == 8 ? 2 : 4) mmvq_sb_kernel
         // the row loop is warp-uniform (both half-warps iterate together): the shuffles below use the full mask
         for (int r0 = warp * RPW; r0 < rows; r0 += SB_CONSUMER_WARPS * RPW) {
             const int r = r0 + sub;
+            if constexpr (NC > 1) {
+                float accn[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) accn[c] = 0.0f;
+                if (r < rows) {
+                    const uint8_t * row = st + (size_t)r * p.row_bytes;
+                    for (int t = l; t < p.ntasks_row; t += LPR) task_dot_nc<T, NC>(row + (size_t)t * F::TASK_B, rec, p.A.bytes, t, p.ncols, accn);
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                    for (int o = LPR / 2; o > 0; o >>= 1) accn[c] += __shfl_xor_sync(0xffffffffu, accn[c], o);
+                }
+                if (l == 0 && r < rows) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) if (c < p.ncols) p.y[(size_t)c * p.M + row0 + r] = accn[c];
+                }
+                continue;
+            }
             float acc = 0.0f;
             if (r < rows) {
                 const uint8_t * row = st + (size_t)r * p.row_bytes;
@@ -550,7 +663,7 @@ __global__ void gather_wait_kernel(const uint32_t * flags, int world, uint32_t e
     __threadfence_system();
 }
 
-struct sb_plan { sb_params p; int grid, smem, nw; };
+struct sb_plan { sb_params p; int grid, smem, nw, nc; };
 
 // device control block: [0,64) global control words, [64, 64 + 64*8) 64 per-launch scheduling slots, byte 4096.. trace
 static unsigned int * sb_counters() {
@@ -566,7 +679,10 @@ static unsigned int * sb_counters() {
 
 template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_plan & pl) {
     using F = sbfmt<T>;
-    if (a.N != 1 || a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
+    if (a.N < 1 || a.N > 8 || a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
+    if (a.N > 1 && ((a.nb11 & 3) != 0 || a.nb11 < (size_t)a.K * 4)) return false;
+    const int nc = a.N == 1 ? 1 : a.N == 2 ? 2 : a.N <= 4 ? 4 : 8;       // kernel instantiation (columns beyond N are skipped)
+    pl.nc = nc;
     if (a.K % 256 != 0 || a.K < 256 || a.M < 1 || a.K > 32768) return false;
     const size_t rb = row_bytes(a.type, a.K);
     if (a.nb01 != rb || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0) return false;
@@ -574,7 +690,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     // Two operating points (profiles/r01_gemv_q4k_final.md): launches flagged independent of their predecessor (SRC1_STATIC) run as
     // small CTAs (4 consumer warps, 18 KB stages) of which four launches share an SM, a deep pipeline ACROSS launches; a dependent
     // launch wants its prologue short and its prefetch deep: 8 consumer warps, 36 KB stages, two launches per SM, W pulled into L2.
-    const bool ind = (a.flags & GGML_B200_MM_SRC1_STATIC) != 0;
+    const bool ind = (a.flags & GGML_B200_MM_SRC1_STATIC) != 0 && a.N == 1;
     static const int e_stage_kb = getenv("GGML_B200_SB_STAGE_KB") ? atoi(getenv("GGML_B200_SB_STAGE_KB")) : 0;
     static const int env_stages = getenv("GGML_B200_SB_STAGES")   ? atoi(getenv("GGML_B200_SB_STAGES"))   : 0;
     static const int env_ctas   = getenv("GGML_B200_SB_CTAS")     ? atoi(getenv("GGML_B200_SB_CTAS"))     : 1;
@@ -584,7 +700,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     const int env_warps    = e_warps    ? e_warps    : (ind ? 4 : 8);
     const int env_resident = e_resident ? e_resident : (ind ? 4 : 2);
     const int env_stage_kb = e_stage_kb ? e_stage_kb : (ind ? 18 : 36);
-    const int SB_CONSUMER_WARPS = env_warps == 4 ? 4 : 8;
+    const int SB_CONSUMER_WARPS = (env_warps == 4 && nc == 1) ? 4 : 8;
     pl.nw = SB_CONSUMER_WARPS;
     constexpr int RPW = 32 / F::LPR;
     int granule = 1; while ((granule * rb) % 16 != 0) granule *= 2;
@@ -612,10 +728,11 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     static std::atomic<unsigned> dbg_seq{0};
     p.dbg = (env_dbg && p.ctl) ? (unsigned long long *)(p.ctl + 1024) + (dbg_seq.fetch_add(1) % 32u) * 8 : nullptr;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
+    p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
     for (int q = 0; q < 8; ++q) { p.y_peers[q] = nullptr; p.flag_peers[q] = nullptr; }
     if (!p.counters) return false;
-    auto smem_of = [&]() { return p.nstages * p.stage_bytes + p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
-    const int max_res = SB_CONSUMER_WARPS == 8 ? 2 : 4;                       // register-limited residency (__launch_bounds__)
+    auto smem_of = [&]() { return p.nstages * p.stage_bytes + nc * p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
+    const int max_res = nc > 1 ? 1 : SB_CONSUMER_WARPS == 8 ? 2 : 4;                       // register-limited residency (__launch_bounds__)
     int ctas = env_ctas < 1 ? 1 : env_ctas > max_res ? max_res : env_ctas;
     int resident = env_resident < ctas ? ctas : env_resident > max_res ? max_res : env_resident;
     if (p.nstages <= 0) {
@@ -635,10 +752,10 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     return true;
 }
 
-template <int T, int NW> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
+template <int T, int NW, int NC> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         attr_set = true;
     }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
@@ -648,7 +765,7 @@ template <int T, int NW> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<T, NW>, pl.p));
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<T, NW, NC>, pl.p));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -661,7 +778,13 @@ template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const gg
         pl.p.world = ga->world; pl.p.rank = ga->rank; pl.p.row_offset = ga->row_offset; pl.p.epoch = ga->epoch;
         for (int q = 0; q < ga->world; ++q) { pl.p.y_peers[q] = ga->y_peers[q]; pl.p.flag_peers[q] = ga->flag_peers[q]; }
     }
-    return pl.nw == 4 ? launch_sb_nw<T, 4>(pl, st) : launch_sb_nw<T, 8>(pl, st);
+    if (pl.nc > 1 && (ga || (ep && ep->bias))) { set_error("mul_mat: the fused epilogue / gather exist for n = 1 only"); return GGML_B200_EUNSUPPORTED; }
+    switch (pl.nc) {
+        case 1:  return pl.nw == 4 ? launch_sb_nw<T, 4, 1>(pl, st) : launch_sb_nw<T, 8, 1>(pl, st);
+        case 2:  return launch_sb_nw<T, 8, 2>(pl, st);
+        case 4:  return launch_sb_nw<T, 8, 4>(pl, st);
+        default: return launch_sb_nw<T, 8, 8>(pl, st);
+    }
 }
 
 bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {

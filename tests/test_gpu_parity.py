@@ -136,6 +136,23 @@ def test_gemv_vs_oracle(t, n, g, oracle):
 
 
 @pytest.mark.parametrize("t", TYPES, ids=IDS)
+def test_small_batch_columns_match_single_column(t, g, oracle):
+    """2 <= n <= 8 runs the same superblock kernel with the weights decoded once per task: every column must be bit-identical
+    to the n = 1 product with that column (same integer dots, same f32 operations in the same order)."""
+    M, K = 1536, 4096
+    W = dev(weights(oracle, t, M, K, seed=99))
+    rng = np.random.default_rng(7)
+    for n in (2, 3, 4, 7, 8):
+        if g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
+            continue
+        X = rng.uniform(-1, 1, (n, K)).astype(np.float32)
+        Y = g.mul_mat(t, W, dev(X), M, n, K, flags=g.MM_GEMV).cpu().numpy()[0, 0]
+        for c in range(n):
+            y1 = g.mul_mat(t, W, dev(X[c]), M, 1, K, flags=g.MM_GEMV).cpu().numpy()[0, 0, 0]
+            assert np.array_equal(Y[c], y1), (n, c)
+
+
+@pytest.mark.parametrize("t", TYPES, ids=IDS)
 def test_generic_shapes_vs_oracle(t, g, oracle):
     # the reference's own sweep: m=16, k=256, n=1..9 (tests/test-backend-ops.cpp:4005-4009), + ragged sizes
     cases = [(16, n, 256) for n in range(1, 10)] + [(5, 3, 512), (33, 17, 1024), (1, 1, 256)]
