@@ -23,13 +23,16 @@ lo, hi = shards[rank]
 Wd = torch.from_numpy(W[lo * rb:hi * rb]).cuda(); Xd = torch.from_numpy(X).cuda()
 ex = g.PeerExchange(M_total, rank, world, lo)
 Yl = torch.empty((1, 1, 1, hi - lo), device="cuda")
-a = g.mul_mat_args(t, Wd, Xd, Yl, hi - lo, 1, K)
-for it in range(3):
-    ex.mul_mat_gather(a); ex.wait()
-torch.cuda.synchronize()
-y = ex.y_full().cpu().numpy()
 want = orc.mul_mat(t, W, X, M_total, 1, K)[0]
-err = O.nmse(y, want)
+# both operating points of the kernel: dependent launch (8-warp CTAs) and independent launch (4-warp CTAs, what bench.py uses)
+for fl in (0, g.MM_SRC0_STATIC | g.MM_SRC1_STATIC):
+    a = g.mul_mat_args(t, Wd, Xd, Yl, hi - lo, 1, K, flags=fl)
+    for it in range(3):
+        ex.mul_mat_gather(a); ex.wait()
+    torch.cuda.synchronize()
+    y = ex.y_full().cpu().numpy()
+    err = O.nmse(y, want)
+    assert err < 1e-10, (fl, err)
 # NCCL reference exchange
 yl = g.mul_mat(t, Wd, Xd, hi - lo, 1, K).view(-1)
 buf = torch.empty(M_total, device="cuda")
