@@ -1,20 +1,25 @@
-// mmvq_sb.cu — the bandwidth-path quantized mat-vec (n = 1), second generation: "one lane per 256-weight task".
+// mmvq_sb.cu — the bandwidth-path quantized mat-vec (1 <= n <= 8), second generation: "one lane per 256-weight task".
 //
 // Why (profiles/r01_gemv_q4k_v1.md): the first TMA kernel moved exactly the algorithmic bytes from DRAM but spent
 // 5.0 M warp-instructions on a 45 M-weight matrix (6-bit scale decode repeated per 64 weights with a run-time
 // sub-block index, activation quantization repeated by 444 small CTAs on their critical path, 12 warps per SM),
 // i.e. it was issue/latency-bound at 30 % of the HBM roofline.  Here:
 //   * a lane owns a whole TASK = 256 consecutive weights of one row (a K-quant superblock, or 8 Q4_0 / 4 Q8_0
-//     blocks): the 12-byte scale pack is decoded once, every sub-block index is a compile-time constant, the high
-//     nibbles are used in place (u8 dp4a of q & 0xF0 = 16 x the nibble dot) -> ~0.8 instructions per weight;
+//     blocks): the 12-byte scale pack is decoded four sub-blocks at a time with packed-byte arithmetic, the mins are
+//     applied with dp2a against int16 activation sums, the high nibbles are used in place (u8 dp4a of q & 0xF0 = 16 x
+//     the nibble dot), every shared-memory load is "base + immediate" -> ~1.1 instructions per weight;
 //   * LPR lanes cooperate on a row (tasks strided by LPR), so a row's dot product is finished by 4-5 shuffles inside
 //     a (half-)warp and written straight to y: no cross-warp reduction, no block-wide barrier per stage;
-//   * CTAs are fat (8 consumer warps + 1 producer warp, two CTAs per SM): the activation vector is quantized once
-//     per CTA by all warps in parallel while the first TMA stages are in flight, into a task-interleaved layout
-//     that makes every LDS.128 of it bank-conflict-free;
+//   * the activation vector is quantized once per CTA (one 256-value act-task per half-warp) while the first TMA
+//     stages are in flight, into per-task records whose 368-byte pitch makes every LDS.128 bank-conflict-free;
 //   * a dedicated producer warp keeps a ring of TMA bulk copies (cp.async.bulk + mbarrier complete_tx) in flight;
 //     consumers release stages through per-stage "empty" mbarriers; chunks after the first are handed out by an
-//     atomic counter (self-resetting), so SMs stay balanced to one chunk.
+//     atomic counter (self-resetting, one slot per launch), so SMs stay balanced to one chunk;
+//   * programmatic dependent launch: an independent launch (SRC0|SRC1_STATIC) runs as 4-warp CTAs of which four
+//     launches share an SM -- a pipeline across launches; a dependent launch runs 8-warp CTAs, prefetches its first
+//     stages and pulls W into L2 while its predecessor still runs, and only then waits for the predecessor's output;
+//   * 2 <= n <= 8: one activation record per column, the weights of a task are decoded once and dotted with every
+//     column (bit-identical, column by column, to the n = 1 result).
 // Weights are read once from HBM in the reference's packed layout.  Numerics are those of b200_quants.cuh
 // (int8 activations quantized as ggml-cpu does, integer dots, f32 scaling); only the f32 summation order differs.
 #include "b200_internal.h"
