@@ -11,6 +11,9 @@
  * order is unspecified by the reference), and tests/golden/ holds vectors produced by that
  * reference (tests/golden/make_golden.py) for boxes where oracle/_ref cannot be rebuilt.
  *
+ * The SURVEY §8f-2 "next" formats (Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, and the Q8_1 activation format the CPU backend pairs with
+ * Q4_1/Q5_1) are restated and pinned the same way (same tests, same golden fixtures); their CUDA kernels follow in a later round.
+ *
  * Algorithms restated (reference @ 9a4acb37, paths relative to /root/reference):
  *   block layouts ............ src/ggml-common.h:161-166 (q4_0) 203-208 (q8_0) 279-290 (q4_K)
  *                              296-308 (q5_K) 314-320 (q6_K) 323-328 (q8_K)
@@ -89,8 +92,8 @@ uint16_t oq_fp32_to_fp16(float f) {
 int64_t oq_blck_size(int type) {
     switch (type) {
         case OQ_F32: case OQ_F16: return 1;
-        case OQ_Q4_0: case OQ_Q8_0: return 32;
-        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: return 256;
+        case OQ_Q4_0: case OQ_Q8_0: case OQ_Q4_1: case OQ_Q5_0: case OQ_Q5_1: case OQ_Q8_1: return 32;
+        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: case OQ_Q2_K: case OQ_Q3_K: return 256;
         default: return 0;
     }
 }
@@ -98,6 +101,8 @@ size_t oq_type_size(int type) {
     switch (type) {
         case OQ_F32: return 4;   case OQ_F16: return 2;
         case OQ_Q4_0: return 18; case OQ_Q8_0: return 34;
+        case OQ_Q4_1: return 20; case OQ_Q5_0: return 22; case OQ_Q5_1: return 24; case OQ_Q8_1: return 36;
+        case OQ_Q2_K: return 84; case OQ_Q3_K: return 110;
         case OQ_Q4_K: return 144; case OQ_Q5_K: return 176; case OQ_Q6_K: return 210; case OQ_Q8_K: return 292;
         default: return 0;
     }
@@ -180,6 +185,74 @@ static void deq_q6_K(const uint8_t * b, float * y, int64_t k) {
         y += 256;
     }
 }
+/* ---- SURVEY §8f-2 "next" formats (oracle first; the CUDA side follows in a later round) ----
+ * Q4_1 (src/ggml-common.h:168-180, dequantize_row_q4_1 src/ggml-quants.c:275-294): d @0, m @2, 16 nibble bytes: code * d + m
+ * Q5_0 (:182-188, :296-320): d @0, 32 fifth bits @2 (bit j -> element j, bit j+16 -> element j+16), nibbles @6: (code - 16) * d
+ * Q5_1 (:190-203, :322-348): d @0, m @2, fifth bits @4, nibbles @8: code * d + m */
+static void deq_q4_1(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, b += 20, y += 32) {
+        const float d = oq_fp16_to_fp32(rd16(b)), m = oq_fp16_to_fp32(rd16(b + 2));
+        for (int j = 0; j < 16; ++j) {
+            y[j]      = (float)(b[4 + j] & 0x0F) * d + m;
+            y[j + 16] = (float)(b[4 + j] >> 4)   * d + m;
+        }
+    }
+}
+static inline uint32_t rd32(const uint8_t * p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline int q5_code(const uint8_t * qs, uint32_t qh, int e) {      /* element e (0..31) of a Q5 block: nibble | fifth bit << 4 */
+    const int nib = e < 16 ? (qs[e] & 0x0F) : (qs[e - 16] >> 4);
+    return nib | (int)(((qh >> e) & 1u) << 4);
+}
+static void deq_q5_0(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, b += 22, y += 32) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        const uint32_t qh = rd32(b + 2);
+        for (int e = 0; e < 32; ++e) y[e] = (float)(q5_code(b + 6, qh, e) - 16) * d;
+    }
+}
+static void deq_q5_1(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, b += 24, y += 32) {
+        const float d = oq_fp16_to_fp32(rd16(b)), m = oq_fp16_to_fp32(rd16(b + 2));
+        const uint32_t qh = rd32(b + 4);
+        for (int e = 0; e < 32; ++e) y[e] = (float)q5_code(b + 8, qh, e) * d + m;
+    }
+}
+/* Q2_K (src/ggml-common.h:247-262, dequantize_row_q2_K src/ggml-quants.c:712-745): 84 bytes = scales[16] (low nibble scale, high
+ * nibble min of each 16-element group) @0, qs[64] @16 (2-bit codes), d @80, dmin @82.  Element e = 128 h + 32 j + l (h half,
+ * j = 0..3 bit pair, l = 0..31) has its code in bits 2j..2j+1 of qs[32 h + l] and belongs to group 8 h + 2 j + l / 16. */
+static inline int q2_code(const uint8_t * qs, int e) { return (qs[32 * (e >> 7) + (e & 31)] >> (2 * ((e >> 5) & 3))) & 3; }
+static inline int k_group16(int e) { return 8 * (e >> 7) + 2 * ((e >> 5) & 3) + ((e & 31) >> 4); }
+static void deq_q2_K(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 84, y += 256) {
+        const float d = oq_fp16_to_fp32(rd16(b + 80)), dmin = oq_fp16_to_fp32(rd16(b + 82));
+        for (int e = 0; e < 256; ++e) {
+            const uint8_t sc = b[k_group16(e)];
+            const float dl = d * (float)(sc & 0x0F), ml = dmin * (float)(sc >> 4);
+            y[e] = dl * (float)q2_code(b + 16, e) - ml;
+        }
+    }
+}
+/* Q3_K (src/ggml-common.h:264-276, dequantize_row_q3_K src/ggml-quants.c:1056-1104): 110 bytes = hmask[32] @0 (bit 4 h + j of
+ * hmask[l] CLEAR means "subtract 4"), qs[64] @32 (low 2 bits, same element order as Q2_K), scales[12] @96 (sixteen 6-bit
+ * scales, value - 32), d @108. */
+static inline int q3_scale(const uint8_t * s, int g) {                   /* 6-bit scale of 16-element group g, biased by 32 */
+    const int lo = g < 8 ? (s[g] & 0x0F) : (s[g - 8] >> 4);
+    const int hi = (s[8 + (g & 3)] >> (2 * (g >> 2))) & 3;
+    return (lo | (hi << 4)) - 32;
+}
+static inline int q3_code(const uint8_t * hm, const uint8_t * qs, int e) {
+    const int bit = 4 * (e >> 7) + ((e >> 5) & 3);
+    return q2_code(qs, e) - (((hm[e & 31] >> bit) & 1) ? 0 : 4);
+}
+static void deq_q3_K(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 110, y += 256) {
+        const float d_all = oq_fp16_to_fp32(rd16(b + 108));
+        for (int e = 0; e < 256; ++e) {
+            const float dl = d_all * (float)q3_scale(b + 96, k_group16(e));
+            y[e] = dl * (float)q3_code(b, b + 32, e);
+        }
+    }
+}
 static void deq_q8_K(const uint8_t * b, float * y, int64_t k) {
     for (int64_t i = 0; i < k / 256; ++i, b += 292, y += 256) {
         float d; memcpy(&d, b, 4);
@@ -198,6 +271,11 @@ int oq_dequantize_row(int type, const void * src, float * dst, int64_t k) {
         case OQ_Q5_K: deq_q5_K(b, dst, k); return 0;
         case OQ_Q6_K: deq_q6_K(b, dst, k); return 0;
         case OQ_Q8_K: deq_q8_K(b, dst, k); return 0;
+        case OQ_Q4_1: deq_q4_1(b, dst, k); return 0;
+        case OQ_Q5_0: deq_q5_0(b, dst, k); return 0;
+        case OQ_Q5_1: deq_q5_1(b, dst, k); return 0;
+        case OQ_Q2_K: deq_q2_K(b, dst, k); return 0;
+        case OQ_Q3_K: deq_q3_K(b, dst, k); return 0;
         default: return -1;
     }
 }
@@ -247,6 +325,21 @@ void oq_quantize_row_q8_0_simd(const float * x, void * dst, int64_t k) {
         for (int j = 0; j < 32; ++j) b[2 + j] = (uint8_t)(int8_t)nearbyintf(x[j] * id); /* ties to even (vroundps) */
     }
 }
+/* Q8_1 as the CPU backend produces it on x86 (quantize_row_q8_1, AVX2 branch, src/ggml-cpu/ggml-cpu-quants.c:1076-1130):
+ * 36 bytes = d @0, s @2, 32 int8; d = fp16(amax / 127), codes = rne(x * (127 / amax)), s = fp16(d_unrounded * sum of codes) */
+void oq_quantize_row_q8_1_simd(const float * x, void * dst, int64_t k) {
+    uint8_t * b = (uint8_t *)dst;
+    for (int64_t i = 0; i < k / 32; ++i, x += 32, b += 36) {
+        float amax = 0.0f;
+        for (int j = 0; j < 32; ++j) if (fabsf(x[j]) > amax) amax = fabsf(x[j]);
+        const float d = amax / 127.0f;
+        const float id = amax != 0.0f ? 127.0f / amax : 0.0f;
+        int sum = 0;
+        for (int j = 0; j < 32; ++j) { const int q = (int)nearbyintf(x[j] * id); b[4 + j] = (uint8_t)(int8_t)q; sum += q; }
+        wr16(b, oq_fp32_to_fp16(d));
+        wr16(b + 2, oq_fp32_to_fp16(d * (float)sum));
+    }
+}
 static void quant_q8_K(const float * x, uint8_t * b, int64_t k) {
     for (int64_t i = 0; i < k / 256; ++i, x += 256, b += 292) {
         float amax = 0.0f, vmax = 0.0f;
@@ -278,8 +371,9 @@ int oq_quantize_row_ref(int type, const float * src, void * dst, int64_t k) {
 
 int oq_vec_dot_type(int type) {
     switch (type) {
-        case OQ_Q4_0: case OQ_Q8_0: return OQ_Q8_0;
-        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: return OQ_Q8_K;
+        case OQ_Q4_0: case OQ_Q8_0: case OQ_Q5_0: return OQ_Q8_0;
+        case OQ_Q4_1: case OQ_Q5_1: return OQ_Q8_1;
+        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q2_K: case OQ_Q3_K: return OQ_Q8_K;
         default: return -1;
     }
 }
@@ -362,6 +456,70 @@ static float dot_q6_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
     return acc;
 }
 
+/* ---- "next" formats.  ggml_vec_dot_q4_1_q8_1 / q5_0_q8_0 / q5_1_q8_1 (src/ggml-cpu/ggml-cpu-quants.c:2313, :2606, :2961):
+ * per block (d_w * d_y) * sum(code * q) [+ m_w * s_y for the formats with a minimum]; Q8_1 block = d @0, s @2, qs @4 */
+static float dot_q4_1_q8_1(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f, mins = 0.0f;
+    for (int64_t i = 0; i < k / 32; ++i, w += 20, y += 36) {
+        int s = 0;
+        for (int j = 0; j < 16; ++j) s += (int)(w[4 + j] & 0x0F) * (int)(int8_t)y[4 + j] + (int)(w[4 + j] >> 4) * (int)(int8_t)y[4 + j + 16];
+        acc  += (oq_fp16_to_fp32(rd16(w)) * oq_fp16_to_fp32(rd16(y))) * (float)s;
+        mins += oq_fp16_to_fp32(rd16(w + 2)) * oq_fp16_to_fp32(rd16(y + 2));
+    }
+    return acc + mins;
+}
+static float dot_q5_0_q8_0(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 32; ++i, w += 22, y += 34) {
+        const uint32_t qh = rd32(w + 2);
+        int s = 0;
+        for (int e = 0; e < 32; ++e) s += (q5_code(w + 6, qh, e) - 16) * (int)(int8_t)y[2 + e];
+        acc += (oq_fp16_to_fp32(rd16(w)) * oq_fp16_to_fp32(rd16(y))) * (float)s;
+    }
+    return acc;
+}
+static float dot_q5_1_q8_1(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f, mins = 0.0f;
+    for (int64_t i = 0; i < k / 32; ++i, w += 24, y += 36) {
+        const uint32_t qh = rd32(w + 4);
+        int s = 0;
+        for (int e = 0; e < 32; ++e) s += q5_code(w + 8, qh, e) * (int)(int8_t)y[4 + e];
+        acc  += (oq_fp16_to_fp32(rd16(w)) * oq_fp16_to_fp32(rd16(y))) * (float)s;
+        mins += oq_fp16_to_fp32(rd16(w + 2)) * oq_fp16_to_fp32(rd16(y + 2));
+    }
+    return acc + mins;
+}
+/* ggml_vec_dot_q2_K_q8_K (:4190) / q3_K_q8_K (:4768): per superblock  d_w * d_y * sum_g scale_g * (codes . q)_g  and, for Q2_K,
+ * - dmin_w * d_y * sum_g min_g * bsum_g.  Q8_K block = f32 d @0, 256 int8 @4, sixteen int16 bsums @260 */
+static float dot_q2_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 84, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int part[16] = { 0 }, isum = 0, msum = 0;
+        for (int e = 0; e < 256; ++e) part[k_group16(e)] += q2_code(w + 16, e) * (int)q8[e];
+        for (int g = 0; g < 16; ++g) {
+            isum += (int)(w[g] & 0x0F) * part[g];
+            msum += (int)(w[g] >> 4) * (int)(int16_t)rd16(y + 260 + 2 * g);
+        }
+        const float dall = yd * oq_fp16_to_fp32(rd16(w + 80)), dmin = yd * oq_fp16_to_fp32(rd16(w + 82));
+        acc += dall * (float)isum - dmin * (float)msum;
+    }
+    return acc;
+}
+static float dot_q3_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 110, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int part[16] = { 0 }, isum = 0;
+        for (int e = 0; e < 256; ++e) part[k_group16(e)] += q3_code(w, w + 32, e) * (int)q8[e];
+        for (int g = 0; g < 16; ++g) isum += q3_scale(w + 96, g) * part[g];
+        acc += (oq_fp16_to_fp32(rd16(w + 108)) * yd) * (float)isum;
+    }
+    return acc;
+}
+
 float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
     const uint8_t * w = (const uint8_t *)wrow, * y = (const uint8_t *)yq;
     switch (type) {
@@ -370,6 +528,11 @@ float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
         case OQ_Q4_K: return dot_q45_K_q8_K(0, k, w, y);
         case OQ_Q5_K: return dot_q45_K_q8_K(1, k, w, y);
         case OQ_Q6_K: return dot_q6_K_q8_K(k, w, y);
+        case OQ_Q4_1: return dot_q4_1_q8_1(k, w, y);
+        case OQ_Q5_0: return dot_q5_0_q8_0(k, w, y);
+        case OQ_Q5_1: return dot_q5_1_q8_1(k, w, y);
+        case OQ_Q2_K: return dot_q2_K_q8_K(k, w, y);
+        case OQ_Q3_K: return dot_q3_K_q8_K(k, w, y);
         default: return NAN;
     }
 }
@@ -382,8 +545,9 @@ static uint8_t * quantize_activations(int vdt, const float * X, int64_t rows, in
     if (!q) return NULL;
     #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < rows; ++r) {
-        if (vdt == OQ_Q8_0) oq_quantize_row_q8_0_simd(X + r * K, q + rb * r, K);
-        else                quant_q8_K(X + r * K, q + rb * r, K);
+        if (vdt == OQ_Q8_0)      oq_quantize_row_q8_0_simd(X + r * K, q + rb * r, K);
+        else if (vdt == OQ_Q8_1) oq_quantize_row_q8_1_simd(X + r * K, q + rb * r, K);
+        else                     quant_q8_K(X + r * K, q + rb * r, K);
     }
     *row_bytes = rb;
     return q;

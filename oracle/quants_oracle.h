@@ -10,7 +10,7 @@ extern "C" {
 
 /* type ids = enum ggml_type (reference include/ggml.h:351-390) */
 enum {
-    OQ_F32 = 0, OQ_F16 = 1, OQ_Q4_0 = 2, OQ_Q4_1 = 3, OQ_Q5_0 = 6, OQ_Q5_1 = 7, OQ_Q8_0 = 8,
+    OQ_F32 = 0, OQ_F16 = 1, OQ_Q4_0 = 2, OQ_Q4_1 = 3, OQ_Q5_0 = 6, OQ_Q5_1 = 7, OQ_Q8_0 = 8, OQ_Q8_1 = 9,
     OQ_Q2_K = 10, OQ_Q3_K = 11, OQ_Q4_K = 12, OQ_Q5_K = 13, OQ_Q6_K = 14, OQ_Q8_K = 15,
 };
 
@@ -25,8 +25,9 @@ size_t  oq_row_size(int type, int64_t k);
 int  oq_dequantize_row(int type, const void * src, float * dst, int64_t k);
 /* f32 -> blocks: Q4_0/Q8_0 (quantize_row_*_ref), Q8_K */
 int  oq_quantize_row_ref(int type, const float * src, void * dst, int64_t k);
-/* activation quantizer as executed by the CPU backend on x86 (AVX2 flavour of quantize_row_q8_0) */
+/* activation quantizers as executed by the CPU backend on x86 (AVX2 flavours of quantize_row_q8_0 / quantize_row_q8_1) */
 void oq_quantize_row_q8_0_simd(const float * src, void * dst, int64_t k);
+void oq_quantize_row_q8_1_simd(const float * src, void * dst, int64_t k);
 /* which activation format the CPU backend pairs with a weight type (type_traits_cpu[].vec_dot_type) */
 int  oq_vec_dot_type(int type);
 /* integer block dot of one weight row with one quantized activation row */

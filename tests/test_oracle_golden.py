@@ -8,7 +8,7 @@ import pytest
 from oracle import oracle as O
 
 G = Path(__file__).resolve().parent / "golden"
-TYPES = list(O.HOT_TYPES)
+TYPES = list(O.HOT_TYPES) + list(O.NEXT_TYPES)      # hot-path formats + the SURVEY §8f-2 formats (oracle pinned first)
 IDS = [O.TYPE_NAMES[t] for t in TYPES]
 
 
@@ -26,6 +26,7 @@ def test_quantizers_golden(oracle):
     z = np.load(G / "act_q8.npz")
     x = z["x"]
     assert np.array_equal(oracle.quantize(O.Q8_0, x, simd_q8_0=True), z["q8_0"])
+    assert np.array_equal(oracle.quantize(O.Q8_1, x), z["q8_1"])
     assert np.array_equal(oracle.quantize(O.Q8_0, x), z["q8_0_ref"])
     assert np.array_equal(oracle.quantize(O.Q4_0, x), z["q4_0_ref"])
     a = oracle.quantize(O.Q8_K, x).reshape(-1, 292).copy(); b = z["q8_K"].reshape(-1, 292).copy()

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import oracle as O
 
-TYPES = list(O.HOT_TYPES)
+TYPES = list(O.HOT_TYPES) + list(O.NEXT_TYPES)      # the hot-path formats + the SURVEY §8f-2 formats (oracle first)
 IDS = [O.TYPE_NAMES[t] for t in TYPES]
 
 
@@ -82,6 +82,7 @@ def test_activation_quantizer_matches_cpu_backend(oracle, ref):
     for x in (synth(4096), rng.uniform(-1, 1, 4096).astype(np.float32), (rng.standard_normal(8192) * 5).astype(np.float32),
               np.round(rng.uniform(-127, 127, 4096)).astype(np.float32) / 2):
         assert np.array_equal(ref.cpu_from_float(O.Q8_0, x), oracle.quantize(O.Q8_0, x, simd_q8_0=True))
+        assert np.array_equal(ref.cpu_from_float(O.Q8_1, x), oracle.quantize(O.Q8_1, x))
         a = ref.cpu_from_float(O.Q8_K, x); b = oracle.quantize(O.Q8_K, x)
         assert np.array_equal(a, b)
 
