@@ -22,7 +22,7 @@
 namespace b200 {
 
 // enum ggml_type ids (reference include/ggml.h:351-390)
-enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
+enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
 
 template <int T> struct fmt;
 template <> struct fmt<T_Q4_0> { static constexpr int QK = 32,  BYTES = 18,  ACT_K = 0; };
@@ -30,10 +30,22 @@ template <> struct fmt<T_Q8_0> { static constexpr int QK = 32,  BYTES = 34,  ACT
 template <> struct fmt<T_Q4_K> { static constexpr int QK = 256, BYTES = 144, ACT_K = 1; };
 template <> struct fmt<T_Q5_K> { static constexpr int QK = 256, BYTES = 176, ACT_K = 1; };
 template <> struct fmt<T_Q6_K> { static constexpr int QK = 256, BYTES = 210, ACT_K = 1; };
+// SURVEY §8f-2 formats (generic mat-vec / MUL_MAT_ID / dequantize paths; decode logic checked on the host by tests/hostemu):
+//   Q4_1 20 B / 32 (src/ggml-common.h:168-180)   Q5_0 22 B / 32 (:182-188)   Q5_1 24 B / 32 (:190-203)
+//   Q2_K 84 B / 256 (:247-262)   Q3_K 110 B / 256 (:264-276)
+// Q4_1 / Q5_1 carry a per-block minimum: the CPU backend pairs them with Q8_1 activations (d and s = d * sum of codes).
+template <> struct fmt<T_Q4_1> { static constexpr int QK = 32,  BYTES = 20,  ACT_K = 0; };
+template <> struct fmt<T_Q5_0> { static constexpr int QK = 32,  BYTES = 22,  ACT_K = 0; };
+template <> struct fmt<T_Q5_1> { static constexpr int QK = 32,  BYTES = 24,  ACT_K = 0; };
+template <> struct fmt<T_Q2_K> { static constexpr int QK = 256, BYTES = 84,  ACT_K = 1; };
+template <> struct fmt<T_Q3_K> { static constexpr int QK = 256, BYTES = 110, ACT_K = 1; };
 
-__host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 ? 32 : 256; }
-__host__ __device__ inline int    type_bytes(int t) { return t == T_Q4_0 ? 18 : t == T_Q8_0 ? 34 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : 0; }
-__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K; }
+__host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 ? 32 : 256; }
+__host__ __device__ inline int    type_bytes(int t) {
+    return t == T_Q4_0 ? 18 : t == T_Q8_0 ? 34 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210
+         : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : 0;
+}
+__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K || t == T_Q2_K || t == T_Q3_K; }
 __host__ __device__ inline size_t row_bytes(int t, int64_t k) { return (size_t)(k / type_qk(t)) * type_bytes(t); }
 
 // ------------------------------------------------------------------ quantized activation record
@@ -41,15 +53,18 @@ __host__ __device__ inline size_t row_bytes(int t, int64_t k) { return (size_t)(
 //   q   : int8[K]
 //   bs  : int16[K/16]   sums of q over groups of 16 (block_q8_K.bsums; also gives Q4_0's "-8" term)
 //   d   : float[K/32] (fp16-rounded, Q8_0 family) or float[K/256] (Q8_K family)
-// laid out q | bs | d, each part 16-byte aligned.
+//   s   : float[K/32], Q8_0 family only: block_q8_1.s = fp16(d_unrounded * sum of the block's codes), for weights with a minimum
+// laid out q | bs | d | s, each part 16-byte aligned.
+#define B200_ACT_HAS_S 1
 struct act_layout {
-    int32_t off_bs, off_d, bytes;
+    int32_t off_bs, off_d, off_s, bytes;
 };
 __host__ __device__ inline act_layout make_act_layout(int64_t K, bool kq) {
     act_layout L;
     L.off_bs = (int32_t)((K + 15) & ~(int64_t)15);
     L.off_d  = L.off_bs + (int32_t)(((K / 16) * 2 + 15) & ~(int64_t)15);
-    L.bytes  = L.off_d + (int32_t)((((kq ? K / 256 : K / 32)) * 4 + 15) & ~(int64_t)15);
+    L.off_s  = L.off_d + (int32_t)((((kq ? K / 256 : K / 32)) * 4 + 15) & ~(int64_t)15);
+    L.bytes  = L.off_s + (kq ? 0 : (int32_t)(((K / 32) * 4 + 15) & ~(int64_t)15));
     return L;
 }
 
@@ -84,7 +99,9 @@ struct unit_act {
     int   q[16];   // 64 int8
     int   bs[4];   // sums of the four groups of 16
     float d[2];    // Q8_0 family: scales of the two 32-blocks; Q8_K family: d[0] = superblock scale
+    float s[2];    // Q8_1's s of the two 32-blocks (only loaded for weight formats with a minimum)
 };
+template <int T> struct needs_s { static constexpr bool value = (T == T_Q4_1 || T == T_Q5_1); };
 
 // k offset of 16-piece g of unit u
 template <int T> __device__ __forceinline__ int unit_piece_k(int u, int g) {
@@ -103,6 +120,8 @@ template <int T> __device__ __forceinline__ void load_unit_act(const uint8_t * r
     const float * d = (const float *)(rec + L.off_d);
     if constexpr (fmt<T>::ACT_K) { A.d[0] = d[u >> 2]; A.d[1] = 0.0f; }
     else                        { A.d[0] = d[2 * u]; A.d[1] = d[2 * u + 1]; }
+    if constexpr (needs_s<T>::value) { const float * sv = (const float *)(rec + L.off_s); A.s[0] = sv[2 * u]; A.s[1] = sv[2 * u + 1]; }
+    else                             { A.s[0] = 0.0f; A.s[1] = 0.0f; }
 }
 
 // ------------------------------------------------------------------ unit dot products
@@ -231,6 +250,149 @@ template <> __device__ __forceinline__ float unit_dot<T_Q6_K>(const uint8_t * ro
     return d * (float)tot;
 }
 
+// ---- SURVEY §8f-2 formats ------------------------------------------------------------------------------------------------
+// four fifth-bits (bits 0..3 of x) -> bit 4 of the four bytes of a word
+__device__ __forceinline__ uint32_t spread4_to_bit4(uint32_t x) { return (((x & 0xF) * 0x00204081u) & 0x01010101u) << 4; }
+
+// dot of the 32 5-bit codes of a Q5 block (nibble words q[4], fifth bits qh) with the block's 32 int8 activations
+__device__ __forceinline__ int q5_block_dot(const uint32_t (&q)[4], uint32_t qh, const int * y) {
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s = dp4a_s((int)((q[i] & 0x0F0F0F0F)        | spread4_to_bit4(qh >> (4 * i))),      y[i],     s);   // elements 4i .. 4i+3
+        s = dp4a_s((int)(((q[i] >> 4) & 0x0F0F0F0F) | spread4_to_bit4(qh >> (16 + 4 * i))), y[4 + i], s);   // elements 16+4i ..
+    }
+    return s;
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q4_1>(const uint8_t * row, int u, const unit_act & A) {
+    uint32_t w[10];
+    load_words_a2<10>(row + 40 * u, w);                    // block: d | m, qs[16]
+    int s0 = 0, s1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s0 = dp4a_s(w[1 + i] & 0x0F0F0F0F,        A.q[i],      s0);
+        s0 = dp4a_s((w[1 + i] >> 4) & 0x0F0F0F0F, A.q[4 + i],  s0);
+        s1 = dp4a_s(w[6 + i] & 0x0F0F0F0F,        A.q[8 + i],  s1);
+        s1 = dp4a_s((w[6 + i] >> 4) & 0x0F0F0F0F, A.q[12 + i], s1);
+    }
+    return (h2f(w[0] & 0xFFFF) * A.d[0]) * (float)s0 + h2f(w[0] >> 16) * A.s[0]
+         + (h2f(w[5] & 0xFFFF) * A.d[1]) * (float)s1 + h2f(w[5] >> 16) * A.s[1];
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q5_0>(const uint8_t * row, int u, const unit_act & A) {
+    uint32_t w[11];
+    load_words_a2<11>(row + 44 * u, w);                    // block: d (2 B), qh (4 B), qs[16]; the second block starts at byte 22
+    uint32_t qa[4], qb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qa[i] = __funnelshift_r(w[1 + i], w[2 + i], 16); qb[i] = w[7 + i]; }
+    const uint32_t qha = __funnelshift_r(w[0], w[1], 16), qhb = w[6];
+    const int s0 = q5_block_dot(qa, qha, A.q)     - 16 * (A.bs[0] + A.bs[1]);
+    const int s1 = q5_block_dot(qb, qhb, A.q + 8) - 16 * (A.bs[2] + A.bs[3]);
+    return (h2f(w[0] & 0xFFFF) * A.d[0]) * (float)s0 + (h2f(w[5] >> 16) * A.d[1]) * (float)s1;
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q5_1>(const uint8_t * row, int u, const unit_act & A) {
+    uint32_t w[12];
+    load_words_a2<12>(row + 48 * u, w);                    // block: d | m, qh, qs[16]
+    const uint32_t qa[4] = { w[2], w[3], w[4], w[5] }, qb[4] = { w[8], w[9], w[10], w[11] };
+    const int s0 = q5_block_dot(qa, w[1], A.q), s1 = q5_block_dot(qb, w[7], A.q + 8);
+    return (h2f(w[0] & 0xFFFF) * A.d[0]) * (float)s0 + h2f(w[0] >> 16) * A.s[0]
+         + (h2f(w[6] & 0xFFFF) * A.d[1]) * (float)s1 + h2f(w[6] >> 16) * A.s[1];
+}
+
+// byte k of a little-endian word array
+template <int N> __device__ __forceinline__ int word_byte(const uint32_t (&w)[N], int k) { return (int)((w[k >> 2] >> (8 * (k & 3))) & 0xFF); }
+
+// Q2_K / Q3_K: element 128 h + 32 j + l of a superblock has its 2-bit code in bits 2j..2j+1 of qs[32 h + l] and belongs to the
+// 16-element group 8 h + 2 j + l / 16.  Unit u (64 weights) = half h = (u % 4) / 2, bit pairs j0 = 2 (u % 2) and j0 + 1;
+// its pieces g = 0..3 are (j0, l < 16), (j0, l >= 16), (j0 + 1, l < 16), (j0 + 1, l >= 16): contiguous activations.
+template <> __device__ __forceinline__ float unit_dot<T_Q2_K>(const uint8_t * row, int u, const unit_act & A) {
+    const uint8_t * sb = row + 84 * (u >> 2);               // scales[16] @0, qs[64] @16, d @80, dmin @82
+    const int h = (u >> 1) & 1, j0 = 2 * (u & 1);
+    uint32_t sc[4], q[8];
+    load_words_a2<4>(sb, sc);
+    load_words_a2<8>(sb + 16 + 32 * h, q);
+    int isum = 0, msum = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int jj = j0 + (g >> 1), half16 = g & 1;
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p = dp4a_s((int)((q[4 * half16 + i] >> (2 * jj)) & 0x03030303), A.q[4 * g + i], p);
+        const int s = word_byte(sc, 8 * h + 2 * jj + half16);
+        isum += (s & 0x0F) * p;
+        msum += (s >> 4) * A.bs[g];
+    }
+    const float dall = A.d[0] * h2f(load_u16(sb + 80)), dmin = A.d[0] * h2f(load_u16(sb + 82));
+    return dall * (float)isum - dmin * (float)msum;
+}
+
+template <> __device__ __forceinline__ float unit_dot<T_Q3_K>(const uint8_t * row, int u, const unit_act & A) {
+    const uint8_t * sb = row + 110 * (u >> 2);              // hmask[32] @0, qs[64] @32, scales[12] @96, d @108 (2-byte aligned)
+    const int h = (u >> 1) & 1, j0 = 2 * (u & 1);
+    uint32_t hm[8], q[8], sc[3];
+    load_words_a2<8>(sb, hm);
+    load_words_a2<8>(sb + 32 + 32 * h, q);
+    load_words_a2<3>(sb + 96, sc);
+    int isum = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int jj = j0 + (g >> 1), half16 = g & 1, bit = 4 * h + jj;
+        int p = 0, low = 0;                                  // low = sum of the activations whose high bit is clear (code - 4)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            p   = dp4a_s((int)((q[4 * half16 + i] >> (2 * jj)) & 0x03030303), A.q[4 * g + i], p);
+            low = dp4a_s((int)(~(hm[4 * half16 + i] >> bit) & 0x01010101),    A.q[4 * g + i], low);
+        }
+        const int g16 = 8 * h + 2 * jj + half16;
+        const int lo = g16 < 8 ? (word_byte(sc, g16) & 0x0F) : (word_byte(sc, g16 - 8) >> 4);
+        const int hi = (word_byte(sc, 8 + (g16 & 3)) >> (2 * (g16 >> 2))) & 3;
+        isum += ((lo | (hi << 4)) - 32) * (p - 4 * low);
+    }
+    return (h2f(load_u16(sb + 108)) * A.d[0]) * (float)isum;
+}
+
+// single trailing 32-block of a row of a 32-element-block format whose block count is odd (K % 64 == 32)
+template <int T> __device__ __forceinline__ float tail_block_dot(const uint8_t * blk, const uint8_t * rec, const act_layout & L, int kblk) {
+    const int * aq = (const int *)(rec + kblk * 32);
+    const float ad = ((const float *)(rec + L.off_d))[kblk];
+    int s = 0;
+    if constexpr (T == T_Q4_0) {
+        uint32_t w[5];
+        load_words_a2<5>(blk, w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t q = __funnelshift_r(w[i], w[i + 1], 16);
+            s = __dp4a((int)(q & 0x0F0F0F0F), aq[i], s);
+            s = __dp4a((int)((q >> 4) & 0x0F0F0F0F), aq[4 + i], s);
+        }
+        const int16_t * bs = (const int16_t *)(rec + L.off_bs);
+        s -= 8 * (bs[2 * kblk] + bs[2 * kblk + 1]);
+        return (float)s * h2f(w[0] & 0xFFFF) * ad;
+    } else if constexpr (T == T_Q8_0) {
+        uint32_t w[9];
+        load_words_a2<9>(blk, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = __dp4a((int)__funnelshift_r(w[i], w[i + 1], 16), aq[i], s);
+        return (float)s * (h2f(w[0] & 0xFFFF) * ad);
+    } else {
+        // the other 32-block formats: the unit dot product on a private copy of the block followed by an all-zero block
+        // (zero scale and minimum: contributes exactly 0) against a unit whose second half is zero
+        __align__(4) uint8_t tmp[2 * fmt<T>::BYTES + 8];
+#pragma unroll
+        for (int i = 0; i < 2 * fmt<T>::BYTES + 8; ++i) tmp[i] = i < fmt<T>::BYTES ? blk[i] : (uint8_t)0;
+        unit_act A;
+        const int16_t * bs = (const int16_t *)(rec + L.off_bs);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { A.q[i] = aq[i]; A.q[8 + i] = 0; }
+        A.bs[0] = bs[2 * kblk]; A.bs[1] = bs[2 * kblk + 1]; A.bs[2] = 0; A.bs[3] = 0;
+        A.d[0] = ad; A.d[1] = 0.0f;
+        A.s[0] = needs_s<T>::value ? ((const float *)(rec + L.off_s))[kblk] : 0.0f; A.s[1] = 0.0f;
+        return unit_dot<T>(tmp, 0, A);
+    }
+}
+
 // ------------------------------------------------------------------ activation quantizers (device)
 __device__ __forceinline__ float4 load_f4(const float * p) {
     if (((uintptr_t)p & 15) == 0) return *(const float4 *)p;
@@ -256,10 +418,15 @@ __device__ __forceinline__ void warp_quantize_q8_0_x256(const float * x, int kva
         int s = q0 + q1 + q2 + q3;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);      // sum over 16 elements (4 lanes)
+        const int s32 = s + __shfl_xor_sync(0xffffffffu, s, 4);                      // sum over the 32-block (8 lanes); all lanes take part
         if (k < kvalid) {
             *(uint32_t *)(rec + k0 + k) = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
             if ((lane & 3) == 0) *(int16_t *)(rec + L.off_bs + ((k0 + k) >> 4) * 2) = (int16_t)s;
-            if ((lane & 7) == 0) ((float *)(rec + L.off_d))[(k0 + k) >> 5] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
+            if ((lane & 7) == 0) {
+                const float dun = __fdiv_rn(amax, 127.0f);                                // block_q8_1: d = fp16(dun), s = fp16(dun * sum)
+                ((float *)(rec + L.off_d))[(k0 + k) >> 5] = __half2float(__float2half_rn(dun));
+                ((float *)(rec + L.off_s))[(k0 + k) >> 5] = __half2float(__float2half_rn(__fmul_rn(dun, (float)s32)));
+            }
         }
     }
 }

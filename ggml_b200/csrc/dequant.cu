@@ -8,6 +8,7 @@
 // Each thread produces 4 consecutive outputs, so stores are coalesced 16-byte vectors.
 #include "b200_internal.h"
 #include "b200_quants.cuh"
+#include "b200_dequant.cuh"
 
 namespace b200 {
 
@@ -21,11 +22,6 @@ template <> __device__ __forceinline__ void store4<__half>(__half * dst, float a
     *(uint2 *)dst = v;
 }
 
-__device__ __forceinline__ void k4_scale_min_bytes(const uint8_t * s, int j, int & sc, int & mn) {
-    if (j < 4) { sc = s[j] & 63; mn = s[j + 4] & 63; }
-    else       { sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4); mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4); }
-}
-
 // one thread -> elements [4*t, 4*t+4) of the flat tensor
 template <int T, typename OUT>
 __global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t * __restrict__ src, OUT * __restrict__ dst, int64_t n4) {
@@ -33,48 +29,7 @@ __global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t * __restr
     if (t >= n4) return;
     const int64_t e = t * 4;
     float o[4];
-    if constexpr (T == T_Q4_0) {
-        const uint8_t * b = src + (e / 32) * 18;
-        const int j = (int)(e % 32);
-        const float d = h2f(load_u16(b));
-        const uint8_t * q = b + 2 + (j & 15);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = __fmul_rn((float)((j < 16 ? (q[i] & 0x0F) : (q[i] >> 4)) - 8), d);
-    } else if constexpr (T == T_Q8_0) {
-        const uint8_t * b = src + (e / 32) * 34;
-        const int j = (int)(e % 32);
-        const float d = h2f(load_u16(b));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = __fmul_rn((float)(int8_t)b[2 + j + i], d);
-    } else if constexpr (T == T_Q4_K || T == T_Q5_K) {
-        constexpr int BYTES = fmt<T>::BYTES;
-        const uint8_t * b = src + (e / 256) * BYTES;
-        const int w = (int)(e % 256), c = w / 64, l = w % 32, hi = (w % 64) / 32;
-        const float d = h2f(load_u16(b)), dmin = h2f(load_u16(b + 2));
-        int sc, mn;
-        k4_scale_min_bytes(b + 4, 2 * c + hi, sc, mn);
-        const float dd = __fmul_rn(d, (float)sc), mm = __fmul_rn(dmin, (float)mn);
-        const uint8_t * q = b + (T == T_Q5_K ? 48 : 16) + 32 * c + l;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int v = hi ? (q[i] >> 4) : (q[i] & 0x0F);
-            if constexpr (T == T_Q5_K) v += ((b[16 + l + i] >> (2 * c + hi)) & 1) << 4;
-            o[i] = __fsub_rn(__fmul_rn(dd, (float)v), mm);
-        }
-    } else { // Q6_K
-        const uint8_t * b = src + (e / 256) * 210;
-        const int w = (int)(e % 256), h = w / 128, pos = (w % 128) / 32, l = w % 32;
-        const float d = h2f(load_u16(b + 208));
-        const int sc = (int)(int8_t)b[192 + 8 * h + l / 16 + 2 * pos];
-        const float ds = __fmul_rn(d, (float)sc);
-        const uint8_t * ql = b + 64 * h + (pos & 1) * 32 + l, * qh = b + 128 + 32 * h + l;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int lo = pos >= 2 ? (ql[i] >> 4) : (ql[i] & 0x0F);
-            const int v = (int)(int8_t)(lo | (((qh[i] >> (2 * pos)) & 3) << 4)) - 32;
-            o[i] = __fmul_rn(ds, (float)v);
-        }
-    }
+    dequant4<T>(src, e, o);
     store4<OUT>(dst + e, o[0], o[1], o[2], o[3]);
 }
 
@@ -88,6 +43,11 @@ template <typename OUT> static int dequantize_dispatch(int type, const void * sr
         case T_Q4_K: dequantize_kernel<T_Q4_K, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         case T_Q5_K: dequantize_kernel<T_Q5_K, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         case T_Q6_K: dequantize_kernel<T_Q6_K, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_Q4_1: dequantize_kernel<T_Q4_1, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_Q5_0: dequantize_kernel<T_Q5_0, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_Q5_1: dequantize_kernel<T_Q5_1, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_Q2_K: dequantize_kernel<T_Q2_K, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_Q3_K: dequantize_kernel<T_Q3_K, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         default: set_error("dequantize: unsupported type %d", type); return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

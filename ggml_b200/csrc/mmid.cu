@@ -43,31 +43,7 @@ __global__ void __launch_bounds__(128) mmid_kernel(mmid_params p) {
             acc += unit_dot<T>(row, u, A);
         }
         if constexpr (fmt<T>::QK == 32) {
-            if ((p.K & 63) != 0 && lane == 0) {
-                // single trailing 32-block
-                const uint8_t * blk = row + (size_t)nunits * 2 * fmt<T>::BYTES;
-                const int kb = nunits * 2;
-                const int * aq = (const int *)(rec + kb * 32);
-                const float ad = ((const float *)(rec + p.L.off_d))[kb];
-                int s = 0;
-                if constexpr (T == T_Q4_0) {
-                    uint32_t w[5]; load_words_a2<5>(blk, w);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t q = __funnelshift_r(w[i], w[i + 1], 16);
-                        s = __dp4a((int)(q & 0x0F0F0F0F), aq[i], s);
-                        s = __dp4a((int)((q >> 4) & 0x0F0F0F0F), aq[4 + i], s);
-                    }
-                    const int16_t * bs = (const int16_t *)(rec + p.L.off_bs);
-                    s -= 8 * (bs[2 * kb] + bs[2 * kb + 1]);
-                    acc += (float)s * h2f(w[0] & 0xFFFF) * ad;
-                } else {
-                    uint32_t w[9]; load_words_a2<9>(blk, w);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) s = __dp4a((int)__funnelshift_r(w[i], w[i + 1], 16), aq[i], s);
-                    acc += (float)s * (h2f(w[0] & 0xFFFF) * ad);
-                }
-            }
+            if ((p.K & 63) != 0 && lane == 0) acc += tail_block_dot<T>(row + (size_t)nunits * 2 * fmt<T>::BYTES, rec, p.L, nunits * 2);
         }
     }
     acc = warp_sum_id(acc);
@@ -113,6 +89,11 @@ int ggml_b200_mul_mat_id(const ggml_b200_mul_mat_id_args * a, void * stream) {
         case T_Q4_K: mmid_kernel<T_Q4_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_Q5_K: mmid_kernel<T_Q5_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_Q6_K: mmid_kernel<T_Q6_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q4_1: mmid_kernel<T_Q4_1><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q5_0: mmid_kernel<T_Q5_0><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q5_1: mmid_kernel<T_Q5_1><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q2_K: mmid_kernel<T_Q2_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q3_K: mmid_kernel<T_Q3_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

@@ -86,32 +86,6 @@ struct generic_params {
     int64_t nrg;      // row groups = ceil(M / warps per CTA)
 };
 
-// single trailing 32-block of a Q4_0 / Q8_0 row whose block count is odd
-template <int T> __device__ __forceinline__ float tail_block_dot(const uint8_t * blk, const uint8_t * rec, const act_layout & L, int kblk) {
-    const int * aq = (const int *)(rec + kblk * 32);
-    const float ad = ((const float *)(rec + L.off_d))[kblk];
-    int s = 0;
-    if constexpr (T == T_Q4_0) {
-        uint32_t w[5];
-        load_words_a2<5>(blk, w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t q = __funnelshift_r(w[i], w[i + 1], 16);
-            s = __dp4a((int)(q & 0x0F0F0F0F), aq[i], s);
-            s = __dp4a((int)((q >> 4) & 0x0F0F0F0F), aq[4 + i], s);
-        }
-        const int16_t * bs = (const int16_t *)(rec + L.off_bs);
-        s -= 8 * (bs[2 * kblk] + bs[2 * kblk + 1]);
-        return (float)s * h2f(w[0] & 0xFFFF) * ad;
-    } else {
-        uint32_t w[9];
-        load_words_a2<9>(blk, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = __dp4a((int)__funnelshift_r(w[i], w[i + 1], 16), aq[i], s);
-        return (float)s * (h2f(w[0] & 0xFFFF) * ad);
-    }
-}
-
 template <int T>
 __global__ void __launch_bounds__(128) mmvq_generic_kernel(generic_params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,6 +136,11 @@ int launch_mmvq_generic(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q4_K: mmvq_generic_kernel<T_Q4_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_Q5_K: mmvq_generic_kernel<T_Q5_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_Q6_K: mmvq_generic_kernel<T_Q6_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q4_1: mmvq_generic_kernel<T_Q4_1><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q5_0: mmvq_generic_kernel<T_Q5_0><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q5_1: mmvq_generic_kernel<T_Q5_1><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q2_K: mmvq_generic_kernel<T_Q2_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_Q3_K: mmvq_generic_kernel<T_Q3_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();
@@ -301,6 +280,7 @@ struct tma_plan {
 };
 
 static bool make_tma_plan(const ggml_b200_mul_mat_args & a, tma_plan & pl) {
+    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && a.type != T_Q6_K) return false;   // the other formats: generic kernel
     if (a.N < 1 || a.N > 8 || a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
     if (a.K % 64 != 0 || a.K < 64 || a.M < 1) return false;                 // whole units; Q4_0/Q8_0 pairs 4-byte aligned
     const size_t rb = row_bytes(a.type, a.K);

@@ -1,0 +1,61 @@
+// hostemu.cpp — TEST INFRASTRUCTURE ONLY: the per-thread decode logic of ggml_b200/csrc (unit dot products, element decoders)
+// compiled for the host through tests/hostemu/shim, exported with a C ABI for tests/test_hostemu_kernel_logic.py.
+// It checks indexing / bit manipulation of the block formats on the CPU; it says nothing about scheduling, memory movement or
+// the PTX-level instructions (dp2a, prmt, tcgen05 ...) of the fast kernels — those are covered by the `-m gpu` parity tests.
+#include "cuda_shim.h"
+#include "../../ggml_b200/csrc/b200_dequant.cuh"
+
+using namespace b200;
+
+template <int T> static float row_dot(const uint8_t * row, int64_t K, const uint8_t * rec) {
+    const act_layout L = make_act_layout(K, fmt<T>::ACT_K != 0);
+    float acc = 0.0f;
+    for (int u = 0; u < (int)(K / 64); ++u) {
+        unit_act A;
+        load_unit_act<T>(rec, L, u, A);
+        acc += unit_dot<T>(row, u, A);
+    }
+    if constexpr (fmt<T>::QK == 32) {                       // odd number of 32-blocks: the kernels' trailing-block path
+        const int nunits = (int)(K / 64);
+        if ((K & 63) != 0) acc += tail_block_dot<T>(row + (size_t)nunits * 2 * fmt<T>::BYTES, rec, L, nunits * 2);
+    }
+    return acc;
+}
+template <int T> static void dequant_all(const uint8_t * src, float * dst, int64_t n) {
+    for (int64_t e = 0; e < n; e += 4) { float o[4]; dequant4<T>(src, e, o); for (int i = 0; i < 4; ++i) dst[e + i] = o[i]; }
+}
+
+#define FOR_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_Q2_K) X(T_Q3_K)
+
+extern "C" {
+
+// offsets of the activation record sections: out = { off_bs, off_d, off_s (or -1), bytes }
+void emu_act_layout(int64_t K, int kq, int32_t * out) {
+    const act_layout L = make_act_layout(K, kq != 0);
+    out[0] = L.off_bs; out[1] = L.off_d; out[2] = -1; out[3] = L.bytes;
+#ifdef B200_ACT_HAS_S
+    out[2] = L.off_s;
+#endif
+}
+int emu_type_is_kquant(int type) { return type_is_kquant(type) ? 1 : 0; }
+int64_t emu_row_bytes(int type, int64_t K) { return (int64_t)row_bytes(type, K); }
+
+// dot product of one packed weight row with one activation record (K % 32 == 0 for 32-block formats, else K % 256 == 0)
+float emu_row_dot(int type, const uint8_t * row, int64_t K, const uint8_t * rec) {
+    switch (type) {
+#define X(T) case T: return row_dot<T>(row, K, rec);
+        FOR_TYPES(X)
+#undef X
+        default: return NAN;
+    }
+}
+int emu_dequant(int type, const uint8_t * src, float * dst, int64_t n) {
+    switch (type) {
+#define X(T) case T: dequant_all<T>(src, dst, n); return 0;
+        FOR_TYPES(X)
+#undef X
+        default: return -1;
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,49 @@
+// cuda_shim.h — TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile the *decode logic* of
+// ggml_b200/csrc/b200_quants.cuh (format traits, unit dot products, element decoders) with the host compiler, so that indexing /
+// bit-twiddling mistakes in a block format are caught by the CPU-only test suite, before any GPU time is spent.
+// Nothing here is part of the product; warp collectives are stubs (the activation quantizers are not exercised on the host).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <algorithm>
+#include <immintrin.h>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+struct int4   { int x, y, z, w; };
+struct uint4  { unsigned x, y, z, w; };
+struct uint2  { unsigned x, y; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+struct dim3_shim { unsigned x = 0, y = 0, z = 0; };
+static dim3_shim threadIdx, blockDim, blockIdx;
+
+struct __half { uint16_t x; };
+static inline __half __ushort_as_half(unsigned short u) { return __half{u}; }
+static inline float  __half2float(__half h) { return _cvtsh_ss(h.x); }
+static inline __half __float2half_rn(float f) { return __half{(uint16_t)_cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT)}; }
+
+static inline int __dp4a(int a, int b, int c) {                       // signed x signed bytes
+    for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+    return c;
+}
+static inline int __dp4a(unsigned a, int b, int c) { return __dp4a((int)a, b, c); }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)(v >> (shift & 31));
+}
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline int   __float2int_rn(float v) { return (int)nearbyintf(v); }
+template <typename V> static inline V __shfl_xor_sync(unsigned, V v, int) { return v; }   // stub: collectives are not emulated
+using std::min;
+using std::max;

@@ -51,9 +51,11 @@ def test_shim_validates_arguments_without_a_device():
     import ggml_b200 as g
     L = g.lib()
     assert L.ggml_b200_row_size(g.Q4_K, 4096) == 2304 and L.ggml_b200_row_size(g.Q6_K, 256) == 210
+    assert L.ggml_b200_row_size(g.Q4_1, 64) == 40 and L.ggml_b200_row_size(g.Q5_0, 64) == 44 and L.ggml_b200_row_size(g.Q5_1, 64) == 48
+    assert L.ggml_b200_row_size(g.Q2_K, 512) == 168 and L.ggml_b200_row_size(g.Q3_K, 512) == 220
     assert L.ggml_b200_row_size(g.Q4_0, 4096) == 2304 and L.ggml_b200_row_size(g.Q8_0, 4096) == 4352 and L.ggml_b200_row_size(g.Q5_K, 256) == 176
     a = g.MulMatArgs()
-    a.type, a.K, a.M, a.N = 3, 4096, 16, 1                  # Q4_1: not implemented -> explicit error, not a fallback
+    a.type, a.K, a.M, a.N = 16, 4096, 16, 1                 # IQ2_XXS: not implemented -> explicit error, not a fallback
     a.ne02 = a.ne03 = a.ne12 = a.ne13 = 1
     assert L.ggml_b200_mul_mat_plan(C.byref(a)) == -1
     a.type, a.K = g.Q4_K, 100                               # K not a multiple of the block size

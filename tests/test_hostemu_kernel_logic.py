@@ -1,0 +1,111 @@
+"""CPU-only: the per-thread decode logic of the CUDA kernels (format traits, 64-weight unit dot products, element decoders of
+ggml_b200/csrc/b200_quants.cuh / b200_dequant.cuh) compiled for the HOST through tests/hostemu/shim and checked against the oracle.
+Catches indexing / bit-twiddling mistakes in a block format without a GPU; the `-m gpu` parity tests remain the gate for the
+kernels themselves (scheduling, memory movement, PTX-level instructions)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+EMU = ROOT / "tests" / "hostemu"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = EMU / "_build"
+    out.mkdir(exist_ok=True)
+    so = out / "libhostemu.so"
+    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h", ROOT / "ggml_b200" / "csrc" / "b200_quants.cuh", ROOT / "ggml_b200" / "csrc" / "b200_dequant.cuh"]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
+        cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
+               f"-I{EMU / 'shim'}", "-o", str(so), str(EMU / "hostemu.cpp")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(str(so))
+    L.emu_row_dot.restype = C.c_float
+    L.emu_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.emu_dequant.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+    L.emu_act_layout.argtypes = [C.c_int64, C.c_int, C.c_void_p]
+    L.emu_row_bytes.restype = C.c_int64
+    L.emu_row_bytes.argtypes = [C.c_int, C.c_int64]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def supported(emu, t):
+    return emu.emu_row_bytes(t, 256) > 0
+
+
+def act_record(emu, oracle, t, x):
+    """the device-side activation record (q | bs | d [| s]) built from the ORACLE's quantized activations"""
+    K = x.size
+    kq = bool(emu.emu_type_is_kquant(t))
+    lay = np.zeros(4, dtype=np.int32)
+    emu.emu_act_layout(K, int(kq), _p(lay))
+    off_bs, off_d, off_s, nbytes = (int(v) for v in lay)
+    rec = np.zeros(nbytes + 64, dtype=np.uint8)
+    vdt = oracle.vec_dot_type(t)
+    yq = oracle.quantize(vdt, x, simd_q8_0=(vdt == O.Q8_0))
+    if vdt == O.Q8_K:
+        b = yq.reshape(-1, 292)
+        q = b[:, 4:260].reshape(-1).view(np.int8)
+        d = b[:, :4].copy().view(np.float32).reshape(-1)
+    else:
+        bs_ = 34 if vdt == O.Q8_0 else 36
+        b = yq.reshape(-1, bs_)
+        q = b[:, bs_ - 32:].reshape(-1).view(np.int8)
+        d = b[:, :2].copy().view(np.float16).astype(np.float32).reshape(-1)
+        if vdt == O.Q8_1:
+            assert off_s >= 0, "the record needs the Q8_1 's' section for formats with a minimum"
+            s = b[:, 2:4].copy().view(np.float16).astype(np.float32).reshape(-1)
+            rec[off_s:off_s + 4 * s.size] = s.view(np.uint8)
+    rec[:K] = q.view(np.uint8)
+    bsum = q.reshape(-1, 16).astype(np.int32).sum(1).astype(np.int16)
+    rec[off_bs:off_bs + 2 * bsum.size] = bsum.view(np.uint8)
+    rec[off_d:off_d + 4 * d.size] = d.view(np.uint8)
+    return rec, yq
+
+
+ALL = list(O.HOT_TYPES) + list(O.NEXT_TYPES)
+
+
+@pytest.mark.parametrize("t", ALL, ids=[O.TYPE_NAMES[t] for t in ALL])
+def test_element_decoders_bit_exact(t, emu, oracle):
+    if not supported(emu, t):
+        pytest.skip("format not implemented in ggml_b200/csrc yet")
+    rng = np.random.default_rng(300 + t)
+    nb = 512
+    blocks = O.random_blocks(t, nb, rng)
+    n = nb * oracle.blck_size(t)
+    out = np.empty(n, dtype=np.float32)
+    assert emu.emu_dequant(t, _p(blocks), _p(out), n) == 0
+    assert np.array_equal(out.view(np.uint32), oracle.dequantize(t, blocks, n).view(np.uint32))
+    z = np.load(ROOT / "tests" / "golden" / f"quant_{O.TYPE_NAMES[t]}.npz")          # the reference's own blocks
+    out = np.empty(z["x"].size, dtype=np.float32)
+    assert emu.emu_dequant(t, _p(np.ascontiguousarray(z["blocks"])), _p(out), out.size) == 0
+    assert np.array_equal(out.view(np.uint32), z["deq"].view(np.uint32))
+
+
+@pytest.mark.parametrize("t", ALL, ids=[O.TYPE_NAMES[t] for t in ALL])
+def test_unit_dot_products_match_oracle(t, emu, oracle):
+    if not supported(emu, t):
+        pytest.skip("format not implemented in ggml_b200/csrc yet")
+    rng = np.random.default_rng(400 + t)
+    for K in (256, 1024, 4096) + ((32, 96, 160) if oracle.blck_size(t) == 32 else ()):          # odd block counts: trailing-block path
+        x = rng.uniform(-1, 1, K).astype(np.float32)
+        rec, yq = act_record(emu, oracle, t, x)
+        for trial in range(6):
+            w = O.random_blocks(t, K // oracle.blck_size(t), rng)
+            w = np.concatenate([w, np.zeros(64, dtype=np.uint8)])                      # the kernels read aligned words past 2-byte-aligned rows
+            got = float(emu.emu_row_dot(t, _p(w), K, _p(rec)))
+            want = oracle.vec_dot(t, K, w[:-64], yq)
+            scale = float(np.linalg.norm(oracle.dequantize(t, w[:-64], K)) * np.linalg.norm(x)) + 1e-30
+            assert abs(got - want) <= 2e-6 * scale, (K, trial, got, want)
