@@ -15,6 +15,13 @@ extern std::atomic<uint64_t> g_launches;
 void set_error(const char * fmt, ...);
 int  sm_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember it per (kernel instantiation, device), so that a
+// process that drives several B200s through the backend (one ggml device per GPU) configures every one of them.
+struct per_device_flag {
+    bool done[64] = {};
+    bool & here() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0; return done[d]; }
+};
+
 #define B200_CUDA_TRY(expr)                                                                         \
     do {                                                                                            \
         cudaError_t e_ = (expr);                                                                    \

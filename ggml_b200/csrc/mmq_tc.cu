@@ -541,8 +541,8 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
     tc_params p;
     p.y = a.dst; p.partials = partials; p.flags = flags; p.inv_scale = inv_scale; p.M = a.M; p.N = a.N;
     p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages;
-    static bool attr_set = false;
-    if (!attr_set) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc_kernel<T, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+    static per_device_flag attr_set;
+    if (!attr_set.here()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc_kernel<T, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.here() = true; }
     mmq_tc_kernel<T, HALVES><<<pl.grid, TC_THREADS, pl.smem, st>>>(map_w, map_x, p);
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;

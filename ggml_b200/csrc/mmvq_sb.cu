@@ -758,10 +758,10 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
 }
 
 template <int T, int NW, int NC> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static per_device_flag attr_set;
+    if (!attr_set.here()) {
         B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-        attr_set = true;
+        attr_set.here() = true;
     }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
     cudaLaunchConfig_t cfg = {};
