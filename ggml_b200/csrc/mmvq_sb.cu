@@ -24,6 +24,7 @@
 // (int8 activations quantized as ggml-cpu does, integer dots, f32 scaling); only the f32 summation order differs.
 #include "b200_internal.h"
 #include "b200_quants.cuh"
+#include "b200_sb_tasks.cuh"   // dp4a_us, task geometry, activation-record layout, task dot products (also compiled for the host by tests/hostemu)
 
 #include <atomic>
 #include <cstdlib>
@@ -65,41 +66,6 @@ __device__ __forceinline__ void sb_prefetch_l2(const void * src_gmem, uint32_t b
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-
-// mixed-sign dp4a: bytes of a are unsigned, bytes of b signed
-__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-// ----------------------------------------------------------------------------- task geometry
-// TASK_W weights per task, TASK_B bytes; LPR lanes per row.
-template <int T> struct sbfmt;
-template <> struct sbfmt<T_Q4_K> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 1; };
-template <> struct sbfmt<T_Q5_K> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 1; };
-template <> struct sbfmt<T_Q6_K> { static constexpr int TASK_W = 256, TASK_B = 210, LPR = 16, KQ = 1; };
-template <> struct sbfmt<T_Q4_0> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
-template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 136, LPR = 32, KQ = 0; };
-
-// Activation record in shared memory: one SB_REC-byte record per act-task (256 consecutive activations), task t at rec + t * SB_REC:
-//   +0   q    : 256 int8 (chunk j = values 16 j .. 16 j + 15 at +16 j)
-//   +256 s32  : eight int32 sums of 32 values
-//   +288 s16  : sixteen int16 sums of 16 values
-//   +320 h32  : the eight 32-sums again as int16 (operand of dp2a against packed 6-bit mins)
-//   +336 d    : Q8_K family: one float;  Q8_0 family: eight floats (fp16-rounded block scales)
-// SB_REC = 23 x 16: an odd number of 16-byte units, so lanes working on consecutive tasks hit different bank groups with every
-// LDS.128 (conflict-free), and every load address is "task base + immediate" -- no address arithmetic inside the dot products.
-constexpr int SB_REC = 368, SB_OFF_S32 = 256, SB_OFF_S16 = 288, SB_OFF_H32 = 320, SB_OFF_D = 336;
-struct sb_act {
-    int32_t ntask, bytes;
-};
-__host__ __device__ inline sb_act make_sb_act(int64_t K) {
-    sb_act A;
-    A.ntask = (int32_t)(K / 256);
-    A.bytes = A.ntask * SB_REC;
-    return A;
-}
 
 // Half a warp (16 lanes) quantizes act-task t: lane l owns values 16 l .. 16 l + 15 (= chunk l of the record), so the chunk, its
 // 16-sum and most of the amax search are lane-local; 4 shuffle rounds, and two tasks per warp run side by side.
@@ -163,289 +129,6 @@ template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const floa
             *(int32_t *)(rb + SB_OFF_S32 + 4 * (l >> 1)) = s2;
             *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)s2;          // |s2| <= 32 * 127
         }
-    }
-}
-
-__device__ __forceinline__ int4 lds128(const uint8_t * p) { return *(const int4 *)p; }
-// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (lo) / b.byte2, b.byte3 (hi); a halves signed, b bytes unsigned (su) or signed (ss)
-__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-__device__ __forceinline__ int dp2a_lo_ss(int a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-__device__ __forceinline__ int dp2a_hi_ss(int a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-template <int B> __device__ __forceinline__ int ubyte(uint32_t x) { return (int)__byte_perm(x, 0, 0x4440 + B); }             // zero-extended byte B
-// sign-extended byte B: PTX prmt in default mode replicates the sign of the selected byte when bit 3 of a selector nibble is set
-// (__byte_perm only honours 3 selector bits, hence the inline PTX)
-template <int B> __device__ __forceinline__ int sbyte(uint32_t x) {
-    int d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"((uint32_t)(B | ((8 | B) << 4) | ((8 | B) << 8) | ((8 | B) << 12))));
-    return d;
-}
-
-// ----------------------------------------------------------------------------- task dot products
-// `w` points at the task's first byte in the shared-memory stage, `rec` at the activation record, `t` = task index in the row.
-template <int T> __device__ __forceinline__ float task_dot(const uint8_t * w, const uint8_t * rec, int t);
-
-// one 64-weight chunk C of a Q4_K / Q5_K superblock: sub-block 2C in the low nibbles (scale sc0), 2C+1 in the high ones (sc1)
-template <int C, bool FIVE>
-__device__ __forceinline__ void q45_chunk(const uint8_t * qs, const uint32_t (&qh)[8], const uint8_t * a, int sc0, int sc1, int & acc_s) {
-    const int4 qa = lds128(qs + 32 * C), qb = lds128(qs + 32 * C + 16);
-    const uint32_t q[8] = { (uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w, (uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w };
-    int p0 = 0, p1 = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int4 ylo = lds128(a + (4 * C + h) * 16);                              // values 64C + 16h ..   (sub-block 2C)
-        const int4 yhi = lds128(a + (4 * C + 2 + h) * 16);                          // values 64C + 32 + 16h (sub-block 2C+1)
-        const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t qq = q[4 * h + i];
-            if constexpr (FIVE) {
-                const uint32_t hb = qh[4 * h + i] >> (2 * C);
-                p0 = __dp4a((int)((qq & 0x0F0F0F0F) | ((hb & 0x01010101) << 4)), yl[i], p0);
-                p1 = __dp4a((int)(((qq >> 4) & 0x0F0F0F0F) | ((hb & 0x02020202) << 3)), yh[i], p1);
-            } else {
-                p0 = __dp4a((int)(qq & 0x0F0F0F0F), yl[i], p0);
-                p1 = dp4a_us(qq & 0xF0F0F0F0u, yh[i], p1);                          // 16 x (high nibbles . y)
-            }
-        }
-    }
-    if constexpr (!FIVE) p1 >>= 4;                                                  // exact: a multiple of 16
-    acc_s += sc0 * p0 + sc1 * p1;
-}
-
-template <bool FIVE> __device__ __forceinline__ float q45_task(const uint8_t * w, const uint8_t * rec, int t) {
-    const uint8_t * a = rec + (size_t)t * SB_REC;
-    const int4 hdr = lds128(w);                                     // d | dmin | scales[12]
-    const int4 h32 = lds128(a + SB_OFF_H32);                        // eight 32-sums, int16
-    uint32_t qh[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    if constexpr (FIVE) {
-        const int4 ha = lds128(w + 16), hb = lds128(w + 32);
-        qh[0] = ha.x; qh[1] = ha.y; qh[2] = ha.z; qh[3] = ha.w; qh[4] = hb.x; qh[5] = hb.y; qh[6] = hb.z; qh[7] = hb.w;
-    }
-    const uint8_t * qs = w + (FIVE ? 48 : 16);
-    // the 6-bit (scale, min) pairs of get_scale_min_k4, four sub-blocks per word
-    const uint32_t s0 = hdr.y, s1 = hdr.z, s2 = hdr.w;
-    const uint32_t sc_lo = s0 & 0x3F3F3F3Fu, mn_lo = s1 & 0x3F3F3F3Fu;                                   // sub-blocks 0..3
-    const uint32_t sc_hi = (s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u);                               // sub-blocks 4..7
-    const uint32_t mn_hi = ((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u);
-    int acc_m = dp2a_lo_su(h32.x, mn_lo, 0);                        // sum_j min_j * (sum of the 32 activations of sub-block j)
-    acc_m = dp2a_hi_su(h32.y, mn_lo, acc_m);
-    acc_m = dp2a_lo_su(h32.z, mn_hi, acc_m);
-    acc_m = dp2a_hi_su(h32.w, mn_hi, acc_m);
-    int acc_s = 0;
-    q45_chunk<0, FIVE>(qs, qh, a, ubyte<0>(sc_lo), ubyte<1>(sc_lo), acc_s);
-    q45_chunk<1, FIVE>(qs, qh, a, ubyte<2>(sc_lo), ubyte<3>(sc_lo), acc_s);
-    q45_chunk<2, FIVE>(qs, qh, a, ubyte<0>(sc_hi), ubyte<1>(sc_hi), acc_s);
-    q45_chunk<3, FIVE>(qs, qh, a, ubyte<2>(sc_hi), ubyte<3>(sc_hi), acc_s);
-    const float yd = *(const float *)(a + SB_OFF_D);
-    const float d = h2f((uint32_t)hdr.x & 0xFFFF) * yd, dmin = h2f((uint32_t)hdr.x >> 16) * yd;
-    return d * (float)acc_s - dmin * (float)acc_m;
-}
-template <> __device__ __forceinline__ float task_dot<T_Q4_K>(const uint8_t * w, const uint8_t * rec, int t) { return q45_task<false>(w, rec, t); }
-template <> __device__ __forceinline__ float task_dot<T_Q5_K>(const uint8_t * w, const uint8_t * rec, int t) { return q45_task<true>(w, rec, t); }
-
-// Q4_0: task = 8 blocks of 18 bytes = 144 bytes (16-byte aligned), act-task == task
-template <> __device__ __forceinline__ float task_dot<T_Q4_0>(const uint8_t * w, const uint8_t * rec, int t) {
-    const uint8_t * a = rec + (size_t)t * SB_REC;
-    uint32_t ww[37];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { const int4 v = lds128(w + 16 * i); ww[4 * i] = v.x; ww[4 * i + 1] = v.y; ww[4 * i + 2] = v.z; ww[4 * i + 3] = v.w; }
-    ww[36] = 0;
-    const int4 sa = lds128(a + SB_OFF_S32), sb = lds128(a + SB_OFF_S32 + 16);
-    const int s32[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-    const int4 da = lds128(a + SB_OFF_D), db = lds128(a + SB_OFF_D + 16);
-    const float yd[8] = { __int_as_float(da.x), __int_as_float(da.y), __int_as_float(da.z), __int_as_float(da.w),
-                          __int_as_float(db.x), __int_as_float(db.y), __int_as_float(db.z), __int_as_float(db.w) };
-    float acc = 0.0f;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        // block b starts at byte 18 b = word 4.5 b: even b word-aligned, odd b half-word shifted (all compile-time)
-        const int w0 = (18 * b) / 4;
-        const bool odd = (b & 1) != 0;
-        uint32_t q[4];
-        uint32_t dbits;
-        if (!odd) {
-            dbits = ww[w0] & 0xFFFF;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = __funnelshift_r(ww[w0 + i], ww[w0 + i + 1], 16);
-        } else {
-            dbits = ww[w0] >> 16;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = ww[w0 + 1 + i];
-        }
-        const int4 ylo = lds128(a + (2 * b) * 16), yhi = lds128(a + (2 * b + 1) * 16);
-        const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
-        int p0 = 0, p1 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            p0 = __dp4a((int)(q[i] & 0x0F0F0F0F), yl[i], p0);
-            p1 = dp4a_us(q[i] & 0xF0F0F0F0u, yh[i], p1);
-        }
-        const int s = p0 + (p1 >> 4) - 8 * s32[b];
-        acc += (float)s * h2f(dbits) * yd[b];
-    }
-    return acc;
-}
-
-// Q8_0: task = 4 blocks of 34 bytes = 136 bytes (8-byte aligned); two tasks per 256-value act-task
-template <> __device__ __forceinline__ float task_dot<T_Q8_0>(const uint8_t * w, const uint8_t * rec, int t) {
-    uint32_t ww[35];
-#pragma unroll
-    for (int i = 0; i < 17; ++i) { const uint2 v = *(const uint2 *)(w + 8 * i); ww[2 * i] = v.x; ww[2 * i + 1] = v.y; }
-    ww[34] = 0;
-    const int at = t >> 1, hf = t & 1;                                             // act-task, which half of it
-    const uint8_t * a = rec + (size_t)at * SB_REC + hf * 128;                      // q chunks 8 hf .. 8 hf + 7
-    const int4 dv = lds128(rec + (size_t)at * SB_REC + SB_OFF_D + hf * 16);
-    const float yd[4] = { __int_as_float(dv.x), __int_as_float(dv.y), __int_as_float(dv.z), __int_as_float(dv.w) };
-    float acc = 0.0f;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int w0 = (34 * b) / 4;
-        const bool odd = (b & 1) != 0;                                             // 34 b mod 4 = 2 for odd b
-        const uint32_t dbits = odd ? (ww[w0] >> 16) : (ww[w0] & 0xFFFF);
-        const int4 y0 = lds128(a + (2 * b) * 16), y1 = lds128(a + (2 * b + 1) * 16);
-        const int y[8] = { y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w };
-        int s = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t q = odd ? ww[w0 + 1 + i] : __funnelshift_r(ww[w0 + i], ww[w0 + i + 1], 16);
-            s = __dp4a((int)q, y[i], s);
-        }
-        acc += (float)s * (h2f(dbits) * yd[b]);
-    }
-    return acc;
-}
-
-// Q6_K: 210-byte superblocks are only 2-byte aligned: aligned words + one run-time funnel shift (0 or 16 bits)
-template <> __device__ __forceinline__ float task_dot<T_Q6_K>(const uint8_t * w, const uint8_t * rec, int t) {
-    const uint8_t * a = rec + (size_t)t * SB_REC;
-    const uint32_t sh = ((uint32_t)(uintptr_t)w & 2) * 8;
-    const uint32_t * wa = (const uint32_t *)((uintptr_t)w & ~(uintptr_t)3);
-    auto word = [&](int i) { return __funnelshift_r(wa[i], wa[i + 1], sh); };     // 32-bit word i of the superblock
-    const int4 sa = lds128(a + SB_OFF_S16), sb = lds128(a + SB_OFF_S16 + 16);
-    const int s16w[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };       // sixteen 16-sums, int16 pairs
-    int tot = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t scw0 = word(48 + 2 * h), scw1 = word(48 + 2 * h + 1);       // int8 scales[8h .. 8h+7]
-        // value = d * sc * (q - 32): the "- 32" part is sum_g sc_g * (16-sum)_g, two groups per dp2a
-        int off = dp2a_lo_ss(s16w[4 * h], scw0, 0);
-        off = dp2a_hi_ss(s16w[4 * h + 1], scw0, off);
-        off = dp2a_lo_ss(s16w[4 * h + 2], scw1, off);
-        off = dp2a_hi_ss(s16w[4 * h + 3], scw1, off);
-        tot -= 32 * off;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {                                              // l-range 16 j .. 16 j + 15
-            int p[4] = { 0, 0, 0, 0 };
-            const int4 yv0 = lds128(a + (8 * h + j) * 16), yv1 = lds128(a + (8 * h + j + 2) * 16);
-            const int4 yv2 = lds128(a + (8 * h + j + 4) * 16), yv3 = lds128(a + (8 * h + j + 6) * 16);
-            const int ya[4] = { yv0.x, yv0.y, yv0.z, yv0.w }, yb[4] = { yv1.x, yv1.y, yv1.z, yv1.w };
-            const int yc[4] = { yv2.x, yv2.y, yv2.z, yv2.w }, yd4[4] = { yv3.x, yv3.y, yv3.z, yv3.w };
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t la = word(16 * h + 4 * j + i), lb = word(16 * h + 8 + 4 * j + i), qh = word(32 + 8 * h + 4 * j + i);
-                p[0] = __dp4a((int)((la & 0x0F0F0F0F)        | ((qh << 4) & 0x30303030)), ya[i], p[0]);
-                p[1] = __dp4a((int)((lb & 0x0F0F0F0F)        | ((qh << 2) & 0x30303030)), yb[i], p[1]);
-                p[2] = __dp4a((int)(((la >> 4) & 0x0F0F0F0F) | ( qh       & 0x30303030)), yc[i], p[2]);
-                p[3] = __dp4a((int)(((lb >> 4) & 0x0F0F0F0F) | ((qh >> 2) & 0x30303030)), yd4[i], p[3]);
-            }
-            // scales[8h + j + 2g] multiplies p[g]
-            if (j == 0) tot += sbyte<0>(scw0) * p[0] + sbyte<2>(scw0) * p[1] + sbyte<0>(scw1) * p[2] + sbyte<2>(scw1) * p[3];
-            else        tot += sbyte<1>(scw0) * p[0] + sbyte<3>(scw0) * p[1] + sbyte<1>(scw1) * p[2] + sbyte<3>(scw1) * p[3];
-        }
-    }
-    const float d = h2f(word(52) & 0xFFFF) * *(const float *)(a + SB_OFF_D);
-    return d * (float)tot;
-}
-
-// ----------------------------------------------------------------------------- several activation columns (2 <= n <= 8)
-// The weights of a task are decoded once and dotted with every column's record (records of column c at rec + c * rec_stride).
-// Per column the floating-point operations are exactly those of the n = 1 path, so column c of an n-column product is
-// bit-identical to the n = 1 product with that column.
-template <int C, bool FIVE, int NC>
-__device__ __forceinline__ void q45_chunk_nc(const uint8_t * qs, const uint32_t (&qh)[8], const uint8_t * a0, int rec_stride, int ncols, int sc0, int sc1, int (&acc_s)[NC]) {
-    const int4 qa = lds128(qs + 32 * C), qb = lds128(qs + 32 * C + 16);
-    const uint32_t q[8] = { (uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w, (uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w };
-    uint32_t lo[8], hi[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if constexpr (FIVE) {
-            const uint32_t hb = qh[i] >> (2 * C);
-            lo[i] = (q[i] & 0x0F0F0F0F) | ((hb & 0x01010101) << 4);
-            hi[i] = ((q[i] >> 4) & 0x0F0F0F0F) | ((hb & 0x02020202) << 3);
-        } else {
-            lo[i] = q[i] & 0x0F0F0F0F;
-            hi[i] = q[i] & 0xF0F0F0F0u;                                               // 16 x the high nibbles
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        if (c < ncols) {
-            const uint8_t * a = a0 + c * rec_stride;
-            int p0 = 0, p1 = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int4 ylo = lds128(a + (4 * C + h) * 16), yhi = lds128(a + (4 * C + 2 + h) * 16);
-                const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    p0 = __dp4a((int)lo[4 * h + i], yl[i], p0);
-                    if constexpr (FIVE) p1 = __dp4a((int)hi[4 * h + i], yh[i], p1);
-                    else                p1 = dp4a_us(hi[4 * h + i], yh[i], p1);
-                }
-            }
-            if constexpr (!FIVE) p1 >>= 4;
-            acc_s[c] += sc0 * p0 + sc1 * p1;
-        }
-    }
-}
-
-template <bool FIVE, int NC>
-__device__ __forceinline__ void q45_task_nc(const uint8_t * w, const uint8_t * rec, int rec_stride, int t, int ncols, float (&acc)[NC]) {
-    const uint8_t * a0 = rec + (size_t)t * SB_REC;
-    const int4 hdr = lds128(w);
-    uint32_t qh[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    if constexpr (FIVE) {
-        const int4 ha = lds128(w + 16), hb = lds128(w + 32);
-        qh[0] = ha.x; qh[1] = ha.y; qh[2] = ha.z; qh[3] = ha.w; qh[4] = hb.x; qh[5] = hb.y; qh[6] = hb.z; qh[7] = hb.w;
-    }
-    const uint8_t * qs = w + (FIVE ? 48 : 16);
-    const uint32_t s0 = hdr.y, s1 = hdr.z, s2 = hdr.w;
-    const uint32_t sc_lo = s0 & 0x3F3F3F3Fu, mn_lo = s1 & 0x3F3F3F3Fu;
-    const uint32_t sc_hi = (s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u);
-    const uint32_t mn_hi = ((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u);
-    int acc_s[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) acc_s[c] = 0;
-    q45_chunk_nc<0, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<0>(sc_lo), ubyte<1>(sc_lo), acc_s);
-    q45_chunk_nc<1, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<2>(sc_lo), ubyte<3>(sc_lo), acc_s);
-    q45_chunk_nc<2, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<0>(sc_hi), ubyte<1>(sc_hi), acc_s);
-    q45_chunk_nc<3, FIVE, NC>(qs, qh, a0, rec_stride, ncols, ubyte<2>(sc_hi), ubyte<3>(sc_hi), acc_s);
-    const float wd = h2f((uint32_t)hdr.x & 0xFFFF), wm = h2f((uint32_t)hdr.x >> 16);
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        if (c < ncols) {
-            const uint8_t * a = a0 + c * rec_stride;
-            const int4 h32 = lds128(a + SB_OFF_H32);
-            int acc_m = dp2a_lo_su(h32.x, mn_lo, 0);
-            acc_m = dp2a_hi_su(h32.y, mn_lo, acc_m);
-            acc_m = dp2a_lo_su(h32.z, mn_hi, acc_m);
-            acc_m = dp2a_hi_su(h32.w, mn_hi, acc_m);
-            const float yd = *(const float *)(a + SB_OFF_D);
-            const float d = wd * yd, dmin = wm * yd;
-            acc[c] += d * (float)acc_s[c] - dmin * (float)acc_m;
-        }
-    }
-}
-
-template <int T, int NC>
-__device__ __forceinline__ void task_dot_nc(const uint8_t * w, const uint8_t * rec, int rec_stride, int t, int ncols, float (&acc)[NC]) {
-    if constexpr (T == T_Q4_K)      q45_task_nc<false, NC>(w, rec, rec_stride, t, ncols, acc);
-    else if constexpr (T == T_Q5_K) q45_task_nc<true, NC>(w, rec, rec_stride, t, ncols, acc);
-    else {
-        // other formats: the single-column dot product per column (the weight bytes are re-read from shared memory, not from HBM)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) if (c < ncols) acc[c] += task_dot<T>(w, rec + c * rec_stride, t);
     }
 }
 

@@ -2,8 +2,10 @@
 // compiled for the host through tests/hostemu/shim, exported with a C ABI for tests/test_hostemu_kernel_logic.py.
 // It checks indexing / bit manipulation of the block formats on the CPU; it says nothing about scheduling, memory movement or
 // the PTX-level instructions (dp2a, prmt, tcgen05 ...) of the fast kernels — those are covered by the `-m gpu` parity tests.
+#define B200_HOST_EMU 1
 #include "cuda_shim.h"
 #include "../../ggml_b200/csrc/b200_dequant.cuh"
+#include "../../ggml_b200/csrc/b200_sb_tasks.cuh"
 
 using namespace b200;
 
@@ -27,6 +29,16 @@ template <int T> static void dequant_all(const uint8_t * src, float * dst, int64
 
 #define FOR_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_Q2_K) X(T_Q3_K)
 
+template <int T> static float sb_row(const uint8_t * row, int64_t K, const uint8_t * rec) {
+    float acc = 0.0f;
+    for (int t = 0; t < (int)(K / sbfmt<T>::TASK_W); ++t) acc += task_dot<T>(row + (size_t)t * sbfmt<T>::TASK_B, rec, t);
+    return acc;
+}
+template <int T> static void sb_row_nc(const uint8_t * row, int64_t K, const uint8_t * rec, int rec_stride, int ncols, float * out) {
+    float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int t = 0; t < (int)(K / sbfmt<T>::TASK_W); ++t) task_dot_nc<T, 8>(row + (size_t)t * sbfmt<T>::TASK_B, rec, rec_stride, t, ncols, acc);
+    for (int c = 0; c < 8; ++c) out[c] = acc[c];
+}
 extern "C" {
 
 // offsets of the activation record sections: out = { off_bs, off_d, off_s (or -1), bytes }
@@ -53,6 +65,36 @@ int emu_dequant(int type, const uint8_t * src, float * dst, int64_t n) {
     switch (type) {
 #define X(T) case T: dequant_all<T>(src, dst, n); return 0;
         FOR_TYPES(X)
+#undef X
+        default: return -1;
+    }
+}
+
+// ---- the superblock mat-vec kernel's per-lane task dot products (b200_sb_tasks.cuh); hot-path formats only
+#define FOR_SB_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K)
+// out = { TASK_W, TASK_B, SB_REC, SB_OFF_S32, SB_OFF_S16, SB_OFF_H32, SB_OFF_D }
+int emu_sb_geometry(int type, int32_t * out) {
+    switch (type) {
+#define X(T) case T: out[0] = sbfmt<T>::TASK_W; out[1] = sbfmt<T>::TASK_B; break;
+        FOR_SB_TYPES(X)
+#undef X
+        default: return -1;
+    }
+    out[2] = SB_REC; out[3] = SB_OFF_S32; out[4] = SB_OFF_S16; out[5] = SB_OFF_H32; out[6] = SB_OFF_D;
+    return 0;
+}
+float emu_sb_row_dot(int type, const uint8_t * row, int64_t K, const uint8_t * rec) {
+    switch (type) {
+#define X(T) case T: return sb_row<T>(row, K, rec);
+        FOR_SB_TYPES(X)
+#undef X
+        default: return NAN;
+    }
+}
+int emu_sb_row_dot_nc(int type, const uint8_t * row, int64_t K, const uint8_t * rec, int rec_stride, int ncols, float * out) {
+    switch (type) {
+#define X(T) case T: sb_row_nc<T>(row, K, rec, rec_stride, ncols, out); return 0;
+        FOR_SB_TYPES(X)
 #undef X
         default: return -1;
     }

@@ -39,10 +39,18 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift)
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (shift & 31));
 }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel) {     // 3-bit selectors, as the CUDA intrinsic
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+static inline int   __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 static inline int   __float2int_rn(float v) { return (int)nearbyintf(v); }
 template <typename V> static inline V __shfl_xor_sync(unsigned, V v, int) { return v; }   // stub: collectives are not emulated
 using std::min;

@@ -20,7 +20,7 @@ def emu():
     out = EMU / "_build"
     out.mkdir(exist_ok=True)
     so = out / "libhostemu.so"
-    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h", ROOT / "ggml_b200" / "csrc" / "b200_quants.cuh", ROOT / "ggml_b200" / "csrc" / "b200_dequant.cuh"]
+    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh")]
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
                f"-I{EMU / 'shim'}", "-o", str(so), str(EMU / "hostemu.cpp")]
@@ -33,6 +33,10 @@ def emu():
     L.emu_act_layout.argtypes = [C.c_int64, C.c_int, C.c_void_p]
     L.emu_row_bytes.restype = C.c_int64
     L.emu_row_bytes.argtypes = [C.c_int, C.c_int64]
+    L.emu_sb_geometry.argtypes = [C.c_int, C.c_void_p]
+    L.emu_sb_row_dot.restype = C.c_float
+    L.emu_sb_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.emu_sb_row_dot_nc.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return L
 
 
@@ -109,3 +113,63 @@ def test_unit_dot_products_match_oracle(t, emu, oracle):
             want = oracle.vec_dot(t, K, w[:-64], yq)
             scale = float(np.linalg.norm(oracle.dequantize(t, w[:-64], K)) * np.linalg.norm(x)) + 1e-30
             assert abs(got - want) <= 2e-6 * scale, (K, trial, got, want)
+
+
+def sb_record(emu, oracle, t, x):
+    """the superblock kernel's per-act-task activation records (q | s32 | s16 | h32 | d) built from the ORACLE's quantized activations"""
+    geo = np.zeros(7, dtype=np.int32)
+    assert emu.emu_sb_geometry(t, _p(geo)) == 0
+    _, _, REC, OFF_S32, OFF_S16, OFF_H32, OFF_D = (int(v) for v in geo)
+    K = x.size
+    ntask = K // 256
+    vdt = oracle.vec_dot_type(t)
+    yq = oracle.quantize(vdt, x, simd_q8_0=(vdt == O.Q8_0))
+    if vdt == O.Q8_K:
+        b = yq.reshape(-1, 292)
+        q = b[:, 4:260].copy().view(np.int8).reshape(ntask, 256)
+        d = b[:, :4].copy().view(np.float32).reshape(ntask, 1)
+    else:
+        b = yq.reshape(-1, 34)
+        q = b[:, 2:].copy().view(np.int8).reshape(ntask, 256)
+        d = b[:, :2].copy().view(np.float16).astype(np.float32).reshape(ntask, 8)
+    rec = np.zeros(ntask * REC + 64, dtype=np.uint8)
+    for tt in range(ntask):
+        base = tt * REC
+        rec[base:base + 256] = q[tt].view(np.uint8)
+        s32 = q[tt].reshape(8, 32).astype(np.int32).sum(1).astype(np.int32)
+        s16 = q[tt].reshape(16, 16).astype(np.int32).sum(1).astype(np.int16)
+        rec[base + OFF_S32:base + OFF_S32 + 32] = s32.view(np.uint8)
+        rec[base + OFF_S16:base + OFF_S16 + 32] = s16.view(np.uint8)
+        rec[base + OFF_H32:base + OFF_H32 + 16] = s32.astype(np.int16).view(np.uint8)
+        dd = d[tt].astype(np.float32)
+        rec[base + OFF_D:base + OFF_D + 4 * dd.size] = dd.view(np.uint8)
+    return rec, yq, ntask * REC
+
+
+HOT = list(O.HOT_TYPES)
+
+
+@pytest.mark.parametrize("t", HOT, ids=[O.TYPE_NAMES[t] for t in HOT])
+def test_superblock_task_dot_products_match_oracle(t, emu, oracle):
+    """mmvq_sb.cu's per-lane task dot products (packed 6-bit scale decode, dp2a mins, in-place high nibbles, 2-byte-aligned Q6_K
+    words, ...) and their multi-column form: against the oracle, and column by column bit-identical to the single-column form"""
+    rng = np.random.default_rng(500 + t)
+    for K in (256, 768, 4096):
+        xs = [rng.uniform(-1, 1, K).astype(np.float32) for _ in range(5)]
+        recs = [sb_record(emu, oracle, t, x) for x in xs]
+        stride = recs[0][2]
+        allrec = np.concatenate([r[0][:stride] for r in recs] + [np.zeros(64, dtype=np.uint8)])
+        for trial in range(4):
+            w = O.random_blocks(t, K // oracle.blck_size(t), rng)
+            wp = np.concatenate([w, np.zeros(64, dtype=np.uint8)])
+            singles = []
+            for (rec, yq, _), x in zip(recs, xs):
+                got = float(emu.emu_sb_row_dot(t, _p(wp), K, _p(rec)))
+                want = oracle.vec_dot(t, K, w, yq)
+                scale = float(np.linalg.norm(oracle.dequantize(t, w, K)) * np.linalg.norm(x)) + 1e-30
+                assert abs(got - want) <= 2e-6 * scale, (K, trial, got, want)
+                singles.append(np.float32(got))
+            out = np.zeros(8, dtype=np.float32)
+            assert emu.emu_sb_row_dot_nc(t, _p(wp), K, _p(allrec), stride, 5, _p(out)) == 0
+            assert np.array_equal(out[:5].view(np.uint32), np.array(singles, dtype=np.float32).view(np.uint32)), (K, trial)
+            assert np.all(out[5:] == 0)
