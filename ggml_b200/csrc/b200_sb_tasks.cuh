@@ -26,6 +26,11 @@ template <> struct sbfmt<T_Q5_K> { static constexpr int TASK_W = 256, TASK_B = 1
 template <> struct sbfmt<T_Q6_K> { static constexpr int TASK_W = 256, TASK_B = 210, LPR = 16, KQ = 1; };
 template <> struct sbfmt<T_Q4_0> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 136, LPR = 32, KQ = 0; };
+// SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu); not yet dispatched by mmvq_sb.cu (their rows
+// run on the generic kernel until the fast path has been validated and measured on a B200)
+template <> struct sbfmt<T_Q5_0> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 0; };
+template <> struct sbfmt<T_Q2_K> { static constexpr int TASK_W = 256, TASK_B = 84,  LPR = 16, KQ = 1; };
+template <> struct sbfmt<T_Q3_K> { static constexpr int TASK_W = 256, TASK_B = 110, LPR = 16, KQ = 1; };
 
 // Activation record in shared memory: one SB_REC-byte record per act-task (256 consecutive activations), task t at rec + t * SB_REC:
 //   +0   q    : 256 int8 (chunk j = values 16 j .. 16 j + 15 at +16 j)
@@ -250,6 +255,107 @@ template <> __device__ __forceinline__ float task_dot<T_Q6_K>(const uint8_t * w,
     }
     const float d = h2f(word(52) & 0xFFFF) * *(const float *)(a + SB_OFF_D);
     return d * (float)tot;
+}
+
+// ---- SURVEY §8f-2 formats (host-verified; see sbfmt above) --------------------------------------------------------------
+// Q5_0: task = 8 blocks of 22 bytes = 176 bytes (16-byte aligned); block = d (2 B), 32 fifth bits (4 B), 16 nibble bytes
+template <> __device__ __forceinline__ float task_dot<T_Q5_0>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    uint32_t ww[45];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) { const int4 v = lds128(w + 16 * i); ww[4 * i] = v.x; ww[4 * i + 1] = v.y; ww[4 * i + 2] = v.z; ww[4 * i + 3] = v.w; }
+    ww[44] = 0;
+    const int4 sa = lds128(a + SB_OFF_S32), sb = lds128(a + SB_OFF_S32 + 16);
+    const int s32[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+    const int4 da = lds128(a + SB_OFF_D), db = lds128(a + SB_OFF_D + 16);
+    const float yd[8] = { __int_as_float(da.x), __int_as_float(da.y), __int_as_float(da.z), __int_as_float(da.w),
+                          __int_as_float(db.x), __int_as_float(db.y), __int_as_float(db.z), __int_as_float(db.w) };
+    float acc = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        // block b starts at byte 22 b = word 5.5 b: even b word-aligned, odd b half-word shifted (all compile-time)
+        const int w0 = (22 * b) / 4;
+        const bool odd = (b & 1) != 0;
+        uint32_t q[4], dbits, qh;
+        if (!odd) {
+            dbits = ww[w0] & 0xFFFF;
+            qh = __funnelshift_r(ww[w0], ww[w0 + 1], 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = __funnelshift_r(ww[w0 + 1 + i], ww[w0 + 2 + i], 16);
+        } else {
+            dbits = ww[w0] >> 16;
+            qh = ww[w0 + 1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = ww[w0 + 2 + i];
+        }
+        const int4 ylo = lds128(a + (2 * b) * 16), yhi = lds128(a + (2 * b + 1) * 16);
+        const int y[8] = { ylo.x, ylo.y, ylo.z, ylo.w, yhi.x, yhi.y, yhi.z, yhi.w };
+        const int s = q5_block_dot(q, qh, y) - 16 * s32[b];
+        acc += (h2f(dbits) * yd[b]) * (float)s;
+    }
+    return acc;
+}
+
+// Q2_K: 84-byte superblocks are 4-byte aligned: 32-bit loads.  scales[16] (low nibble scale, high nibble min) words 0..3,
+// qs words 4..19, d | dmin word 20.  Group g = 8 h + 2 j + l / 16 of the superblock = 16-value chunk g of the activations.
+template <> __device__ __forceinline__ float task_dot<T_Q2_K>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    const uint32_t * wp = (const uint32_t *)w;
+    const int4 sa = lds128(a + SB_OFF_S16), sb = lds128(a + SB_OFF_S16 + 16);
+    const int s16w[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };       // sixteen 16-sums, int16 pairs
+    int isum = 0, msum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                                  // scale word k = groups 4k .. 4k+3
+        const uint32_t scw = wp[k];
+        const uint32_t mins = (scw >> 4) & 0x0F0F0F0Fu, scs = scw & 0x0F0F0F0Fu;
+        msum = dp2a_lo_su(s16w[2 * k], mins, msum);
+        msum = dp2a_hi_su(s16w[2 * k + 1], mins, msum);
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+            const int g = 4 * k + gg, h = g >> 3, jj = (g >> 1) & 3, half16 = g & 1;
+            const int4 yv = lds128(a + g * 16);
+            const int y[4] = { yv.x, yv.y, yv.z, yv.w };
+            int p = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p = __dp4a((int)((wp[4 + 8 * h + 4 * half16 + i] >> (2 * jj)) & 0x03030303u), y[i], p);
+            const int sc = gg == 0 ? ubyte<0>(scs) : gg == 1 ? ubyte<1>(scs) : gg == 2 ? ubyte<2>(scs) : ubyte<3>(scs);
+            isum += sc * p;
+        }
+    }
+    const float yd = *(const float *)(a + SB_OFF_D);
+    const float dall = yd * h2f(wp[20] & 0xFFFF), dmin = yd * h2f(wp[20] >> 16);
+    return dall * (float)isum - dmin * (float)msum;
+}
+
+// Q3_K: 110-byte superblocks are 2-byte aligned (as Q6_K): hmask words 0..7, qs words 8..23, scales words 24..26, d = low half of word 27
+template <> __device__ __forceinline__ float task_dot<T_Q3_K>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    const uint32_t sh = ((uint32_t)(uintptr_t)w & 2) * 8;
+    const uint32_t * wa = (const uint32_t *)((uintptr_t)w & ~(uintptr_t)3);
+    auto word = [&](int i) { return __funnelshift_r(wa[i], wa[i + 1], sh); };
+    // sixteen 6-bit scales (value - 32), four per word: low nibbles from bytes 0..7, two high bits each from bytes 8..11
+    const uint32_t s0 = word(24), s1 = word(25), s2 = word(26);
+    const uint32_t aux[4] = { ( s0       & 0x0F0F0F0Fu) | (( s2       & 0x03030303u) << 4),
+                              ( s1       & 0x0F0F0F0Fu) | (((s2 >> 2) & 0x03030303u) << 4),
+                              ((s0 >> 4) & 0x0F0F0F0Fu) | (((s2 >> 4) & 0x03030303u) << 4),
+                              ((s1 >> 4) & 0x0F0F0F0Fu) | (((s2 >> 6) & 0x03030303u) << 4) };
+    int isum = 0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        const int h = g >> 3, jj = (g >> 1) & 3, half16 = g & 1, bit = 4 * h + jj;
+        const int4 yv = lds128(a + g * 16);
+        const int y[4] = { yv.x, yv.y, yv.z, yv.w };
+        int p = 0, low = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            p   = __dp4a((int)((word(8 + 8 * h + 4 * half16 + i) >> (2 * jj)) & 0x03030303u), y[i], p);
+            low = __dp4a((int)(~(word(4 * half16 + i) >> bit) & 0x01010101u), y[i], low);        // activations whose high bit is clear
+        }
+        const uint32_t ax = aux[g >> 2];
+        const int sc = ((g & 3) == 0 ? ubyte<0>(ax) : (g & 3) == 1 ? ubyte<1>(ax) : (g & 3) == 2 ? ubyte<2>(ax) : ubyte<3>(ax)) - 32;
+        isum += sc * (p - 4 * low);
+    }
+    return (h2f(word(27) & 0xFFFF) * *(const float *)(a + SB_OFF_D)) * (float)isum;
 }
 
 // ----------------------------------------------------------------------------- several activation columns (2 <= n <= 8)
