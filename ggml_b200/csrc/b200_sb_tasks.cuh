@@ -29,6 +29,8 @@ template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 1
 // SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu); not yet dispatched by mmvq_sb.cu (their rows
 // run on the generic kernel until the fast path has been validated and measured on a B200)
 template <> struct sbfmt<T_Q5_0> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 0; };
+template <> struct sbfmt<T_Q4_1> { static constexpr int TASK_W = 256, TASK_B = 160, LPR = 16, KQ = 0; };   // needs the Q8_1 s values: see task_dot<T_Q4_1>
+template <> struct sbfmt<T_Q5_1> { static constexpr int TASK_W = 256, TASK_B = 192, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q2_K> { static constexpr int TASK_W = 256, TASK_B = 84,  LPR = 16, KQ = 1; };
 template <> struct sbfmt<T_Q3_K> { static constexpr int TASK_W = 256, TASK_B = 110, LPR = 16, KQ = 1; };
 
@@ -292,6 +294,64 @@ template <> __device__ __forceinline__ float task_dot<T_Q5_0>(const uint8_t * w,
         const int y[8] = { ylo.x, ylo.y, ylo.z, ylo.w, yhi.x, yhi.y, yhi.z, yhi.w };
         const int s = q5_block_dot(q, qh, y) - 16 * s32[b];
         acc += (h2f(dbits) * yd[b]) * (float)s;
+    }
+    return acc;
+}
+
+// Q4_1 / Q5_1 (block minimum m): the CPU backend pairs them with Q8_1 activations, whose s = fp16(d_unrounded * sum of the block's
+// codes) multiplies m.  The eight s values of an act-task are expected as fp16 in the H32 slot of the record, which the Q8_0 family
+// does not otherwise use (the in-kernel quantizer does not write them yet: these two dot products are host-verified only).
+__device__ __forceinline__ void sb_load_q8_1_s(const uint8_t * a, float (&ys)[8]) {
+    const int4 sv = lds128(a + SB_OFF_H32);
+    const uint32_t u[4] = { (uint32_t)sv.x, (uint32_t)sv.y, (uint32_t)sv.z, (uint32_t)sv.w };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ys[2 * i] = h2f(u[i] & 0xFFFF); ys[2 * i + 1] = h2f(u[i] >> 16); }
+}
+// Q4_1: task = 8 blocks of 20 bytes = 160 bytes; block = d | m (one word), 16 nibble bytes (four words)
+template <> __device__ __forceinline__ float task_dot<T_Q4_1>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    uint32_t ww[40];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { const int4 v = lds128(w + 16 * i); ww[4 * i] = v.x; ww[4 * i + 1] = v.y; ww[4 * i + 2] = v.z; ww[4 * i + 3] = v.w; }
+    const int4 da = lds128(a + SB_OFF_D), db = lds128(a + SB_OFF_D + 16);
+    const float yd[8] = { __int_as_float(da.x), __int_as_float(da.y), __int_as_float(da.z), __int_as_float(da.w),
+                          __int_as_float(db.x), __int_as_float(db.y), __int_as_float(db.z), __int_as_float(db.w) };
+    float ys[8];
+    sb_load_q8_1_s(a, ys);
+    float acc = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int4 ylo = lds128(a + (2 * b) * 16), yhi = lds128(a + (2 * b + 1) * 16);
+        const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
+        int p0 = 0, p1 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            p0 = __dp4a((int)(ww[5 * b + 1 + i] & 0x0F0F0F0F), yl[i], p0);
+            p1 = dp4a_us(ww[5 * b + 1 + i] & 0xF0F0F0F0u, yh[i], p1);
+        }
+        acc += (h2f(ww[5 * b] & 0xFFFF) * yd[b]) * (float)(p0 + (p1 >> 4)) + h2f(ww[5 * b] >> 16) * ys[b];
+    }
+    return acc;
+}
+// Q5_1: task = 8 blocks of 24 bytes = 192 bytes; block = d | m, 32 fifth bits, 16 nibble bytes (six words)
+template <> __device__ __forceinline__ float task_dot<T_Q5_1>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    uint32_t ww[48];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { const int4 v = lds128(w + 16 * i); ww[4 * i] = v.x; ww[4 * i + 1] = v.y; ww[4 * i + 2] = v.z; ww[4 * i + 3] = v.w; }
+    const int4 da = lds128(a + SB_OFF_D), db = lds128(a + SB_OFF_D + 16);
+    const float yd[8] = { __int_as_float(da.x), __int_as_float(da.y), __int_as_float(da.z), __int_as_float(da.w),
+                          __int_as_float(db.x), __int_as_float(db.y), __int_as_float(db.z), __int_as_float(db.w) };
+    float ys[8];
+    sb_load_q8_1_s(a, ys);
+    float acc = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int4 ylo = lds128(a + (2 * b) * 16), yhi = lds128(a + (2 * b + 1) * 16);
+        const int y[8] = { ylo.x, ylo.y, ylo.z, ylo.w, yhi.x, yhi.y, yhi.z, yhi.w };
+        const uint32_t q[4] = { ww[6 * b + 2], ww[6 * b + 3], ww[6 * b + 4], ww[6 * b + 5] };
+        const int s = q5_block_dot(q, ww[6 * b + 1], y);
+        acc += (h2f(ww[6 * b] & 0xFFFF) * yd[b]) * (float)s + h2f(ww[6 * b] >> 16) * ys[b];
     }
     return acc;
 }

@@ -71,7 +71,7 @@ int emu_dequant(int type, const uint8_t * src, float * dst, int64_t n) {
 }
 
 // ---- the superblock mat-vec kernel's per-lane task dot products (b200_sb_tasks.cuh); hot-path formats only
-#define FOR_SB_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q5_0) X(T_Q2_K) X(T_Q3_K)
+#define FOR_SB_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q5_0) X(T_Q2_K) X(T_Q3_K) X(T_Q4_1) X(T_Q5_1)
 // out = { TASK_W, TASK_B, SB_REC, SB_OFF_S32, SB_OFF_S16, SB_OFF_H32, SB_OFF_D }
 int emu_sb_geometry(int type, int32_t * out) {
     switch (type) {

@@ -129,9 +129,11 @@ def sb_record(emu, oracle, t, x):
         q = b[:, 4:260].copy().view(np.int8).reshape(ntask, 256)
         d = b[:, :4].copy().view(np.float32).reshape(ntask, 1)
     else:
-        b = yq.reshape(-1, 34)
-        q = b[:, 2:].copy().view(np.int8).reshape(ntask, 256)
+        hb = 2 if vdt == O.Q8_0 else 4                        # Q8_0: d | 32 codes;  Q8_1: d | s | 32 codes
+        b = yq.reshape(-1, 32 + hb)
+        q = b[:, hb:].copy().view(np.int8).reshape(ntask, 256)
         d = b[:, :2].copy().view(np.float16).astype(np.float32).reshape(ntask, 8)
+        s_half = b[:, 2:4].copy().reshape(ntask, 16) if vdt == O.Q8_1 else None
     rec = np.zeros(ntask * REC + 64, dtype=np.uint8)
     for tt in range(ntask):
         base = tt * REC
@@ -141,12 +143,14 @@ def sb_record(emu, oracle, t, x):
         rec[base + OFF_S32:base + OFF_S32 + 32] = s32.view(np.uint8)
         rec[base + OFF_S16:base + OFF_S16 + 32] = s16.view(np.uint8)
         rec[base + OFF_H32:base + OFF_H32 + 16] = s32.astype(np.int16).view(np.uint8)
+        if vdt == O.Q8_1:                                     # formats with a minimum: the H32 slot carries the eight fp16 s values
+            rec[base + OFF_H32:base + OFF_H32 + 16] = s_half[tt]
         dd = d[tt].astype(np.float32)
         rec[base + OFF_D:base + OFF_D + 4 * dd.size] = dd.view(np.uint8)
     return rec, yq, ntask * REC
 
 
-HOT = list(O.HOT_TYPES) + [O.Q5_0, O.Q2_K, O.Q3_K]      # + the next formats whose fast-path task dot products are written (not yet dispatched)
+HOT = list(O.HOT_TYPES) + [O.Q5_0, O.Q2_K, O.Q3_K, O.Q4_1, O.Q5_1]      # + the next formats whose fast-path task dot products are written (not yet dispatched)
 
 
 @pytest.mark.parametrize("t", HOT, ids=[O.TYPE_NAMES[t] for t in HOT])
