@@ -418,6 +418,84 @@ template <> __device__ __forceinline__ float task_dot<T_Q3_K>(const uint8_t * w,
     return (h2f(word(27) & 0xFFFF) * *(const float *)(a + SB_OFF_D)) * (float)isum;
 }
 
+// ----------------------------------------------------------------------------- two rows against one activation task
+// Round-2 experiment, host-verified only (not dispatched): the same lane dots task t of TWO weight rows, so every activation chunk
+// is read from shared memory once instead of twice (activation reads are ~47 % of the kernel's shared-memory traffic,
+// profiles/r01_gemv_q4k_final.md).  Per row the operations are those of q45_task, so results are bit-identical to task_dot.
+template <int C, bool FIVE>
+__device__ __forceinline__ void q45_chunk2(const uint8_t * qs0, const uint8_t * qs1, const uint32_t (&qh0)[8], const uint32_t (&qh1)[8], const uint8_t * a,
+                                            int sa0, int sa1, int sb0, int sb1, int & acc0, int & acc1) {
+    const int4 qa0 = lds128(qs0 + 32 * C), qb0 = lds128(qs0 + 32 * C + 16), qa1 = lds128(qs1 + 32 * C), qb1 = lds128(qs1 + 32 * C + 16);
+    const uint32_t q0[8] = { (uint32_t)qa0.x, (uint32_t)qa0.y, (uint32_t)qa0.z, (uint32_t)qa0.w, (uint32_t)qb0.x, (uint32_t)qb0.y, (uint32_t)qb0.z, (uint32_t)qb0.w };
+    const uint32_t q1[8] = { (uint32_t)qa1.x, (uint32_t)qa1.y, (uint32_t)qa1.z, (uint32_t)qa1.w, (uint32_t)qb1.x, (uint32_t)qb1.y, (uint32_t)qb1.z, (uint32_t)qb1.w };
+    int p00 = 0, p01 = 0, p10 = 0, p11 = 0;                       // p<row><low/high sub-block>
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int4 ylo = lds128(a + (4 * C + h) * 16), yhi = lds128(a + (4 * C + 2 + h) * 16);
+        const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x0 = q0[4 * h + i], x1 = q1[4 * h + i];
+            if constexpr (FIVE) {
+                const uint32_t h0 = qh0[4 * h + i] >> (2 * C), h1 = qh1[4 * h + i] >> (2 * C);
+                p00 = __dp4a((int)((x0 & 0x0F0F0F0F) | ((h0 & 0x01010101) << 4)), yl[i], p00);
+                p01 = __dp4a((int)(((x0 >> 4) & 0x0F0F0F0F) | ((h0 & 0x02020202) << 3)), yh[i], p01);
+                p10 = __dp4a((int)((x1 & 0x0F0F0F0F) | ((h1 & 0x01010101) << 4)), yl[i], p10);
+                p11 = __dp4a((int)(((x1 >> 4) & 0x0F0F0F0F) | ((h1 & 0x02020202) << 3)), yh[i], p11);
+            } else {
+                p00 = __dp4a((int)(x0 & 0x0F0F0F0F), yl[i], p00);
+                p01 = dp4a_us(x0 & 0xF0F0F0F0u, yh[i], p01);
+                p10 = __dp4a((int)(x1 & 0x0F0F0F0F), yl[i], p10);
+                p11 = dp4a_us(x1 & 0xF0F0F0F0u, yh[i], p11);
+            }
+        }
+    }
+    if constexpr (!FIVE) { p01 >>= 4; p11 >>= 4; }
+    acc0 += sa0 * p00 + sb0 * p01;
+    acc1 += sa1 * p10 + sb1 * p11;
+}
+
+template <bool FIVE> __device__ __forceinline__ void q45_task2(const uint8_t * w0, const uint8_t * w1, const uint8_t * rec, int t, float & r0, float & r1) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    const int4 hdr0 = lds128(w0), hdr1 = lds128(w1);
+    const int4 h32 = lds128(a + SB_OFF_H32);
+    uint32_t qh0[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, qh1[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if constexpr (FIVE) {
+        const int4 a0 = lds128(w0 + 16), b0 = lds128(w0 + 32), a1 = lds128(w1 + 16), b1 = lds128(w1 + 32);
+        qh0[0] = a0.x; qh0[1] = a0.y; qh0[2] = a0.z; qh0[3] = a0.w; qh0[4] = b0.x; qh0[5] = b0.y; qh0[6] = b0.z; qh0[7] = b0.w;
+        qh1[0] = a1.x; qh1[1] = a1.y; qh1[2] = a1.z; qh1[3] = a1.w; qh1[4] = b1.x; qh1[5] = b1.y; qh1[6] = b1.z; qh1[7] = b1.w;
+    }
+    const uint8_t * qs0 = w0 + (FIVE ? 48 : 16), * qs1 = w1 + (FIVE ? 48 : 16);
+    int accs[2] = { 0, 0 }, accm[2];
+    uint32_t sc_lo[2], sc_hi[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int4 & hdr = r == 0 ? hdr0 : hdr1;
+        const uint32_t s0 = hdr.y, s1 = hdr.z, s2 = hdr.w;
+        const uint32_t mn_lo = s1 & 0x3F3F3F3Fu, mn_hi = ((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u);
+        sc_lo[r] = s0 & 0x3F3F3F3Fu;
+        sc_hi[r] = (s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u);
+        int m = dp2a_lo_su(h32.x, mn_lo, 0);
+        m = dp2a_hi_su(h32.y, mn_lo, m);
+        m = dp2a_lo_su(h32.z, mn_hi, m);
+        m = dp2a_hi_su(h32.w, mn_hi, m);
+        accm[r] = m;
+    }
+    q45_chunk2<0, FIVE>(qs0, qs1, qh0, qh1, a, ubyte<0>(sc_lo[0]), ubyte<0>(sc_lo[1]), ubyte<1>(sc_lo[0]), ubyte<1>(sc_lo[1]), accs[0], accs[1]);
+    q45_chunk2<1, FIVE>(qs0, qs1, qh0, qh1, a, ubyte<2>(sc_lo[0]), ubyte<2>(sc_lo[1]), ubyte<3>(sc_lo[0]), ubyte<3>(sc_lo[1]), accs[0], accs[1]);
+    q45_chunk2<2, FIVE>(qs0, qs1, qh0, qh1, a, ubyte<0>(sc_hi[0]), ubyte<0>(sc_hi[1]), ubyte<1>(sc_hi[0]), ubyte<1>(sc_hi[1]), accs[0], accs[1]);
+    q45_chunk2<3, FIVE>(qs0, qs1, qh0, qh1, a, ubyte<2>(sc_hi[0]), ubyte<2>(sc_hi[1]), ubyte<3>(sc_hi[0]), ubyte<3>(sc_hi[1]), accs[0], accs[1]);
+    const float yd = *(const float *)(a + SB_OFF_D);
+    {
+        const float d = h2f((uint32_t)hdr0.x & 0xFFFF) * yd, dmin = h2f((uint32_t)hdr0.x >> 16) * yd;
+        r0 = d * (float)accs[0] - dmin * (float)accm[0];
+    }
+    {
+        const float d = h2f((uint32_t)hdr1.x & 0xFFFF) * yd, dmin = h2f((uint32_t)hdr1.x >> 16) * yd;
+        r1 = d * (float)accs[1] - dmin * (float)accm[1];
+    }
+}
+
 // ----------------------------------------------------------------------------- several activation columns (2 <= n <= 8)
 // The weights of a task are decoded once and dotted with every column's record (records of column c at rec + c * rec_stride).
 // Per column the floating-point operations are exactly those of the n = 1 path, so column c of an n-column product is

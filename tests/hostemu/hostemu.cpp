@@ -83,6 +83,19 @@ int emu_sb_geometry(int type, int32_t * out) {
     out[2] = SB_REC; out[3] = SB_OFF_S32; out[4] = SB_OFF_S16; out[5] = SB_OFF_H32; out[6] = SB_OFF_D;
     return 0;
 }
+// two rows sharing the activation loads (Q4_K / Q5_K): out[0], out[1]
+int emu_sb_two_row_dot(int type, const uint8_t * row0, const uint8_t * row1, int64_t K, const uint8_t * rec, float * out) {
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int t = 0; t < (int)(K / 256); ++t) {
+        float r0, r1;
+        if (type == T_Q4_K)      q45_task2<false>(row0 + (size_t)t * 144, row1 + (size_t)t * 144, rec, t, r0, r1);
+        else if (type == T_Q5_K) q45_task2<true>(row0 + (size_t)t * 176, row1 + (size_t)t * 176, rec, t, r0, r1);
+        else return -1;
+        a0 += r0; a1 += r1;
+    }
+    out[0] = a0; out[1] = a1;
+    return 0;
+}
 float emu_sb_row_dot(int type, const uint8_t * row, int64_t K, const uint8_t * rec) {
     switch (type) {
 #define X(T) case T: return sb_row<T>(row, K, rec);

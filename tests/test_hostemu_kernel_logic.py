@@ -36,6 +36,7 @@ def emu():
     L.emu_sb_geometry.argtypes = [C.c_int, C.c_void_p]
     L.emu_sb_row_dot.restype = C.c_float
     L.emu_sb_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.emu_sb_two_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.emu_sb_row_dot_nc.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return L
 
@@ -177,3 +178,19 @@ def test_superblock_task_dot_products_match_oracle(t, emu, oracle):
             assert emu.emu_sb_row_dot_nc(t, _p(wp), K, _p(allrec), stride, 5, _p(out)) == 0
             assert np.array_equal(out[:5].view(np.uint32), np.array(singles, dtype=np.float32).view(np.uint32)), (K, trial)
             assert np.all(out[5:] == 0)
+
+
+@pytest.mark.parametrize("t", [O.Q4_K, O.Q5_K], ids=["q4_K", "q5_K"])
+def test_two_row_task_dot_is_bit_identical_to_single_row(t, emu, oracle):
+    """the round-2 variant that shares the activation loads between two weight rows (not dispatched yet)"""
+    rng = np.random.default_rng(600 + t)
+    for K in (256, 4096):
+        x = rng.uniform(-1, 1, K).astype(np.float32)
+        rec, _, _ = sb_record(emu, oracle, t, x)
+        for trial in range(4):
+            w0 = np.concatenate([O.random_blocks(t, K // 256, rng), np.zeros(64, dtype=np.uint8)])
+            w1 = np.concatenate([O.random_blocks(t, K // 256, rng), np.zeros(64, dtype=np.uint8)])
+            out = np.zeros(2, dtype=np.float32)
+            assert emu.emu_sb_two_row_dot(t, _p(w0), _p(w1), K, _p(rec), _p(out)) == 0
+            want = np.array([emu.emu_sb_row_dot(t, _p(w0), K, _p(rec)), emu.emu_sb_row_dot(t, _p(w1), K, _p(rec))], dtype=np.float32)
+            assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (K, trial)
