@@ -53,6 +53,72 @@ __host__ __device__ inline sb_act make_sb_act(int64_t K) {
     return A;
 }
 
+// ----------------------------------------------------------------------------- in-kernel activation quantizer
+// Half a warp (16 lanes) quantizes act-task t: lane l owns values 16 l .. 16 l + 15 (= chunk l of the record), so the chunk, its
+// 16-sum and most of the amax search are lane-local; 4 shuffle rounds, and two tasks per warp run side by side.
+// Shuffles use xor distances < 16, i.e. they never cross the half-warp; all 32 lanes must call this together.
+// Numerics: exactly ggml-cpu's quantize_row_q8_K (KQ) / AVX2 quantize_row_q8_0 (see b200_quants.cuh).
+template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * rec, int t) {
+    const int l = threadIdx.x & 15;
+    float v[16];
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 f = load_f4(x + (size_t)t * 256 + 16 * l + 4 * i); v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    }
+    uint8_t * rb = rec + (size_t)t * SB_REC;
+    int q[16];
+    if constexpr (KQ) {
+        float amax = 0.0f, vmax = 0.0f; int imax = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float ax = fabsf(v[i]); if (ax > amax) { amax = ax; vmax = v[i]; imax = 16 * l + i; } }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const float oa = __shfl_xor_sync(0xffffffffu, amax, o), ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+            const int   oi = __shfl_xor_sync(0xffffffffu, imax, o);
+            if (oa > amax || (oa == amax && oi < imax)) { amax = oa; vmax = ov; imax = oi; }
+        }
+        float d = 0.0f;
+        if (amax != 0.0f) {
+            const float iscale = __fdiv_rn(-127.0f, vmax);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] = min(127, __float2int_rn(iscale * v[i]));
+            d = __fdiv_rn(1.0f, iscale);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] = 0;
+        }
+        if (l == 0 && valid) *(float *)(rb + SB_OFF_D) = d;
+    } else {
+        float amax = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));               // 32-value block = lanes 2b, 2b+1
+        const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) q[i] = __float2int_rn(v[i] * id);
+        if ((l & 1) == 0 && valid) *(float *)(rb + SB_OFF_D + 4 * (l >> 1)) = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
+    }
+    int4 pk; int s = 0;
+    int * pw = &pk.x;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        pw[w] = (int)((uint32_t)(q[4 * w] & 0xFF) | ((uint32_t)(q[4 * w + 1] & 0xFF) << 8) | ((uint32_t)(q[4 * w + 2] & 0xFF) << 16) | ((uint32_t)(q[4 * w + 3] & 0xFF) << 24));
+        s += q[4 * w] + q[4 * w + 1] + q[4 * w + 2] + q[4 * w + 3];
+    }
+    const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);
+    if (valid) {
+        *(int4 *)(rb + 16 * l) = pk;
+        *(int16_t *)(rb + SB_OFF_S16 + 2 * l) = (int16_t)s;
+        if ((l & 1) == 0) {
+            *(int32_t *)(rb + SB_OFF_S32 + 4 * (l >> 1)) = s2;
+            *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)s2;          // |s2| <= 32 * 127
+        }
+    }
+}
+
 __device__ __forceinline__ int4 lds128(const uint8_t * p) { return *(const int4 *)p; }
 // d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (lo) / b.byte2, b.byte3 (hi); a halves signed, b bytes unsigned (su) or signed (ss)
 #ifndef B200_HOST_EMU

@@ -70,6 +70,27 @@ int emu_dequant(int type, const uint8_t * src, float * dst, int64_t n) {
     }
 }
 
+// ---- activation quantizers, one emulated warp (32 host threads in lockstep; shuffles = exchanges between barriers)
+// generic-path record (q | bs | d | s): quantize_act_kernel's cta_quantize_row with a one-warp CTA
+int emu_quantize_record(int kq, const float * x, int64_t K, uint8_t * rec) {
+    const act_layout L = make_act_layout(K, kq != 0);
+    warp_emu::run([&] { if (kq) cta_quantize_row<true>(x, K, rec, L); else cta_quantize_row<false>(x, K, rec, L); });
+    return L.bytes;
+}
+// superblock-kernel records (SB_REC bytes per act-task): the kernel's quantization loop for one column, one warp
+int emu_sb_quantize(int kq, const float * x, int64_t K, uint8_t * rec) {
+    const int ntask = (int)(K / 256);
+    warp_emu::run([&] {
+        const int lane = (int)(threadIdx.x & 31);
+        for (int i0 = 0; i0 < ntask; i0 += 2) {
+            const int t = i0 + (lane >> 4);
+            const bool ok = t < ntask;
+            if (kq) sb_quantize_task_h<true>(x, ok, rec, ok ? t : 0); else sb_quantize_task_h<false>(x, ok, rec, ok ? t : 0);
+        }
+    });
+    return ntask * SB_REC;
+}
+
 // ---- the superblock mat-vec kernel's per-lane task dot products (b200_sb_tasks.cuh); hot-path formats only
 #define FOR_SB_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q5_0) X(T_Q2_K) X(T_Q3_K) X(T_Q4_1) X(T_Q5_1)
 // out = { TASK_W, TASK_B, SB_REC, SB_OFF_S32, SB_OFF_S16, SB_OFF_H32, SB_OFF_D }

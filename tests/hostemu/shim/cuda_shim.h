@@ -8,6 +8,8 @@
 #include <cstring>
 #include <algorithm>
 #include <immintrin.h>
+#include <pthread.h>
+#include <thread>
 
 #define __host__
 #define __device__
@@ -23,7 +25,8 @@ struct uint2  { unsigned x, y; };
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 struct dim3_shim { unsigned x = 0, y = 0, z = 0; };
-static dim3_shim threadIdx, blockDim, blockIdx;
+static thread_local dim3_shim threadIdx;          // one host thread per emulated lane (warp_emu below)
+static dim3_shim blockDim, blockIdx;
 
 struct __half { uint16_t x; };
 static inline __half __ushort_as_half(unsigned short u) { return __half{u}; }
@@ -52,6 +55,34 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline int   __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 static inline int   __float2int_rn(float v) { return (int)nearbyintf(v); }
-template <typename V> static inline V __shfl_xor_sync(unsigned, V v, int) { return v; }   // stub: collectives are not emulated
+// Warp collectives: when a warp is being emulated (warp_emu::run: 32 host threads in lockstep, one per lane) a shuffle is an
+// exchange through a shared slot array between two barriers; outside of it, the identity (single-lane code paths).
+namespace warp_emu {
+    inline pthread_barrier_t & barrier() { static pthread_barrier_t b; return b; }
+    inline uint64_t * slots() { static uint64_t s[32]; return s; }
+    inline bool & active() { static bool a = false; return a; }
+    template <typename F> inline void run(F && fn) {            // fn() is executed by 32 lanes; every lane must reach the same shuffles
+        pthread_barrier_init(&barrier(), nullptr, 32);
+        active() = true;
+        blockDim.x = 32;
+        std::thread th[32];
+        for (int l = 0; l < 32; ++l) th[l] = std::thread([&, l] { threadIdx.x = (unsigned)l; fn(); });
+        for (auto & t : th) t.join();
+        active() = false;
+        pthread_barrier_destroy(&barrier());
+    }
+}
+template <typename V> static inline V __shfl_xor_sync(unsigned, V v, int o) {
+    static_assert(sizeof(V) <= 8, "shuffle payload");
+    if (!warp_emu::active()) return v;
+    const int lane = (int)(threadIdx.x & 31);
+    uint64_t raw = 0; std::memcpy(&raw, &v, sizeof(V));
+    warp_emu::slots()[lane] = raw;
+    pthread_barrier_wait(&warp_emu::barrier());
+    const uint64_t got = warp_emu::slots()[lane ^ o];
+    pthread_barrier_wait(&warp_emu::barrier());
+    V r; std::memcpy(&r, &got, sizeof(V));
+    return r;
+}
 using std::min;
 using std::max;

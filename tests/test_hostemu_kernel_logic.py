@@ -22,7 +22,7 @@ def emu():
     so = out / "libhostemu.so"
     srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh")]
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
-        cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
+        cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
                f"-I{EMU / 'shim'}", "-o", str(so), str(EMU / "hostemu.cpp")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
@@ -33,6 +33,8 @@ def emu():
     L.emu_act_layout.argtypes = [C.c_int64, C.c_int, C.c_void_p]
     L.emu_row_bytes.restype = C.c_int64
     L.emu_row_bytes.argtypes = [C.c_int, C.c_int64]
+    L.emu_quantize_record.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.emu_sb_quantize.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.emu_sb_geometry.argtypes = [C.c_int, C.c_void_p]
     L.emu_sb_row_dot.restype = C.c_float
     L.emu_sb_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
@@ -70,7 +72,10 @@ def act_record(emu, oracle, t, x):
         d = b[:, :2].copy().view(np.float16).astype(np.float32).reshape(-1)
         if vdt == O.Q8_1:
             assert off_s >= 0, "the record needs the Q8_1 's' section for formats with a minimum"
-            s = b[:, 2:4].copy().view(np.float16).astype(np.float32).reshape(-1)
+        if off_s >= 0:                                        # the device quantizer fills 's' for the whole Q8_0 family (same codes and d as Q8_0)
+            b1 = oracle.quantize(O.Q8_1, x).reshape(-1, 36)
+            assert np.array_equal(b1[:, 4:].reshape(-1).view(np.int8), q)
+            s = b1[:, 2:4].copy().view(np.float16).astype(np.float32).reshape(-1)
             rec[off_s:off_s + 4 * s.size] = s.view(np.uint8)
     rec[:K] = q.view(np.uint8)
     bsum = q.reshape(-1, 16).astype(np.int32).sum(1).astype(np.int16)
@@ -194,3 +199,31 @@ def test_two_row_task_dot_is_bit_identical_to_single_row(t, emu, oracle):
             assert emu.emu_sb_two_row_dot(t, _p(w0), _p(w1), K, _p(rec), _p(out)) == 0
             want = np.array([emu.emu_sb_row_dot(t, _p(w0), K, _p(rec)), emu.emu_sb_row_dot(t, _p(w1), K, _p(rec))], dtype=np.float32)
             assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (K, trial)
+
+
+def _inputs(K):
+    rng = np.random.default_rng(700 + K)
+    z = np.load(ROOT / "tests" / "golden" / "act_q8.npz")["x"]
+    reps = (K + z.size - 1) // z.size
+    return [np.tile(z, reps)[:K].astype(np.float32), rng.uniform(-1, 1, K).astype(np.float32), (rng.standard_normal(K) * 7).astype(np.float32),
+            np.zeros(K, dtype=np.float32), (np.round(rng.uniform(-127, 127, K)) / 2).astype(np.float32)]
+
+
+@pytest.mark.parametrize("t", [O.Q4_0, O.Q4_1, O.Q4_K], ids=["q8_0-family", "q8_1-family", "q8_K-family"])
+def test_activation_quantizers_in_an_emulated_warp(t, emu, oracle):
+    """the device activation quantizers (warp shuffles emulated by 32 host threads in lockstep) are bit-exact against the oracle's
+    restatement of the CPU backend's quantizers: both record layouts, including the Q8_1 's' section"""
+    kq = bool(emu.emu_type_is_kquant(t))
+    for K in (256, 768, 3072) + (() if kq else (32, 96, 160, 288)):          # the Q8_0 family also takes K % 256 != 0
+        for x in _inputs(K):
+            want_rec, _ = act_record(emu, oracle, t, x)
+            got = np.zeros(want_rec.size, dtype=np.uint8)
+            n = emu.emu_quantize_record(int(kq), _p(x), K, _p(got))
+            if kq:                                            # bsums of all-zero superblocks: the reference leaves them uninitialised, the device writes 0
+                pass
+            assert np.array_equal(got[:n], want_rec[:n]), (K,)
+            if t != O.Q4_1 and K % 256 == 0:                  # the superblock-kernel record (whole act-tasks; no Q8_1 's' yet)
+                want_sb, _, nb = sb_record(emu, oracle, t, x)
+                got_sb = np.zeros(want_sb.size, dtype=np.uint8)
+                assert emu.emu_sb_quantize(int(kq), _p(x), K, _p(got_sb)) == nb
+                assert np.array_equal(got_sb[:nb], want_sb[:nb]), (K,)
