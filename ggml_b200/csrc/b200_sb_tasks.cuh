@@ -26,8 +26,8 @@ template <> struct sbfmt<T_Q5_K> { static constexpr int TASK_W = 256, TASK_B = 1
 template <> struct sbfmt<T_Q6_K> { static constexpr int TASK_W = 256, TASK_B = 210, LPR = 16, KQ = 1; };
 template <> struct sbfmt<T_Q4_0> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 136, LPR = 32, KQ = 0; };
-// SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu); not yet dispatched by mmvq_sb.cu (their rows
-// run on the generic kernel until the fast path has been validated and measured on a B200)
+// SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu).  Q5_0 / Q2_K / Q3_K are dispatched by mmvq_sb.cu
+// (GPU check: tests/test_gpu_next_formats.py); Q4_1 / Q5_1 wait for the Q8_1 's' values in the record and run on the generic kernel
 template <> struct sbfmt<T_Q5_0> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q4_1> { static constexpr int TASK_W = 256, TASK_B = 160, LPR = 16, KQ = 0; };   // needs the Q8_1 s values: see task_dot<T_Q4_1>
 template <> struct sbfmt<T_Q5_1> { static constexpr int TASK_W = 256, TASK_B = 192, LPR = 16, KQ = 0; };

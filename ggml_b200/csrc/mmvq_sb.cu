@@ -418,6 +418,10 @@ bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {
         case T_Q4_K: return make_sb_plan<T_Q4_K>(a, pl);
         case T_Q5_K: return make_sb_plan<T_Q5_K>(a, pl);
         case T_Q6_K: return make_sb_plan<T_Q6_K>(a, pl);
+        // next formats whose task dot products do not need the Q8_1 's' values (host-verified; tests/test_gpu_next_formats.py)
+        case T_Q5_0: return make_sb_plan<T_Q5_0>(a, pl);
+        case T_Q2_K: return make_sb_plan<T_Q2_K>(a, pl);
+        case T_Q3_K: return make_sb_plan<T_Q3_K>(a, pl);
         default: return false;
     }
 }
@@ -429,6 +433,9 @@ int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml
         case T_Q4_K: return launch_sb<T_Q4_K>(a, ga, st, ep);
         case T_Q5_K: return launch_sb<T_Q5_K>(a, ga, st, ep);
         case T_Q6_K: return launch_sb<T_Q6_K>(a, ga, st, ep);
+        case T_Q5_0: return launch_sb<T_Q5_0>(a, ga, st, ep);
+        case T_Q2_K: return launch_sb<T_Q2_K>(a, ga, st, ep);
+        case T_Q3_K: return launch_sb<T_Q3_K>(a, ga, st, ep);
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }
