@@ -26,8 +26,8 @@ template <> struct sbfmt<T_Q5_K> { static constexpr int TASK_W = 256, TASK_B = 1
 template <> struct sbfmt<T_Q6_K> { static constexpr int TASK_W = 256, TASK_B = 210, LPR = 16, KQ = 1; };
 template <> struct sbfmt<T_Q4_0> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 136, LPR = 32, KQ = 0; };
-// SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu).  Q5_0 / Q2_K / Q3_K are dispatched by mmvq_sb.cu
-// (GPU check: tests/test_gpu_next_formats.py); Q4_1 / Q5_1 wait for the Q8_1 's' values in the record and run on the generic kernel
+// SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu), dispatched by mmvq_sb.cu
+// like the hot-path formats (GPU check: tests/test_gpu_next_formats.py)
 template <> struct sbfmt<T_Q5_0> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q4_1> { static constexpr int TASK_W = 256, TASK_B = 160, LPR = 16, KQ = 0; };   // needs the Q8_1 s values: see task_dot<T_Q4_1>
 template <> struct sbfmt<T_Q5_1> { static constexpr int TASK_W = 256, TASK_B = 192, LPR = 16, KQ = 0; };
@@ -58,7 +58,9 @@ __host__ __device__ inline sb_act make_sb_act(int64_t K) {
 // 16-sum and most of the amax search are lane-local; 4 shuffle rounds, and two tasks per warp run side by side.
 // Shuffles use xor distances < 16, i.e. they never cross the half-warp; all 32 lanes must call this together.
 // Numerics: exactly ggml-cpu's quantize_row_q8_K (KQ) / AVX2 quantize_row_q8_0 (see b200_quants.cuh).
-template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * rec, int t) {
+// Q81S (Q8_0 family only): the H32 slot receives block_q8_1.s = fp16(d_unrounded * sum of the block's codes) instead of the int16 sums
+// (weight formats with a minimum, Q4_1 / Q5_1).  Q81S = false is the code path of the hot-path formats, unchanged.
+template <bool KQ, bool Q81S = false> __device__ __forceinline__ void sb_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * rec, int t) {
     const int l = threadIdx.x & 15;
     float v[16];
     if (valid) {
@@ -70,6 +72,7 @@ template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const floa
     }
     uint8_t * rb = rec + (size_t)t * SB_REC;
     int q[16];
+    float dun = 0.0f;                                            // Q8_0 family: the block's unrounded scale amax / 127
     if constexpr (KQ) {
         float amax = 0.0f, vmax = 0.0f; int imax = 0;
 #pragma unroll
@@ -99,7 +102,8 @@ template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const floa
         const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) q[i] = __float2int_rn(v[i] * id);
-        if ((l & 1) == 0 && valid) *(float *)(rb + SB_OFF_D + 4 * (l >> 1)) = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
+        dun = __fdiv_rn(amax, 127.0f);
+        if ((l & 1) == 0 && valid) *(float *)(rb + SB_OFF_D + 4 * (l >> 1)) = __half2float(__float2half_rn(dun));
     }
     int4 pk; int s = 0;
     int * pw = &pk.x;
@@ -114,7 +118,8 @@ template <bool KQ> __device__ __forceinline__ void sb_quantize_task_h(const floa
         *(int16_t *)(rb + SB_OFF_S16 + 2 * l) = (int16_t)s;
         if ((l & 1) == 0) {
             *(int32_t *)(rb + SB_OFF_S32 + 4 * (l >> 1)) = s2;
-            *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)s2;          // |s2| <= 32 * 127
+            if constexpr (!KQ && Q81S) *(__half *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = __float2half_rn(__fmul_rn(dun, (float)s2));
+            else                       *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)s2;   // |s2| <= 32 * 127
         }
     }
 }

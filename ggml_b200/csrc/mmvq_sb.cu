@@ -178,7 +178,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
         const int i = i0 + (lane >> 4);
         const bool ok = i < p.ncols * p.A.ntask;
         const int c = NC == 1 ? 0 : (ok ? i / p.A.ntask : 0), t = NC == 1 ? i : (ok ? i % p.A.ntask : 0);
-        sb_quantize_task_h<F::KQ != 0>(p.x + (size_t)c * p.x_stride, ok, rec + c * p.A.bytes, t);
+        sb_quantize_task_h<F::KQ != 0, needs_s<T>::value>(p.x + (size_t)c * p.x_stride, ok, rec + c * p.A.bytes, t);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");        // consumers only
 
@@ -418,7 +418,9 @@ bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {
         case T_Q4_K: return make_sb_plan<T_Q4_K>(a, pl);
         case T_Q5_K: return make_sb_plan<T_Q5_K>(a, pl);
         case T_Q6_K: return make_sb_plan<T_Q6_K>(a, pl);
-        // next formats whose task dot products do not need the Q8_1 's' values (host-verified; tests/test_gpu_next_formats.py)
+        // next formats (host-verified task dots and quantizer; GPU check: tests/test_gpu_next_formats.py)
+        case T_Q4_1: return make_sb_plan<T_Q4_1>(a, pl);
+        case T_Q5_1: return make_sb_plan<T_Q5_1>(a, pl);
         case T_Q5_0: return make_sb_plan<T_Q5_0>(a, pl);
         case T_Q2_K: return make_sb_plan<T_Q2_K>(a, pl);
         case T_Q3_K: return make_sb_plan<T_Q3_K>(a, pl);
@@ -433,6 +435,8 @@ int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml
         case T_Q4_K: return launch_sb<T_Q4_K>(a, ga, st, ep);
         case T_Q5_K: return launch_sb<T_Q5_K>(a, ga, st, ep);
         case T_Q6_K: return launch_sb<T_Q6_K>(a, ga, st, ep);
+        case T_Q4_1: return launch_sb<T_Q4_1>(a, ga, st, ep);
+        case T_Q5_1: return launch_sb<T_Q5_1>(a, ga, st, ep);
         case T_Q5_0: return launch_sb<T_Q5_0>(a, ga, st, ep);
         case T_Q2_K: return launch_sb<T_Q2_K>(a, ga, st, ep);
         case T_Q3_K: return launch_sb<T_Q3_K>(a, ga, st, ep);

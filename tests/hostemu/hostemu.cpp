@@ -78,14 +78,16 @@ int emu_quantize_record(int kq, const float * x, int64_t K, uint8_t * rec) {
     return L.bytes;
 }
 // superblock-kernel records (SB_REC bytes per act-task): the kernel's quantization loop for one column, one warp
-int emu_sb_quantize(int kq, const float * x, int64_t K, uint8_t * rec) {
+int emu_sb_quantize(int kq, const float * x, int64_t K, uint8_t * rec, int with_q8_1_s) {
     const int ntask = (int)(K / 256);
     warp_emu::run([&] {
         const int lane = (int)(threadIdx.x & 31);
         for (int i0 = 0; i0 < ntask; i0 += 2) {
             const int t = i0 + (lane >> 4);
             const bool ok = t < ntask;
-            if (kq) sb_quantize_task_h<true>(x, ok, rec, ok ? t : 0); else sb_quantize_task_h<false>(x, ok, rec, ok ? t : 0);
+            if (kq) sb_quantize_task_h<true>(x, ok, rec, ok ? t : 0);
+            else if (with_q8_1_s) sb_quantize_task_h<false, true>(x, ok, rec, ok ? t : 0);
+            else sb_quantize_task_h<false>(x, ok, rec, ok ? t : 0);
         }
     });
     return ntask * SB_REC;

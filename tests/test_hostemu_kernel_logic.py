@@ -34,7 +34,7 @@ def emu():
     L.emu_row_bytes.restype = C.c_int64
     L.emu_row_bytes.argtypes = [C.c_int, C.c_int64]
     L.emu_quantize_record.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
-    L.emu_sb_quantize.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.emu_sb_quantize.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     L.emu_sb_geometry.argtypes = [C.c_int, C.c_void_p]
     L.emu_sb_row_dot.restype = C.c_float
     L.emu_sb_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
@@ -222,8 +222,8 @@ def test_activation_quantizers_in_an_emulated_warp(t, emu, oracle):
             if kq:                                            # bsums of all-zero superblocks: the reference leaves them uninitialised, the device writes 0
                 pass
             assert np.array_equal(got[:n], want_rec[:n]), (K,)
-            if t != O.Q4_1 and K % 256 == 0:                  # the superblock-kernel record (whole act-tasks; no Q8_1 's' yet)
+            if K % 256 == 0:                                  # the superblock-kernel record (whole act-tasks); Q4_1: Q8_1 's' in the H32 slot
                 want_sb, _, nb = sb_record(emu, oracle, t, x)
                 got_sb = np.zeros(want_sb.size, dtype=np.uint8)
-                assert emu.emu_sb_quantize(int(kq), _p(x), K, _p(got_sb)) == nb
+                assert emu.emu_sb_quantize(int(kq), _p(x), K, _p(got_sb), int(t == O.Q4_1)) == nb
                 assert np.array_equal(got_sb[:nb], want_sb[:nb]), (K,)
