@@ -6,6 +6,7 @@
 #include "cuda_shim.h"
 #include "../../ggml_b200/csrc/b200_dequant.cuh"
 #include "../../ggml_b200/csrc/b200_sb_tasks.cuh"
+#include "../../ggml_b200/csrc/b200_tc_dequant.cuh"
 
 using namespace b200;
 
@@ -28,6 +29,21 @@ template <int T> static void dequant_all(const uint8_t * src, float * dst, int64
 }
 
 #define FOR_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_Q2_K) X(T_Q3_K)
+
+// tcgen05 GEMM operand preparation: one W row -> K fp16 values (swizzle key 0: the 8 chunks of a K-step land in order)
+template <int T> static void tc_row(const uint8_t * row, int64_t K, uint16_t * out) {
+    constexpr int UK = tcfmt<T>::UNIT_KSTEPS, UW = tcfmt<T>::UNIT_WORDS;
+    const int64_t nunits = K / (64 * UK);
+    const size_t unit_bytes = (size_t)row_bytes(T, 64 * UK);
+    for (int64_t u = 0; u < nunits; ++u) {
+        uint32_t regs[UW];
+        tc_load_unit<T>(row + u * unit_bytes, regs);
+        uint8_t * dst = (uint8_t *)(out + (u * UK) * 64);
+        dq64<T, 0>(regs, dst, 0);
+        dq64<T, 1>(regs, dst + 128, 0);
+        if constexpr (UK == 4) { dq64<T, 2>(regs, dst + 256, 0); dq64<T, 3>(regs, dst + 384, 0); }
+    }
+}
 
 template <int T> static float sb_row(const uint8_t * row, int64_t K, const uint8_t * rec) {
     float acc = 0.0f;
@@ -91,6 +107,17 @@ int emu_sb_quantize(int kq, const float * x, int64_t K, uint8_t * rec, int with_
         }
     });
     return ntask * SB_REC;
+}
+
+// ---- GEMM operand preparation (b200_tc_dequant.cuh): K fp16 values of one packed row
+#define FOR_TC_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K)
+int emu_tc_dequant_row(int type, const uint8_t * row, int64_t K, uint16_t * out) {
+    switch (type) {
+#define X(T) case T: tc_row<T>(row, K, out); return 0;
+        FOR_TC_TYPES(X)
+#undef X
+        default: return -1;
+    }
 }
 
 // ---- the superblock mat-vec kernel's per-lane task dot products (b200_sb_tasks.cuh); hot-path formats only

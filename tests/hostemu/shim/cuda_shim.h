@@ -33,6 +33,16 @@ static inline __half __ushort_as_half(unsigned short u) { return __half{u}; }
 static inline float  __half2float(__half h) { return _cvtsh_ss(h.x); }
 static inline __half __float2half_rn(float f) { return __half{(uint16_t)_cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT)}; }
 
+// packed halves: every operation is computed exactly (double) and rounded once to fp16, as the hardware does
+struct __half2 { __half x, y; };
+static inline __half h_rn(double v) { return __float2half_rn((float)v); }   // float(v) is exact or innocuously double-rounded: |mantissa| >= 2 * 11 + 2
+static inline __half2 __float2half2_rn(float f) { const __half h = __float2half_rn(f); return __half2{h, h}; }
+static inline __half2 __hsub2(__half2 a, __half2 b) { return __half2{h_rn((double)__half2float(a.x) - __half2float(b.x)), h_rn((double)__half2float(a.y) - __half2float(b.y))}; }
+static inline __half2 __hmul2(__half2 a, __half2 b) { return __half2{h_rn((double)__half2float(a.x) * __half2float(b.x)), h_rn((double)__half2float(a.y) * __half2float(b.y))}; }
+static inline __half2 __hfma2(__half2 a, __half2 b, __half2 c) {
+    return __half2{h_rn((double)__half2float(a.x) * __half2float(b.x) + __half2float(c.x)), h_rn((double)__half2float(a.y) * __half2float(b.y) + __half2float(c.y))};
+}
+
 static inline int __dp4a(int a, int b, int c) {                       // signed x signed bytes
     for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
     return c;

@@ -20,7 +20,7 @@ def emu():
     out = EMU / "_build"
     out.mkdir(exist_ok=True)
     so = out / "libhostemu.so"
-    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh")]
+    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh", "b200_tc_dequant.cuh")]
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
                f"-I{EMU / 'shim'}", "-o", str(so), str(EMU / "hostemu.cpp")]
@@ -33,6 +33,7 @@ def emu():
     L.emu_act_layout.argtypes = [C.c_int64, C.c_int, C.c_void_p]
     L.emu_row_bytes.restype = C.c_int64
     L.emu_row_bytes.argtypes = [C.c_int, C.c_int64]
+    L.emu_tc_dequant_row.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.emu_quantize_record.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.emu_sb_quantize.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     L.emu_sb_geometry.argtypes = [C.c_int, C.c_void_p]
@@ -227,3 +228,28 @@ def test_activation_quantizers_in_an_emulated_warp(t, emu, oracle):
                 got_sb = np.zeros(want_sb.size, dtype=np.uint8)
                 assert emu.emu_sb_quantize(int(kq), _p(x), K, _p(got_sb), int(t == O.Q4_1)) == nb
                 assert np.array_equal(got_sb[:nb], want_sb[:nb]), (K,)
+
+
+TC_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K]
+
+
+@pytest.mark.parametrize("t", TC_TYPES, ids=[O.TYPE_NAMES[t] for t in TC_TYPES])
+def test_gemm_operand_dequantization_matches_oracle(t, emu, oracle):
+    """mmq_tc.cu's packed-half dequantization (integer code -> 1024 + code by PRMT, HSUB2, HMUL2 / HFMA2): every fp16 weight within
+    fp16 rounding of the oracle's exact dequantization (the scale product and the result are each rounded once to fp16)"""
+    rng = np.random.default_rng(800 + t)
+    K = 1024
+    for trial in range(6):
+        w = O.random_blocks(t, K // oracle.blck_size(t), rng) if trial % 2 else None
+        if w is None:
+            z = np.load(ROOT / "tests" / "golden" / f"quant_{O.TYPE_NAMES[t]}.npz")
+            w = np.ascontiguousarray(z["blocks"][:oracle.row_size(t, K)])
+        wp = np.concatenate([w, np.zeros(64, dtype=np.uint8)])
+        out = np.zeros(K, dtype=np.uint16)
+        rc = emu.emu_tc_dequant_row(t, _p(wp), K, _p(out))
+        if rc != 0:
+            pytest.skip("format not in the tcgen05 GEMM yet")
+        got = out.view(np.float16).astype(np.float32)
+        want = oracle.dequantize(t, w, K)
+        blk = np.abs(want).reshape(-1, 32).max(1).repeat(32) + 1e-12
+        assert np.all(np.abs(got - want) <= 1.5e-3 * blk), (trial, float(np.max(np.abs(got - want) / blk)))
