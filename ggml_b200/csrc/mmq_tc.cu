@@ -161,7 +161,10 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
                 const int rs = u & 1;
                 if (u >= 2) tc_wait(&raw_empty[rs], (uint32_t)((u >> 1) - 1) & 1u);
                 tc_expect_tx(&raw_full[rs], ROWS * RAW);
-                tc_tma_2d(raw + rs * ROWS * RAW, &map_w, (ubeg + u) * tcfmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tcfmt<T>::ODD_BACK_WORDS, tm * ROWS, &raw_full[rs]);
+                int coord;                                        // first 4-byte word of the box: 16-byte aligned start at or below the unit
+                if constexpr (T == T_Q6_K) coord = (((ubeg + u) * 210) & ~15) >> 2;       // 210-byte units: up to 14 bytes of lead in a 224-byte box
+                else                       coord = (ubeg + u) * tcfmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tcfmt<T>::ODD_BACK_WORDS;
+                tc_tma_2d(raw + rs * ROWS * RAW, &map_w, coord, tm * ROWS, &raw_full[rs]);
                 for (int q = 0; q < UK; ++q) {
                     const int step = UK * u + q, s = step % p.nstages;
                     if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
@@ -203,7 +206,10 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
         for (int u = 0; u < nunits; ++u) {
             const int rs = u & 1;
             tc_wait(&raw_full[rs], (uint32_t)(u >> 1) & 1u);
-            tc_load_unit<T>(raw + rs * ROWS * RAW + row * RAW + ((ubeg + u) & 1) * (4 * tcfmt<T>::ODD_BACK_WORDS), ub);
+            int lead;                                             // bytes between the box start and the unit's first byte
+            if constexpr (T == T_Q6_K) lead = ((ubeg + u) * 210) & 15;
+            else                       lead = ((ubeg + u) & 1) * (4 * tcfmt<T>::ODD_BACK_WORDS);
+            tc_load_unit<T>(raw + rs * ROWS * RAW + row * RAW + lead, ub);
             __syncwarp();
             if (lane == 0) tc_arrive(&raw_empty[rs]);            // the unit is in registers: the buffer can be refilled
             if constexpr (HALVES == 2) {
@@ -341,7 +347,9 @@ struct tc_plan {
 };
 
 static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
-    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K) return false;
+    // Q6_K: decoder host-verified, kernel path not yet validated on a B200: opt-in (GGML_B200_TC_Q6K=1) until it is
+    static const bool env_q6k = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) != 0;
+    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && !(a.type == T_Q6_K && env_q6k)) return false;
     if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
     if (a.N < 16 || a.K % 256 != 0 || a.K < 256 || a.M < 1) return false;
     const size_t rb = row_bytes(a.type, a.K);
@@ -360,6 +368,7 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     static const int env_halves = getenv("GGML_B200_TC_HALVES") ? atoi(getenv("GGML_B200_TC_HALVES")) : 0;
     const int tiles256 = (int)((a.M + 255) / 256) * pl.n_tiles;
     pl.halves = env_halves == 1 || env_halves == 2 ? env_halves : (tiles256 >= sm_count() / 2 ? 2 : 1);
+    if (a.type == T_Q6_K) pl.halves = 1;                         // 224-byte raw boxes: two 256-row buffers would not leave room for the operand ring
     const int rows = pl.halves * TC_BM;
     pl.m_tiles = (int)((a.M + rows - 1) / rows);
     const int tiles = pl.m_tiles * pl.n_tiles;
@@ -367,7 +376,7 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     static const int env_splitk = getenv("GGML_B200_TC_SPLITK") ? atoi(getenv("GGML_B200_TC_SPLITK")) : 0;
     if (env_splitk > 0 && env_splitk <= pl.chunks) splitk = env_splitk;
     pl.splitk = splitk;
-    const int raw = a.type == T_Q5_K ? 176 : 144;                 // tcfmt<T>::RAW
+    const int raw = a.type == T_Q5_K ? 176 : a.type == T_Q6_K ? 224 : 144;   // tcfmt<T>::RAW
     auto smem_of = [&](int ns) { return ns * (rows * TC_BK * 2 + BN * TC_BK * 2) + 2 * rows * raw + 256 + 1024; };
     int nstages = TC_MAX_STAGES;
     while (nstages > 2 && smem_of(nstages) > 227 * 1024) nstages--;
@@ -441,6 +450,7 @@ int launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q8_0: return pl.halves == 2 ? launch_tc<T_Q8_0, 2>(a, pl, st) : launch_tc<T_Q8_0, 1>(a, pl, st);
         case T_Q4_K: return pl.halves == 2 ? launch_tc<T_Q4_K, 2>(a, pl, st) : launch_tc<T_Q4_K, 1>(a, pl, st);
         case T_Q5_K: return pl.halves == 2 ? launch_tc<T_Q5_K, 2>(a, pl, st) : launch_tc<T_Q5_K, 1>(a, pl, st);
+        case T_Q6_K: return pl.halves == 2 ? launch_tc<T_Q6_K, 2>(a, pl, st) : launch_tc<T_Q6_K, 1>(a, pl, st);
         default: set_error("mul_mat: unsupported weight type %d for the tcgen05 kernel", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }

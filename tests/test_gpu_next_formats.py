@@ -20,3 +20,12 @@ def test_next_formats_parity_subprocess():
     p = subprocess.run([sys.executable, str(ROOT / "tests" / "gpu_next_formats_check.py")], capture_output=True, text=True, timeout=300)
     print(p.stdout[-2000:])
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in tcgen05 path for Q6_K (GGML_B200_TC_Q6K=1): decoder host-verified, kernel path not yet validated on a B200")
+def test_q6k_gemm_opt_in_subprocess():
+    import os
+    env = dict(os.environ, GGML_B200_TC_Q6K="1")
+    p = subprocess.run([sys.executable, str(ROOT / "tests" / "gpu_q6k_gemm_check.py")], capture_output=True, text=True, timeout=300, env=env)
+    print(p.stdout[-2000:])
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
