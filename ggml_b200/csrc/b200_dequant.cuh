@@ -54,6 +54,13 @@ template <int T> __device__ __forceinline__ void dequant4(const uint8_t * __rest
             const int v = (int)(int8_t)(lo | (((qh[i] >> (2 * pos)) & 3) << 4)) - 32;
             o[i] = __fmul_rn(ds, (float)v);
         }
+    } else if constexpr (T == T_IQ4_NL) {
+        const uint8_t * b = src + (e / 32) * 18;             // dequantize_row_iq4_nl, src/ggml-quants.c:2436-2452
+        const int j = (int)(e % 32);
+        const float d = h2f(load_u16(b));
+        const uint8_t * q = b + 2 + (j & 15);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __fmul_rn(d, (float)iq4nl_value(j < 16 ? (q[i] & 0x0F) : (q[i] >> 4)));
     } else if constexpr (T == T_Q4_1) {
         const uint8_t * b = src + (e / 32) * 20;             // d @0, m @2, qs[16] @4 (dequantize_row_q4_1, src/ggml-quants.c:275-294)
         const int j = (int)(e % 32);

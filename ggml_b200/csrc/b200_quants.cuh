@@ -22,7 +22,7 @@
 namespace b200 {
 
 // enum ggml_type ids (reference include/ggml.h:351-390)
-enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
+enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14, T_IQ4_NL = 20 };
 
 template <int T> struct fmt;
 template <> struct fmt<T_Q4_0> { static constexpr int QK = 32,  BYTES = 18,  ACT_K = 0; };
@@ -39,11 +39,13 @@ template <> struct fmt<T_Q5_0> { static constexpr int QK = 32,  BYTES = 22,  ACT
 template <> struct fmt<T_Q5_1> { static constexpr int QK = 32,  BYTES = 24,  ACT_K = 0; };
 template <> struct fmt<T_Q2_K> { static constexpr int QK = 256, BYTES = 84,  ACT_K = 1; };
 template <> struct fmt<T_Q3_K> { static constexpr int QK = 256, BYTES = 110, ACT_K = 1; };
+// IQ4_NL (src/ggml-common.h:398-403): the Q4_0 layout, the nibble indexes a fixed non-linear int8 codebook (kvalues_iq4nl, src/ggml-quants.c:2434)
+template <> struct fmt<T_IQ4_NL> { static constexpr int QK = 32, BYTES = 18, ACT_K = 0; };
 
-__host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 ? 32 : 256; }
+__host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_IQ4_NL ? 32 : 256; }
 __host__ __device__ inline int    type_bytes(int t) {
     return t == T_Q4_0 ? 18 : t == T_Q8_0 ? 34 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210
-         : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : 0;
+         : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : t == T_IQ4_NL ? 18 : 0;
 }
 __host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K || t == T_Q2_K || t == T_Q3_K; }
 __host__ __device__ inline size_t row_bytes(int t, int64_t k) { return (size_t)(k / type_qk(t)) * type_bytes(t); }
@@ -299,6 +301,39 @@ template <> __device__ __forceinline__ float unit_dot<T_Q5_1>(const uint8_t * ro
     const int s0 = q5_block_dot(qa, w[1], A.q), s1 = q5_block_dot(qb, w[7], A.q + 8);
     return (h2f(w[0] & 0xFFFF) * A.d[0]) * (float)s0 + h2f(w[0] >> 16) * A.s[0]
          + (h2f(w[6] & 0xFFFF) * A.d[1]) * (float)s1 + h2f(w[6] >> 16) * A.s[1];
+}
+
+// IQ4_NL codebook, four int8 entries per word (little endian): { -127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113 }
+#define B200_IQ4NL_W0 0xBFAD9881u
+#define B200_IQ4NL_W1 0xF6EADDCFu
+#define B200_IQ4NL_W2 0x26190D01u
+#define B200_IQ4NL_W3 0x71594535u
+__device__ __forceinline__ int iq4nl_value(int n) {              // codebook[n], n = 0..15
+    const uint32_t w = n < 4 ? B200_IQ4NL_W0 : n < 8 ? B200_IQ4NL_W1 : n < 12 ? B200_IQ4NL_W2 : B200_IQ4NL_W3;
+    return (int)(int8_t)((w >> (8 * (n & 3))) & 0xFF);
+}
+// four nibbles (low nibble of each byte of x) -> their four int8 codebook entries, one per byte: two 8-entry byte permutes
+// (selector = nibble & 7) and a per-byte choice by bit 3 of the nibble
+__device__ __forceinline__ uint32_t iq4nl_lookup4(uint32_t x) {
+    const uint32_t q7 = x & 0x07070707u;
+    const uint32_t sel = (q7 & 0x7u) | ((q7 >> 4) & 0x70u) | ((q7 >> 8) & 0x700u) | ((q7 >> 12) & 0x7000u);
+    const uint32_t lo = __byte_perm(B200_IQ4NL_W0, B200_IQ4NL_W1, sel), hi = __byte_perm(B200_IQ4NL_W2, B200_IQ4NL_W3, sel);
+    const uint32_t m = ((x >> 3) & 0x01010101u) * 0xFFu;        // 0xFF in the bytes whose nibble is >= 8
+    return (lo & ~m) | (hi & m);
+}
+template <> __device__ __forceinline__ float unit_dot<T_IQ4_NL>(const uint8_t * row, int u, const unit_act & A) {
+    uint32_t w[9];
+    load_words_a2<9>(row + 36 * u, w);                     // as Q4_0: block 0 d = w0[15:0], qs bytes 2..17; block 1 d = w4[31:16], qs = w5..w8
+    int s0 = 0, s1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t qa = __funnelshift_r(w[i], w[i + 1], 16), qb = w[5 + i];
+        s0 = dp4a_s((int)iq4nl_lookup4(qa),      A.q[i],      s0);
+        s0 = dp4a_s((int)iq4nl_lookup4(qa >> 4), A.q[4 + i],  s0);
+        s1 = dp4a_s((int)iq4nl_lookup4(qb),      A.q[8 + i],  s1);
+        s1 = dp4a_s((int)iq4nl_lookup4(qb >> 4), A.q[12 + i], s1);
+    }
+    return (A.d[0] * h2f(w[0] & 0xFFFF)) * (float)s0 + (A.d[1] * h2f(w[4] >> 16)) * (float)s1;
 }
 
 // byte k of a little-endian word array

@@ -29,6 +29,7 @@ template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 1
 // SURVEY §8f-2 formats: task dot products written and host-verified (tests/hostemu), dispatched by mmvq_sb.cu
 // like the hot-path formats (GPU check: tests/test_gpu_next_formats.py)
 template <> struct sbfmt<T_Q5_0> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 0; };
+template <> struct sbfmt<T_IQ4_NL> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q4_1> { static constexpr int TASK_W = 256, TASK_B = 160, LPR = 16, KQ = 0; };   // needs the Q8_1 s values: see task_dot<T_Q4_1>
 template <> struct sbfmt<T_Q5_1> { static constexpr int TASK_W = 256, TASK_B = 192, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q2_K> { static constexpr int TASK_W = 256, TASK_B = 84,  LPR = 16, KQ = 1; };
@@ -365,6 +366,44 @@ template <> __device__ __forceinline__ float task_dot<T_Q5_0>(const uint8_t * w,
         const int y[8] = { ylo.x, ylo.y, ylo.z, ylo.w, yhi.x, yhi.y, yhi.z, yhi.w };
         const int s = q5_block_dot(q, qh, y) - 16 * s32[b];
         acc += (h2f(dbits) * yd[b]) * (float)s;
+    }
+    return acc;
+}
+
+// IQ4_NL: the Q4_0 task (8 blocks of 18 bytes) with the nibbles mapped through the non-linear codebook (two byte permutes per word)
+template <> __device__ __forceinline__ float task_dot<T_IQ4_NL>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    uint32_t ww[37];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int4 v = lds128(w + 16 * i); ww[4 * i] = v.x; ww[4 * i + 1] = v.y; ww[4 * i + 2] = v.z; ww[4 * i + 3] = v.w; }
+    ww[36] = 0;
+    const int4 da = lds128(a + SB_OFF_D), db = lds128(a + SB_OFF_D + 16);
+    const float yd[8] = { __int_as_float(da.x), __int_as_float(da.y), __int_as_float(da.z), __int_as_float(da.w),
+                          __int_as_float(db.x), __int_as_float(db.y), __int_as_float(db.z), __int_as_float(db.w) };
+    float acc = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int w0 = (18 * b) / 4;
+        const bool odd = (b & 1) != 0;
+        uint32_t q[4], dbits;
+        if (!odd) {
+            dbits = ww[w0] & 0xFFFF;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = __funnelshift_r(ww[w0 + i], ww[w0 + i + 1], 16);
+        } else {
+            dbits = ww[w0] >> 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = ww[w0 + 1 + i];
+        }
+        const int4 ylo = lds128(a + (2 * b) * 16), yhi = lds128(a + (2 * b + 1) * 16);
+        const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s = __dp4a((int)iq4nl_lookup4(q[i]), yl[i], s);
+            s = __dp4a((int)iq4nl_lookup4(q[i] >> 4), yh[i], s);
+        }
+        acc += (yd[b] * h2f(dbits)) * (float)s;
     }
     return acc;
 }

@@ -92,7 +92,7 @@ uint16_t oq_fp32_to_fp16(float f) {
 int64_t oq_blck_size(int type) {
     switch (type) {
         case OQ_F32: case OQ_F16: return 1;
-        case OQ_Q4_0: case OQ_Q8_0: case OQ_Q4_1: case OQ_Q5_0: case OQ_Q5_1: case OQ_Q8_1: return 32;
+        case OQ_Q4_0: case OQ_Q8_0: case OQ_Q4_1: case OQ_Q5_0: case OQ_Q5_1: case OQ_Q8_1: case OQ_IQ4_NL: return 32;
         case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: case OQ_Q2_K: case OQ_Q3_K: return 256;
         default: return 0;
     }
@@ -102,7 +102,7 @@ size_t oq_type_size(int type) {
         case OQ_F32: return 4;   case OQ_F16: return 2;
         case OQ_Q4_0: return 18; case OQ_Q8_0: return 34;
         case OQ_Q4_1: return 20; case OQ_Q5_0: return 22; case OQ_Q5_1: return 24; case OQ_Q8_1: return 36;
-        case OQ_Q2_K: return 84; case OQ_Q3_K: return 110;
+        case OQ_Q2_K: return 84; case OQ_Q3_K: return 110; case OQ_IQ4_NL: return 18;
         case OQ_Q4_K: return 144; case OQ_Q5_K: return 176; case OQ_Q6_K: return 210; case OQ_Q8_K: return 292;
         default: return 0;
     }
@@ -253,6 +253,18 @@ static void deq_q3_K(const uint8_t * b, float * y, int64_t k) {
         }
     }
 }
+/* IQ4_NL (src/ggml-common.h:398-403, dequantize_row_iq4_nl src/ggml-quants.c:2436-2452): the Q4_0 layout (d @0, 16 nibble bytes)
+ * with the nibble indexing a fixed non-linear 16-entry int8 codebook (kvalues_iq4nl, src/ggml-quants.c:2434): value = d * codebook[nibble] */
+static const int8_t iq4nl_codebook[16] = { -127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113 };
+static void deq_iq4_nl(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 32; ++i, b += 18, y += 32) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int j = 0; j < 16; ++j) {
+            y[j]      = d * (float)iq4nl_codebook[b[2 + j] & 0x0F];
+            y[j + 16] = d * (float)iq4nl_codebook[b[2 + j] >> 4];
+        }
+    }
+}
 static void deq_q8_K(const uint8_t * b, float * y, int64_t k) {
     for (int64_t i = 0; i < k / 256; ++i, b += 292, y += 256) {
         float d; memcpy(&d, b, 4);
@@ -276,6 +288,7 @@ int oq_dequantize_row(int type, const void * src, float * dst, int64_t k) {
         case OQ_Q5_1: deq_q5_1(b, dst, k); return 0;
         case OQ_Q2_K: deq_q2_K(b, dst, k); return 0;
         case OQ_Q3_K: deq_q3_K(b, dst, k); return 0;
+        case OQ_IQ4_NL: deq_iq4_nl(b, dst, k); return 0;
         default: return -1;
     }
 }
@@ -371,7 +384,7 @@ int oq_quantize_row_ref(int type, const float * src, void * dst, int64_t k) {
 
 int oq_vec_dot_type(int type) {
     switch (type) {
-        case OQ_Q4_0: case OQ_Q8_0: case OQ_Q5_0: return OQ_Q8_0;
+        case OQ_Q4_0: case OQ_Q8_0: case OQ_Q5_0: case OQ_IQ4_NL: return OQ_Q8_0;
         case OQ_Q4_1: case OQ_Q5_1: return OQ_Q8_1;
         case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q2_K: case OQ_Q3_K: return OQ_Q8_K;
         default: return -1;
@@ -489,6 +502,16 @@ static float dot_q5_1_q8_1(int64_t k, const uint8_t * w, const uint8_t * y) {
     }
     return acc + mins;
 }
+/* ggml_vec_dot_iq4_nl_q8_0 (src/ggml-cpu/ggml-cpu-quants.c): per block (d_y * d_w) * sum(codebook[nibble] * q) */
+static float dot_iq4_nl_q8_0(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 32; ++i, w += 18, y += 34) {
+        int s = 0;
+        for (int j = 0; j < 16; ++j) s += (int)iq4nl_codebook[w[2 + j] & 0x0F] * (int)(int8_t)y[2 + j] + (int)iq4nl_codebook[w[2 + j] >> 4] * (int)(int8_t)y[2 + j + 16];
+        acc += (oq_fp16_to_fp32(rd16(y)) * oq_fp16_to_fp32(rd16(w))) * (float)s;
+    }
+    return acc;
+}
 /* ggml_vec_dot_q2_K_q8_K (:4190) / q3_K_q8_K (:4768): per superblock  d_w * d_y * sum_g scale_g * (codes . q)_g  and, for Q2_K,
  * - dmin_w * d_y * sum_g min_g * bsum_g.  Q8_K block = f32 d @0, 256 int8 @4, sixteen int16 bsums @260 */
 static float dot_q2_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
@@ -533,6 +556,7 @@ float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
         case OQ_Q5_1: return dot_q5_1_q8_1(k, w, y);
         case OQ_Q2_K: return dot_q2_K_q8_K(k, w, y);
         case OQ_Q3_K: return dot_q3_K_q8_K(k, w, y);
+        case OQ_IQ4_NL: return dot_iq4_nl_q8_0(k, w, y);
         default: return NAN;
     }
 }

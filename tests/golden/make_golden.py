@@ -30,7 +30,7 @@ def synth(n, off):
     return (0.1 + 2.0 * np.cos(i + np.float32(off))).astype(np.float32)
 
 
-B32 = (O.Q4_0, O.Q8_0, O.Q4_1, O.Q5_0, O.Q5_1)     # 32-element-block formats
+B32 = (O.Q4_0, O.Q8_0, O.Q4_1, O.Q5_0, O.Q5_1, O.IQ4_NL)     # 32-element-block formats
 
 
 def main(types):
