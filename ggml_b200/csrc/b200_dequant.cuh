@@ -61,6 +61,14 @@ template <int T> __device__ __forceinline__ void dequant4(const uint8_t * __rest
         const uint8_t * q = b + 2 + (j & 15);
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = __fmul_rn(d, (float)iq4nl_value(j < 16 ? (q[i] & 0x0F) : (q[i] >> 4)));
+    } else if constexpr (T == T_IQ4_XS) {
+        const uint8_t * b = src + (e / 256) * 136;           // dequantize_row_iq4_xs: d @0, scales_h @2, scales_l @4, qs @8
+        const int w = (int)(e % 256), ib = w >> 5, j = w & 31;
+        const uint32_t w0 = (uint32_t)load_u16(b) | ((uint32_t)load_u16(b + 2) << 16), w1 = (uint32_t)load_u16(b + 4) | ((uint32_t)load_u16(b + 6) << 16);
+        const float dl = __fmul_rn(h2f(w0 & 0xFFFF), (float)iq4xs_scale(w0, w1, ib));
+        const uint8_t * q = b + 8 + 16 * ib + (j & 15);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __fmul_rn(dl, (float)iq4nl_value(j < 16 ? (q[i] & 0x0F) : (q[i] >> 4)));
     } else if constexpr (T == T_Q4_1) {
         const uint8_t * b = src + (e / 32) * 20;             // d @0, m @2, qs[16] @4 (dequantize_row_q4_1, src/ggml-quants.c:275-294)
         const int j = (int)(e % 32);

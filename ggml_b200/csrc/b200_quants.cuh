@@ -22,7 +22,7 @@
 namespace b200 {
 
 // enum ggml_type ids (reference include/ggml.h:351-390)
-enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14, T_IQ4_NL = 20 };
+enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14, T_IQ4_NL = 20, T_IQ4_XS = 23 };
 
 template <int T> struct fmt;
 template <> struct fmt<T_Q4_0> { static constexpr int QK = 32,  BYTES = 18,  ACT_K = 0; };
@@ -41,13 +41,15 @@ template <> struct fmt<T_Q2_K> { static constexpr int QK = 256, BYTES = 84,  ACT
 template <> struct fmt<T_Q3_K> { static constexpr int QK = 256, BYTES = 110, ACT_K = 1; };
 // IQ4_NL (src/ggml-common.h:398-403): the Q4_0 layout, the nibble indexes a fixed non-linear int8 codebook (kvalues_iq4nl, src/ggml-quants.c:2434)
 template <> struct fmt<T_IQ4_NL> { static constexpr int QK = 32, BYTES = 18, ACT_K = 0; };
+// IQ4_XS (:406-411): 136 B / 256 = d, scales_h (u16), scales_l[4], qs[128]; eight 32-value sub-blocks with 6-bit scales (value - 32), same codebook
+template <> struct fmt<T_IQ4_XS> { static constexpr int QK = 256, BYTES = 136, ACT_K = 1; };
 
 __host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_IQ4_NL ? 32 : 256; }
 __host__ __device__ inline int    type_bytes(int t) {
     return t == T_Q4_0 ? 18 : t == T_Q8_0 ? 34 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210
-         : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : t == T_IQ4_NL ? 18 : 0;
+         : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : t == T_IQ4_NL ? 18 : t == T_IQ4_XS ? 136 : 0;
 }
-__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K || t == T_Q2_K || t == T_Q3_K; }
+__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K || t == T_Q2_K || t == T_Q3_K || t == T_IQ4_XS; }   // Q8_K activations
 __host__ __device__ inline size_t row_bytes(int t, int64_t k) { return (size_t)(k / type_qk(t)) * type_bytes(t); }
 
 // ------------------------------------------------------------------ quantized activation record
@@ -334,6 +336,30 @@ template <> __device__ __forceinline__ float unit_dot<T_IQ4_NL>(const uint8_t * 
         s1 = dp4a_s((int)iq4nl_lookup4(qb >> 4), A.q[12 + i], s1);
     }
     return (A.d[0] * h2f(w[0] & 0xFFFF)) * (float)s0 + (A.d[1] * h2f(w[4] >> 16)) * (float)s1;
+}
+
+// 6-bit scale (biased by 32) of sub-block ib of an IQ4_XS superblock: w0 = d | scales_h << 16, w1 = scales_l[4]
+__device__ __forceinline__ int iq4xs_scale(uint32_t w0, uint32_t w1, int ib) {
+    return (int)(((w1 >> (4 * ib)) & 0x0F) | ((((w0 >> 16) >> (2 * ib)) & 3) << 4)) - 32;
+}
+template <> __device__ __forceinline__ float unit_dot<T_IQ4_XS>(const uint8_t * row, int u, const unit_act & A) {
+    const uint8_t * sb = row + 136 * (u >> 2);              // 8-byte aligned superblocks
+    const int c = u & 3;                                    // sub-blocks 2c, 2c+1: 32 bytes of qs at 8 + 32 c
+    uint32_t hd[2], q[8];
+    load_words_a2<2>(sb, hd);
+    load_words_a2<8>(sb + 8 + 32 * c, q);
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                           // sub-block 2c + k: low nibbles = its elements 0..15 (piece 2k), high = 16..31 (piece 2k+1)
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s = dp4a_s((int)iq4nl_lookup4(q[4 * k + i]),      A.q[8 * k + i],     s);
+            s = dp4a_s((int)iq4nl_lookup4(q[4 * k + i] >> 4), A.q[8 * k + 4 + i], s);
+        }
+        tot += iq4xs_scale(hd[0], hd[1], 2 * c + k) * s;
+    }
+    return (h2f(hd[0] & 0xFFFF) * A.d[0]) * (float)tot;
 }
 
 // byte k of a little-endian word array

@@ -30,6 +30,7 @@ template <> struct sbfmt<T_Q8_0> { static constexpr int TASK_W = 128, TASK_B = 1
 // like the hot-path formats (GPU check: tests/test_gpu_next_formats.py)
 template <> struct sbfmt<T_Q5_0> { static constexpr int TASK_W = 256, TASK_B = 176, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_IQ4_NL> { static constexpr int TASK_W = 256, TASK_B = 144, LPR = 16, KQ = 0; };
+template <> struct sbfmt<T_IQ4_XS> { static constexpr int TASK_W = 256, TASK_B = 136, LPR = 16, KQ = 1; };
 template <> struct sbfmt<T_Q4_1> { static constexpr int TASK_W = 256, TASK_B = 160, LPR = 16, KQ = 0; };   // needs the Q8_1 s values: see task_dot<T_Q4_1>
 template <> struct sbfmt<T_Q5_1> { static constexpr int TASK_W = 256, TASK_B = 192, LPR = 16, KQ = 0; };
 template <> struct sbfmt<T_Q2_K> { static constexpr int TASK_W = 256, TASK_B = 84,  LPR = 16, KQ = 1; };
@@ -406,6 +407,28 @@ template <> __device__ __forceinline__ float task_dot<T_IQ4_NL>(const uint8_t * 
         acc += (yd[b] * h2f(dbits)) * (float)s;
     }
     return acc;
+}
+
+// IQ4_XS: 136-byte superblocks are 8-byte aligned: 64-bit loads.  words: d | scales_h, scales_l, then 32 words of qs
+template <> __device__ __forceinline__ float task_dot<T_IQ4_XS>(const uint8_t * w, const uint8_t * rec, int t) {
+    const uint8_t * a = rec + (size_t)t * SB_REC;
+    uint32_t ww[34];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) { const uint2 v = *(const uint2 *)(w + 8 * i); ww[2 * i] = v.x; ww[2 * i + 1] = v.y; }
+    int tot = 0;
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) {
+        const int4 ylo = lds128(a + (2 * ib) * 16), yhi = lds128(a + (2 * ib + 1) * 16);
+        const int yl[4] = { ylo.x, ylo.y, ylo.z, ylo.w }, yh[4] = { yhi.x, yhi.y, yhi.z, yhi.w };
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s = __dp4a((int)iq4nl_lookup4(ww[2 + 4 * ib + i]), yl[i], s);
+            s = __dp4a((int)iq4nl_lookup4(ww[2 + 4 * ib + i] >> 4), yh[i], s);
+        }
+        tot += iq4xs_scale(ww[0], ww[1], ib) * s;
+    }
+    return (h2f(ww[0] & 0xFFFF) * *(const float *)(a + SB_OFF_D)) * (float)tot;
 }
 
 // Q4_1 / Q5_1 (block minimum m): the CPU backend pairs them with Q8_1 activations, whose s = fp16(d_unrounded * sum of the block's

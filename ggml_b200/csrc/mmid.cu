@@ -95,6 +95,7 @@ int ggml_b200_mul_mat_id(const ggml_b200_mul_mat_id_args * a, void * stream) {
         case T_Q2_K: mmid_kernel<T_Q2_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_Q3_K: mmid_kernel<T_Q3_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ4_NL: mmid_kernel<T_IQ4_NL><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ4_XS: mmid_kernel<T_IQ4_XS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

@@ -423,6 +423,7 @@ bool mmvq_sb_eligible(const ggml_b200_mul_mat_args & a) {
         case T_Q5_1: return make_sb_plan<T_Q5_1>(a, pl);
         case T_Q5_0: return make_sb_plan<T_Q5_0>(a, pl);
         case T_IQ4_NL: return make_sb_plan<T_IQ4_NL>(a, pl);
+        case T_IQ4_XS: return make_sb_plan<T_IQ4_XS>(a, pl);
         case T_Q2_K: return make_sb_plan<T_Q2_K>(a, pl);
         case T_Q3_K: return make_sb_plan<T_Q3_K>(a, pl);
         default: return false;
@@ -440,6 +441,7 @@ int launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml
         case T_Q5_1: return launch_sb<T_Q5_1>(a, ga, st, ep);
         case T_Q5_0: return launch_sb<T_Q5_0>(a, ga, st, ep);
         case T_IQ4_NL: return launch_sb<T_IQ4_NL>(a, ga, st, ep);
+        case T_IQ4_XS: return launch_sb<T_IQ4_XS>(a, ga, st, ep);
         case T_Q2_K: return launch_sb<T_Q2_K>(a, ga, st, ep);
         case T_Q3_K: return launch_sb<T_Q3_K>(a, ga, st, ep);
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;

@@ -93,7 +93,7 @@ int64_t oq_blck_size(int type) {
     switch (type) {
         case OQ_F32: case OQ_F16: return 1;
         case OQ_Q4_0: case OQ_Q8_0: case OQ_Q4_1: case OQ_Q5_0: case OQ_Q5_1: case OQ_Q8_1: case OQ_IQ4_NL: return 32;
-        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: case OQ_Q2_K: case OQ_Q3_K: return 256;
+        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: case OQ_Q2_K: case OQ_Q3_K: case OQ_IQ4_XS: return 256;
         default: return 0;
     }
 }
@@ -102,7 +102,7 @@ size_t oq_type_size(int type) {
         case OQ_F32: return 4;   case OQ_F16: return 2;
         case OQ_Q4_0: return 18; case OQ_Q8_0: return 34;
         case OQ_Q4_1: return 20; case OQ_Q5_0: return 22; case OQ_Q5_1: return 24; case OQ_Q8_1: return 36;
-        case OQ_Q2_K: return 84; case OQ_Q3_K: return 110; case OQ_IQ4_NL: return 18;
+        case OQ_Q2_K: return 84; case OQ_Q3_K: return 110; case OQ_IQ4_NL: return 18; case OQ_IQ4_XS: return 136;
         case OQ_Q4_K: return 144; case OQ_Q5_K: return 176; case OQ_Q6_K: return 210; case OQ_Q8_K: return 292;
         default: return 0;
     }
@@ -265,6 +265,26 @@ static void deq_iq4_nl(const uint8_t * b, float * y, int64_t k) {
         }
     }
 }
+/* IQ4_XS (src/ggml-common.h:406-411, dequantize_row_iq4_xs src/ggml-quants.c): 136 bytes = d @0, scales_h @2 (2 high bits of each of
+ * the eight 6-bit sub-block scales), scales_l[4] @4 (their low nibbles), qs[128] @8; sub-block ib (32 values, Q4_0 nibble order):
+ * value = d * (scale_ib - 32) * codebook[nibble] */
+static inline int iq4xs_scale(const uint8_t * b, int ib) {
+    const int lo = (b[4 + ib / 2] >> (4 * (ib % 2))) & 0x0F, hi = (rd16(b + 2) >> (2 * ib)) & 3;
+    return (lo | (hi << 4)) - 32;
+}
+static void deq_iq4_xs(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 136) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int ib = 0; ib < 8; ++ib, y += 32) {
+            const float dl = d * (float)iq4xs_scale(b, ib);
+            const uint8_t * q = b + 8 + 16 * ib;
+            for (int j = 0; j < 16; ++j) {
+                y[j]      = dl * (float)iq4nl_codebook[q[j] & 0x0F];
+                y[j + 16] = dl * (float)iq4nl_codebook[q[j] >> 4];
+            }
+        }
+    }
+}
 static void deq_q8_K(const uint8_t * b, float * y, int64_t k) {
     for (int64_t i = 0; i < k / 256; ++i, b += 292, y += 256) {
         float d; memcpy(&d, b, 4);
@@ -289,6 +309,7 @@ int oq_dequantize_row(int type, const void * src, float * dst, int64_t k) {
         case OQ_Q2_K: deq_q2_K(b, dst, k); return 0;
         case OQ_Q3_K: deq_q3_K(b, dst, k); return 0;
         case OQ_IQ4_NL: deq_iq4_nl(b, dst, k); return 0;
+        case OQ_IQ4_XS: deq_iq4_xs(b, dst, k); return 0;
         default: return -1;
     }
 }
@@ -386,7 +407,7 @@ int oq_vec_dot_type(int type) {
     switch (type) {
         case OQ_Q4_0: case OQ_Q8_0: case OQ_Q5_0: case OQ_IQ4_NL: return OQ_Q8_0;
         case OQ_Q4_1: case OQ_Q5_1: return OQ_Q8_1;
-        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q2_K: case OQ_Q3_K: return OQ_Q8_K;
+        case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q2_K: case OQ_Q3_K: case OQ_IQ4_XS: return OQ_Q8_K;
         default: return -1;
     }
 }
@@ -512,6 +533,23 @@ static float dot_iq4_nl_q8_0(int64_t k, const uint8_t * w, const uint8_t * y) {
     }
     return acc;
 }
+/* ggml_vec_dot_iq4_xs_q8_K: per superblock (d_w * d_y) * sum_ib (scale_ib - 32) * sum(codebook[nibble] * q) */
+static float dot_iq4_xs_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float acc = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 136, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int tot = 0;
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint8_t * q = w + 8 + 16 * ib;
+            int s = 0;
+            for (int j = 0; j < 16; ++j) s += (int)iq4nl_codebook[q[j] & 0x0F] * (int)q8[32 * ib + j] + (int)iq4nl_codebook[q[j] >> 4] * (int)q8[32 * ib + j + 16];
+            tot += iq4xs_scale(w, ib) * s;
+        }
+        acc += (oq_fp16_to_fp32(rd16(w)) * yd) * (float)tot;
+    }
+    return acc;
+}
 /* ggml_vec_dot_q2_K_q8_K (:4190) / q3_K_q8_K (:4768): per superblock  d_w * d_y * sum_g scale_g * (codes . q)_g  and, for Q2_K,
  * - dmin_w * d_y * sum_g min_g * bsum_g.  Q8_K block = f32 d @0, 256 int8 @4, sixteen int16 bsums @260 */
 static float dot_q2_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
@@ -557,6 +595,7 @@ float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
         case OQ_Q2_K: return dot_q2_K_q8_K(k, w, y);
         case OQ_Q3_K: return dot_q3_K_q8_K(k, w, y);
         case OQ_IQ4_NL: return dot_iq4_nl_q8_0(k, w, y);
+        case OQ_IQ4_XS: return dot_iq4_xs_q8_K(k, w, y);
         default: return NAN;
     }
 }

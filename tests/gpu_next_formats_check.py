@@ -1,5 +1,5 @@
 """Run by tests/test_gpu_next_formats.py in a SUBPROCESS (its own CUDA context): parity of the SURVEY §8f-2 formats
-(Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, IQ4_NL) through the C ABI — dequantize bit-exact, generic MUL_MAT and MUL_MAT_ID within NMSE 1e-10 of the
+(Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS) through the C ABI — dequantize bit-exact, generic MUL_MAT and MUL_MAT_ID within NMSE 1e-10 of the
 oracle and of the reference's golden vectors.  Exit code 0 = all checks passed."""
 import sys
 from pathlib import Path

@@ -1,4 +1,4 @@
-"""GPU: the SURVEY §8f-2 formats (Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, IQ4_NL) on the superblock and generic mat-vec / MUL_MAT_ID / dequantize kernels.
+"""GPU: the SURVEY §8f-2 formats (Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS) on the superblock and generic mat-vec / MUL_MAT_ID / dequantize kernels.
 
 Status (round 1): the oracle is pinned against the reference and the kernels' decode logic is verified on the host
 (tests/test_hostemu_kernel_logic.py), but these kernels were added after the round's GPU budget was spent, so this module has not yet

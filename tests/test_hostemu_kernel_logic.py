@@ -157,7 +157,7 @@ def sb_record(emu, oracle, t, x):
     return rec, yq, ntask * REC
 
 
-HOT = list(O.HOT_TYPES) + [O.Q5_0, O.Q2_K, O.Q3_K, O.Q4_1, O.Q5_1, O.IQ4_NL]      # + the next formats whose fast-path task dot products are written (not yet dispatched)
+HOT = list(O.HOT_TYPES) + [O.Q5_0, O.Q2_K, O.Q3_K, O.Q4_1, O.Q5_1, O.IQ4_NL, O.IQ4_XS]      # + the next formats whose fast-path task dot products are written (not yet dispatched)
 
 
 @pytest.mark.parametrize("t", HOT, ids=[O.TYPE_NAMES[t] for t in HOT])
