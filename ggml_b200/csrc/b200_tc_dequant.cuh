@@ -21,7 +21,16 @@ template <> struct tcfmt<T_Q4_K> { static constexpr int RAW = 144, STRIDE_WORDS 
 template <> struct tcfmt<T_Q5_K> { static constexpr int RAW = 176, STRIDE_WORDS = 44, UNIT_WORDS = 44, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
 // Q6_K: 210-byte superblocks, 2-byte aligned.  The decoder below is host-verified; the kernel does not dispatch it yet (its TMA box
 // has to start on the 16-byte boundary below the unit and carry up to 14 bytes of lead: RAW = 224, payload offset 210 u mod 16).
-template <> struct tcfmt<T_Q6_K> { static constexpr int RAW = 224, STRIDE_WORDS = 0, UNIT_WORDS = 53, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 2; };
+template <> struct tcfmt<T_Q6_K> { static constexpr int RAW = 224, STRIDE_WORDS = 0, UNIT_WORDS = 53, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 2, UNIT_BYTES = 210; };
+// SURVEY §8f-2 formats (decoders host-verified; first B200 run pending).  16-byte-multiple units are loaded like Q4_0; the others
+// (LOAD_BYTES = 2) use the variable-lead box: RAW = UNIT_BYTES + largest lead, rounded up to 16.
+template <> struct tcfmt<T_Q4_1>   { static constexpr int RAW = 160, STRIDE_WORDS = 40, UNIT_WORDS = 40, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
+template <> struct tcfmt<T_Q5_0>   { static constexpr int RAW = 176, STRIDE_WORDS = 44, UNIT_WORDS = 44, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
+template <> struct tcfmt<T_Q5_1>   { static constexpr int RAW = 192, STRIDE_WORDS = 48, UNIT_WORDS = 48, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
+template <> struct tcfmt<T_IQ4_NL> { static constexpr int RAW = 144, STRIDE_WORDS = 36, UNIT_WORDS = 36, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
+template <> struct tcfmt<T_Q2_K>   { static constexpr int RAW = 96,  STRIDE_WORDS = 0,  UNIT_WORDS = 21, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 2, UNIT_BYTES = 84;  };
+template <> struct tcfmt<T_Q3_K>   { static constexpr int RAW = 128, STRIDE_WORDS = 0,  UNIT_WORDS = 28, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 2, UNIT_BYTES = 110; };
+template <> struct tcfmt<T_IQ4_XS> { static constexpr int RAW = 144, STRIDE_WORDS = 0,  UNIT_WORDS = 34, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 2, UNIT_BYTES = 136; };
 
 template <int T> __device__ __forceinline__ void tc_load_unit(const uint8_t * g, uint32_t (&u)[tcfmt<T>::UNIT_WORDS]) {   // g: shared memory
     if constexpr (tcfmt<T>::LOAD_BYTES == 2) {
@@ -118,6 +127,109 @@ template <int T, int KS> __device__ __forceinline__ void dq64(const uint32_t (&u
                 const uint32_t ql = u[16 * h + 8 * (pos & 1) + (l0 >> 2) + half], qh = u[32 + 8 * h + (l0 >> 2) + half];
                 const uint32_t code = ((ql >> (4 * pp)) & 0x0F0F0F0Fu) | (((qh >> (2 * pos)) & 0x03030303u) << 4);
                 if (half == 0) codes4_scale(code, bias, d, r.x, r.y); else codes4_scale(code, bias, d, r.z, r.w);
+            }
+            TC_OUT(c, r);
+        }
+    } else if constexpr (T == T_Q4_1 || T == T_Q5_0 || T == T_Q5_1 || T == T_IQ4_NL) {
+        // 32-element blocks 2KS, 2KS+1 of the unit; block layouts: Q4_1 d|m, qs[16] (5 words); Q5_0 d, qh, qs (22 B, 2-byte granular);
+        // Q5_1 d|m, qh, qs (6 words); IQ4_NL d, qs (18 B)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            constexpr int dummy = 0; (void)dummy;
+            const int blk = 2 * KS + b;
+            uint32_t q[4], qh = 0, dbits, mbits = 0;
+            if constexpr (T == T_Q4_1) {
+                dbits = u[5 * blk] & 0xFFFF; mbits = u[5 * blk] >> 16;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = u[5 * blk + 1 + i];
+            } else if constexpr (T == T_Q5_1) {
+                dbits = u[6 * blk] & 0xFFFF; mbits = u[6 * blk] >> 16; qh = u[6 * blk + 1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = u[6 * blk + 2 + i];
+            } else if constexpr (T == T_Q5_0) {
+                const int w0 = (22 * blk) / 4;                   // byte 22 blk: word-aligned for even blk, half-word shifted for odd blk
+                if ((blk & 1) == 0) {
+                    dbits = u[w0] & 0xFFFF; qh = __funnelshift_r(u[w0], u[w0 + 1], 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = __funnelshift_r(u[w0 + 1 + i], u[w0 + 2 + i], 16);
+                } else {
+                    dbits = u[w0] >> 16; qh = u[w0 + 1];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = u[w0 + 2 + i];
+                }
+            } else {                                             // IQ4_NL: as Q4_0
+                const int w0 = (18 * blk) / 4;
+                if ((blk & 1) == 0) {
+                    dbits = u[w0] & 0xFFFF;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = __funnelshift_r(u[w0 + i], u[w0 + i + 1], 16);
+                } else {
+                    dbits = u[w0] >> 16;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = u[w0 + 1 + i];
+                }
+            }
+            const __half2 d = u2h(dbits | (dbits << 16)), m = u2h(mbits | (mbits << 16));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int hi = c >> 1;                           // chunks 0,1: elements 0..15 (low nibbles); 2,3: 16..31 (high nibbles)
+                uint32_t qa = (q[2 * (c & 1)] >> (4 * hi)) & 0x0F0F0F0F, qb = (q[2 * (c & 1) + 1] >> (4 * hi)) & 0x0F0F0F0F;
+                uint4 r;
+                if constexpr (T == T_Q4_1) {
+                    codes4_affine(qa, d, m, r.x, r.y); codes4_affine(qb, d, m, r.z, r.w);
+                } else if constexpr (T == T_IQ4_NL) {
+                    const __half2 bias = __float2half2_rn(1152.0f);   // codebook entries are int8: offset to 0..255 first
+                    codes4_scale(iq4nl_lookup4(qa) ^ 0x80808080u, bias, d, r.x, r.y); codes4_scale(iq4nl_lookup4(qb) ^ 0x80808080u, bias, d, r.z, r.w);
+                } else {
+                    const int bit0 = 16 * hi + 8 * (c & 1);      // fifth bit of the chunk's first element
+                    qa |= spread4_to_bit4(qh >> bit0); qb |= spread4_to_bit4(qh >> (bit0 + 4));
+                    if constexpr (T == T_Q5_1) { codes4_affine(qa, d, m, r.x, r.y); codes4_affine(qb, d, m, r.z, r.w); }
+                    else { const __half2 bias = __float2half2_rn(1040.0f); codes4_scale(qa, bias, d, r.x, r.y); codes4_scale(qb, bias, d, r.z, r.w); }
+                }
+                TC_OUT(4 * b + c, r);
+            }
+        }
+    } else if constexpr (T == T_IQ4_XS) {
+        // sub-blocks 2KS, 2KS+1 (32 values each, Q4_0 nibble order); words: d | scales_h, scales_l, qs from word 2
+        const float dd = h2f(u[0] & 0xFFFF);
+        const __half2 bias = __float2half2_rn(1152.0f);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int ib = 2 * KS + b;
+            const __half2 d = __float2half2_rn(dd * (float)iq4xs_scale(u[0], u[1], ib));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int hi = c >> 1;
+                const uint32_t qa = u[2 + 4 * ib + 2 * (c & 1)] >> (4 * hi), qb = u[2 + 4 * ib + 2 * (c & 1) + 1] >> (4 * hi);
+                uint4 r;
+                codes4_scale(iq4nl_lookup4(qa) ^ 0x80808080u, bias, d, r.x, r.y); codes4_scale(iq4nl_lookup4(qb) ^ 0x80808080u, bias, d, r.z, r.w);
+                TC_OUT(4 * b + c, r);
+            }
+        }
+    } else if constexpr (T == T_Q2_K || T == T_Q3_K) {
+        // K-step KS = half h = KS / 2, bit pairs jj0 = 2 (KS % 2) (chunks 0..3) and jj0 + 1 (chunks 4..7); chunk c: l = 8 (c % 4) ..
+        constexpr bool THREE = (T == T_Q3_K);
+        constexpr int h = KS >> 1, jj0 = 2 * (KS & 1);
+        constexpr int QS0 = THREE ? 8 : 4;                       // first qs word (Q3_K: after hmask[32]; Q2_K: after scales[16])
+        const float dd = THREE ? h2f(u[27] & 0xFFFF) : h2f(u[20] & 0xFFFF), dmn = THREE ? 0.0f : h2f(u[20] >> 16);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int jj = jj0 + (c >> 2), l0 = 8 * (c & 3), g16 = 8 * h + 2 * jj + (l0 >> 4);
+            const uint32_t wa = u[QS0 + 8 * h + (l0 >> 2)], wb = u[QS0 + 8 * h + (l0 >> 2) + 1];
+            uint32_t qa = (wa >> (2 * jj)) & 0x03030303u, qb = (wb >> (2 * jj)) & 0x03030303u;
+            uint4 r;
+            if constexpr (!THREE) {
+                const int sc = (int)((u[g16 >> 2] >> (8 * (g16 & 3))) & 0xFF);
+                const __half2 d = __float2half2_rn(dd * (float)(sc & 0x0F)), m = __float2half2_rn(-(dmn * (float)(sc >> 4)));
+                codes4_affine(qa, d, m, r.x, r.y); codes4_affine(qb, d, m, r.z, r.w);
+            } else {
+                const int bit = 4 * h + jj;
+                qa |= ((u[(l0 >> 2)] >> bit) & 0x01010101u) << 2;                    // high bit set: code + 4 (then - 4 for every code)
+                qb |= ((u[(l0 >> 2) + 1] >> bit) & 0x01010101u) << 2;
+                const int lo = g16 < 8 ? (int)((u[24 + (g16 >> 2)] >> (8 * (g16 & 3))) & 0x0F) : (int)((u[24 + ((g16 - 8) >> 2)] >> (8 * ((g16 - 8) & 3) + 4)) & 0x0F);
+                const int hi2 = (int)((u[26] >> (8 * (g16 & 3) + 2 * (g16 >> 2))) & 3);
+                const __half2 d = __float2half2_rn(dd * (float)((lo | (hi2 << 4)) - 32)), bias = __float2half2_rn(1028.0f);
+                codes4_scale(qa, bias, d, r.x, r.y); codes4_scale(qb, bias, d, r.z, r.w);
             }
             TC_OUT(c, r);
         }

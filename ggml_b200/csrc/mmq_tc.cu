@@ -162,7 +162,7 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
                 if (u >= 2) tc_wait(&raw_empty[rs], (uint32_t)((u >> 1) - 1) & 1u);
                 tc_expect_tx(&raw_full[rs], ROWS * RAW);
                 int coord;                                        // first 4-byte word of the box: 16-byte aligned start at or below the unit
-                if constexpr (T == T_Q6_K) coord = (((ubeg + u) * 210) & ~15) >> 2;       // 210-byte units: up to 14 bytes of lead in a 224-byte box
+                if constexpr (tcfmt<T>::LOAD_BYTES == 2) coord = (((ubeg + u) * tcfmt<T>::UNIT_BYTES) & ~15) >> 2;   // unaligned units: lead bytes in front of the payload
                 else                       coord = (ubeg + u) * tcfmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tcfmt<T>::ODD_BACK_WORDS;
                 tc_tma_2d(raw + rs * ROWS * RAW, &map_w, coord, tm * ROWS, &raw_full[rs]);
                 for (int q = 0; q < UK; ++q) {
@@ -207,7 +207,7 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
             const int rs = u & 1;
             tc_wait(&raw_full[rs], (uint32_t)(u >> 1) & 1u);
             int lead;                                             // bytes between the box start and the unit's first byte
-            if constexpr (T == T_Q6_K) lead = ((ubeg + u) * 210) & 15;
+            if constexpr (tcfmt<T>::LOAD_BYTES == 2) lead = ((ubeg + u) * tcfmt<T>::UNIT_BYTES) & 15;
             else                       lead = ((ubeg + u) & 1) * (4 * tcfmt<T>::ODD_BACK_WORDS);
             tc_load_unit<T>(raw + rs * ROWS * RAW + row * RAW + lead, ub);
             __syncwarp();
@@ -349,7 +349,8 @@ struct tc_plan {
 static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     // Q6_K: decoder host-verified, kernel path not yet validated on a B200: opt-in (GGML_B200_TC_Q6K=1) until it is
     static const bool env_q6k = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) != 0;
-    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && !(a.type == T_Q6_K && env_q6k)) return false;
+    const bool next_fmt = a.type == T_Q4_1 || a.type == T_Q5_0 || a.type == T_Q5_1 || a.type == T_IQ4_NL || a.type == T_IQ4_XS || a.type == T_Q2_K || a.type == T_Q3_K;
+    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && !(a.type == T_Q6_K && env_q6k) && !next_fmt) return false;
     if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
     if (a.N < 16 || a.K % 256 != 0 || a.K < 256 || a.M < 1) return false;
     const size_t rb = row_bytes(a.type, a.K);
@@ -376,7 +377,16 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     static const int env_splitk = getenv("GGML_B200_TC_SPLITK") ? atoi(getenv("GGML_B200_TC_SPLITK")) : 0;
     if (env_splitk > 0 && env_splitk <= pl.chunks) splitk = env_splitk;
     pl.splitk = splitk;
-    const int raw = a.type == T_Q5_K ? 176 : a.type == T_Q6_K ? 224 : 144;   // tcfmt<T>::RAW
+    int raw = 144;                                               // tcfmt<T>::RAW
+    switch (a.type) {
+        case T_Q5_K: case T_Q5_0: raw = 176; break;
+        case T_Q6_K: raw = 224; break;
+        case T_Q4_1: raw = 160; break;
+        case T_Q5_1: raw = 192; break;
+        case T_Q2_K: raw = 96;  break;
+        case T_Q3_K: raw = 128; break;
+        default: break;                                          // Q4_0, Q8_0 (half units), Q4_K, IQ4_NL, IQ4_XS: 144
+    }
     auto smem_of = [&](int ns) { return ns * (rows * TC_BK * 2 + BN * TC_BK * 2) + 2 * rows * raw + 256 + 1024; };
     int nstages = TC_MAX_STAGES;
     while (nstages > 2 && smem_of(nstages) > 227 * 1024) nstages--;
@@ -451,6 +461,13 @@ int launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q4_K: return pl.halves == 2 ? launch_tc<T_Q4_K, 2>(a, pl, st) : launch_tc<T_Q4_K, 1>(a, pl, st);
         case T_Q5_K: return pl.halves == 2 ? launch_tc<T_Q5_K, 2>(a, pl, st) : launch_tc<T_Q5_K, 1>(a, pl, st);
         case T_Q6_K: return pl.halves == 2 ? launch_tc<T_Q6_K, 2>(a, pl, st) : launch_tc<T_Q6_K, 1>(a, pl, st);
+        case T_Q4_1: return pl.halves == 2 ? launch_tc<T_Q4_1, 2>(a, pl, st) : launch_tc<T_Q4_1, 1>(a, pl, st);
+        case T_Q5_0: return pl.halves == 2 ? launch_tc<T_Q5_0, 2>(a, pl, st) : launch_tc<T_Q5_0, 1>(a, pl, st);
+        case T_Q5_1: return pl.halves == 2 ? launch_tc<T_Q5_1, 2>(a, pl, st) : launch_tc<T_Q5_1, 1>(a, pl, st);
+        case T_IQ4_NL: return pl.halves == 2 ? launch_tc<T_IQ4_NL, 2>(a, pl, st) : launch_tc<T_IQ4_NL, 1>(a, pl, st);
+        case T_IQ4_XS: return pl.halves == 2 ? launch_tc<T_IQ4_XS, 2>(a, pl, st) : launch_tc<T_IQ4_XS, 1>(a, pl, st);
+        case T_Q2_K: return pl.halves == 2 ? launch_tc<T_Q2_K, 2>(a, pl, st) : launch_tc<T_Q2_K, 1>(a, pl, st);
+        case T_Q3_K: return pl.halves == 2 ? launch_tc<T_Q3_K, 2>(a, pl, st) : launch_tc<T_Q3_K, 1>(a, pl, st);
         default: set_error("mul_mat: unsupported weight type %d for the tcgen05 kernel", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }

@@ -35,9 +35,10 @@ def main():
         z = np.load(G / f"mulmat_{name}.npz")
         for ci in range(int(z["ncases"])):
             M, N, K = (int(v) for v in z[f"shape{ci}"])
-            for flags in (g.MM_AUTO, g.MM_GENERIC):           # AUTO = the superblock kernel where it is dispatched (Q5_0, Q2_K, Q3_K; n <= 8)
+            for flags in (g.MM_AUTO, g.MM_GENERIC):           # AUTO = superblock kernel (n <= 8) / tcgen05 GEMM (n >= 16) where eligible
                 Y = g.mul_mat(t, dev(z[f"W{ci}"]), dev(z[f"X{ci}"]), M, N, K, flags=flags).cpu().numpy()[0, 0]
-                assert O.nmse(Y, z[f"Y{ci}"]) < TOL, ("golden mul_mat", name, ci, flags)
+                tol = 1e-4 if g.mul_mat_plan(t, M, N, K, flags) == g.MM_GEMM else TOL     # fp16 operands on the tensor-core path
+                assert O.nmse(Y, z[f"Y{ci}"]) < tol, ("golden mul_mat", name, ci, flags)
         rng = np.random.default_rng(900 + t)
         for (M, N, K) in [(16, 1, 256), (33, 5, 1024), (1000, 2, 4096), (257, 17, 512), (4096, 1, 4096), (1536, 8, 2048)] + ([(7, 2, 96), (16, 3, 160)] if orc.blck_size(t) == 32 else []):
             W = O.random_blocks(t, M * K // orc.blck_size(t), rng)
@@ -45,7 +46,21 @@ def main():
             want = orc.mul_mat(t, W, X, M, N, K)
             for flags in (g.MM_AUTO, g.MM_GENERIC):
                 Y = g.mul_mat(t, dev(W), dev(X), M, N, K, flags=flags).cpu().numpy()[0, 0]
-                assert O.nmse(Y, want) < TOL, ("oracle mul_mat", name, M, N, K, flags)
+                tol = 1e-4 if g.mul_mat_plan(t, M, N, K, flags) == g.MM_GEMM else TOL
+                assert O.nmse(Y, want) < tol, ("oracle mul_mat", name, M, N, K, flags)
+        # tensor-core path (fp16 operands): against the exact product of the dequantized weights, sampled rows
+        for (M, N, K) in [(512, 64, 2048), (1000, 512, 4096)]:
+            if g.mul_mat_plan(t, M, N, K) != g.MM_GEMM:
+                continue
+            W = O.random_blocks(t, M * K // orc.blck_size(t), rng)
+            X = rng.uniform(-1, 1, N * K).astype(np.float32)
+            Y = g.mul_mat(t, dev(W), dev(X), M, N, K).cpu().numpy()[0, 0]
+            assert np.isfinite(Y).all(), ("gemm finite", name, M, N, K)
+            rows = rng.choice(M, 24, replace=False)
+            rb = orc.row_size(t, K)
+            Wsub = np.concatenate([W[r * rb:(r + 1) * rb] for r in rows])
+            want = orc.mul_mat(t, Wsub, X, len(rows), N, K, f64=True)
+            assert O.nmse(Y[:, rows], want) < 2e-5, ("gemm", name, M, N, K)
         z = np.load(G / f"mulmatid_{name}.npz")
         ne, nu, nb1, ntok, M, K = (int(v) for v in z["cfg"])
         Y = g.mul_mat_id(t, dev(z["W"]), dev(z["X"]), dev(z["ids"]), M, K, ne, nu, nb1, ntok).cpu().numpy()

@@ -110,7 +110,7 @@ int emu_sb_quantize(int kq, const float * x, int64_t K, uint8_t * rec, int with_
 }
 
 // ---- GEMM operand preparation (b200_tc_dequant.cuh): K fp16 values of one packed row
-#define FOR_TC_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K)
+#define FOR_TC_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_IQ4_NL) X(T_IQ4_XS) X(T_Q2_K) X(T_Q3_K)
 int emu_tc_dequant_row(int type, const uint8_t * row, int64_t K, uint16_t * out) {
     switch (type) {
 #define X(T) case T: tc_row<T>(row, K, out); return 0;

@@ -230,7 +230,7 @@ def test_activation_quantizers_in_an_emulated_warp(t, emu, oracle):
                 assert np.array_equal(got_sb[:nb], want_sb[:nb]), (K,)
 
 
-TC_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K]
+TC_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K, O.Q4_1, O.Q5_0, O.Q5_1, O.IQ4_NL, O.IQ4_XS, O.Q2_K, O.Q3_K]
 
 
 @pytest.mark.parametrize("t", TC_TYPES, ids=[O.TYPE_NAMES[t] for t in TC_TYPES])
