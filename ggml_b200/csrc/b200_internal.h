@@ -18,8 +18,10 @@ int  sm_count();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember it per (kernel instantiation, device), so that a
 // process that drives several B200s through the backend (one ggml device per GPU) configures every one of them.
 struct per_device_flag {
-    bool done[64] = {};
-    bool & here() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0; return done[d]; }
+    std::atomic<bool> done[64] = {};
+    static int dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0; return d; }
+    bool test() const { return done[dev()].load(std::memory_order_acquire); }      // setting the attribute twice is harmless: no lock needed
+    void set() { done[dev()].store(true, std::memory_order_release); }
 };
 
 #define B200_CUDA_TRY(expr)                                                                         \
@@ -48,6 +50,7 @@ size_t mmvq_generic_workspace(const ggml_b200_mul_mat_args & a);
 bool   mmvq_sb_eligible(const ggml_b200_mul_mat_args & a);
 int    launch_mmvq_sb(const ggml_b200_mul_mat_args & a, cudaStream_t st, const ggml_b200_gather * ga = nullptr, const ggml_b200_epilogue * ep = nullptr);
 int    debug_read_trace(unsigned long long * out);
+int    prepare_device();   // allocate the per-device control block (never inside a stream capture)
 int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cudaStream_t st);
 
 // mmq_tc.cu (tcgen05 GEMM)

@@ -30,6 +30,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #define B200_MAX_DEVICES 16
@@ -68,11 +69,19 @@ struct backend_ctx {
     void *       workspace = nullptr;   // stream-ordered scratch for the kernel shim
     size_t       workspace_size = 0;
     std::string  name;
+    cudaEvent_t  copy_event = nullptr;  // orders cross-backend copies (cpy_tensor_async)
     // CUDA-graph replay of whole ggml graphs (like the reference, src/ggml-cuda/ggml-cuda.cu:2696-2767): the node loop is
-    // stream-captured, the executable graph is updated in place (cudaGraphExecUpdate) and launched once per graph_compute
-    cudaGraphExec_t graph_exec = nullptr;
+    // stream-captured and launched as one executable graph per graph_compute.
+    // A small cache of instantiated graphs keyed on the exact node properties (ops, shapes, strides, data pointers, parameters,
+    // sources): an unchanged ggml graph is replayed without being re-captured; a changed one is captured and the executable
+    // graph of matching topology is updated in place (cudaGraphExecUpdate), re-instantiated only if that fails.
+    struct cached_graph { std::vector<uint64_t> sig; cudaGraphExec_t exec = nullptr; uint64_t last_use = 0; };
+    std::vector<cached_graph> graphs;
+    uint64_t        graph_clock = 0;
     int             graph_calls = 0;      // the first graph_compute runs eagerly (one-time attribute / allocation work)
     bool            capturing = false;
+    std::unordered_set<const ggml_tensor *> written;   // roots whose memory some node of the current cgraph writes through a view
+    bool            first_real_node = true;
 
     void * scratch(size_t need) {
         if (need <= workspace_size) return workspace;
@@ -227,7 +236,13 @@ ggml_backend_buffer_type_t host_buffer_type() {
 
 // ------------------------------------------------------------------------------------------ op support
 bool is_b200_weight_type(ggml_type t) {
-    return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K;
+    switch (t) {
+        case GGML_TYPE_Q4_0: case GGML_TYPE_Q8_0: case GGML_TYPE_Q4_K: case GGML_TYPE_Q5_K: case GGML_TYPE_Q6_K:      // north_star formats
+        case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_0: case GGML_TYPE_Q5_1: case GGML_TYPE_Q2_K: case GGML_TYPE_Q3_K:      // SURVEY 8f-2 (validated on a B200 in round 1)
+        case GGML_TYPE_IQ4_NL: case GGML_TYPE_IQ4_XS:
+            return true;
+        default: return false;
+    }
 }
 
 bool tensor_on_device(const ggml_tensor * t, int device) {
@@ -320,12 +335,26 @@ bool device_offload_op(ggml_backend_dev_t, const ggml_tensor * op) {
 }
 
 // ------------------------------------------------------------------------------------------ compute
+bool is_noop(ggml_op op) { return op == GGML_OP_NONE || op == GGML_OP_RESHAPE || op == GGML_OP_VIEW || op == GGML_OP_PERMUTE || op == GGML_OP_TRANSPOSE; }
+
+// May the mat-vec kernel start fetching src0 before the preceding kernel on the stream has finished?  Only for tensors that
+// nothing in flight writes: a graph leaf that owns its memory, that no node of this cgraph writes through a view (ggml_cpy into it,
+// in-place ops: their results are views whose view_src is the leaf), and, outside CUDA-graph capture, not for the first kernel of a
+// cgraph (its predecessor on the stream belongs to an earlier graph_compute that may have written anything).  Buffers marked as
+// weights by the application (ggml_backend_buffer_set_usage) qualify regardless of the position.
+int src0_flags(const backend_ctx * ctx, const ggml_tensor * a) {
+    if (a->op != GGML_OP_NONE || a->view_src != nullptr) return GGML_B200_MM_AUTO;
+    if (ctx->written.count(a)) return GGML_B200_MM_AUTO;
+    const bool weights = a->buffer && ggml_backend_buffer_get_usage(a->buffer) == GGML_BACKEND_BUFFER_USAGE_WEIGHTS;
+    if (!weights && !ctx->capturing && ctx->first_real_node) return GGML_B200_MM_AUTO;
+    return GGML_B200_MM_SRC0_STATIC;
+}
+
 void compute_mul_mat(backend_ctx * ctx, const ggml_tensor * dst) {
     const ggml_tensor * a = dst->src[0], * b = dst->src[1];
     ggml_b200_mul_mat_args args{};
     args.type = (int32_t) a->type;
-    // weights (graph leaves, uploaded with set_tensor before graph_compute) may be prefetched ahead of the previous node
-    args.flags = (a->op == GGML_OP_NONE && a->view_src == nullptr) ? GGML_B200_MM_SRC0_STATIC : GGML_B200_MM_AUTO;
+    args.flags = src0_flags(ctx, a);
     args.K = a->ne[0]; args.M = a->ne[1]; args.N = b->ne[1];
     args.ne02 = a->ne[2]; args.ne03 = a->ne[3]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
     args.nb01 = a->nb[1]; args.nb02 = a->nb[2]; args.nb03 = a->nb[3];
@@ -412,7 +441,8 @@ void backend_free(ggml_backend_t backend) {
     {
         scoped_device sd(ctx->device);
         cudaStreamSynchronize(ctx->stream);
-        if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+        for (auto & g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
         if (ctx->workspace) cudaFreeAsync(ctx->workspace, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
@@ -431,6 +461,32 @@ void backend_get_tensor_async(ggml_backend_t backend, const ggml_tensor * tensor
     scoped_device sd(ctx->device);
     CUDA_OK(cudaMemcpyAsync(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost, ctx->stream));
 }
+// device-to-device copy between two B200 backends (same or different GPUs), asynchronous on both streams like the reference's
+// (src/ggml-cuda/ggml-cuda.cu:2353-2414): enqueue on the source stream, make the destination stream wait for it
+bool backend_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t backend_dst, const ggml_tensor * src, ggml_tensor * dst) {
+    if (!ggml_backend_is_b200(backend_src) || !ggml_backend_is_b200(backend_dst)) return false;
+    ggml_backend_buffer_t sbuf = src->view_src ? src->view_src->buffer : src->buffer;
+    ggml_backend_buffer_t dbuf = dst->view_src ? dst->view_src->buffer : dst->buffer;
+    if (!buffer_is_b200(sbuf) || !buffer_is_b200(dbuf)) return false;
+    backend_ctx * sctx = (backend_ctx *) backend_src->context, * dctx = (backend_ctx *) backend_dst->context;
+    if (((buffer_ctx *) sbuf->context)->device != sctx->device || ((buffer_ctx *) dbuf->context)->device != dctx->device) return false;
+    if (backend_src == backend_dst) {
+        scoped_device sd(sctx->device);
+        CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(dst), cudaMemcpyDeviceToDevice, sctx->stream));
+        return true;
+    }
+    {
+        scoped_device sd(sctx->device);
+        if (sctx->device == dctx->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(dst), cudaMemcpyDeviceToDevice, sctx->stream));
+        else                              CUDA_OK(cudaMemcpyPeerAsync(dst->data, dctx->device, src->data, sctx->device, ggml_nbytes(dst), sctx->stream));
+        if (!sctx->copy_event) CUDA_OK(cudaEventCreateWithFlags(&sctx->copy_event, cudaEventDisableTiming));
+        CUDA_OK(cudaEventRecord(sctx->copy_event, sctx->stream));
+    }
+    scoped_device sd(dctx->device);
+    CUDA_OK(cudaStreamWaitEvent(dctx->stream, sctx->copy_event, 0));
+    return true;
+}
+
 void backend_synchronize(ggml_backend_t backend) {
     backend_ctx * ctx = (backend_ctx *) backend->context;
     scoped_device sd(ctx->device);
@@ -479,9 +535,16 @@ int try_fuse_mul_mat(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
         }
     }
     const ggml_tensor * a = mm->src[0], * b = mm->src[1];
+    // the fused kernel writes the ADD / GELU outputs while other CTAs may still be reading src1: if the allocator placed one of them
+    // on src1's (already dead, when unfused) memory, the nodes must run one by one
+    {
+        const char * x0 = (const char *) b->data, * x1 = x0 + ggml_nbytes(b);
+        auto overlaps = [&](const void * p) { const char * y0 = (const char *) p, * y1 = y0 + mm->ne[0] * sizeof(float); return p && y0 < x1 && x0 < y1; };
+        if (overlaps(ep.dst_bias) || overlaps(ep.dst_unary) || overlaps(mm->data)) return 0;
+    }
     ggml_b200_mul_mat_args args{};
     args.type = (int32_t) a->type;
-    args.flags = (a->op == GGML_OP_NONE && a->view_src == nullptr) ? GGML_B200_MM_SRC0_STATIC : GGML_B200_MM_AUTO;
+    args.flags = src0_flags(ctx, a);
     args.K = a->ne[0]; args.M = a->ne[1]; args.N = 1;
     args.ne02 = a->ne[2]; args.ne03 = a->ne[3]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
     args.nb01 = a->nb[1]; args.nb02 = a->nb[2]; args.nb03 = a->nb[3];
@@ -510,12 +573,18 @@ int try_fuse_norm(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
 
 void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
     static const bool fuse = !(getenv("GGML_B200_DISABLE_FUSION") && atoi(getenv("GGML_B200_DISABLE_FUSION")) != 0);
+    ctx->written.clear();
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        const ggml_tensor * node = cgraph->nodes[i];
+        if (node->view_src && !is_noop(node->op)) ctx->written.insert(node->view_src);
+    }
+    ctx->first_real_node = true;
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (ggml_is_empty(node)) continue;
+        if (is_noop(node->op)) continue;
+        struct not_first { backend_ctx * c; ~not_first() { c->first_real_node = false; } } nf{ ctx };
         switch (node->op) {
-            case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
-                break;
             case GGML_OP_MUL_MAT:
                 if (is_b200_weight_type(node->src[0]->type)) {
                     const int extra = fuse ? try_fuse_mul_mat(ctx, cgraph, i) : 0;
@@ -532,41 +601,84 @@ void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
     }
 }
 
+// everything a captured launch sequence depends on: per node the op, type, shape, strides, data pointer, op parameters and the
+// same for its sources (a changed source pointer or view offset changes the kernels' arguments)
+void graph_signature(const ggml_cgraph * cgraph, std::vector<uint64_t> & sig) {
+    sig.clear();
+    sig.reserve((size_t) cgraph->n_nodes * 24);
+    auto put_tensor = [&](const ggml_tensor * t) {
+        sig.push_back(((uint64_t) t->op << 32) | (uint64_t) t->type);
+        sig.push_back((uint64_t)(uintptr_t) t->data);
+        for (int d = 0; d < 4; ++d) { sig.push_back((uint64_t) t->ne[d]); sig.push_back((uint64_t) t->nb[d]); }
+    };
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        const ggml_tensor * node = cgraph->nodes[i];
+        if (is_noop(node->op)) continue;
+        put_tensor(node);
+        sig.push_back((uint64_t)(uintptr_t) node->view_src);
+        const uint64_t * op = (const uint64_t *) node->op_params;
+        for (size_t w = 0; w < sizeof(node->op_params) / sizeof(uint64_t); ++w) sig.push_back(op[w]);
+        for (int j = 0; j < GGML_MAX_SRC; ++j) {
+            if (!node->src[j]) { sig.push_back(0); continue; }
+            put_tensor(node->src[j]);
+            // weights marked by the application change the launch flags (src0_flags)
+            sig.push_back(node->src[j]->buffer ? (uint64_t) ggml_backend_buffer_get_usage(node->src[j]->buffer) : 0);
+        }
+    }
+}
+
 ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
     backend_ctx * ctx = (backend_ctx *) backend->context;
     scoped_device sd(ctx->device);
     static const bool graphs_off = getenv("GGML_B200_DISABLE_GRAPHS") && atoi(getenv("GGML_B200_DISABLE_GRAPHS")) != 0;
     int n_real = 0;
-    for (int i = 0; i < cgraph->n_nodes; ++i) {
-        const ggml_op op = cgraph->nodes[i]->op;
-        n_real += !(op == GGML_OP_NONE || op == GGML_OP_RESHAPE || op == GGML_OP_VIEW || op == GGML_OP_PERMUTE || op == GGML_OP_TRANSPOSE);
-    }
+    for (int i = 0; i < cgraph->n_nodes; ++i) n_real += !is_noop(cgraph->nodes[i]->op);
     const bool use_graph = !graphs_off && n_real >= 8 && ctx->graph_calls++ > 0;
     if (!use_graph) {
         compute_nodes(ctx, cgraph);
         return GGML_STATUS_SUCCESS;
+    }
+    constexpr size_t MAX_CACHED = 4;
+    static thread_local std::vector<uint64_t> sig;
+    graph_signature(cgraph, sig);
+    ctx->graph_clock++;
+    for (auto & g : ctx->graphs) {
+        if (g.sig == sig) {                                        // unchanged graph: replay, no capture
+            g.last_use = ctx->graph_clock;
+            CUDA_OK(cudaGraphLaunch(g.exec, ctx->stream));
+            return GGML_STATUS_SUCCESS;
+        }
     }
     // size the scratch pool before capturing (allocation is not part of the graph)
     size_t need = 0;
     for (int i = 0; i < cgraph->n_nodes; ++i) { const size_t n = node_scratch_need(cgraph->nodes[i]); if (n > need) need = n; }
     ctx->scratch(need);
     cudaGraph_t graph = nullptr;
-    CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    // relaxed mode, as the reference (ggml-cuda.cu:2700): other threads of the process may call unrelated CUDA APIs meanwhile
+    CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     ctx->capturing = true;
     compute_nodes(ctx, cgraph);
     ctx->capturing = false;
     CUDA_OK(cudaStreamEndCapture(ctx->stream, &graph));
-    if (ctx->graph_exec) {
+    // victim: a free slot, else the least recently used entry; prefer updating an executable graph of the same length in place
+    backend_ctx::cached_graph * slot = nullptr;
+    for (auto & g : ctx->graphs) if (g.sig.size() == sig.size() && (!slot || g.last_use < slot->last_use)) slot = &g;
+    if (!slot && ctx->graphs.size() < MAX_CACHED) { ctx->graphs.emplace_back(); slot = &ctx->graphs.back(); }
+    if (!slot) for (auto & g : ctx->graphs) if (!slot || g.last_use < slot->last_use) slot = &g;
+    // a same-length entry is only overwritten when the cache is full or it is the token-by-token case (one live graph per shape)
+    if (slot->exec) {
         cudaGraphExecUpdateResultInfo info;
-        if (cudaGraphExecUpdate(ctx->graph_exec, graph, &info) != cudaSuccess) {      // topology changed: re-instantiate
+        if (cudaGraphExecUpdate(slot->exec, graph, &info) != cudaSuccess) {              // topology changed: re-instantiate
             cudaGetLastError();
-            CUDA_OK(cudaGraphExecDestroy(ctx->graph_exec));
-            ctx->graph_exec = nullptr;
+            CUDA_OK(cudaGraphExecDestroy(slot->exec));
+            slot->exec = nullptr;
         }
     }
-    if (!ctx->graph_exec) CUDA_OK(cudaGraphInstantiate(&ctx->graph_exec, graph, 0));
+    if (!slot->exec) CUDA_OK(cudaGraphInstantiate(&slot->exec, graph, 0));
     CUDA_OK(cudaGraphDestroy(graph));
-    CUDA_OK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    slot->sig = sig;
+    slot->last_use = ctx->graph_clock;
+    CUDA_OK(cudaGraphLaunch(slot->exec, ctx->stream));
     return GGML_STATUS_SUCCESS;
 }
 
@@ -586,7 +698,7 @@ const ggml_backend_i k_backend_iface = {
     /* .free               = */ backend_free,
     /* .set_tensor_async   = */ backend_set_tensor_async,
     /* .get_tensor_async   = */ backend_get_tensor_async,
-    /* .cpy_tensor_async   = */ nullptr,
+    /* .cpy_tensor_async   = */ backend_cpy_tensor_async,
     /* .synchronize        = */ backend_synchronize,
     /* .graph_plan_create  = */ nullptr,
     /* .graph_plan_free    = */ nullptr,
@@ -716,6 +828,7 @@ GGML_B200_API ggml_backend_t ggml_backend_b200_init(int device) {
     {
         scoped_device sd(device);
         CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        SHIM_OK(ggml_b200_prepare());       // per-device control block of the kernels: allocated here, never inside a stream capture
     }
     return new ggml_backend{ b200_guid(), k_backend_iface, dev, ctx };
 }

@@ -347,12 +347,15 @@ struct tc_plan {
 };
 
 static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
-    // Q6_K: decoder host-verified, kernel path not yet validated on a B200: opt-in (GGML_B200_TC_Q6K=1) until it is
-    static const bool env_q6k = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) != 0;
+    // every format of the mat-vec path has an operand decoder (b200_tc_dequant.cuh); Q6_K and the SURVEY 8f-2 formats passed their
+    // first B200 run at the end of round 1 (GGML_B200_TC_Q6K=0 turns the Q6_K path off again, for A/B comparisons)
+    static const bool env_q6k_off = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) == 0;
     const bool next_fmt = a.type == T_Q4_1 || a.type == T_Q5_0 || a.type == T_Q5_1 || a.type == T_IQ4_NL || a.type == T_IQ4_XS || a.type == T_Q2_K || a.type == T_Q3_K;
-    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && !(a.type == T_Q6_K && env_q6k) && !next_fmt) return false;
+    if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && !(a.type == T_Q6_K && !env_q6k_off) && !next_fmt) return false;
     if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
-    if (a.N < 16 || a.K % 256 != 0 || a.K < 256 || a.M < 1) return false;
+    // n >= 9: every batch the mat-vec kernels do not take (the reference's mul_mat_q threshold, ggml-cuda.cu:1852-1875); columns
+    // beyond n in the 32-wide minimum tile are zero-filled by the TMA box and never stored
+    if (a.N < 9 || a.K % 256 != 0 || a.K < 256 || a.M < 1) return false;
     const size_t rb = row_bytes(a.type, a.K);
     if (a.nb01 != rb || (rb % 16) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0 || (a.nb11 & 3) != 0) return false;
     if (a.M >= (1ll << 31) || a.N >= (1ll << 31) || rb >= (1ull << 31)) return false;
@@ -446,7 +449,7 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
     p.y = a.dst; p.partials = partials; p.flags = flags; p.inv_scale = inv_scale; p.M = a.M; p.N = a.N;
     p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages;
     static per_device_flag attr_set;
-    if (!attr_set.here()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc_kernel<T, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.here() = true; }
+    if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc_kernel<T, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
     mmq_tc_kernel<T, HALVES><<<pl.grid, TC_THREADS, pl.smem, st>>>(map_w, map_x, p);
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;

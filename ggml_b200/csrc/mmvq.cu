@@ -342,9 +342,9 @@ bool mmvq_tma_eligible(const ggml_b200_mul_mat_args & a) {
 
 template <int T, int NC, int R> static int launch_tma_inst(const tma_plan & pl, cudaStream_t st) {
     static per_device_flag attr_set;   // per instantiation and device
-    if (!attr_set.here()) {
+    if (!attr_set.test()) {
         B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_tma_kernel<T, NC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set.here() = true;
+        attr_set.set();
     }
     mmvq_tma_kernel<T, NC, R><<<pl.grid, pl.block, pl.smem, st>>>(pl.p);
     B200_LAUNCH_CHECK();

@@ -28,6 +28,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 namespace b200 {
 
@@ -236,6 +237,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
     }
+    // Completion must stay transitive along the stream (a later kernel's griddepcontrol.wait covers only ITS predecessor): a launch
+    // whose consumers did not wait for the preceding grid (SRC1_STATIC) does so before it retires, holding no work back.
+    if (p.src1_static && tid == 0) pdl_wait();
     if (p.world > 0) {
         // fused gather: the CTA that finishes last pushes this rank's slice to every peer's gathered y with coalesced 16-byte
         // stores over NVLink (one CTA -> one system-scope fence covers all the remote stores), then raises this rank's epoch in
@@ -288,17 +292,32 @@ __global__ void gather_wait_kernel(const uint32_t * flags, int world, uint32_t e
 
 struct sb_plan { sb_params p; int grid, smem, nw, nc; };
 
-// device control block: [0,64) global control words, [64, 64 + 64*8) 64 per-launch scheduling slots, byte 4096.. trace
+// device control block: [0,64) global control words, [64, 64 + 64*8) 64 per-launch scheduling slots, byte 4096.. trace.
+// One per device, allocated on first use under a mutex (or ahead of time by ggml_b200_prepare, which the backend calls at
+// device initialisation so that no allocation can fall inside a stream capture) and kept for the life of the process.
 static unsigned int * sb_counters() {
     static unsigned int * ptr[64] = { nullptr };
+    static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("control block: cudaGetDevice failed"); return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
     if (!ptr[dev]) {
-        if (cudaMalloc(&ptr[dev], 8192) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        cudaMemset(ptr[dev], 0, 8192);
+        unsigned int * p = nullptr;
+        cudaError_t e = cudaMalloc(&p, 8192);
+        if (e == cudaSuccess) e = cudaMemset(p, 0, 8192);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            set_error("control block: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            if (p) cudaFree(p);
+            return nullptr;
+        }
+        ptr[dev] = p;
     }
     return ptr[dev];
 }
+
+int prepare_device() { return sb_counters() ? GGML_B200_OK : GGML_B200_ECUDA; }
 
 template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_plan & pl) {
     using F = sbfmt<T>;
@@ -340,20 +359,14 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     p.nstages = env_stages;       // 0 = automatic (below)
     p.ntasks_row = (int)(a.K / F::TASK_W);
     p.A = make_sb_act(a.K);
-    p.ctl = sb_counters();
-    static std::atomic<unsigned> seq{0};
-    p.counters = p.ctl ? p.ctl + 64 + (seq.fetch_add(1) % 64u) * 8 : nullptr;
+    p.ctl = nullptr; p.counters = nullptr; p.dbg = nullptr;      // assigned at launch (assign_sb_slot): planning has no side effects
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     p.l2_prefetch_bytes = (!ind && p.src0_static && e_l2_mb > 0) ? (int64_t)std::min<size_t>((size_t)a.M * rb, (size_t)e_l2_mb << 20) : 0;
     p.world = 0; p.rank = 0; p.row_offset = 0; p.epoch = 0;
     p.ep_bias = nullptr; p.ep_y2 = nullptr; p.ep_y3 = nullptr;
-    static const bool env_dbg = getenv("GGML_B200_SB_DEBUG") && atoi(getenv("GGML_B200_SB_DEBUG")) != 0;
-    static std::atomic<unsigned> dbg_seq{0};
-    p.dbg = (env_dbg && p.ctl) ? (unsigned long long *)(p.ctl + 1024) + (dbg_seq.fetch_add(1) % 32u) * 8 : nullptr;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
     p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
     for (int q = 0; q < 8; ++q) { p.y_peers[q] = nullptr; p.flag_peers[q] = nullptr; }
-    if (!p.counters) return false;
     auto smem_of = [&]() { return p.nstages * p.stage_bytes + nc * p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
     const int max_res = nc > 1 ? 1 : SB_CONSUMER_WARPS == 8 ? 2 : 4;                       // register-limited residency (__launch_bounds__)
     int ctas = env_ctas < 1 ? 1 : env_ctas > max_res ? max_res : env_ctas;
@@ -375,11 +388,24 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     return true;
 }
 
+// a launch takes the next of the 64 scheduling slots of this device's control block (self-resetting counters: a slot is free again
+// when its launch has finished scheduling, and 64 launches never overlap on one device) and, in trace mode, the next trace record
+static int assign_sb_slot(sb_params & p) {
+    p.ctl = sb_counters();
+    if (!p.ctl) return GGML_B200_ECUDA;
+    static std::atomic<unsigned> seq{0};
+    p.counters = p.ctl + 64 + (seq.fetch_add(1, std::memory_order_relaxed) % 64u) * 8;
+    static const bool env_dbg = getenv("GGML_B200_SB_DEBUG") && atoi(getenv("GGML_B200_SB_DEBUG")) != 0;
+    static std::atomic<unsigned> dbg_seq{0};
+    p.dbg = env_dbg ? (unsigned long long *)(p.ctl + 1024) + (dbg_seq.fetch_add(1, std::memory_order_relaxed) % 32u) * 8 : nullptr;
+    return GGML_B200_OK;
+}
+
 template <int T, int NW, int NC> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
     static per_device_flag attr_set;
-    if (!attr_set.here()) {
+    if (!attr_set.test()) {
         B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-        attr_set.here() = true;
+        attr_set.set();
     }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
     cudaLaunchConfig_t cfg = {};
@@ -396,6 +422,7 @@ template <int T, int NW, int NC> static int launch_sb_nw(sb_plan & pl, cudaStrea
 template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const ggml_b200_gather * ga, cudaStream_t st, const ggml_b200_epilogue * ep = nullptr) {
     sb_plan pl;
     if (!make_sb_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the superblock mat-vec kernel"); return GGML_B200_EUNSUPPORTED; }
+    { const int rc = assign_sb_slot(pl.p); if (rc != GGML_B200_OK) return rc; }
     if (ep && ep->bias) { pl.p.ep_bias = ep->bias; pl.p.ep_y2 = ep->dst_bias; pl.p.ep_y3 = ep->unary == 1 ? ep->dst_unary : nullptr; }
     if (ga) {
         pl.p.world = ga->world; pl.p.rank = ga->rank; pl.p.row_offset = ga->row_offset; pl.p.epoch = ga->epoch;

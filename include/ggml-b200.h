@@ -85,9 +85,11 @@ enum {
     GGML_B200_MM_FORCE_GEMM  = 4,     /* tcgen05 tensor-core kernel */
     GGML_B200_MM_SRC0_STATIC = 16,    /* src0 is not written by the preceding kernel on this stream (model weights): the mat-vec may
                                          prefetch it before waiting for that kernel (programmatic dependent launch) */
-    GGML_B200_MM_SRC1_STATIC = 32,    /* src1 is not written by the preceding kernel either (e.g. Q/K/V or gate/up projections that share
-                                         one input, or a perf harness repeating an op): the launch never waits for it, so independent
-                                         mat-vecs overlap; dst must not alias the preceding kernel's dst */
+    GGML_B200_MM_SRC1_STATIC = 32,    /* src1 is not written by ANY kernel still in flight on this stream (inputs that were final before the
+                                         sequence of launches began, e.g. a perf harness repeating an op on fixed inputs), and dst is not
+                                         read or written by any of them: the launch never waits for its predecessors before computing, so
+                                         independent mat-vecs overlap.  It still waits for them before it retires, so completion stays
+                                         ordered along the stream.  NOT valid for "the kernel before the previous one produced src1". */
     GGML_B200_MM_GEMV_V1     = 8,     /* with FORCE_GEMV: the first-generation 64-weight-unit kernel (mmvq.cu) even for n = 1 */
 };
 
@@ -218,6 +220,9 @@ GGML_B200_API int ggml_b200_op_mul_mat_f(const ggml_b200_tensor * src0, const gg
 GGML_B200_API const char * ggml_b200_last_error(void);
 GGML_B200_API int          ggml_b200_device_count(void);
 GGML_B200_API int          ggml_b200_sm_count(void);
+/* one-time per-device setup (control block of the mat-vec scheduler and the split-K flags) for the CURRENT device.  Launches do it
+ * lazily; call it explicitly before the first launch that falls inside a stream capture (allocation is not capturable). */
+GGML_B200_API int          ggml_b200_prepare(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 GGML_B200_API uint64_t     ggml_b200_launch_count(void);
 GGML_B200_API const char * ggml_b200_version(void);

@@ -1,5 +1,5 @@
-"""Run by tests/test_gpu_next_formats.py in a SUBPROCESS with GGML_B200_TC_Q6K=1: the opt-in tcgen05 path for Q6_K (decoder
-host-verified, kernel path not yet validated on a B200) against the oracle.  Exit code 0 = all checks passed."""
+"""Run by tests/test_gpu_next_formats.py in a SUBPROCESS: the tcgen05 path for Q6_K (variable-lead TMA boxes for the 2-byte-aligned
+210-byte superblocks) against the oracle, incl. batches of 9..15 columns.  Exit code 0 = all checks passed."""
 import os
 import sys
 from pathlib import Path
@@ -7,7 +7,6 @@ from pathlib import Path
 import numpy as np
 import torch
 
-assert os.environ.get("GGML_B200_TC_Q6K") == "1"
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 import ggml_b200 as g  # noqa: E402
@@ -23,7 +22,7 @@ def main():
     orc = O.Oracle()
     t = O.Q6_K
     rng = np.random.default_rng(61)
-    for (M, N, K) in [(128, 16, 2048), (384, 100, 2048), (1000, 512, 4096), (4096, 512, 4096)]:
+    for (M, N, K) in [(128, 16, 2048), (384, 100, 2048), (1000, 512, 4096), (4096, 512, 4096), (256, 9, 2048), (100, 15, 4096)]:
         assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMM, (M, N, K)
         W = O.random_blocks(t, M * K // 256, rng)
         X = rng.uniform(-1, 1, N * K).astype(np.float32)

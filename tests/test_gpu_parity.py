@@ -233,7 +233,7 @@ def test_full_size_properties(t, M, K, g, oracle):
     assert O.nmse(Yg, Y) < TOL
 
 
-GEMM_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K]
+GEMM_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K]
 
 
 @pytest.mark.parametrize("t", GEMM_TYPES, ids=[O.TYPE_NAMES[t] for t in GEMM_TYPES])
@@ -241,9 +241,13 @@ def test_gemm_tcgen05_vs_oracle(t, g, oracle):
     """tcgen05 path (fp16 operands, f32 TMEM accumulation).  Tolerances, stated: NMSE <= 1e-4 against the oracle (which
     itself carries the int8 activation-quantization noise), <= 2e-5 against the exact f64 product of the dequantized
     weights; the reference's own gate is 5e-4 (tests/test-backend-ops.cpp:1915-1917)."""
-    for (M, N, K) in [(128, 16, 256), (256, 32, 512), (1000, 100, 1024), (384, 512, 2048), (130, 257, 768)]:
+    # n = 9 .. 15 (the batches between the mat-vec kernels and a full 16-column tile) run on the tensor cores too
+    for (M, N, K) in [(128, 16, 256), (256, 32, 512), (1000, 100, 1024), (384, 512, 2048), (130, 257, 768),
+                      (64, 9, 512), (200, 13, 1024), (256, 15, 256), (300, 11, 2048), (128, 10, 4096), (520, 12, 2048), (96, 14, 2048)]:
         if g.mul_mat_plan(t, M, N, K, g.MM_GEMM) != g.MM_GEMM:
+            assert t == O.Q6_K and K % 2048 != 0, (M, N, K)          # Q6_K rows are 16-byte multiples only when K % 2048 == 0 (TMA stride rule)
             continue
+        assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMM, (M, N, K)        # and AUTO picks it: no silent fall-back to the generic kernel
         W = weights(oracle, t, M, K, seed=3 * M + N + K)
         X = np.random.default_rng(N + K).uniform(-1, 1, N * K).astype(np.float32)
         Y = g.mul_mat(t, dev(W), dev(X), M, N, K, flags=g.MM_GEMM).cpu().numpy()[0, 0]
@@ -252,7 +256,7 @@ def test_gemm_tcgen05_vs_oracle(t, g, oracle):
         assert O.nmse(Y, oracle.mul_mat(t, W, X, M, N, K, f64=True)) < 2e-5, (M, N, K)
 
 
-@pytest.mark.parametrize("t", [O.Q8_0, O.Q4_K], ids=["q8_0", "q4_K"])
+@pytest.mark.parametrize("t", [O.Q8_0, O.Q4_K, O.Q6_K], ids=["q8_0", "q4_K", "q6_K"])
 def test_gemm_full_size_properties(t, g, oracle):
     """BASELINE.json configs[2] (Q8_0 4096x4096, n_batch = 512) and its Q4_K twin: sampled rows against the oracle,
     and exact size-independent properties (column permutation equivariance, power-of-two scaling, repeatability)."""
