@@ -231,7 +231,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
                         if (p.ep_y3) p.ep_y3[row0 + r] = gelu_ggml(v2);
                     }
                 }
-                else p.y_peers[p.rank][p.row_offset + row0 + r] = acc;       // own slot of the gathered y; pushed to the peers below
+                else {
+                    // row-sharded multi-GPU: straight into the gathered y of every rank (own one included) over NVLink
+                    const int64_t gi = p.row_offset + row0 + r;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q < p.world) p.y_peers[q][gi] = acc;
+                }
             }
         }
         __syncwarp();
@@ -241,37 +246,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
     // whose consumers did not wait for the preceding grid (SRC1_STATIC) does so before it retires, holding no work back.
     if (p.src1_static && tid == 0) pdl_wait();
     if (p.world > 0) {
-        // fused gather: the CTA that finishes last pushes this rank's slice to every peer's gathered y with coalesced 16-byte
-        // stores over NVLink (one CTA -> one system-scope fence covers all the remote stores), then raises this rank's epoch in
-        // every peer's flag array.  The other SMs are already free for the next (overlapping) launch.
-        __shared__ int s_last;
-        __threadfence();
+        // fused gather, publication: every row was already stored into every rank's gathered y by the lane that finished it (the row
+        // loop above), so the exchange traffic is spread over all SMs and overlaps the streaming of the remaining rows.  Here each
+        // thread makes its own remote stores visible system-wide, the CTA counts itself done, and the CTA that finishes last raises
+        // this rank's epoch in every peer's flag array (stores -> fence.sys -> counter -> fence.sys -> release flag: causally ordered).
+        // The griddepcontrol.wait above keeps the publications of overlapping launches in launch order.
+        __threadfence_system();
         asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
-        if (tid == 0) {
-            s_last = atomicAdd(&p.counters[2], 1u) == gridDim.x - 1;
-            if (s_last) { p.counters[2] = 0; __threadfence(); }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
-        if (s_last) {
-            const float * src = p.y_peers[p.rank] + p.row_offset;
-            const int64_t n = p.M;
-            const bool vec = ((p.row_offset | n) & 3) == 0;
-            for (int q = 0; q < p.world; ++q) {
-                if (q == p.rank) continue;
-                float * dst = p.y_peers[q] + p.row_offset;
-                if (vec) { for (int64_t i = tid; i < n / 4; i += SB_CONSUMER_WARPS * 32) ((float4 *)dst)[i] = __ldcg((const float4 *)src + i); }
-                else     { for (int64_t i = tid; i < n; i += SB_CONSUMER_WARPS * 32) dst[i] = __ldcg(src + i); }
-            }
+        if (tid == 0 && atomicAdd(&p.counters[2], 1u) == gridDim.x - 1) {
+            p.counters[2] = 0;
+            // the exchange epoch lives on the device (ctl[0]) so that a CUDA graph can replay the launch; the flags only ever grow
+            const uint32_t e = p.epoch ? p.epoch : atomicAdd(&p.ctl[0], 1u) + 1u;
             __threadfence_system();
-            asm volatile("bar.sync 1, %0;" ::"n"(SB_CONSUMER_WARPS * 32) : "memory");
-            if (tid == 0) {
-                // the exchange epoch lives on the device (ctl[0]) so that a CUDA graph can replay the launch
-                // (atomic: independent launches overlap, two grids may finish together; the flags only ever grow)
-                const uint32_t e = p.epoch ? p.epoch : atomicAdd(&p.ctl[0], 1u) + 1u;
-                __threadfence_system();
-                for (int q = 0; q < p.world; ++q)
-                    asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(p.flag_peers[q] + p.rank), "r"(e) : "memory");
-            }
+            for (int q = 0; q < p.world; ++q)
+                asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(p.flag_peers[q] + p.rank), "r"(e) : "memory");
         }
     }
 }

@@ -169,8 +169,20 @@ double probe_mul_mat_sweep(const char * dev, int type_a, const void * W, const f
     ggml_backend_tensor_set(b, X, 0, ggml_nbytes(b));
     for (int i = 0; i < warmup; ++i) ggml_backend_graph_compute(h.be, gf);
     ggml_backend_synchronize(h.be);
+    // e2e == 1: synchronous public calls (tensor_set, graph_compute, one tensor_get per output);
+    // e2e == 2: the asynchronous public calls a pipelined application uses (tensor_set_async, graph_compute_async, tensor_get_async
+    //           per output into distinct host rows, one synchronize per iteration); identical to mode 1 on backends without async copies
+    std::vector<float> host_out;
+    if (e2e == 2) host_out.resize((size_t) nw * M * N);
     double t0 = now_s();
     for (int i = 0; i < iters; ++i) {
+        if (e2e == 2) {
+            ggml_backend_tensor_set_async(h.be, b, X, 0, ggml_nbytes(b));
+            ggml_backend_graph_compute_async(h.be, gf);
+            for (int r = 0; r < nw; ++r) ggml_backend_tensor_get_async(h.be, outs[r], host_out.data() + (size_t) r * M * N, 0, ggml_nbytes(outs[r]));
+            ggml_backend_synchronize(h.be);
+            continue;
+        }
         if (e2e) ggml_backend_tensor_set(b, X, 0, ggml_nbytes(b));
         ggml_backend_graph_compute(h.be, gf);
         if (e2e) for (ggml_tensor * c : outs) ggml_backend_tensor_get(c, Y, 0, ggml_nbytes(c));
