@@ -57,5 +57,11 @@ int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cud
 bool   mmq_tc_eligible(const ggml_b200_mul_mat_args & a);
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a);
 int    launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+// mmq_tc2.cu (tcgen05 GEMM on CTA pairs, cta_group::2)
+bool   mmq_tc2_eligible(const ggml_b200_mul_mat_args & a);
+size_t mmq_tc2_workspace(const ggml_b200_mul_mat_args & a);
+int    launch_mmq_tc2(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+unsigned int * tc_flag_slot();   // a zeroed, self-cleaning block of split-K flags from the device's control block (nullptr on error)
+int    tc_prepare_device();
 
 } // namespace b200

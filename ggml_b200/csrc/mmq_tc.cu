@@ -25,6 +25,7 @@
 #include "b200_internal.h"
 #include "b200_quants.cuh"
 #include "b200_tc_dequant.cuh"   // raw-unit geometry, tc_load_unit, dq64 (also compiled for the host by tests/hostemu)
+#include "b200_tc_ptx.cuh"       // mbarrier / TMA / TMEM / UMMA inline PTX
 
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -33,61 +34,6 @@
 #include <mutex>
 
 namespace b200 {
-
-// ----------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t tc_smem(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tc_mbar_init(uint64_t * b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(b)), "r"(c) : "memory"); }
-__device__ __forceinline__ void tc_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_expect_tx(uint64_t * b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem(b)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void tc_arrive(uint64_t * b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem(b)) : "memory"); }
-__device__ __forceinline__ void tc_wait(uint64_t * b, uint32_t parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nTC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TC_DONE;\nbra TC_WAIT;\nTC_DONE:\n}\n" ::"r"(tc_smem(b)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tc_tma_2d(void * dst, const CUtensorMap * map, int c0, int c1, uint64_t * bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(tc_smem(dst)), "l"(map), "r"(tc_smem(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_prefetch_map(const CUtensorMap * map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
-__device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_tmem_alloc(uint32_t * dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t * bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
 
 // ----------------------------------------------------------------------------- kernel
 // CTA tile = HALVES x 128 W rows x BN activation rows.  HALVES = 2: two 128-row tcgen05 sub-tiles share every B (activation)
@@ -103,7 +49,6 @@ struct tc_params {
     int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages;
 };
 
-__host__ __device__ inline uint32_t tc_tmem_cols(int cols) { return cols <= 32 ? 32u : cols <= 64 ? 64u : cols <= 128 ? 128u : cols <= 256 ? 256u : 512u; }
 
 template <int T, int KS>
 __device__ __forceinline__ void tc_dequant_step(int nstages, int step, bool valid, const uint32_t (&u)[tcfmt<T>::UNIT_WORDS], uint8_t * a_ring, int stage_bytes, int a_row_off,
@@ -297,6 +242,10 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
 // a row of fp16 subnormals, whatever the row's magnitude), then the conversion.  inv_scale[n] is applied to column n of the
 // result in the GEMM epilogue.
 __global__ void __launch_bounds__(256) x_to_f16_kernel(const float * __restrict__ x, size_t nb11, __half * __restrict__ xh, float * __restrict__ inv_scale, int64_t K) {
+    // programmatic dependent launch (no-ops for a plain launch): the GEMM that follows may start its prologue and its weight stream
+    // now; this kernel itself waits for its predecessor (which may have produced x, and may still be reading the fp16 buffer)
+    tc_pdl_launch_dependents();
+    tc_pdl_wait();
     const int64_t n = blockIdx.x;
     const float * xr = (const float *)((const uint8_t *)x + n * nb11);
     __shared__ float s_max[8];
@@ -327,9 +276,19 @@ __global__ void __launch_bounds__(256) x_to_f16_kernel(const float * __restrict_
 }
 
 // ----------------------------------------------------------------------------- host side
-typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static encode_tiled_fn get_encode() {
+int tc_launch_x_to_f16(const float * x, size_t nb11, __half * xh, float * inv_scale, int64_t K, int64_t N, cudaStream_t st, bool pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, x_to_f16_kernel, x, nb11, xh, inv_scale, K));
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+encode_tiled_fn tc_get_encode() {
     static encode_tiled_fn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -359,7 +318,7 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     const size_t rb = row_bytes(a.type, a.K);
     if (a.nb01 != rb || (rb % 16) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0 || (a.nb11 & 3) != 0) return false;
     if (a.M >= (1ll << 31) || a.N >= (1ll << 31) || rb >= (1ull << 31)) return false;
-    if (!get_encode()) return false;
+    if (!tc_get_encode()) return false;
     int BN = a.N >= 256 ? 256 : (int)((a.N + 15) / 16 * 16);
     if (BN > 128 && BN < 256) BN = 256;
     if (BN > 64 && BN < 128) BN = 128;
@@ -405,6 +364,7 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
 
 bool mmq_tc_eligible(const ggml_b200_mul_mat_args & a) { tc_plan pl; return make_tc_plan(a, pl); }
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a) {
+    if (mmq_tc2_eligible(a)) return mmq_tc2_workspace(a);
     tc_plan pl;
     if (!make_tc_plan(a, pl)) return 0;
     return pl.xb_bytes + pl.partial_bytes + pl.flags_bytes + pl.scale_bytes + 1024;
@@ -421,10 +381,7 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
 
     // flags must start at zero: the tile owners leave them clean, but the workspace may be fresh memory
     B200_CUDA_TRY(cudaMemsetAsync(flags, 0, pl.flags_bytes, st));
-    {
-        x_to_f16_kernel<<<(unsigned)a.N, 256, 0, st>>>(a.src1, a.nb11, xb, inv_scale, a.K);
-        B200_LAUNCH_CHECK();
-    }
+    { const int rc = tc_launch_x_to_f16(a.src1, a.nb11, xb, inv_scale, a.K, a.N, st, false); if (rc != GGML_B200_OK) return rc; }
     const size_t rb = row_bytes(a.type, a.K);
     alignas(64) CUtensorMap map_w, map_x;
     {
@@ -432,7 +389,7 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
         const cuuint64_t strides[1] = { (cuuint64_t)rb };
         const cuuint32_t box[2] = { (cuuint32_t)(tcfmt<T>::RAW / 4), (cuuint32_t)(HALVES * TC_BM) };
         const cuuint32_t es[2] = { 1, 1 };
-        CUresult r = get_encode()(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)a.src0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = tc_get_encode()(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)a.src0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(W) failed: %d", (int)r); return GGML_B200_ECUDA; }
     }
@@ -441,7 +398,7 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
         const cuuint64_t strides[1] = { (cuuint64_t)a.K * 2 };
         const cuuint32_t box[2] = { (cuuint32_t)TC_BK, (cuuint32_t)pl.BN };
         const cuuint32_t es[2] = { 1, 1 };
-        CUresult r = get_encode()(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)xb, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = tc_get_encode()(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)xb, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(X) failed: %d", (int)r); return GGML_B200_ECUDA; }
     }
@@ -456,6 +413,7 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
 }
 
 int launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+    if (mmq_tc2_eligible(a)) return launch_mmq_tc2(a, st);              // CTA pairs (cta_group::2) where the problem is large enough
     tc_plan pl;
     if (!make_tc_plan(a, pl)) { set_error("mul_mat: shape not eligible for the tcgen05 kernel"); return GGML_B200_EUNSUPPORTED; }
     switch (a.type) {

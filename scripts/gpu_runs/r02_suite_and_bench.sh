@@ -1,11 +1,22 @@
 #!/bin/bash
-# round 2: the whole GPU suite, smoke, and the full bench line (all BASELINE configurations + parity + plug-in e2e)
+# round 2: pair-kernel sanity (isolated), the whole GPU suite, smoke, and the full bench line (all BASELINE configurations + parity + plug-in e2e)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | head -2
 nproc
+echo "== pair kernel check"
+if timeout 150 python tests/gpu_tc2_check.py --time > gpurun_out/tc2_check.log 2>&1; then
+  tail -14 gpurun_out/tc2_check.log
+  for cfg in "128 0" "256 1" "128 2" "64 0"; do set -- $cfg; GGML_B200_TC2_BN=$1 GGML_B200_TC_SPLITK=$2 timeout 100 python tests/gpu_tc2_check.py --time 2>&1 | grep "^time"; done
+else
+  echo "PAIR KERNEL CHECK FAILED (rc=$?): continuing with GGML_B200_TC_PAIR=0"; tail -25 gpurun_out/tc2_check.log
+  export GGML_B200_TC_PAIR=0
+  nvidia-smi --query-gpu=name --format=csv,noheader | head -1
+fi
+echo "== suite"
 timeout 1500 python -m pytest tests -q -m gpu --timeout 900 -x 2>&1 | tail -12
 timeout 120 python -c "import __graft_entry__ as e; e.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02a.json 2> gpurun_out/bench_r02a.err; echo "bench rc=$?"; tail -c 300 gpurun_out/bench_r02a.err; python - <<'PY'
+echo "== bench"
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02a.json 2> gpurun_out/bench_r02a.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_r02a.err; python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/bench_r02a.json").read().strip().splitlines()[-1])
