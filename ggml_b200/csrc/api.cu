@@ -142,6 +142,10 @@ int ggml_b200_mul_mat_gather(const ggml_b200_mul_mat_args * args, const ggml_b20
     return launch_mmvq_sb(*args, (cudaStream_t)stream, ga);
 }
 
+int ggml_b200_mul_mat_gather_supported(const ggml_b200_mul_mat_args * args) {
+    return validate(args) == GGML_B200_OK && args->N == 1 && mmvq_sb_eligible(*args) ? 1 : 0;
+}
+
 int ggml_b200_debug_trace(unsigned long long * out256) { return debug_read_trace(out256); }
 
 int ggml_b200_gather_wait(const uint32_t * flags_local, int32_t world, uint32_t epoch, void * stream) {

@@ -82,6 +82,16 @@ struct backend_ctx {
     bool            capturing = false;
     std::unordered_set<const ggml_tensor *> written;   // roots whose memory some node of the current cgraph writes through a view
     bool            first_real_node = true;
+    // split-buffer mat-muls: one auxiliary stream per other device (+ staging for the activations, the n > 1 result, kernel scratch)
+    struct split_peer {
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+        void * x_stage = nullptr; size_t x_cap = 0; void * y_stage = nullptr; size_t y_cap = 0; void * ws = nullptr; size_t ws_cap = 0;
+        bool peer_access = false;
+    };
+    split_peer   peers[B200_MAX_DEVICES];
+    cudaEvent_t  split_fork = nullptr;
+    uint32_t *   split_flags = nullptr;      // on this device: one arrival flag per participating device (fused gather)
+    uint32_t     split_epoch = 0;
 
     void * scratch(size_t need) {
         if (need <= workspace_size) return workspace;
@@ -234,6 +244,177 @@ ggml_backend_buffer_type_t host_buffer_type() {
     return &buft;
 }
 
+
+// ------------------------------------------------------------------------------------------ split buffers (row-sharded weights)
+// The reference's multi-GPU entry (src/ggml-cuda/ggml-cuda.cu:716-1040): a buffer type whose 2-D weight tensors are split by ROWS over the
+// visible devices according to `tensor_split`; only MUL_MAT may consume them.  One process drives every device.  Each device's shard is
+// allocated in init_tensor; set_tensor / get_tensor scatter / gather the row ranges.  The mat-mul itself (compute_mul_mat_split below):
+// every device computes its rows on its own stream and the mat-vec kernel stores them straight into the main device's dst over NVLink
+// (the fused gather of ggml-b200.h, here with the main device as the only "peer"), flags instead of events; batches (n > 1) go through a
+// per-device staging buffer and a strided peer copy, ordered with events like the reference (:1333-1351, 1621-1647).
+constexpr int64_t SPLIT_ROW_ROUNDING = 64;      // shard boundaries: multiples of 64 rows (every block format then starts 16-byte aligned)
+
+struct split_buft_ctx {
+    int         main_device = 0;
+    float       split[B200_MAX_DEVICES] = {};   // cumulative start fractions per device index (position in the registry), like the reference
+    std::string name;
+};
+
+struct split_tensor_extra {
+    void *  data[B200_MAX_DEVICES] = {};        // row shard on registry device i (nullptr: no rows)
+    int64_t row_low[B200_MAX_DEVICES] = {}, row_high[B200_MAX_DEVICES] = {};
+};
+
+struct split_buffer_ctx {
+    std::vector<split_tensor_extra *> extras;
+    ~split_buffer_ctx();
+};
+
+int registry_device_count();
+int registry_device_index(int i);               // CUDA ordinal of registry device i
+
+split_buffer_ctx::~split_buffer_ctx() {
+    for (split_tensor_extra * e : extras) {
+        for (int i = 0; i < registry_device_count(); ++i)
+            if (e->data[i]) { scoped_device sd(registry_device_index(i)); cudaFree(e->data[i]); }
+        delete e;
+    }
+}
+
+void split_rows(const split_buft_ctx * bc, const ggml_tensor * t, int i, int64_t * lo, int64_t * hi) {
+    const int n = registry_device_count();
+    const int64_t nrows = ggml_nrows(t);
+    int64_t l = i == 0 ? 0 : (int64_t)(nrows * bc->split[i]);
+    l -= l % SPLIT_ROW_ROUNDING;
+    int64_t h;
+    if (i == n - 1) h = nrows;
+    else { h = (int64_t)(nrows * bc->split[i + 1]); h -= h % SPLIT_ROW_ROUNDING; }
+    if (h < l) h = l;
+    *lo = l; *hi = h;
+}
+
+const char * split_buft_get_name(ggml_backend_buffer_type_t buft) { return ((split_buft_ctx *) buft->context)->name.c_str(); }
+bool buft_is_b200_split(ggml_backend_buffer_type_t buft) { return buft && buft->iface.get_name == split_buft_get_name; }
+bool tensor_in_split_buffer(const ggml_tensor * t) { return t && t->buffer && buft_is_b200_split(t->buffer->buft); }
+
+void split_buffer_free(ggml_backend_buffer_t buffer) { delete (split_buffer_ctx *) buffer->context; }
+void * split_buffer_get_base(ggml_backend_buffer_t) { return (void *) 0x1000; }    // never dereferenced: the shards hang off tensor->extra
+
+void split_buffer_init_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor) {
+    GGML_ASSERT(tensor->view_src == nullptr && "views of split tensors are not supported");
+    split_buffer_ctx * ctx = (split_buffer_ctx *) buffer->context;
+    const split_buft_ctx * bc = (const split_buft_ctx *) buffer->buft->context;
+    split_tensor_extra * e = new split_tensor_extra;
+    ctx->extras.push_back(e);
+    for (int i = 0; i < registry_device_count(); ++i) {
+        split_rows(bc, tensor, i, &e->row_low[i], &e->row_high[i]);
+        const int64_t rows = e->row_high[i] - e->row_low[i];
+        if (rows == 0) continue;
+        scoped_device sd(registry_device_index(i));
+        const size_t size = (size_t) rows * ggml_row_size(tensor->type, tensor->ne[0]);
+        CUDA_OK(cudaMalloc(&e->data[i], size + 256));          // + 256: see buft_alloc_buffer
+        CUDA_OK(cudaMemset((char *) e->data[i] + size, 0, 256));
+    }
+    tensor->extra = e;
+}
+
+void split_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
+    GGML_ASSERT(offset == 0 && size == ggml_nbytes(tensor) && "split tensors are set in their entirety");
+    (void) buffer;
+    const split_tensor_extra * e = (const split_tensor_extra *) tensor->extra;
+    const size_t rb = ggml_row_size(tensor->type, tensor->ne[0]);
+    for (int i = 0; i < registry_device_count(); ++i) {
+        if (!e->data[i]) continue;
+        scoped_device sd(registry_device_index(i));
+        CUDA_OK(cudaMemcpyAsync(e->data[i], (const char *) data + e->row_low[i] * rb, (size_t)(e->row_high[i] - e->row_low[i]) * rb, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    }
+    for (int i = 0; i < registry_device_count(); ++i) {
+        if (!e->data[i]) continue;
+        scoped_device sd(registry_device_index(i));
+        CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+    }
+}
+
+void split_buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
+    GGML_ASSERT(offset == 0 && size == ggml_nbytes(tensor) && "split tensors are read in their entirety");
+    (void) buffer;
+    const split_tensor_extra * e = (const split_tensor_extra *) tensor->extra;
+    const size_t rb = ggml_row_size(tensor->type, tensor->ne[0]);
+    for (int i = 0; i < registry_device_count(); ++i) {
+        if (!e->data[i]) continue;
+        scoped_device sd(registry_device_index(i));
+        CUDA_OK(cudaMemcpyAsync((char *) data + e->row_low[i] * rb, e->data[i], (size_t)(e->row_high[i] - e->row_low[i]) * rb, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    }
+    for (int i = 0; i < registry_device_count(); ++i) {
+        if (!e->data[i]) continue;
+        scoped_device sd(registry_device_index(i));
+        CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+    }
+}
+void split_buffer_clear(ggml_backend_buffer_t, uint8_t) {}
+
+const ggml_backend_buffer_i k_split_buffer_iface = {
+    /* .free_buffer   = */ split_buffer_free,
+    /* .get_base      = */ split_buffer_get_base,
+    /* .init_tensor   = */ split_buffer_init_tensor,
+    /* .memset_tensor = */ nullptr,
+    /* .set_tensor    = */ split_buffer_set_tensor,
+    /* .get_tensor    = */ split_buffer_get_tensor,
+    /* .cpy_tensor    = */ nullptr,
+    /* .clear         = */ split_buffer_clear,
+    /* .reset         = */ nullptr,
+};
+
+ggml_backend_buffer_t split_buft_alloc_buffer(ggml_backend_buffer_type_t buft, size_t size) {
+    // the exact split is only known per tensor (rounding): the shards are allocated in init_tensor; `size` is the cumulative bound
+    // that ggml-alloc enforces through get_alloc_size
+    return ggml_backend_buffer_init(buft, k_split_buffer_iface, new split_buffer_ctx, size);
+}
+size_t split_buft_get_alloc_size(ggml_backend_buffer_type_t buft, const ggml_tensor * tensor) {
+    const split_buft_ctx * bc = (const split_buft_ctx *) buft->context;
+    size_t total = 0;
+    for (int i = 0; i < registry_device_count(); ++i) {
+        int64_t lo, hi;
+        split_rows(bc, tensor, i, &lo, &hi);
+        total += (size_t)(hi - lo) * ggml_row_size(tensor->type, tensor->ne[0]);
+    }
+    return total;
+}
+bool split_buft_is_host(ggml_backend_buffer_type_t) { return false; }
+
+ggml_backend_buffer_type_t split_buffer_type(int main_device, const float * tensor_split) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    static std::vector<ggml_backend_buffer_type *> bufts;      // never freed, like every buffer type
+    const int n = registry_device_count();
+    if (n == 0) return nullptr;
+    int main_index = -1;
+    for (int i = 0; i < n; ++i) if (registry_device_index(i) == main_device) main_index = i;
+    if (main_index < 0) { GGML_LOG_ERROR("ggml-b200: split buffer type: invalid main device %d\n", main_device); return nullptr; }
+    float split[B200_MAX_DEVICES] = {};
+    bool all_zero = tensor_split == nullptr;
+    if (!all_zero) { all_zero = true; for (int i = 0; i < n; ++i) if (tensor_split[i] != 0.0f) all_zero = false; }
+    if (all_zero) { for (int i = 0; i < n; ++i) split[i] = (float) i / (float) n; }          // B200s are identical: equal shares
+    else {
+        float sum = 0.0f;
+        for (int i = 0; i < n; ++i) { split[i] = sum; sum += tensor_split[i]; }
+        for (int i = 0; i < n; ++i) split[i] /= sum;
+    }
+    for (auto * b : bufts) {
+        const split_buft_ctx * c = (const split_buft_ctx *) b->context;
+        if (c->main_device == main_device && memcmp(c->split, split, sizeof(split)) == 0) return b;
+    }
+    split_buft_ctx * c = new split_buft_ctx;
+    c->main_device = main_device;
+    memcpy(c->split, split, sizeof(split));
+    c->name = "B200" + std::to_string(main_device) + "_Split";
+    ggml_backend_buffer_type * b = new ggml_backend_buffer_type{
+        { split_buft_get_name, split_buft_alloc_buffer, buft_get_alignment, nullptr, split_buft_get_alloc_size, split_buft_is_host },
+        ggml_backend_reg_dev_get(b200_reg(), (size_t) main_index), c };
+    bufts.push_back(b);
+    return b;
+}
+
 // ------------------------------------------------------------------------------------------ op support
 bool is_b200_weight_type(ggml_type t) {
     switch (t) {
@@ -312,6 +493,15 @@ bool supports_small_op(const ggml_tensor * op) {
 
 bool device_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
     const int device = ((device_ctx *) dev->context)->index;
+    // split buffers can only be used with GGML_OP_MUL_MAT (src0), on the buffer type's main device (ggml-cuda.cu:2944-2951)
+    for (int i = 0; i < GGML_MAX_SRC; ++i) {
+        if (!tensor_in_split_buffer(op->src[i])) continue;
+        if (op->op != GGML_OP_MUL_MAT || i != 0) return false;
+        if (((const split_buft_ctx *) op->src[i]->buffer->buft->context)->main_device != device) return false;
+        const ggml_tensor * a = op->src[0], * b = op->src[1];
+        if (a->ne[2] != 1 || a->ne[3] != 1 || b->ne[2] != 1 || b->ne[3] != 1 || !ggml_is_contiguous(a)) return false;
+        return supports_mul_mat(op) && tensor_on_device(b, device);
+    }
     for (int i = 0; i < GGML_MAX_SRC; ++i)
         if (op->src[i] && !tensor_on_device(op->src[i], device)) return false;
     switch (op->op) {
@@ -324,7 +514,7 @@ bool device_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
 }
 
 bool device_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_type_t buft) {
-    if (buft_is_b200(buft)) return buft->device == dev;
+    if (buft_is_b200(buft) || buft_is_b200_split(buft)) return buft->device == dev;
     return false;
 }
 
@@ -380,6 +570,117 @@ void compute_mul_mat_id(backend_ctx * ctx, const ggml_tensor * dst) {
     args.workspace = ctx->scratch(need);
     args.workspace_size = ctx->workspace_size;
     SHIM_OK(ggml_b200_mul_mat_id(&args, ctx->stream));
+}
+
+
+// grow-only device allocation on the current device (split path only: never inside a stream capture)
+void grow(void ** ptr, size_t * cap, size_t need) {
+    if (need <= *cap) return;
+    if (*ptr) CUDA_OK(cudaFree(*ptr));
+    const size_t sz = (need + need / 4 + 4095) & ~(size_t) 4095;
+    CUDA_OK(cudaMalloc(ptr, sz));
+    *cap = sz;
+}
+
+// MUL_MAT whose weights live in a split buffer: every device computes its row range concurrently and delivers it into dst on the main
+// device.  n = 1: the mat-vec kernel stores its rows into dst over NVLink itself and raises a flag (ggml_b200_mul_mat_gather with the
+// main device as the only peer); the main stream then waits for the flags of all participating devices.  n > 1: result staged on the
+// computing device, strided peer copy into dst, event.  Replaces ggml_cuda_op_mul_mat's split path (src/ggml-cuda/ggml-cuda.cu:1333-1647).
+void compute_mul_mat_split(backend_ctx * ctx, const ggml_tensor * dst) {
+    const ggml_tensor * a = dst->src[0], * b = dst->src[1];
+    const split_tensor_extra * e = (const split_tensor_extra *) a->extra;
+    GGML_ASSERT(e && "split tensor without shards (init_tensor not called?)");
+    const int64_t K = a->ne[0], M = a->ne[1], N = b->ne[1];
+    const size_t rb = ggml_row_size(a->type, K);
+    const int ndev = registry_device_count();
+    if (!ctx->split_fork) CUDA_OK(cudaEventCreateWithFlags(&ctx->split_fork, cudaEventDisableTiming));
+    if (!ctx->split_flags) { CUDA_OK(cudaMalloc((void **) &ctx->split_flags, 256)); CUDA_OK(cudaMemset(ctx->split_flags, 0, 256)); CUDA_OK(cudaDeviceSynchronize()); }
+    CUDA_OK(cudaEventRecord(ctx->split_fork, ctx->stream));           // everything dst / src1 depend on is ordered before this point
+
+    const uint32_t epoch = ++ctx->split_epoch;
+    auto shard_args = [&](int i) {
+        ggml_b200_mul_mat_args args{};
+        const int64_t rows = e->row_high[i] - e->row_low[i];
+        args.type = (int32_t) a->type; args.flags = GGML_B200_MM_AUTO;
+        args.K = K; args.M = rows; args.N = N;
+        args.ne02 = args.ne03 = args.ne12 = args.ne13 = 1;
+        args.nb01 = rb; args.nb02 = rb * rows; args.nb03 = rb * rows;
+        args.src0 = e->data[i]; args.src1 = (const float *) b->data; args.dst = (float *) dst->data;
+        args.nb11 = b->nb[1]; args.nb12 = b->nb[1] * N; args.nb13 = b->nb[1] * N;
+        return args;
+    };
+    // fused delivery (n = 1) for all shards or for none: decided before anything is launched
+    bool fused_all = N == 1;
+    for (int i = 0; i < ndev && fused_all; ++i) {
+        if (!e->data[i]) continue;
+        ggml_b200_mul_mat_args args = shard_args(i);
+        fused_all = ggml_b200_mul_mat_gather_supported(&args) != 0;
+    }
+    int j = 0, main_i = -1;
+    // other devices first (they fork off the main stream), the main device's own shard last
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 0; i < ndev; ++i) {
+            if (!e->data[i]) continue;
+            const int d = registry_device_index(i);
+            const bool is_main = d == ctx->device;
+            if (is_main) main_i = i;
+            if ((pass == 0) == is_main) continue;
+            const int64_t lo = e->row_low[i], rows = e->row_high[i] - lo;
+            backend_ctx::split_peer & pr = ctx->peers[i];
+            scoped_device sd(d);
+            cudaStream_t st = ctx->stream;
+            const float * x = (const float *) b->data;
+            size_t nb11 = b->nb[1];
+            if (!is_main) {
+                if (!pr.stream) {
+                    CUDA_OK(cudaStreamCreateWithFlags(&pr.stream, cudaStreamNonBlocking));
+                    CUDA_OK(cudaEventCreateWithFlags(&pr.done, cudaEventDisableTiming));
+                    SHIM_OK(ggml_b200_prepare());
+                }
+                if (!pr.peer_access) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->device, 0);                       // d -> main (dst, flags, src1)
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(pe);
+                    cudaGetLastError();
+                    { scoped_device sm(ctx->device); pe = cudaDeviceEnablePeerAccess(d, 0); if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(pe); cudaGetLastError(); }
+                    pr.peer_access = true;
+                }
+                st = pr.stream;
+                CUDA_OK(cudaStreamWaitEvent(st, ctx->split_fork, 0));
+                grow(&pr.x_stage, &pr.x_cap, (size_t) N * K * sizeof(float));
+                CUDA_OK(cudaMemcpy2DAsync(pr.x_stage, (size_t) K * sizeof(float), b->data, b->nb[1], (size_t) K * sizeof(float), (size_t) N, cudaMemcpyDeviceToDevice, st));
+                x = (const float *) pr.x_stage; nb11 = (size_t) K * sizeof(float);
+            }
+            ggml_b200_mul_mat_args args = shard_args(i);
+            args.src1 = x; args.nb11 = nb11; args.nb12 = nb11 * N; args.nb13 = nb11 * N;
+            if (fused_all) {
+                ggml_b200_gather ga{};
+                ga.world = 1; ga.rank = 0; ga.row_offset = lo; ga.epoch = epoch;
+                ga.y_peers[0] = (float *) dst->data; ga.flag_peers[0] = ctx->split_flags + j;
+                SHIM_OK(ggml_b200_mul_mat_gather(&args, &ga, st));
+            } else {
+                void ** ysp = &pr.y_stage; size_t * ycp = &pr.y_cap;
+                grow(ysp, ycp, (size_t) N * rows * sizeof(float));
+                args.dst = (float *) *ysp;
+                const size_t need = ggml_b200_mul_mat_workspace_size(&args);
+                if (is_main) { args.workspace = ctx->scratch(need); args.workspace_size = ctx->workspace_size; }
+                else { grow(&pr.ws, &pr.ws_cap, need); args.workspace = pr.ws; args.workspace_size = pr.ws_cap; }
+                SHIM_OK(ggml_b200_mul_mat(&args, st));
+                CUDA_OK(cudaMemcpy2DAsync((float *) dst->data + lo, (size_t) M * sizeof(float), *ysp, (size_t) rows * sizeof(float), (size_t) rows * sizeof(float), (size_t) N,
+                                          cudaMemcpyDeviceToDevice, st));
+                if (!is_main) {
+                    CUDA_OK(cudaEventRecord(pr.done, st));
+                    scoped_device sm(ctx->device);
+                    CUDA_OK(cudaStreamWaitEvent(ctx->stream, pr.done, 0));
+                }
+            }
+            ++j;
+        }
+    }
+    (void) main_i;
+    if (fused_all) {
+        scoped_device sm(ctx->device);
+        SHIM_OK(ggml_b200_gather_wait(ctx->split_flags, j, epoch, ctx->stream));        // every participating device has delivered its rows
+    }
 }
 
 ggml_b200_tensor desc(const ggml_tensor * t) {
@@ -443,6 +744,18 @@ void backend_free(ggml_backend_t backend) {
         cudaStreamSynchronize(ctx->stream);
         for (auto & g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
+        if (ctx->split_fork) cudaEventDestroy(ctx->split_fork);
+        if (ctx->split_flags) cudaFree(ctx->split_flags);
+        for (int i = 0; i < B200_MAX_DEVICES; ++i) {
+            backend_ctx::split_peer & pr = ctx->peers[i];
+            if (!pr.stream && !pr.y_stage) continue;
+            scoped_device sp(i < registry_device_count() ? registry_device_index(i) : ctx->device);
+            if (pr.stream) { cudaStreamSynchronize(pr.stream); cudaStreamDestroy(pr.stream); }
+            if (pr.done) cudaEventDestroy(pr.done);
+            if (pr.x_stage) cudaFree(pr.x_stage);
+            if (pr.y_stage) cudaFree(pr.y_stage);
+            if (pr.ws) cudaFree(pr.ws);
+        }
         if (ctx->workspace) cudaFreeAsync(ctx->workspace, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
@@ -586,6 +899,7 @@ void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
         struct not_first { backend_ctx * c; ~not_first() { c->first_real_node = false; } } nf{ ctx };
         switch (node->op) {
             case GGML_OP_MUL_MAT:
+                if (tensor_in_split_buffer(node->src[0])) { compute_mul_mat_split(ctx, node); break; }
                 if (is_b200_weight_type(node->src[0]->type)) {
                     const int extra = fuse ? try_fuse_mul_mat(ctx, cgraph, i) : 0;
                     if (extra > 0) i += extra; else compute_mul_mat(ctx, node);
@@ -632,8 +946,12 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
     scoped_device sd(ctx->device);
     static const bool graphs_off = getenv("GGML_B200_DISABLE_GRAPHS") && atoi(getenv("GGML_B200_DISABLE_GRAPHS")) != 0;
     int n_real = 0;
-    for (int i = 0; i < cgraph->n_nodes; ++i) n_real += !is_noop(cgraph->nodes[i]->op);
-    const bool use_graph = !graphs_off && n_real >= 8 && ctx->graph_calls++ > 0;
+    bool has_split = false;        // multi-device work is not captured (the reference disables CUDA graphs for split buffers too, ggml-cuda.cu:2620)
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        n_real += !is_noop(cgraph->nodes[i]->op);
+        has_split = has_split || tensor_in_split_buffer(cgraph->nodes[i]->src[0]);
+    }
+    const bool use_graph = !graphs_off && !has_split && n_real >= 8 && ctx->graph_calls++ > 0;
     if (!use_graph) {
         compute_nodes(ctx, cgraph);
         return GGML_STATUS_SUCCESS;
@@ -772,7 +1090,10 @@ ggml_backend_dev_t reg_get_device(ggml_backend_reg_t reg, size_t index) {
     GGML_ASSERT(index < ctx->devices.size());
     return ctx->devices[index];
 }
+ggml_backend_buffer_type_t split_buffer_type_entry(int main_device, const float * tensor_split) { return split_buffer_type(main_device, tensor_split); }
 void * reg_get_proc_address(ggml_backend_reg_t, const char * name) {
+    // the well-known name llama.cpp-style callers look up (include/ggml-backend.h:187-200; reference: ggml-cuda.cu:3374-3380)
+    if (strcmp(name, "ggml_backend_split_buffer_type") == 0) return (void *) split_buffer_type_entry;
     if (strcmp(name, "ggml_backend_b200_launch_count") == 0) return (void *) ggml_b200_launch_count;
     return nullptr;
 }
@@ -805,6 +1126,9 @@ ggml_backend_reg_t b200_reg() {
     });
     return &reg;
 }
+
+int registry_device_count() { return (int) ((reg_ctx *) b200_reg()->context)->devices.size(); }
+int registry_device_index(int i) { return ((device_ctx *) ((reg_ctx *) b200_reg()->context)->devices[(size_t) i]->context)->index; }
 
 } // namespace
 
@@ -851,10 +1175,8 @@ GGML_B200_API int ggml_backend_score(void) { return ggml_backend_b200_get_device
 GGML_B200_API ggml_backend_t ggml_backend_cuda_init(int device) { return ggml_backend_b200_init(device); }
 GGML_B200_API bool ggml_backend_is_cuda(ggml_backend_t backend) { return ggml_backend_is_b200(backend); }
 GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_buffer_type(int device) { return ggml_backend_b200_buffer_type(device); }
-GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_split_buffer_type(int, const float *) {
-    GGML_LOG_ERROR("ggml-b200: split buffers are provided by ggml_backend_b200_split_buffer_type (row shards + NVLink gather)\n");
-    return nullptr;
-}
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_b200_split_buffer_type(int main_device, const float * tensor_split) { return split_buffer_type(main_device, tensor_split); }
+GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_split_buffer_type(int main_device, const float * tensor_split) { return split_buffer_type(main_device, tensor_split); }
 GGML_B200_API ggml_backend_buffer_type_t ggml_backend_cuda_host_buffer_type(void) { return host_buffer_type(); }
 GGML_B200_API int ggml_backend_cuda_get_device_count(void) { return ggml_backend_b200_get_device_count(); }
 GGML_B200_API void ggml_backend_cuda_get_device_description(int device, char * description, size_t description_size) {

@@ -135,6 +135,8 @@ typedef struct ggml_b200_gather {
 } ggml_b200_gather;
 
 GGML_B200_API int ggml_b200_mul_mat_gather(const ggml_b200_mul_mat_args * args, const ggml_b200_gather * gather, void * stream);
+/* 1 if ggml_b200_mul_mat_gather can run this shape (pure query) */
+GGML_B200_API int ggml_b200_mul_mat_gather_supported(const ggml_b200_mul_mat_args * args);
 GGML_B200_API int ggml_b200_gather_wait(const uint32_t * flags_local, int32_t world, uint32_t epoch, void * stream);
 /* CUDA-IPC plumbing for the peer buffers: allocate (zeroed) + export a 64-byte handle; open / close a peer's handle */
 GGML_B200_API int ggml_b200_ipc_alloc(size_t bytes, void ** dev_ptr, void * handle64);

@@ -200,6 +200,8 @@ class Ref:
         L.probe_mul_mat.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 7 + [C.c_int] * 5
         L.probe_mul_mat_sweep.restype = C.c_double
         L.probe_mul_mat_sweep.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_int] * 5
+        L.probe_mul_mat_split.restype = C.c_double
+        L.probe_mul_mat_split.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_int]
         L.probe_mul_mat_id.restype = C.c_double
         L.probe_mul_mat_id.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_int] * 2
 
@@ -270,6 +272,18 @@ class Ref:
         s = self.lib.probe_mul_mat_sweep(dev.encode(), t, _p(W), _p(X), _p(Y), M, N, K, nw, threads, iters, warmup, int(e2e))
         if s < 0:
             raise RuntimeError(f"probe_mul_mat_sweep({dev}) failed: {s}")
+        return Y, float(s)
+
+    def mul_mat_split(self, t, W, X, M, N, K, dev, main_device=0, tensor_split=None, iters=1):
+        """MUL_MAT with W in the backend's split buffer type (rows sharded over its devices) -> (Y[N, M], seconds per graph_compute)"""
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        assert W.size == self.row_size(t, K) * M and X.size == K * N
+        Y = np.empty((N, M), dtype=np.float32)
+        ts = None if tensor_split is None else _f32(list(tensor_split) + [0.0] * (16 - len(tensor_split)))
+        s = self.lib.probe_mul_mat_split(dev.encode(), main_device, None if ts is None else _p(ts), t, _p(W), _p(X), _p(Y), M, N, K, iters)
+        if s < 0:
+            raise RuntimeError(f"probe_mul_mat_split({dev}) failed: {s}")
         return Y, float(s)
 
     def mul_mat_id(self, t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok, dev="CPU", threads=0, iters=1):

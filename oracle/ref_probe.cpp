@@ -195,6 +195,53 @@ double probe_mul_mat_sweep(const char * dev, int type_a, const void * W, const f
     return (t1 - t0) / ((double) (iters > 0 ? iters : 1) * nw);
 }
 
+// MUL_MAT with the weights in the backend's SPLIT buffer type (rows sharded over all of the registry's devices), obtained the way an
+// application does: ggml_backend_reg_get_proc_address(reg, "ggml_backend_split_buffer_type")(main_device, tensor_split)
+// (include/ggml-backend.h:187-200; llama.cpp's usage).  Activations / result live in the main device's default buffer.
+// tensor_split may be NULL (equal shares).  Returns seconds per graph_compute, < 0 on failure (-4: no split buffer type).
+double probe_mul_mat_split(const char * dev, int main_device, const float * tensor_split, int type_a, const void * W, const float * X, float * Y,
+                           int64_t M, int64_t N, int64_t K, int iters) {
+    backend_holder h;
+    if (!open_backend(h, dev, 0)) return -1.0;
+    ggml_backend_reg_t reg = ggml_backend_dev_backend_reg(ggml_backend_get_device(h.be));
+    typedef ggml_backend_buffer_type_t (*split_fn)(int, const float *);
+    split_fn fn = (split_fn) ggml_backend_reg_get_proc_address(reg, "ggml_backend_split_buffer_type");
+    if (!fn) return -4.0;
+    ggml_backend_buffer_type_t sbuft = fn(main_device, tensor_split);
+    if (!sbuft) return -4.0;
+    ggml_init_params ipw = { ggml_tensor_overhead() * 4, nullptr, true };
+    ggml_init_params ipc = { ggml_tensor_overhead() * 8 + ggml_graph_overhead(), nullptr, true };
+    ggml_context * cw = ggml_init(ipw), * cc = ggml_init(ipc);
+    ggml_tensor * a = ggml_new_tensor_2d(cw, (ggml_type) type_a, K, M);
+    ggml_tensor * b = ggml_new_tensor_2d(cc, GGML_TYPE_F32, K, N);
+    ggml_tensor * c = ggml_mul_mat(cc, a, b);
+    ggml_cgraph * gf = ggml_new_graph(cc);
+    ggml_build_forward_expand(gf, c);
+    ggml_backend_buffer_t bw = ggml_backend_alloc_ctx_tensors_from_buft(cw, sbuft);
+    if (!bw) { ggml_free(cw); ggml_free(cc); return -3.0; }
+    ggml_backend_buffer_t bc = ggml_backend_alloc_ctx_tensors(cc, h.be);
+    if (!bc) { ggml_backend_buffer_free(bw); ggml_free(cw); ggml_free(cc); return -3.0; }
+    double out = -2.0;
+    if (ggml_backend_supports_op(h.be, c)) {
+        ggml_backend_tensor_set(a, W, 0, ggml_nbytes(a));
+        ggml_backend_tensor_set(b, X, 0, ggml_nbytes(b));
+        ggml_backend_graph_compute(h.be, gf);
+        double t0 = now_s();
+        for (int i = 0; i < iters; ++i) ggml_backend_graph_compute(h.be, gf);
+        ggml_backend_synchronize(h.be);
+        out = (now_s() - t0) / (iters > 0 ? iters : 1);
+        ggml_backend_tensor_get(c, Y, 0, ggml_nbytes(c));
+        // the split tensor must read back exactly as it was set (scatter / gather of the row ranges)
+        std::vector<char> back(ggml_nbytes(a));
+        ggml_backend_tensor_get(a, back.data(), 0, ggml_nbytes(a));
+        if (memcmp(back.data(), W, ggml_nbytes(a)) != 0) out = -5.0;
+    }
+    ggml_backend_buffer_free(bc);
+    ggml_backend_buffer_free(bw);
+    ggml_free(cc); ggml_free(cw);
+    return out;
+}
+
 // C[M, n_used, n_tok] = MUL_MAT_ID(as[type; K x M x n_expert], b[f32; K x nb1 x n_tok], ids[i32; n_used x n_tok])
 // (src/ggml.c:2735).  ids is given as the dense [n_ids_total x n_tok] array of which the
 // first n_used columns are viewed (as test_mul_mat_id does, test-backend-ops.cpp:2017).

@@ -42,31 +42,68 @@ def run(exe, model, n=24, extra=(), env_extra=None):
     return text[0] if text else "", float(ms.group(2)) if ms else None, out
 
 
-# Random weights put the model into a "repeat the last token" regime after four generated tokens, where two logits are tied to
-# ~1e-7 relative: from there on the greedy choice depends on the f32 summation order of the mat-vecs (every kernel is within NMSE
-# 1e-14 of the CPU oracle, tests/test_gpu_parity.py, and test-backend-ops pins every op at 1e-7 through the same vtable).
-# Measured trajectories (deterministic): CPU and the B200 generic kernels (summation order closest to ggml-cpu) agree on the
-# first 8 tokens; the fast superblock kernels agree on the first 4 and take the other branch of the tie at the 5th.
-N_EXACT_FAST, N_EXACT_GENERIC = 4, 8
+def run_dump(exe, model, n, dump, force=None, extra=(), env_extra=None):
+    """the "-dump" variants (oracle/gpt2_logits_hook.cpp): main-backend.cpp unmodified, logits of every sampling step written to `dump`,
+    optionally teacher-forced with the token ids in `force`"""
+    env_extra = dict(env_extra or {})
+    env_extra["GPT2_LOGITS_DUMP"] = str(dump)
+    if force is not None:
+        env_extra["GPT2_FORCE_TOKENS"] = str(force)
+    text, ms, out = run(exe, model, n=n, extra=extra, env_extra=env_extra)
+    import numpy as np
+    logits = np.fromfile(dump, dtype=np.float32).reshape(-1, 50257)
+    return text, logits, out
 
 
-def test_gpt2_backend_tokens_match_cpu(model):
-    cpu_text, cpu_ms, _ = run("gpt-2-backend", model)
-    gpu_text, gpu_ms, out = run("gpt-2-backend-b200", model, extra=("-ngl", "12"))
+N_STEPS = 48
+
+
+@pytest.mark.parametrize("kernels", ["fast", "generic"])
+def test_gpt2_logits_track_cpu_step_by_step(model, kernels):
+    """End-to-end parity of the whole token graph, QUANTIFIED: ggml-cpu generates N_STEPS greedy tokens and dumps its logits; the B200
+    backend is then teacher-forced along the SAME trajectory (so step i sees the identical context on both sides) and its logits are
+    compared step by step.  Asserted, for the default (superblock / fused) kernels and for the generic kernels:
+      * NMSE(logits_b200, logits_cpu) <= 1e-6 at every step (the reference's own per-op gates are 1e-7 .. 5e-4);
+      * the greedy token is IDENTICAL whenever the CPU's top-2 margin exceeds the measured logit noise of that step (4 x the largest
+        absolute deviation) -- i.e. any token difference is a genuine tie inside the f32 summation-order noise, not a bug;
+      * free-running (unforced) generation matches the CPU up to the first such tie."""
+    import numpy as np
+    for exe in ("gpt-2-backend-dump", "gpt-2-backend-b200-dump"):
+        if not (O.REF_DIR / exe).exists():
+            pytest.fail(f"oracle/_ref/{exe} missing (make -C oracle b200bins in the build container)")
+    env = {"GGML_B200_FORCE_GENERIC": "1"} if kernels == "generic" else None
+    cpu_text, cpu_logits, _ = run_dump("gpt-2-backend-dump", model, N_STEPS, TMP / "cpu.logits")
+    ctoks = [int(t) for t in re.findall(r"<(\d+)>", cpu_text)]
+    assert cpu_logits.shape[0] == N_STEPS and len(ctoks) == N_STEPS, (cpu_logits.shape, len(ctoks))
+    assert list(cpu_logits.argmax(1)) == ctoks                                  # the dump is what the sampler saw
+    np.array(ctoks, dtype=np.int32).tofile(TMP / "force.bin")
+    _, gpu_logits, out = run_dump("gpt-2-backend-b200-dump", model, N_STEPS, TMP / f"b200_{kernels}.logits", force=TMP / "force.bin", extra=("-ngl", "12"), env_extra=env)
     assert "using CUDA backend" in out, out[-1500:]
-    ctoks, gtoks = re.findall(r"<(\d+)>", cpu_text), re.findall(r"<(\d+)>", gpu_text)
-    assert len(ctoks) >= 8 and len(gtoks) == len(ctoks), f"\ncpu: {cpu_text}\ngpu: {gpu_text}"
-    assert ctoks[:N_EXACT_FAST] == gtoks[:N_EXACT_FAST], f"\ncpu: {cpu_text}\ngpu: {gpu_text}"
-    # the whole graph (all small ops, KV cache, CUDA-graph replay) with the generic mat-vec kernels: 8 tokens identical
-    gen_text, _, _ = run("gpt-2-backend-b200", model, extra=("-ngl", "12"), env_extra={"GGML_B200_FORCE_GENERIC": "1"})
-    ntoks = re.findall(r"<(\d+)>", gen_text)
-    assert ctoks[:N_EXACT_GENERIC] == ntoks[:N_EXACT_GENERIC], f"\ncpu: {cpu_text}\ngen: {gen_text}"
-    same = sum(1 for a, b in zip(ctoks, gtoks) if a == b)
-    print(f"gpt-2 117M q4_0: cpu {cpu_ms} ms/token, b200 {gpu_ms} ms/token, {same}/{len(ctoks)} greedy tokens identical")
+    assert gpu_logits.shape == cpu_logits.shape
+    ties, worst_nmse, worst_ratio = [], 0.0, 0.0
+    for i in range(N_STEPS):
+        c, g_ = cpu_logits[i], gpu_logits[i]
+        nm = O.nmse(g_, c)
+        worst_nmse = max(worst_nmse, nm)
+        assert nm <= 1e-6, (kernels, i, nm)
+        noise = float(np.abs(g_ - c).max())
+        top2 = np.sort(c)[-2:]
+        margin = float(top2[1] - top2[0])
+        worst_ratio = max(worst_ratio, noise / max(margin, 1e-30))
+        if int(g_.argmax()) != int(c.argmax()):
+            ties.append((i, margin, noise))
+            assert margin <= 4 * noise, f"{kernels}: step {i}: argmax differs although the CPU margin {margin:.3e} exceeds 4 x the logit noise {noise:.3e}"
+    # free-running generation: identical to the CPU until the first tie (if any)
+    free_text, _, _ = run("gpt-2-backend-b200", model, n=N_STEPS, extra=("-ngl", "12"), env_extra=env)
+    ftoks = [int(t) for t in re.findall(r"<(\d+)>", free_text)]
+    first_tie = ties[0][0] if ties else N_STEPS
+    assert ftoks[:first_tie] == ctoks[:first_tie], f"\ncpu: {ctoks}\ngpu: {ftoks}\nties: {ties}"
+    print(f"gpt-2 117M q4_0 [{kernels} kernels]: {N_STEPS} teacher-forced steps, worst logits NMSE {worst_nmse:.2e}, worst noise/margin {worst_ratio:.2e}, "
+          f"argmax differs at {len(ties)} steps (all inside the noise): {ties[:4]}; free-running prefix identical for {first_tie} tokens")
 
 
 def test_gpt2_sched_full_offload(model):
     cpu_text, _, _ = run("gpt-2-backend", model)
     gpu_text, gpu_ms, out = run("gpt-2-sched-b200", model, extra=("-ngl", "99"))
     ctoks, gtoks = re.findall(r"<(\d+)>", cpu_text), re.findall(r"<(\d+)>", gpu_text)
-    assert len(ctoks) >= 8 and ctoks[:N_EXACT_FAST] == gtoks[:N_EXACT_FAST], f"\ncpu: {cpu_text}\ngpu: {gpu_text}\n{out[-1500:]}"
+    assert len(ctoks) >= 8 and ctoks[:4] == gtoks[:4], f"\ncpu: {cpu_text}\ngpu: {gpu_text}\n{out[-1500:]}"
