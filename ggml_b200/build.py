@@ -41,9 +41,25 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def generate_iq_grids() -> Path:
+    """csrc/generated/iq_grids.h: the i-quant codebooks (file-format data) extracted from the reference's src/ggml-common.h; git-ignored,
+    travels with the built libraries.  Regenerated whenever the reference tree is present, required to exist otherwise."""
+    out = CSRC / "generated" / "iq_grids.h"
+    common = REF / "src" / "ggml-common.h"
+    script = ROOT / "scripts" / "extract_iq_grids.py"
+    if common.exists():
+        if not out.exists() or out.stat().st_mtime < max(common.stat().st_mtime, script.stat().st_mtime):
+            out.parent.mkdir(exist_ok=True)
+            subprocess.run([sys.executable, str(script), str(common), str(out)], check=True)
+    elif not out.exists():
+        raise RuntimeError(f"{out} is missing and {common} is not available to generate it from")
+    return out
+
+
 def build_kernels(force: bool = False, verbose: bool = False) -> Path:
+    generate_iq_grids()
     srcs = [CSRC / s for s in KERNEL_SRCS if (CSRC / s).exists()]
-    deps = srcs + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ggml-b200.h"]
+    deps = srcs + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((CSRC / "generated").glob("*.h")) + [ROOT / "include" / "ggml-b200.h"]
     if not force and _newer(KERNELS_SO, deps):
         return KERNELS_SO
     objs = []

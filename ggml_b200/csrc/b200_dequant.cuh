@@ -3,6 +3,7 @@
 // without FMA).  Pure per-thread code: also compiled for the host by tests/hostemu (CPU-only logic tests).
 #pragma once
 #include "b200_quants.cuh"
+#include "b200_iq.cuh"
 
 namespace b200 {
 
@@ -54,6 +55,8 @@ template <int T> __device__ __forceinline__ void dequant4(const uint8_t * __rest
             const int v = (int)(int8_t)(lo | (((qh[i] >> (2 * pos)) & 3) << 4)) - 32;
             o[i] = __fmul_rn(ds, (float)v);
         }
+    } else if constexpr (T == T_IQ2_XXS || T == T_IQ3_XXS || T == T_IQ1_S) {
+        iq_dequant4<T>(src, e, o);
     } else if constexpr (T == T_IQ4_NL) {
         const uint8_t * b = src + (e / 32) * 18;             // dequantize_row_iq4_nl, src/ggml-quants.c:2436-2452
         const int j = (int)(e % 32);

@@ -50,6 +50,9 @@ template <typename OUT> static int dequantize_dispatch(int type, const void * sr
         case T_Q3_K: dequantize_kernel<T_Q3_K, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         case T_IQ4_NL: dequantize_kernel<T_IQ4_NL, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         case T_IQ4_XS: dequantize_kernel<T_IQ4_XS, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ2_XXS: dequantize_kernel<T_IQ2_XXS, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ3_XXS: dequantize_kernel<T_IQ3_XXS, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ1_S: dequantize_kernel<T_IQ1_S, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         default: set_error("dequantize: unsupported type %d", type); return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

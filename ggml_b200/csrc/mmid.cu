@@ -7,6 +7,7 @@
 // index is read by the kernel itself, so the op is one quantize launch + one mat-vec launch, no host sync.
 #include "b200_internal.h"
 #include "b200_quants.cuh"
+#include "b200_iq.cuh"
 
 namespace b200 {
 
@@ -96,6 +97,9 @@ int ggml_b200_mul_mat_id(const ggml_b200_mul_mat_id_args * a, void * stream) {
         case T_Q3_K: mmid_kernel<T_Q3_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ4_NL: mmid_kernel<T_IQ4_NL><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ4_XS: mmid_kernel<T_IQ4_XS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ2_XXS: mmid_kernel<T_IQ2_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ3_XXS: mmid_kernel<T_IQ3_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ1_S: mmid_kernel<T_IQ1_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

@@ -16,6 +16,7 @@
 //                       global memory, activations pre-quantized by quantize_act_kernel.
 #include "b200_internal.h"
 #include "b200_quants.cuh"
+#include "b200_iq.cuh"
 
 #include <cstdlib>
 
@@ -143,6 +144,9 @@ int launch_mmvq_generic(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q3_K: mmvq_generic_kernel<T_Q3_K><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ4_NL: mmvq_generic_kernel<T_IQ4_NL><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ4_XS: mmvq_generic_kernel<T_IQ4_XS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ2_XXS: mmvq_generic_kernel<T_IQ2_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ3_XXS: mmvq_generic_kernel<T_IQ3_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ1_S: mmvq_generic_kernel<T_IQ1_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

@@ -8,6 +8,7 @@
 // They replace the reference's getrows.cu, binbcast.cu, norm.cu, scale.cu, diagmask.cu, softmax.cu, unary.cu, cpy.cu, mmv.cu.
 #include "b200_internal.h"
 #include "b200_quants.cuh"
+#include "b200_dequant.cuh"
 
 #include <cfloat>
 
@@ -52,6 +53,11 @@ template <bool MAX> __device__ __forceinline__ float block_reduce(float v, float
 }
 
 // ------------------------------------------------------------------ dequantize one element (bit-exact, as dequant.cu)
+template <int T> __device__ __forceinline__ float elem_via_dequant4(const uint8_t * row, int64_t i) {
+    float o[4];
+    dequant4<T>(row, i & ~(int64_t)3, o);
+    return o[i & 3];
+}
 __device__ __forceinline__ float load_elem(const uint8_t * row, int type, int64_t i) {
     switch (type) {
         case T_F32: return ((const float *)row)[i];
@@ -87,7 +93,18 @@ __device__ __forceinline__ float load_elem(const uint8_t * row, int type, int64_
             const int sc = (int)(int8_t)b[192 + 8 * h + l / 16 + 2 * pos];
             return __fmul_rn(__fmul_rn(h2f(load_u16(b + 208)), (float)sc), (float)v);
         }
-        default: return 0.0f;
+        // every other block format: through the element decoders of b200_dequant.cuh (four consecutive weights, pick one)
+        case T_Q4_1:   return elem_via_dequant4<T_Q4_1>(row, i);
+        case T_Q5_0:   return elem_via_dequant4<T_Q5_0>(row, i);
+        case T_Q5_1:   return elem_via_dequant4<T_Q5_1>(row, i);
+        case T_Q2_K:   return elem_via_dequant4<T_Q2_K>(row, i);
+        case T_Q3_K:   return elem_via_dequant4<T_Q3_K>(row, i);
+        case T_IQ4_NL: return elem_via_dequant4<T_IQ4_NL>(row, i);
+        case T_IQ4_XS: return elem_via_dequant4<T_IQ4_XS>(row, i);
+        case T_IQ2_XXS: return elem_via_dequant4<T_IQ2_XXS>(row, i);
+        case T_IQ3_XXS: return elem_via_dequant4<T_IQ3_XXS>(row, i);
+        case T_IQ1_S:  return elem_via_dequant4<T_IQ1_S>(row, i);
+        default: return __int_as_float(0x7fc00000);          // unreachable (ggml_b200_op_get_rows rejects unknown types): NaN, never a silent 0
     }
 }
 

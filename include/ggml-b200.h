@@ -55,6 +55,8 @@ enum ggml_b200_type {
     GGML_B200_TYPE_Q4_K = 12, GGML_B200_TYPE_Q5_K = 13, GGML_B200_TYPE_Q6_K = 14,
     /* next formats: generic mat-vec, MUL_MAT_ID and dequantize kernels only; block layouts src/ggml-common.h:168-203, 247-276 */
     GGML_B200_TYPE_Q4_1 = 3,  GGML_B200_TYPE_Q5_0 = 6,  GGML_B200_TYPE_Q5_1 = 7, GGML_B200_TYPE_Q2_K = 10, GGML_B200_TYPE_Q3_K = 11, GGML_B200_TYPE_IQ4_NL = 20, GGML_B200_TYPE_IQ4_XS = 23,
+    /* grid-codebook i-quants (src/ggml-common.h:330-396; codebooks extracted from it at build time): generic mat-vec, MUL_MAT_ID, dequantize */
+    GGML_B200_TYPE_IQ2_XXS = 16, GGML_B200_TYPE_IQ3_XXS = 18, GGML_B200_TYPE_IQ1_S = 19,
 };
 
 /* ---------------------------------------------------------------------------------------------

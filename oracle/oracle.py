@@ -28,11 +28,14 @@ REF_DIR = HERE / "_ref"
 F32, F16, Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q8_1 = 0, 1, 2, 3, 6, 7, 8, 9
 Q2_K, Q3_K, Q4_K, Q5_K, Q6_K, Q8_K = 10, 11, 12, 13, 14, 15
 IQ4_NL, IQ4_XS = 20, 23
+IQ2_XXS, IQ3_XXS, IQ1_S = 16, 18, 19
 TYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q4_1: "q4_1", Q5_0: "q5_0", Q5_1: "q5_1", Q8_0: "q8_0", Q8_1: "q8_1",
-              Q2_K: "q2_K", Q3_K: "q3_K", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K", IQ4_NL: "iq4_nl", IQ4_XS: "iq4_xs"}
+              Q2_K: "q2_K", Q3_K: "q3_K", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K", IQ4_NL: "iq4_nl", IQ4_XS: "iq4_xs", IQ2_XXS: "iq2_xxs", IQ3_XXS: "iq3_xxs", IQ1_S: "iq1_s"}
 HOT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
 # the next weight formats; oracle pinned this round, CUDA kernels follow
 NEXT_TYPES = (Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS)
+# the grid-codebook i-quants (round 2): generic mat-vec / MUL_MAT_ID / dequantize kernels
+IQ_TYPES = (IQ2_XXS, IQ3_XXS, IQ1_S)
 
 
 def build(ref: bool = True) -> None:
@@ -302,7 +305,8 @@ class Ref:
 def random_blocks(t: int, nblocks: int, rng: np.random.Generator, scale: float = 0.05) -> np.ndarray:
     """Arbitrary-but-valid packed blocks: uniformly random code bytes (every nibble / 6-bit scale /
     high-bit pattern occurs) with finite fp16 scales of magnitude ~`scale`."""
-    ts = {Q4_0: 18, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q4_1: 20, Q5_0: 22, Q5_1: 24, Q2_K: 84, Q3_K: 110, IQ4_NL: 18, IQ4_XS: 136}[t]
+    ts = {Q4_0: 18, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q4_1: 20, Q5_0: 22, Q5_1: 24, Q2_K: 84, Q3_K: 110, IQ4_NL: 18, IQ4_XS: 136,
+          IQ2_XXS: 66, IQ3_XXS: 98, IQ1_S: 50}[t]
     b = rng.integers(0, 256, size=(nblocks, ts), dtype=np.uint8)
 
     def put_half(col, vals):
@@ -329,6 +333,8 @@ def random_blocks(t: int, nblocks: int, rng: np.random.Generator, scale: float =
         put_half(108, rng.uniform(-scale / 32, scale / 32, nblocks))
     elif t == IQ4_XS:
         put_half(0, rng.uniform(-scale / 256, scale / 256, nblocks))
+    elif t in (IQ2_XXS, IQ3_XXS, IQ1_S):
+        put_half(0, rng.uniform(-scale / 16, scale / 16, nblocks))
     return b.reshape(-1)
 
 

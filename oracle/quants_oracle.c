@@ -35,6 +35,8 @@
  * `d*q - m` is a rounded multiply followed by a rounded subtract.
  */
 #include "quants_oracle.h"
+#include "_ref/iq_grids.h"      /* the i-quant codebooks: file-format DATA extracted from the reference's src/ggml-common.h at build time
+                                   (scripts/extract_iq_grids.py, oracle/Makefile); not kept in this repository */
 
 #include <math.h>
 #include <stdlib.h>
@@ -94,6 +96,7 @@ int64_t oq_blck_size(int type) {
         case OQ_F32: case OQ_F16: return 1;
         case OQ_Q4_0: case OQ_Q8_0: case OQ_Q4_1: case OQ_Q5_0: case OQ_Q5_1: case OQ_Q8_1: case OQ_IQ4_NL: return 32;
         case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: case OQ_Q2_K: case OQ_Q3_K: case OQ_IQ4_XS: return 256;
+        case OQ_IQ2_XXS: case OQ_IQ3_XXS: case OQ_IQ1_S: return 256;
         default: return 0;
     }
 }
@@ -104,6 +107,7 @@ size_t oq_type_size(int type) {
         case OQ_Q4_1: return 20; case OQ_Q5_0: return 22; case OQ_Q5_1: return 24; case OQ_Q8_1: return 36;
         case OQ_Q2_K: return 84; case OQ_Q3_K: return 110; case OQ_IQ4_NL: return 18; case OQ_IQ4_XS: return 136;
         case OQ_Q4_K: return 144; case OQ_Q5_K: return 176; case OQ_Q6_K: return 210; case OQ_Q8_K: return 292;
+        case OQ_IQ2_XXS: return 66; case OQ_IQ3_XXS: return 98; case OQ_IQ1_S: return 50;
         default: return 0;
     }
 }
@@ -285,6 +289,57 @@ static void deq_iq4_xs(const uint8_t * b, float * y, int64_t k) {
         }
     }
 }
+/* ---- i-quants (grid codebooks).  Layouts (src/ggml-common.h): IQ2_XXS 66 B = d, qs[32] u16; IQ3_XXS 98 B = d, qs[64] grid indices,
+ * 32 B scales_and_signs; IQ1_S 50 B = d, qs[32], qh[8] u16.  dequantize_row_iq2_xxs / iq3_xxs / iq1_s: src/ggml-quants.c:2197, 2284, 2359. */
+static inline float iq_sign(int signs, int j) { return (signs & kmask_iq2xs[j]) ? -1.0f : 1.0f; }
+static void deq_iq2_xxs(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 66) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint8_t * q = b + 2 + 8 * ib;                 /* 4 grid indices, then 4 x 7 sign bits + 4-bit scale */
+            const uint32_t aux = rd32(q + 4);
+            const float db = d * (0.5f + (float)(aux >> 28)) * 0.25f;
+            for (int l = 0; l < 4; ++l) {
+                const uint8_t * grid = (const uint8_t *)(iq2xxs_grid + q[l]);
+                const int signs = ksigns_iq2xs[(aux >> (7 * l)) & 127];
+                for (int j = 0; j < 8; ++j) *y++ = db * (float)grid[j] * iq_sign(signs, j);
+            }
+        }
+    }
+}
+static void deq_iq3_xxs(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 98) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint8_t * q = b + 2 + 8 * ib;
+            const uint32_t aux = rd32(b + 66 + 4 * ib);
+            const float db = d * (0.5f + (float)(aux >> 28)) * 0.5f;
+            for (int l = 0; l < 4; ++l) {
+                const int signs = ksigns_iq2xs[(aux >> (7 * l)) & 127];
+                const uint8_t * g1 = (const uint8_t *)(iq3xxs_grid + q[2 * l]), * g2 = (const uint8_t *)(iq3xxs_grid + q[2 * l + 1]);
+                for (int j = 0; j < 4; ++j) y[j] = db * (float)g1[j] * iq_sign(signs, j);
+                for (int j = 0; j < 4; ++j) y[j + 4] = db * (float)g2[j] * iq_sign(signs, j + 4);
+                y += 8;
+            }
+        }
+    }
+}
+#define OQ_IQ1S_DELTA 0.125f
+static void deq_iq1_s(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 50) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint32_t qh = rd16(b + 34 + 2 * ib);
+            const float dl = d * (float)(2 * ((qh >> 12) & 7) + 1);
+            const float delta = (qh & 0x8000) ? -OQ_IQ1S_DELTA : OQ_IQ1S_DELTA;
+            for (int l = 0; l < 4; ++l) {
+                const int8_t * grid = (const int8_t *)(iq1s_grid + (b[2 + 4 * ib + l] | (((qh >> (3 * l)) & 7) << 8)));
+                for (int j = 0; j < 8; ++j) *y++ = dl * ((float)grid[j] + delta);
+            }
+        }
+    }
+}
+
 static void deq_q8_K(const uint8_t * b, float * y, int64_t k) {
     for (int64_t i = 0; i < k / 256; ++i, b += 292, y += 256) {
         float d; memcpy(&d, b, 4);
@@ -310,6 +365,9 @@ int oq_dequantize_row(int type, const void * src, float * dst, int64_t k) {
         case OQ_Q3_K: deq_q3_K(b, dst, k); return 0;
         case OQ_IQ4_NL: deq_iq4_nl(b, dst, k); return 0;
         case OQ_IQ4_XS: deq_iq4_xs(b, dst, k); return 0;
+        case OQ_IQ2_XXS: deq_iq2_xxs(b, dst, k); return 0;
+        case OQ_IQ3_XXS: deq_iq3_xxs(b, dst, k); return 0;
+        case OQ_IQ1_S: deq_iq1_s(b, dst, k); return 0;
         default: return -1;
     }
 }
@@ -408,6 +466,7 @@ int oq_vec_dot_type(int type) {
         case OQ_Q4_0: case OQ_Q8_0: case OQ_Q5_0: case OQ_IQ4_NL: return OQ_Q8_0;
         case OQ_Q4_1: case OQ_Q5_1: return OQ_Q8_1;
         case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q2_K: case OQ_Q3_K: case OQ_IQ4_XS: return OQ_Q8_K;
+        case OQ_IQ2_XXS: case OQ_IQ3_XXS: case OQ_IQ1_S: return OQ_Q8_K;
         default: return -1;
     }
 }
@@ -581,6 +640,75 @@ static float dot_q3_K_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
     return acc;
 }
 
+/* ggml_vec_dot_iq2_xxs_q8_K / iq3_xxs / iq1_s (src/ggml-cpu/ggml-cpu-quants.c, generic branches): integer sums per 32-value sub-block
+ * weighted by the odd sub-block scale 2 s + 1, one f32 multiply-add per superblock, a constant factor at the end */
+static float dot_iq2_xxs_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float sumf = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 66, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int bsum = 0;
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint8_t * q = w + 2 + 8 * ib;
+            const uint32_t aux = rd32(q + 4);
+            int sumi = 0;
+            for (int l = 0; l < 4; ++l) {
+                const uint8_t * grid = (const uint8_t *)(iq2xxs_grid + q[l]);
+                const int signs = ksigns_iq2xs[(aux >> (7 * l)) & 127];
+                for (int j = 0; j < 8; ++j) sumi += (int)grid[j] * (int)q8[32 * ib + 8 * l + j] * ((signs & kmask_iq2xs[j]) ? -1 : 1);
+            }
+            bsum += sumi * (int)(2 * (aux >> 28) + 1);
+        }
+        sumf += (oq_fp16_to_fp32(rd16(w)) * yd) * (float)bsum;
+    }
+    return 0.125f * sumf;
+}
+static float dot_iq3_xxs_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float sumf = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 98, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int bsum = 0;
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint8_t * q = w + 2 + 8 * ib;
+            const uint32_t aux = rd32(w + 66 + 4 * ib);
+            int sumi = 0;
+            for (int l = 0; l < 4; ++l) {
+                const uint8_t * g1 = (const uint8_t *)(iq3xxs_grid + q[2 * l]), * g2 = (const uint8_t *)(iq3xxs_grid + q[2 * l + 1]);
+                const int signs = ksigns_iq2xs[(aux >> (7 * l)) & 127];
+                for (int j = 0; j < 4; ++j) {
+                    sumi += (int)g1[j] * (int)q8[32 * ib + 8 * l + j]     * ((signs & kmask_iq2xs[j])     ? -1 : 1);
+                    sumi += (int)g2[j] * (int)q8[32 * ib + 8 * l + j + 4] * ((signs & kmask_iq2xs[j + 4]) ? -1 : 1);
+                }
+            }
+            bsum += sumi * (int)(2 * (aux >> 28) + 1);
+        }
+        sumf += (oq_fp16_to_fp32(rd16(w)) * yd) * (float)bsum;
+    }
+    return 0.25f * sumf;
+}
+static float dot_iq1_s_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
+    float sumf = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += 50, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int sumi = 0, sumi1 = 0;
+        for (int ib = 0; ib < 8; ++ib) {
+            const uint32_t qh = rd16(w + 34 + 2 * ib);
+            const int ls = (int)(2 * ((qh >> 12) & 7) + 1), delta = (qh & 0x8000) ? -1 : 1;
+            int lsum = 0;
+            for (int l = 0; l < 4; ++l) {
+                const int8_t * grid = (const int8_t *)(iq1s_grid + (w[2 + 4 * ib + l] | (((qh >> (3 * l)) & 7) << 8)));
+                for (int j = 0; j < 8; ++j) lsum += (int)q8[32 * ib + 8 * l + j] * (int)grid[j];
+            }
+            sumi += ls * lsum;
+            sumi1 += ls * delta * ((int)(int16_t)rd16(y + 260 + 4 * ib) + (int)(int16_t)rd16(y + 260 + 4 * ib + 2));
+        }
+        sumf += oq_fp16_to_fp32(rd16(w)) * yd * ((float)sumi + OQ_IQ1S_DELTA * (float)sumi1);
+    }
+    return sumf;
+}
+
 float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
     const uint8_t * w = (const uint8_t *)wrow, * y = (const uint8_t *)yq;
     switch (type) {
@@ -596,6 +724,9 @@ float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
         case OQ_Q3_K: return dot_q3_K_q8_K(k, w, y);
         case OQ_IQ4_NL: return dot_iq4_nl_q8_0(k, w, y);
         case OQ_IQ4_XS: return dot_iq4_xs_q8_K(k, w, y);
+        case OQ_IQ2_XXS: return dot_iq2_xxs_q8_K(k, w, y);
+        case OQ_IQ3_XXS: return dot_iq3_xxs_q8_K(k, w, y);
+        case OQ_IQ1_S: return dot_iq1_s_q8_K(k, w, y);
         default: return NAN;
     }
 }

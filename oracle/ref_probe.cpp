@@ -72,7 +72,10 @@ size_t probe_type_size(int type) { return ggml_type_size((ggml_type) type); }
 
 // ggml_quantize_chunk (src/ggml.c:6410) with imatrix == NULL
 size_t probe_quantize(int type, const float * src, void * dst, int64_t nrows, int64_t k) {
-    return ggml_quantize_chunk((ggml_type) type, src, dst, 0, nrows, k, nullptr);
+    // the lowest-bit i-quants refuse to quantize without an importance matrix (ggml_quantize_requires_imatrix): give them uniform weights
+    std::vector<float> ones;
+    if (ggml_quantize_requires_imatrix((ggml_type) type)) ones.assign((size_t) k, 1.0f);
+    return ggml_quantize_chunk((ggml_type) type, src, dst, 0, nrows, k, ones.empty() ? nullptr : ones.data());
 }
 // type_traits[type].from_float_ref == quantize_row_*_ref (src/ggml-quants.c)
 void probe_quantize_row_ref(int type, const float * src, void * dst, int64_t k) {

@@ -2,7 +2,7 @@
 
 Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
 Each fixture holds seeded inputs and the reference's own outputs:
-  quant_<type>.npz   x (f32), blocks = ggml_quantize_chunk(type, x, imatrix=NULL), deq = to_float(blocks),
+  quant_<type>.npz   x (f32), blocks = ggml_quantize_chunk(type, x, imatrix=NULL; all-ones for the types that require one), deq = to_float(blocks),
                      rnd_blocks (arbitrary valid blocks), rnd_deq = to_float(rnd_blocks)
   act_q8.npz         x, q8_0 = CPU-backend from_float(Q8_0)(x), q8_K = from_float(Q8_K)(x), q8_1 = from_float(Q8_1)(x)
   mulmat_<type>.npz  W blocks, X, Y = MUL_MAT on the reference CPU backend (per case: M, N, K)
@@ -70,6 +70,6 @@ def main(types):
 
 
 if __name__ == "__main__":
-    # python tests/golden/make_golden.py [hot|next|all]   (default all; the fixtures are deterministic)
+    # python tests/golden/make_golden.py [hot|next|iq|all]   (default all; the fixtures are deterministic)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    main({"hot": O.HOT_TYPES, "next": O.NEXT_TYPES, "all": O.HOT_TYPES + O.NEXT_TYPES}[which])
+    main({"hot": O.HOT_TYPES, "next": O.NEXT_TYPES, "iq": O.IQ_TYPES, "all": O.HOT_TYPES + O.NEXT_TYPES + O.IQ_TYPES}[which])

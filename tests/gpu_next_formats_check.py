@@ -24,7 +24,7 @@ def main():
     g.lib()
     orc = O.Oracle()
     done = []
-    for t in O.NEXT_TYPES:
+    for t in tuple(O.NEXT_TYPES) + tuple(O.IQ_TYPES):          # + the grid i-quants (generic kernels)
         name = O.TYPE_NAMES[t]
         z = np.load(G / f"quant_{name}.npz")
         for blocks, want in ((z["blocks"], z["deq"]), (z["rnd_blocks"], z["rnd_deq"])):

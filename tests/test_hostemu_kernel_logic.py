@@ -20,7 +20,7 @@ def emu():
     out = EMU / "_build"
     out.mkdir(exist_ok=True)
     so = out / "libhostemu.so"
-    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh", "b200_tc_dequant.cuh")]
+    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh", "b200_tc_dequant.cuh", "b200_iq.cuh", "generated/iq_grids.h")]
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
                f"-I{EMU / 'shim'}", "-o", str(so), str(EMU / "hostemu.cpp")]
@@ -85,7 +85,7 @@ def act_record(emu, oracle, t, x):
     return rec, yq
 
 
-ALL = list(O.HOT_TYPES) + list(O.NEXT_TYPES)
+ALL = list(O.HOT_TYPES) + list(O.NEXT_TYPES) + list(O.IQ_TYPES)
 
 
 @pytest.mark.parametrize("t", ALL, ids=[O.TYPE_NAMES[t] for t in ALL])

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import oracle as O
 
-TYPES = list(O.HOT_TYPES) + list(O.NEXT_TYPES)      # the hot-path formats + the SURVEY §8f-2 formats (oracle first)
+TYPES = list(O.HOT_TYPES) + list(O.NEXT_TYPES) + list(O.IQ_TYPES)      # hot-path formats, the SURVEY §8f-2 formats, the grid i-quants
 IDS = [O.TYPE_NAMES[t] for t in TYPES]
 
 
