@@ -282,7 +282,7 @@ class PeerExchange:
 # ---------------------------------------------------------------------------------------------------------------
 # fused epilogue / small ops used by the backend's graph-level fusion (thin ctypes mirrors, for the tests)
 class Epilogue(C.Structure):
-    _fields_ = [("bias", C.c_void_p), ("dst_bias", C.c_void_p), ("unary", C.c_int32), ("dst_unary", C.c_void_p)]
+    _fields_ = [("bias", C.c_void_p), ("dst_bias", C.c_void_p), ("unary", C.c_int32), ("dst_unary", C.c_void_p), ("residual", C.c_void_p)]
 
 
 class TensorDesc(C.Structure):
@@ -305,17 +305,18 @@ def tensor_desc(t) -> TensorDesc:
     return d
 
 
-def mul_mat_fused(t, W, X, M, K, bias, gelu: bool):
-    """y = W.x ; y2 = y + bias ; y3 = gelu(y2) in one launch (n = 1).  Returns (y, y2, y3 or None)."""
+def mul_mat_fused(t, W, X, M, K, bias, gelu: bool, residual=None):
+    """y = W.x ; y2 = y + bias ; y3 = gelu(y2) (or y2 + residual) in one launch (n = 1).  Returns (y, y2, y3 or None)."""
     import torch
     L = lib()
     L.ggml_b200_mul_mat_fused.argtypes = [C.POINTER(MulMatArgs), C.POINTER(Epilogue), C.c_void_p]
     Y = torch.empty((1, 1, 1, M), dtype=torch.float32, device="cuda")
     Y2 = torch.empty(M, dtype=torch.float32, device="cuda")
-    Y3 = torch.empty(M, dtype=torch.float32, device="cuda") if gelu else None
+    Y3 = torch.empty(M, dtype=torch.float32, device="cuda") if (gelu or residual is not None) else None
     a = mul_mat_args(t, W, X, Y, M, 1, K)
     ep = Epilogue()
-    ep.bias, ep.dst_bias, ep.unary, ep.dst_unary = bias.data_ptr(), Y2.data_ptr(), 1 if gelu else 0, (Y3.data_ptr() if gelu else None)
+    ep.bias, ep.dst_bias, ep.unary, ep.dst_unary = bias.data_ptr(), Y2.data_ptr(), (2 if residual is not None else 1 if gelu else 0), (Y3.data_ptr() if Y3 is not None else None)
+    ep.residual = residual.data_ptr() if residual is not None else None
     check(L.ggml_b200_mul_mat_fused(C.byref(a), C.byref(ep), _stream()), "ggml_b200_mul_mat_fused")
     return Y.view(-1), Y2, Y3
 
@@ -349,3 +350,47 @@ def op_norm_affine(x, gain, bias, eps: float, rms: bool = False):
     check(L.ggml_b200_op_norm_affine(int(rms), C.byref(s), C.byref(d1), gain.data_ptr(), C.byref(d2), bias.data_ptr(), C.byref(d3), eps, _stream()),
           "ggml_b200_op_norm_affine")
     return y1, y2, y3
+
+
+def op_scale(x, s: float):
+    import torch
+    L = lib()
+    L.ggml_b200_op_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p]
+    y = torch.empty_like(x)
+    check(L.ggml_b200_op_scale(x.data_ptr(), y.data_ptr(), s, x.numel(), _stream()), "ggml_b200_op_scale")
+    return y
+
+
+def op_diag_mask_inf(x, n_past: int):
+    """x: [..., ne1, ne0] contiguous f32"""
+    import torch
+    L = lib()
+    L.ggml_b200_op_diag_mask_inf.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    y = torch.empty_like(x)
+    check(L.ggml_b200_op_diag_mask_inf(x.data_ptr(), y.data_ptr(), x.shape[-1], x.shape[-2], x.numel(), n_past, _stream()), "ggml_b200_op_diag_mask_inf")
+    return y
+
+
+def op_soft_max(x, scale: float = 1.0, diag_n_past: int = -1):
+    """row softmax of a contiguous f32 [ne3?, ne2, ne1, ne0] tensor; diag_n_past >= 0: the fused SCALE -> DIAG_MASK_INF -> SOFT_MAX pass"""
+    import torch
+    L = lib()
+    L.ggml_b200_op_soft_max_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int64] * 4 + [C.c_float, C.c_float, C.c_int32, C.c_void_p]
+    sh = [1] * (4 - x.dim()) + list(x.shape)
+    y = torch.empty_like(x)
+    check(L.ggml_b200_op_soft_max_diag(x.data_ptr(), None, 0, y.data_ptr(), sh[3], sh[2], sh[1], sh[0], scale, 0.0, diag_n_past, _stream()), "ggml_b200_op_soft_max_diag")
+    return y
+
+
+def op_cpy(src, dst):
+    L = lib()
+    L.ggml_b200_op_cpy.argtypes = [C.POINTER(TensorDesc), C.POINTER(TensorDesc), C.c_void_p]
+    s, d = tensor_desc(src), tensor_desc(dst)
+    check(L.ggml_b200_op_cpy(C.byref(s), C.byref(d), _stream()), "ggml_b200_op_cpy")
+
+
+def op_cpy2(src_a, dst_a, src_b, dst_b):
+    L = lib()
+    L.ggml_b200_op_cpy2.argtypes = [C.POINTER(TensorDesc)] * 4 + [C.c_void_p]
+    a, b, c, d = tensor_desc(src_a), tensor_desc(dst_a), tensor_desc(src_b), tensor_desc(dst_b)
+    check(L.ggml_b200_op_cpy2(C.byref(a), C.byref(b), C.byref(c), C.byref(d), _stream()), "ggml_b200_op_cpy2")

@@ -127,7 +127,7 @@ int ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream) {
 int ggml_b200_mul_mat_fused(const ggml_b200_mul_mat_args * args, const ggml_b200_epilogue * ep, void * stream) {
     int rc = validate(args);
     if (rc != GGML_B200_OK) return rc;
-    if (!ep || !ep->bias || !ep->dst_bias || (ep->unary != 0 && ep->unary != 1) || (ep->unary == 1 && !ep->dst_unary)) { set_error("mul_mat_fused: bad epilogue"); return GGML_B200_EINVAL; }
+    if (!ep || !ep->bias || !ep->dst_bias || (ep->unary < 0 || ep->unary > 2) || (ep->unary != 0 && !ep->dst_unary) || (ep->unary == 2 && !ep->residual)) { set_error("mul_mat_fused: bad epilogue"); return GGML_B200_EINVAL; }
     if (args->N != 1 || plan(*args) != GGML_B200_MM_FORCE_GEMV || !mmvq_sb_eligible(*args)) { set_error("mul_mat_fused: only the n = 1 mat-vec kernel has the fused epilogue"); return GGML_B200_EUNSUPPORTED; }
     if (args->M == 0) return GGML_B200_OK;
     return launch_mmvq_sb(*args, (cudaStream_t)stream, nullptr, ep);

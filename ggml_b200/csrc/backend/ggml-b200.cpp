@@ -78,6 +78,11 @@ struct backend_ctx {
     struct cached_graph { std::vector<uint64_t> sig; cudaGraphExec_t exec = nullptr; uint64_t last_use = 0; };
     std::vector<cached_graph> graphs;
     uint64_t        graph_clock = 0;
+    // a graph that changes on every call (token-by-token decoding: shapes and offsets move with n_past) costs more to re-capture and
+    // update than to launch directly: after a few consecutive misses the nodes are launched eagerly (every kernel is PDL-chained), until
+    // the same graph is seen twice in a row again.  The reference does the same (ggml-cuda.cu: disable_due_to_too_many_updates).
+    int             consecutive_updates = 0;
+    std::vector<uint64_t> last_sig;
     int             graph_calls = 0;      // the first graph_compute runs eagerly (one-time attribute / allocation work)
     bool            capturing = false;
     std::unordered_set<const ggml_tensor *> written;   // roots whose memory some node of the current cgraph writes through a view
@@ -846,6 +851,12 @@ int try_fuse_mul_mat(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
         ggml_tensor * un = cgraph->nodes[i + 2];
         if (un->op == GGML_OP_UNARY && ggml_get_unary_op(un) == GGML_UNARY_OP_GELU && un->src[0] == add && is_f32_contig(un)) {
             ep.unary = 1; ep.dst_unary = (float *) un->data; consumed = 2;
+        } else if (un->op == GGML_OP_ADD && is_f32_contig(un) && ggml_are_same_shape(un, mm) &&
+                   ((un->src[0] == add && is_f32_contig(un->src[1]) && ggml_are_same_shape(un->src[1], mm)) ||
+                    (un->src[1] == add && is_f32_contig(un->src[0]) && ggml_are_same_shape(un->src[0], mm)))) {
+            // the skip connection: cur = (W.x + bias) + residual  (f32 addition commutes exactly)
+            ep.unary = 2; ep.dst_unary = (float *) un->data; consumed = 2;
+            ep.residual = (const float *) (un->src[0] == add ? un->src[1] : un->src[0])->data;
         }
     }
     const ggml_tensor * a = mm->src[0], * b = mm->src[1];
@@ -885,6 +896,53 @@ int try_fuse_norm(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
     return 2;
 }
 
+// does any node other than `except` consume `t` (as a source or through a view)?
+bool has_other_consumer(const ggml_cgraph * cgraph, const ggml_tensor * t, const ggml_tensor * except) {
+    if (t->flags & GGML_TENSOR_FLAG_OUTPUT) return true;
+    for (int j = 0; j < cgraph->n_nodes; ++j) {
+        const ggml_tensor * n = cgraph->nodes[j];
+        if (n == except) continue;
+        if (n->view_src == t) return true;
+        for (int k = 0; k < GGML_MAX_SRC; ++k) if (n->src[k] == t) return true;
+    }
+    return false;
+}
+
+// SCALE -> DIAG_MASK_INF -> SOFT_MAX (the attention-score chain of examples/gpt-2, main-backend.cpp:574-584) in one row pass.  The two
+// intermediates are NOT materialised, so the chain is only fused when nothing else reads them.
+int try_fuse_soft_max(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
+    if (i + 2 >= cgraph->n_nodes) return 0;
+    ggml_tensor * sc = cgraph->nodes[i], * dm = cgraph->nodes[i + 1], * sm = cgraph->nodes[i + 2];
+    if (dm->op != GGML_OP_DIAG_MASK_INF || dm->src[0] != sc || sm->op != GGML_OP_SOFT_MAX || sm->src[0] != dm || sm->src[1] != nullptr) return 0;
+    if (!is_f32_contig(sc->src[0]) || !is_f32_contig(sc) || !is_f32_contig(dm) || !is_f32_contig(sm)) return 0;
+    if (ggml_get_op_params_f32(sm, 0) != 1.0f || ggml_get_op_params_f32(sm, 1) != 0.0f) return 0;
+    const int n_past = ggml_get_op_params_i32(dm, 0);
+    if (n_past < 0) return 0;
+    if (has_other_consumer(cgraph, sc, dm) || has_other_consumer(cgraph, dm, sm)) return 0;
+    SHIM_OK(ggml_b200_op_soft_max_diag((const float *) sc->src[0]->data, nullptr, 0, (float *) sm->data, sm->ne[0], sm->ne[1], sm->ne[2], sm->ne[3],
+                                       ggml_get_op_params_f32(sc, 0), 0.0f, n_past, ctx->stream));
+    return 2;
+}
+
+// two consecutive float CPY nodes of the same size (the K and V cache updates of a layer) -> one launch
+int try_fuse_cpy2(backend_ctx * ctx, ggml_cgraph * cgraph, int i) {
+    if (i + 1 >= cgraph->n_nodes) return 0;
+    ggml_tensor * c0 = cgraph->nodes[i], * c1 = cgraph->nodes[i + 1];
+    if (c1->op != GGML_OP_CPY) return 0;
+    auto fl = [](const ggml_tensor * t) { return t->type == GGML_TYPE_F32 || t->type == GGML_TYPE_F16; };
+    if (!fl(c0->src[0]) || !fl(c0->src[1]) || !fl(c1->src[0]) || !fl(c1->src[1])) return 0;
+    if (ggml_nelements(c0->src[0]) != ggml_nelements(c1->src[0]) || ggml_nelements(c0->src[0]) == 0) return 0;
+    // independent: the second copy must neither read nor write what the first writes (byte spans of the possibly strided views)
+    auto overlap = [](const ggml_tensor * a, const ggml_tensor * b) {
+        const char * a0 = (const char *) a->data, * b0 = (const char *) b->data;
+        return a0 < b0 + ggml_nbytes(b) && b0 < a0 + ggml_nbytes(a);
+    };
+    if (overlap(c1->src[0], c0->src[1]) || overlap(c1->src[1], c0->src[1]) || overlap(c1->src[1], c0->src[0])) return 0;
+    auto s0 = desc(c0->src[0]), d0 = desc(c0->src[1]), s1 = desc(c1->src[0]), d1 = desc(c1->src[1]);
+    SHIM_OK(ggml_b200_op_cpy2(&s0, &d0, &s1, &d1, ctx->stream));
+    return 1;
+}
+
 void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
     static const bool fuse = !(getenv("GGML_B200_DISABLE_FUSION") && atoi(getenv("GGML_B200_DISABLE_FUSION")) != 0);
     ctx->written.clear();
@@ -909,6 +967,14 @@ void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
             case GGML_OP_MUL_MAT_ID: compute_mul_mat_id(ctx, node); break;
             case GGML_OP_NORM: case GGML_OP_RMS_NORM: {
                 const int extra = fuse ? try_fuse_norm(ctx, cgraph, i) : 0;
+                if (extra > 0) i += extra; else compute_small_op(ctx, node);
+            } break;
+            case GGML_OP_SCALE: {
+                const int extra = fuse ? try_fuse_soft_max(ctx, cgraph, i) : 0;
+                if (extra > 0) i += extra; else compute_small_op(ctx, node);
+            } break;
+            case GGML_OP_CPY: {
+                const int extra = fuse ? try_fuse_cpy2(ctx, cgraph, i) : 0;
                 if (extra > 0) i += extra; else compute_small_op(ctx, node);
             } break;
             default: compute_small_op(ctx, node); break;
@@ -964,9 +1030,19 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
     for (auto & g : ctx->graphs) {
         if (g.sig == sig) {                                        // unchanged graph: replay, no capture
             g.last_use = ctx->graph_clock;
+            ctx->consecutive_updates = 0;
+            ctx->last_sig = sig;
             CUDA_OK(cudaGraphLaunch(g.exec, ctx->stream));
             return GGML_STATUS_SUCCESS;
         }
+    }
+    static const int max_updates = getenv("GGML_B200_GRAPH_MAX_UPDATES") ? atoi(getenv("GGML_B200_GRAPH_MAX_UPDATES")) : 3;
+    const bool repeated = sig == ctx->last_sig;                    // the same graph twice in a row: worth capturing (again)
+    ctx->last_sig = sig;
+    if (repeated) ctx->consecutive_updates = 0;
+    else if (++ctx->consecutive_updates > max_updates) {
+        compute_nodes(ctx, cgraph);                                // ever-changing graph: direct launches
+        return GGML_STATUS_SUCCESS;
     }
     // size the scratch pool before capturing (allocation is not part of the graph)
     size_t need = 0;

@@ -83,7 +83,7 @@ struct sb_params {
     int64_t l2_prefetch_bytes;    // dependent launches: bytes of W every CTA's share of which is pulled into L2 while the previous kernel still runs (0 = off)
     // row-sharded multi-GPU: every result is stored straight into each peer's full-length y over NVLink (world == 0: off)
     // fused epilogue (bias add and GELU of the following ggml nodes): y2 = y + bias, y3 = gelu(y2); null = off
-    const float * ep_bias; float * ep_y2; float * ep_y3;
+    const float * ep_bias; float * ep_y2; float * ep_y3; const float * ep_res;    // ep_res: y3 = y2 + residual instead of gelu(y2)
     unsigned long long * dbg;     // optional %globaltimer trace (GGML_B200_SB_DEBUG=1): 32 launches x 8 stamps
     int32_t world, rank;
     int64_t row_offset;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
                     if (p.ep_bias) {
                         const float v2 = acc + p.ep_bias[row0 + r];
                         p.ep_y2[row0 + r] = v2;
-                        if (p.ep_y3) p.ep_y3[row0 + r] = gelu_ggml(v2);
+                        if (p.ep_y3) p.ep_y3[row0 + r] = p.ep_res ? v2 + p.ep_res[row0 + r] : gelu_ggml(v2);
                     }
                 }
                 else {
@@ -351,7 +351,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     p.l2_prefetch_bytes = (!ind && p.src0_static && e_l2_mb > 0) ? (int64_t)std::min<size_t>((size_t)a.M * rb, (size_t)e_l2_mb << 20) : 0;
     p.world = 0; p.rank = 0; p.row_offset = 0; p.epoch = 0;
-    p.ep_bias = nullptr; p.ep_y2 = nullptr; p.ep_y3 = nullptr;
+    p.ep_bias = nullptr; p.ep_y2 = nullptr; p.ep_y3 = nullptr; p.ep_res = nullptr;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
     p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
     for (int q = 0; q < 8; ++q) { p.y_peers[q] = nullptr; p.flag_peers[q] = nullptr; }
@@ -411,7 +411,10 @@ template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const gg
     sb_plan pl;
     if (!make_sb_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the superblock mat-vec kernel"); return GGML_B200_EUNSUPPORTED; }
     { const int rc = assign_sb_slot(pl.p); if (rc != GGML_B200_OK) return rc; }
-    if (ep && ep->bias) { pl.p.ep_bias = ep->bias; pl.p.ep_y2 = ep->dst_bias; pl.p.ep_y3 = ep->unary == 1 ? ep->dst_unary : nullptr; }
+    if (ep && ep->bias) {
+        pl.p.ep_bias = ep->bias; pl.p.ep_y2 = ep->dst_bias; pl.p.ep_y3 = ep->unary != 0 ? ep->dst_unary : nullptr;
+        pl.p.ep_res = ep->unary == 2 ? ep->residual : nullptr;
+    }
     if (ga) {
         pl.p.world = ga->world; pl.p.rank = ga->rank; pl.p.row_offset = ga->row_offset; pl.p.epoch = ga->epoch;
         for (int q = 0; q < ga->world; ++q) { pl.p.y_peers[q] = ga->y_peers[q]; pl.p.flag_peers[q] = ga->flag_peers[q]; }

@@ -11,12 +11,31 @@
 #include "b200_dequant.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace b200 {
 
-// A quantized mat-vec launched after one of these small ops (with the programmatic-serialization attribute) may start its
-// weight prefetch while the small op still runs; it still waits (griddepcontrol.wait) for this kernel's results before reading them.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Programmatic dependent launch for every small op: each kernel is launched with the programmatic-serialization attribute (launch_pdl),
+// so it becomes resident while its predecessor still runs (the launch latency of a ~2 us kernel chain is hidden), waits for the
+// predecessor's completion before touching any global memory (griddepcontrol.wait: completion stays transitive along the stream),
+// and only then lets ITS successor launch -- a one-kernel lookahead.  A quantized mat-vec launched after one of these small ops starts
+// its weight prefetch while the small op runs and waits for this kernel's results before reading them.
+__device__ __forceinline__ void pdl_trigger() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 struct tdesc {      // device-side copy of ggml_b200_tensor
     uint8_t * data; int32_t type; int64_t ne[4]; size_t nb[4];
@@ -223,8 +242,10 @@ __global__ void unary_kernel(int uop, const float * x, float * y, int64_t n) {
 }
 
 // ------------------------------------------------------------------ SOFT_MAX (rows contiguous): softmax(x*scale + mask*slope)
+// diag_n_past >= 0 folds a preceding GGML_OP_DIAG_MASK_INF (and, through `scale`, a preceding GGML_OP_SCALE) into the row pass:
+// element i0 of row i1 is -inf where i0 > diag_n_past + i1 (ggml_compute_forward_diag_mask_f32, src/ggml-cpu/ggml-cpu.c)
 __global__ void soft_max_kernel(const float * x, const uint8_t * mask, int mask_type, float * y, int64_t ne0, int64_t ne1, int64_t ne2,
-                                float scale, float max_bias, float m0, float m1, uint32_t n_head_log2) {
+                                float scale, float max_bias, float m0, float m1, uint32_t n_head_log2, int diag_n_past) {
     pdl_trigger();
     __shared__ float sh[32];
     const int64_t r = blockIdx.x;                 // row = i1 + ne1 * (i2 + ne2 * i3)
@@ -239,6 +260,7 @@ __global__ void soft_max_kernel(const float * x, const uint8_t * mask, int mask_
     const uint8_t * mr = mask ? mask + (size_t)i1 * ne0 * (mask_type == T_F16 ? 2 : 4) : nullptr;
     auto val = [&](int64_t i) {
         float v = xr[i] * scale;
+        if (diag_n_past >= 0 && i > (int64_t)diag_n_past + i1) v = -INFINITY;
         if (mr) v += slope * (mask_type == T_F16 ? __half2float(((const __half *)mr)[i]) : ((const float *)mr)[i]);
         return v;
     };
@@ -257,10 +279,12 @@ __device__ __forceinline__ size_t offset_of(const tdesc & t, int64_t i) {    // 
     const int64_t i0 = i % t.ne[0], i1 = (i / t.ne[0]) % t.ne[1], i2 = (i / (t.ne[0] * t.ne[1])) % t.ne[2], i3 = i / (t.ne[0] * t.ne[1] * t.ne[2]);
     return i0 * t.nb[0] + i1 * t.nb[1] + i2 * t.nb[2] + i3 * t.nb[3];
 }
-__global__ void cpy_kernel(tdesc s, tdesc d, int64_t n) {
+// blockIdx.y selects one of two independent copies of the same size (the K and V cache updates of a layer: one launch)
+__global__ void cpy_kernel(tdesc s, tdesc d, tdesc s2, tdesc d2, int64_t n) {
     pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (blockIdx.y) { s = s2; d = d2; }
     const uint8_t * sp = s.data + offset_of(s, i);
     uint8_t * dp = d.data + offset_of(d, i);
     const float v = s.type == T_F32 ? *(const float *)sp : __half2float(*(const __half *)sp);
@@ -335,7 +359,7 @@ int ggml_b200_op_get_rows(const ggml_b200_tensor * src0, const ggml_b200_tensor 
     REQUIRE(d.nb[0] == 4, "dst rows must be contiguous");
     const int64_t rows = i.ne[0] * i.ne[1] * i.ne[2];
     if (rows == 0 || s.ne[0] == 0) return GGML_B200_OK;
-    get_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(s, i, d);
+    B200_CUDA_TRY(launch_pdl(get_rows_kernel, dim3((unsigned)rows), dim3(256), (cudaStream_t)stream, s, i, d));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -348,10 +372,10 @@ int ggml_b200_op_bin_bcast(int32_t op, const ggml_b200_tensor * src0, const ggml
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned g = blocks_for(n, 256);
     switch (op) {
-        case 0: bin_bcast_kernel<0><<<g, 256, 0, st>>>(a, b, d, n); break;
-        case 1: bin_bcast_kernel<1><<<g, 256, 0, st>>>(a, b, d, n); break;
-        case 2: bin_bcast_kernel<2><<<g, 256, 0, st>>>(a, b, d, n); break;
-        case 3: bin_bcast_kernel<3><<<g, 256, 0, st>>>(a, b, d, n); break;
+        case 0: B200_CUDA_TRY(launch_pdl(bin_bcast_kernel<0>, dim3(g), dim3(256), st, a, b, d, n)); break;
+        case 1: B200_CUDA_TRY(launch_pdl(bin_bcast_kernel<1>, dim3(g), dim3(256), st, a, b, d, n)); break;
+        case 2: B200_CUDA_TRY(launch_pdl(bin_bcast_kernel<2>, dim3(g), dim3(256), st, a, b, d, n)); break;
+        case 3: B200_CUDA_TRY(launch_pdl(bin_bcast_kernel<3>, dim3(g), dim3(256), st, a, b, d, n)); break;
         default: set_error("bin_bcast: bad op %d", op); return GGML_B200_EINVAL;
     }
     B200_LAUNCH_CHECK();
@@ -364,8 +388,8 @@ int ggml_b200_op_norm(int32_t rms, const ggml_b200_tensor * src, const ggml_b200
     const int64_t rows = nrows(s);
     if (rows == 0 || s.ne[0] == 0) return GGML_B200_OK;
     const int threads = s.ne[0] >= 1024 ? 256 : s.ne[0] >= 256 ? 128 : 32;
-    if (rms) norm_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d, eps);
-    else     norm_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d, eps);
+    if (rms) B200_CUDA_TRY(launch_pdl(norm_kernel<true>, dim3((unsigned)rows), dim3(threads), (cudaStream_t)stream, s, d, eps));
+    else     B200_CUDA_TRY(launch_pdl(norm_kernel<false>, dim3((unsigned)rows), dim3(threads), (cudaStream_t)stream, s, d, eps));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -378,22 +402,22 @@ int ggml_b200_op_norm_affine(int32_t rms, const ggml_b200_tensor * src, const gg
     const int64_t rows = nrows(s);
     if (rows == 0 || s.ne[0] == 0) return GGML_B200_OK;
     const int threads = s.ne[0] >= 1024 ? 256 : s.ne[0] >= 256 ? 128 : 32;
-    if (rms) norm_affine_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d1, gain, d2, bias, d3, eps);
-    else     norm_affine_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, d1, gain, d2, bias, d3, eps);
+    if (rms) B200_CUDA_TRY(launch_pdl(norm_affine_kernel<true>, dim3((unsigned)rows), dim3(threads), (cudaStream_t)stream, s, d1, gain, d2, bias, d3, eps));
+    else     B200_CUDA_TRY(launch_pdl(norm_affine_kernel<false>, dim3((unsigned)rows), dim3(threads), (cudaStream_t)stream, s, d1, gain, d2, bias, d3, eps));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
 
 int ggml_b200_op_scale(const float * src, float * dst, float s, int64_t n, void * stream) {
     if (n <= 0) return GGML_B200_OK;
-    scale_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, s, n);
+    B200_CUDA_TRY(launch_pdl(scale_kernel, dim3(blocks_for(n, 256)), dim3(256), (cudaStream_t)stream, src, dst, s, n));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
 
 int ggml_b200_op_diag_mask_inf(const float * src, float * dst, int64_t ne0, int64_t ne1, int64_t n, int32_t n_past, void * stream) {
     if (n <= 0) return GGML_B200_OK;
-    diag_mask_inf_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, ne0, ne1, n_past, n);
+    B200_CUDA_TRY(launch_pdl(diag_mask_inf_kernel, dim3(blocks_for(n, 256)), dim3(256), (cudaStream_t)stream, src, dst, ne0, ne1, n_past, n));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -401,20 +425,25 @@ int ggml_b200_op_diag_mask_inf(const float * src, float * dst, int64_t ne0, int6
 int ggml_b200_op_unary(int32_t uop, const float * src, float * dst, int64_t n, void * stream) {
     if (n <= 0) return GGML_B200_OK;
     if (uop < 0 || uop > U_SQRT) { set_error("unary: bad op %d", uop); return GGML_B200_EINVAL; }
-    unary_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(uop, src, dst, n);
+    B200_CUDA_TRY(launch_pdl(unary_kernel, dim3(blocks_for(n, 256)), dim3(256), (cudaStream_t)stream, uop, src, dst, n));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
 
 int ggml_b200_op_soft_max(const float * src, const void * mask, int32_t mask_type, float * dst, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
                           float scale, float max_bias, void * stream) {
+    return ggml_b200_op_soft_max_diag(src, mask, mask_type, dst, ne0, ne1, ne2, ne3, scale, max_bias, -1, stream);
+}
+
+int ggml_b200_op_soft_max_diag(const float * src, const void * mask, int32_t mask_type, float * dst, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+                               float scale, float max_bias, int32_t diag_n_past, void * stream) {
     const int64_t rows = ne1 * ne2 * ne3;
     if (rows == 0 || ne0 == 0) return GGML_B200_OK;
     const uint32_t n_head = (uint32_t)ne2;
     uint32_t n_head_log2 = 1; while (n_head_log2 * 2 <= n_head) n_head_log2 *= 2;
     const float m0 = powf(2.0f, -(max_bias) / n_head_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / n_head_log2);
     const int threads = ne0 >= 1024 ? 256 : ne0 >= 128 ? 128 : 32;
-    soft_max_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const uint8_t *)mask, mask_type, dst, ne0, ne1, ne2, scale, max_bias, m0, m1, n_head_log2);
+    B200_CUDA_TRY(launch_pdl(soft_max_kernel, dim3((unsigned)rows), dim3(threads), (cudaStream_t)stream, src, (const uint8_t *)mask, mask_type, dst, ne0, ne1, ne2, scale, max_bias, m0, m1, n_head_log2, (int)diag_n_past));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -426,16 +455,28 @@ int ggml_b200_op_cpy(const ggml_b200_tensor * src, const ggml_b200_tensor * dst,
     if (n == 0) return GGML_B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if ((s.type == T_F32 || s.type == T_F16) && (d.type == T_F32 || d.type == T_F16)) {
-        cpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, d, n);
+        B200_CUDA_TRY(launch_pdl(cpy_kernel, dim3(blocks_for(n, 256)), dim3(256), st, s, d, s, d, n));
     } else if (s.type == T_F32 && (d.type == T_Q8_0 || d.type == T_Q4_0)) {
         REQUIRE(s.nb[0] == 4 && s.ne[0] % 32 == 0 && d.ne[0] % 32 == 0, "f32 -> q needs dim-0 contiguous rows of whole blocks");
         const int64_t nb = n / 32;
-        if (d.type == T_Q8_0) cpy_f32_q_kernel<T_Q8_0><<<blocks_for(nb, 128), 128, 0, st>>>(s, d, nb);
-        else                  cpy_f32_q_kernel<T_Q4_0><<<blocks_for(nb, 128), 128, 0, st>>>(s, d, nb);
+        if (d.type == T_Q8_0) B200_CUDA_TRY(launch_pdl(cpy_f32_q_kernel<T_Q8_0>, dim3(blocks_for(nb, 128)), dim3(128), st, s, d, nb));
+        else                  B200_CUDA_TRY(launch_pdl(cpy_f32_q_kernel<T_Q4_0>, dim3(blocks_for(nb, 128)), dim3(128), st, s, d, nb));
     } else {
         set_error("cpy: unsupported type pair %d -> %d", s.type, d.type);
         return GGML_B200_EUNSUPPORTED;
     }
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_cpy2(const ggml_b200_tensor * src_a, const ggml_b200_tensor * dst_a, const ggml_b200_tensor * src_b, const ggml_b200_tensor * dst_b, void * stream) {
+    const tdesc s = T(src_a), d = T(dst_a), s2 = T(src_b), d2 = T(dst_b);
+    const int64_t n = nelem(s);
+    REQUIRE(n == nelem(d) && n == nelem(s2) && n == nelem(d2), "element counts differ");
+    auto fl = [](const tdesc & t) { return t.type == T_F32 || t.type == T_F16; };
+    if (!(fl(s) && fl(d) && fl(s2) && fl(d2))) { set_error("cpy2: float tensors only"); return GGML_B200_EUNSUPPORTED; }
+    if (n == 0) return GGML_B200_OK;
+    B200_CUDA_TRY(launch_pdl(cpy_kernel, dim3(blocks_for(n, 256), 2), dim3(256), (cudaStream_t)stream, s, d, s2, d2, n));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -447,7 +488,7 @@ int ggml_b200_op_mul_mat_f(const ggml_b200_tensor * src0, const ggml_b200_tensor
     REQUIRE(b.ne[2] % a.ne[2] == 0 && b.ne[3] % a.ne[3] == 0, "batch dims do not broadcast");
     const int64_t nout = nelem(d);
     if (nout == 0) return GGML_B200_OK;
-    mul_mat_f_kernel<<<blocks_for(nout, 4), 128, 0, (cudaStream_t)stream>>>(a, b, d, nout);
+    B200_CUDA_TRY(launch_pdl(mul_mat_f_kernel, dim3(blocks_for(nout, 4)), dim3(128), (cudaStream_t)stream, a, b, d, nout));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }

@@ -107,8 +107,9 @@ GGML_B200_API int    ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args)
 typedef struct ggml_b200_epilogue {
     const float * bias;       /* [M] */
     float *       dst_bias;   /* [M] */
-    int32_t       unary;      /* 0 none, 1 GELU */
+    int32_t       unary;      /* 0 none, 1 GELU, 2 residual add: dst_unary = dst_bias + residual (a second GGML_OP_ADD, e.g. the skip connection) */
     float *       dst_unary;  /* [M] or NULL */
+    const float * residual;   /* [M], unary == 2 only; may alias dst_unary */
 } ggml_b200_epilogue;
 GGML_B200_API int    ggml_b200_mul_mat_fused(const ggml_b200_mul_mat_args * args, const ggml_b200_epilogue * epilogue, void * stream);
 
@@ -214,7 +215,13 @@ GGML_B200_API int ggml_b200_op_diag_mask_inf(const float * src, float * dst, int
 GGML_B200_API int ggml_b200_op_unary(int32_t uop, const float * src, float * dst, int64_t n, void * stream);
 GGML_B200_API int ggml_b200_op_soft_max(const float * src, const void * mask, int32_t mask_type, float * dst, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
                                         float scale, float max_bias, void * stream);
+/* SCALE -> DIAG_MASK_INF(n_past) -> SOFT_MAX in one row pass: softmax over x * scale with element i0 of row i1 masked where i0 > diag_n_past + i1
+ * (diag_n_past < 0: no mask; then identical to ggml_b200_op_soft_max) */
+GGML_B200_API int ggml_b200_op_soft_max_diag(const float * src, const void * mask, int32_t mask_type, float * dst, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3,
+                                             float scale, float max_bias, int32_t diag_n_past, void * stream);
 GGML_B200_API int ggml_b200_op_cpy(const ggml_b200_tensor * src, const ggml_b200_tensor * dst, void * stream);
+/* two independent float copies of the same element count in one launch (the K and V cache updates of a layer) */
+GGML_B200_API int ggml_b200_op_cpy2(const ggml_b200_tensor * src_a, const ggml_b200_tensor * dst_a, const ggml_b200_tensor * src_b, const ggml_b200_tensor * dst_b, void * stream);
 /* float mat-mul: src0 f32/f16 [K, M, ne02, ne03] (any strides) x src1 f32 [K, N, ne12, ne13] -> dst f32 */
 GGML_B200_API int ggml_b200_op_mul_mat_f(const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream);
 

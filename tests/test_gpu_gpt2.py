@@ -102,6 +102,21 @@ def test_gpt2_logits_track_cpu_step_by_step(model, kernels):
           f"argmax differs at {len(ties)} steps (all inside the noise): {ties[:4]}; free-running prefix identical for {first_tie} tokens")
 
 
+def test_gpt2_graph_fusions_are_bit_exact(model):
+    """the graph-level fusions (mat-vec + bias + GELU / + residual, norm + gain + bias, scale + mask + soft-max, K/V cache copies) and the
+    launch mode (CUDA-graph capture vs direct PDL-chained launches) must not change a single logit bit: teacher-forced along one trajectory"""
+    import numpy as np
+    toks = np.arange(40, 40 + 16, dtype=np.int32)
+    toks.tofile(TMP / "force16.bin")
+    outs = {}
+    for name, env in (("default", {}), ("nofusion", {"GGML_B200_DISABLE_FUSION": "1"}), ("nographs", {"GGML_B200_DISABLE_GRAPHS": "1"}),
+                      ("always_capture", {"GGML_B200_GRAPH_MAX_UPDATES": "1000000"})):
+        _, logits, _ = run_dump("gpt-2-backend-b200-dump", model, 16, TMP / f"b200_{name}.logits", force=TMP / "force16.bin", extra=("-ngl", "12"), env_extra=env)
+        outs[name] = logits
+    for name in ("nofusion", "nographs", "always_capture"):
+        assert np.array_equal(outs["default"].view(np.uint32), outs[name].view(np.uint32)), name
+
+
 def test_gpt2_sched_full_offload(model):
     cpu_text, _, _ = run("gpt-2-backend", model)
     gpu_text, gpu_ms, out = run("gpt-2-sched-b200", model, extra=("-ngl", "99"))

@@ -320,3 +320,32 @@ def test_fused_norm_affine_matches_separate_ops(g):
         xd = x.double()
         ref = (xd / torch.sqrt((xd * xd).mean(-1, keepdim=True) + 1e-5)) if rms else ((xd - xd.mean(-1, keepdim=True)) / torch.sqrt(xd.var(-1, unbiased=False, keepdim=True) + 1e-5))
         assert O.nmse(y1.cpu().numpy(), ref.float().cpu().numpy()) < 1e-10
+
+
+def test_fused_small_op_chains_match_separate_ops(g, oracle):
+    """the token-graph fusions added for the gpt-2 decode path must write exactly what the separate ops write:
+    SCALE -> DIAG_MASK_INF -> SOFT_MAX in one row pass; two float copies in one launch; MUL_MAT + bias + residual add in the epilogue"""
+    import torch
+    torch.manual_seed(3)
+    for (heads, n1, n0, n_past) in [(12, 1, 37, 36), (12, 5, 9, 4), (3, 64, 200, 136), (1, 1, 1, 0), (12, 1, 1030, 1029)]:
+        x = torch.randn(heads, n1, n0, device="cuda") * 4
+        sep = g.op_soft_max(g.op_diag_mask_inf(g.op_scale(x, 0.125), n_past))
+        fus = g.op_soft_max(x, scale=0.125, diag_n_past=n_past)
+        assert torch.equal(sep, fus), (heads, n1, n0, n_past)
+        ref = torch.softmax((x.double() * 0.125).masked_fill(torch.arange(n0, device="cuda")[None, None, :] > n_past + torch.arange(n1, device="cuda")[None, :, None], float("-inf")), -1)
+        assert O.nmse(fus.cpu().numpy(), ref.float().cpu().numpy()) < 1e-10
+    a, b = torch.randn(3, 768, device="cuda"), torch.randn(3, 768, device="cuda")
+    da, db = torch.zeros(3, 768, device="cuda"), torch.zeros(3, 768, device="cuda", dtype=torch.float16)
+    ea, eb = torch.zeros_like(da), torch.zeros_like(db)
+    g.op_cpy2(a, da, b, db)
+    g.op_cpy(a, ea); g.op_cpy(b, eb)
+    assert torch.equal(da, ea) and torch.equal(db, eb) and torch.equal(da, a)
+    M, K, t = 768, 3072, O.Q4_0
+    W = weights(oracle, t, M, K, seed=15)
+    rng = np.random.default_rng(16)
+    X = rng.uniform(-1, 1, K).astype(np.float32)
+    bias = torch.from_numpy(rng.uniform(-0.5, 0.5, M).astype(np.float32)).cuda()
+    res = torch.from_numpy(rng.uniform(-2, 2, M).astype(np.float32)).cuda()
+    y, y2, y3 = g.mul_mat_fused(t, dev(W), dev(X), M, K, bias, gelu=False, residual=res)
+    y_ref = g.mul_mat(t, dev(W), dev(X), M, 1, K).view(-1)
+    assert torch.equal(y, y_ref) and torch.equal(y2, y_ref + bias) and torch.equal(y3, (y_ref + bias) + res)
