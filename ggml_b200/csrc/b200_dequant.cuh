@@ -57,6 +57,8 @@ template <int T> __device__ __forceinline__ void dequant4(const uint8_t * __rest
         }
     } else if constexpr (T == T_IQ2_XXS || T == T_IQ3_XXS || T == T_IQ1_S) {
         iq_dequant4<T>(src, e, o);
+    } else if constexpr (T == T_IQ2_XS || T == T_IQ2_S || T == T_IQ3_S || T == T_IQ1_M || T == T_TQ1_0 || T == T_TQ2_0) {
+        iq_dequant4_b<T>(src, e, o);
     } else if constexpr (T == T_IQ4_NL) {
         const uint8_t * b = src + (e / 32) * 18;             // dequantize_row_iq4_nl, src/ggml-quants.c:2436-2452
         const int j = (int)(e % 32);

@@ -23,7 +23,7 @@ namespace b200 {
 
 // enum ggml_type ids (reference include/ggml.h:351-390)
 enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14, T_IQ4_NL = 20, T_IQ4_XS = 23,
-              T_IQ2_XXS = 16, T_IQ3_XXS = 18, T_IQ1_S = 19 };
+              T_IQ2_XXS = 16, T_IQ3_XXS = 18, T_IQ1_S = 19, T_IQ2_XS = 17, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ1_M = 29, T_TQ1_0 = 34, T_TQ2_0 = 35 };
 
 template <int T> struct fmt;
 template <> struct fmt<T_Q4_0> { static constexpr int QK = 32,  BYTES = 18,  ACT_K = 0; };
@@ -48,14 +48,22 @@ template <> struct fmt<T_IQ4_XS> { static constexpr int QK = 256, BYTES = 136, A
 template <> struct fmt<T_IQ2_XXS> { static constexpr int QK = 256, BYTES = 66, ACT_K = 1; };
 template <> struct fmt<T_IQ3_XXS> { static constexpr int QK = 256, BYTES = 98, ACT_K = 1; };
 template <> struct fmt<T_IQ1_S>   { static constexpr int QK = 256, BYTES = 50, ACT_K = 1; };
+template <> struct fmt<T_IQ2_XS>  { static constexpr int QK = 256, BYTES = 74, ACT_K = 1; };
+template <> struct fmt<T_IQ2_S>   { static constexpr int QK = 256, BYTES = 82, ACT_K = 1; };
+template <> struct fmt<T_IQ3_S>   { static constexpr int QK = 256, BYTES = 110, ACT_K = 1; };
+template <> struct fmt<T_IQ1_M>   { static constexpr int QK = 256, BYTES = 56, ACT_K = 1; };
+template <> struct fmt<T_TQ1_0>   { static constexpr int QK = 256, BYTES = 54, ACT_K = 1; };
+template <> struct fmt<T_TQ2_0>   { static constexpr int QK = 256, BYTES = 66, ACT_K = 1; };
 
 __host__ __device__ inline int    type_qk(int t)    { return t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_IQ4_NL ? 32 : 256; }
 __host__ __device__ inline int    type_bytes(int t) {
     return t == T_Q4_0 ? 18 : t == T_Q8_0 ? 34 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210
          : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : t == T_IQ4_NL ? 18 : t == T_IQ4_XS ? 136
-         : t == T_IQ2_XXS ? 66 : t == T_IQ3_XXS ? 98 : t == T_IQ1_S ? 50 : 0;
+         : t == T_IQ2_XXS ? 66 : t == T_IQ3_XXS ? 98 : t == T_IQ1_S ? 50
+         : t == T_IQ2_XS ? 74 : t == T_IQ2_S ? 82 : t == T_IQ3_S ? 110 : t == T_IQ1_M ? 56 : t == T_TQ1_0 ? 54 : t == T_TQ2_0 ? 66 : 0;
 }
-__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K || t == T_Q2_K || t == T_Q3_K || t == T_IQ4_XS || t == T_IQ2_XXS || t == T_IQ3_XXS || t == T_IQ1_S; }   // Q8_K activations
+__host__ __device__ inline bool   type_is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K || t == T_Q2_K || t == T_Q3_K || t == T_IQ4_XS || t == T_IQ2_XXS || t == T_IQ3_XXS || t == T_IQ1_S
+                                                               || t == T_IQ2_XS || t == T_IQ2_S || t == T_IQ3_S || t == T_IQ1_M || t == T_TQ1_0 || t == T_TQ2_0; }   // Q8_K activations
 __host__ __device__ inline size_t row_bytes(int t, int64_t k) { return (size_t)(k / type_qk(t)) * type_bytes(t); }
 
 // ------------------------------------------------------------------ quantized activation record

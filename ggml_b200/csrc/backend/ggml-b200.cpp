@@ -427,6 +427,7 @@ bool is_b200_weight_type(ggml_type t) {
         case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_0: case GGML_TYPE_Q5_1: case GGML_TYPE_Q2_K: case GGML_TYPE_Q3_K:      // SURVEY 8f-2 (validated on a B200 in round 1)
         case GGML_TYPE_IQ4_NL: case GGML_TYPE_IQ4_XS:
         case GGML_TYPE_IQ2_XXS: case GGML_TYPE_IQ3_XXS: case GGML_TYPE_IQ1_S:                                         // grid i-quants (generic kernels)
+        case GGML_TYPE_IQ2_XS: case GGML_TYPE_IQ2_S: case GGML_TYPE_IQ3_S: case GGML_TYPE_IQ1_M: case GGML_TYPE_TQ1_0: case GGML_TYPE_TQ2_0:
             return true;
         default: return false;
     }

@@ -53,6 +53,12 @@ template <typename OUT> static int dequantize_dispatch(int type, const void * sr
         case T_IQ2_XXS: dequantize_kernel<T_IQ2_XXS, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         case T_IQ3_XXS: dequantize_kernel<T_IQ3_XXS, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         case T_IQ1_S: dequantize_kernel<T_IQ1_S, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ2_XS: dequantize_kernel<T_IQ2_XS, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ2_S: dequantize_kernel<T_IQ2_S, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ3_S: dequantize_kernel<T_IQ3_S, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_IQ1_M: dequantize_kernel<T_IQ1_M, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_TQ1_0: dequantize_kernel<T_TQ1_0, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
+        case T_TQ2_0: dequantize_kernel<T_TQ2_0, OUT><<<grid, 256, 0, st>>>(s, dst, n4); break;
         default: set_error("dequantize: unsupported type %d", type); return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

@@ -100,6 +100,12 @@ int ggml_b200_mul_mat_id(const ggml_b200_mul_mat_id_args * a, void * stream) {
         case T_IQ2_XXS: mmid_kernel<T_IQ2_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ3_XXS: mmid_kernel<T_IQ3_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ1_S: mmid_kernel<T_IQ1_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ2_XS: mmid_kernel<T_IQ2_XS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ2_S: mmid_kernel<T_IQ2_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ3_S: mmid_kernel<T_IQ3_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ1_M: mmid_kernel<T_IQ1_M><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_TQ1_0: mmid_kernel<T_TQ1_0><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_TQ2_0: mmid_kernel<T_TQ2_0><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

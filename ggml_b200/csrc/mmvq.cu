@@ -147,6 +147,12 @@ int launch_mmvq_generic(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_IQ2_XXS: mmvq_generic_kernel<T_IQ2_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ3_XXS: mmvq_generic_kernel<T_IQ3_XXS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         case T_IQ1_S: mmvq_generic_kernel<T_IQ1_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ2_XS: mmvq_generic_kernel<T_IQ2_XS><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ2_S: mmvq_generic_kernel<T_IQ2_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ3_S: mmvq_generic_kernel<T_IQ3_S><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_IQ1_M: mmvq_generic_kernel<T_IQ1_M><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_TQ1_0: mmvq_generic_kernel<T_TQ1_0><<<(unsigned)nblk, 128, 0, st>>>(p); break;
+        case T_TQ2_0: mmvq_generic_kernel<T_TQ2_0><<<(unsigned)nblk, 128, 0, st>>>(p); break;
         default: set_error("mul_mat: unsupported weight type %d", a.type); return GGML_B200_EUNSUPPORTED;
     }
     B200_LAUNCH_CHECK();

@@ -93,7 +93,7 @@ struct sb_params {
     sb_act A;
 };
 
-template <int T, int NW, int NC>
+template <int T, int NW, int NC, bool TWO = false>
 __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) mmvq_sb_kernel(const sb_params p) {
     using F = sbfmt<T>;
     constexpr int SB_CONSUMER_WARPS = NW;
@@ -193,6 +193,43 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
         const int64_t row0 = (int64_t)chunk * p.rows_per_chunk;
         const int rows = (int)min((int64_t)p.rows_per_chunk, p.M - row0);
         const uint8_t * st = stages + (size_t)s * p.stage_bytes;
+        auto store_row = [&](int64_t grow, float acc) {
+            if (p.world == 0) {
+                p.y[grow] = acc;
+                if (p.ep_bias) {
+                    const float v2 = acc + p.ep_bias[grow];
+                    p.ep_y2[grow] = v2;
+                    if (p.ep_y3) p.ep_y3[grow] = p.ep_res ? v2 + p.ep_res[grow] : gelu_ggml(v2);
+                }
+            } else {
+                // row-sharded multi-GPU: straight into the gathered y of every rank (own one included) over NVLink
+                const int64_t gi = p.row_offset + grow;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (q < p.world) p.y_peers[q][gi] = acc;
+            }
+        };
+        if constexpr (TWO && NC == 1 && (T == T_Q4_K || T == T_Q5_K)) {
+            // two rows per lane group and pass, sharing every activation load (each row's operations and their order are those of the
+            // one-row path: bit-identical results); halves the activation traffic out of shared memory
+            for (int r0 = warp * RPW * 2; r0 < rows; r0 += SB_CONSUMER_WARPS * RPW * 2) {
+                const int r = r0 + 2 * sub;
+                float a0 = 0.0f, a1 = 0.0f;
+                if (r < rows) {
+                    const uint8_t * ra = st + (size_t)r * p.row_bytes, * rb = r + 1 < rows ? ra + p.row_bytes : ra;
+                    for (int t = l; t < p.ntasks_row; t += LPR) {
+                        float x0, x1;
+                        q45_task2<T == T_Q5_K>(ra + (size_t)t * F::TASK_B, rb + (size_t)t * F::TASK_B, rec, t, x0, x1);
+                        a0 += x0; a1 += x1;
+                    }
+                }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+                if (l == 0 && r < rows) { store_row(row0 + r, a0); if (r + 1 < rows) store_row(row0 + r + 1, a1); }
+            }
+            __syncwarp();
+            if (lane == 0) sb_mbar_arrive(&empty[s]);
+            continue;
+        }
         // the row loop is warp-uniform (both half-warps iterate together): the shuffles below use the full mask
         for (int r0 = warp * RPW; r0 < rows; r0 += SB_CONSUMER_WARPS * RPW) {
             const int r = r0 + sub;
@@ -222,22 +259,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
             }
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (l == 0 && r < rows) {
-                if (p.world == 0) {
-                    p.y[row0 + r] = acc;
-                    if (p.ep_bias) {
-                        const float v2 = acc + p.ep_bias[row0 + r];
-                        p.ep_y2[row0 + r] = v2;
-                        if (p.ep_y3) p.ep_y3[row0 + r] = p.ep_res ? v2 + p.ep_res[row0 + r] : gelu_ggml(v2);
-                    }
-                }
-                else {
-                    // row-sharded multi-GPU: straight into the gathered y of every rank (own one included) over NVLink
-                    const int64_t gi = p.row_offset + row0 + r;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) if (q < p.world) p.y_peers[q][gi] = acc;
-                }
-            }
+            if (l == 0 && r < rows) store_row(row0 + r, acc);
         }
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
@@ -278,7 +300,7 @@ __global__ void gather_wait_kernel(const uint32_t * flags, int world, uint32_t e
     __threadfence_system();
 }
 
-struct sb_plan { sb_params p; int grid, smem, nw, nc; };
+struct sb_plan { sb_params p; int grid, smem, nw, nc; bool two; };
 
 // device control block: [0,64) global control words, [64, 64 + 64*8) 64 per-launch scheduling slots, byte 4096.. trace.
 // One per device, allocated on first use under a mutex (or ahead of time by ggml_b200_prepare, which the backend calls at
@@ -333,8 +355,11 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     const int SB_CONSUMER_WARPS = (env_warps == 4 && nc == 1) ? 4 : 8;
     pl.nw = SB_CONSUMER_WARPS;
     constexpr int RPW = 32 / F::LPR;
+    // experiment (GGML_B200_SB_TWOROW=1): two rows per lane group sharing the activation loads (Q4_K / Q5_K, n = 1)
+    static const int e_two = getenv("GGML_B200_SB_TWOROW") ? atoi(getenv("GGML_B200_SB_TWOROW")) : 0;
+    pl.two = nc == 1 && (T == T_Q4_K || T == T_Q5_K) && (e_two == 1 || (e_two == 2 && !ind));
     int granule = 1; while ((granule * rb) % 16 != 0) granule *= 2;
-    int step = SB_CONSUMER_WARPS * RPW; while (step % granule != 0) step *= 2;
+    int step = SB_CONSUMER_WARPS * RPW * (pl.two ? 2 : 1); while (step % granule != 0) step *= 2;
     int rpc = (int)(((size_t)env_stage_kb * 1024) / rb) / step * step; if (rpc < step) rpc = step;
     if ((size_t)rpc * rb > 100 * 1024) {                         // very long rows: fewer rows per chunk than one full pass
         rpc = granule; while ((size_t)(rpc + granule) * rb <= 48 * 1024) rpc += granule;
@@ -389,10 +414,10 @@ static int assign_sb_slot(sb_params & p) {
     return GGML_B200_OK;
 }
 
-template <int T, int NW, int NC> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
+template <int T, int NW, int NC, bool TWO = false> static int launch_sb_nw(sb_plan & pl, cudaStream_t st) {
     static per_device_flag attr_set;
     if (!attr_set.test()) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_sb_kernel<T, NW, NC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         attr_set.set();
     }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
@@ -402,7 +427,7 @@ template <int T, int NW, int NC> static int launch_sb_nw(sb_plan & pl, cudaStrea
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<T, NW, NC>, pl.p));
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<T, NW, NC, TWO>, pl.p));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -421,7 +446,9 @@ template <int T> static int launch_sb(const ggml_b200_mul_mat_args & a, const gg
     }
     if (pl.nc > 1 && (ga || (ep && ep->bias))) { set_error("mul_mat: the fused epilogue / gather exist for n = 1 only"); return GGML_B200_EUNSUPPORTED; }
     switch (pl.nc) {
-        case 1:  return pl.nw == 4 ? launch_sb_nw<T, 4, 1>(pl, st) : launch_sb_nw<T, 8, 1>(pl, st);
+        case 1:
+            if constexpr (T == T_Q4_K || T == T_Q5_K) { if (pl.two) return pl.nw == 4 ? launch_sb_nw<T, 4, 1, true>(pl, st) : launch_sb_nw<T, 8, 1, true>(pl, st); }
+            return pl.nw == 4 ? launch_sb_nw<T, 4, 1>(pl, st) : launch_sb_nw<T, 8, 1>(pl, st);
         case 2:  return launch_sb_nw<T, 8, 2>(pl, st);
         case 4:  return launch_sb_nw<T, 8, 4>(pl, st);
         default: return launch_sb_nw<T, 8, 8>(pl, st);

@@ -123,6 +123,12 @@ __device__ __forceinline__ float load_elem(const uint8_t * row, int type, int64_
         case T_IQ2_XXS: return elem_via_dequant4<T_IQ2_XXS>(row, i);
         case T_IQ3_XXS: return elem_via_dequant4<T_IQ3_XXS>(row, i);
         case T_IQ1_S:  return elem_via_dequant4<T_IQ1_S>(row, i);
+        case T_IQ2_XS: return elem_via_dequant4<T_IQ2_XS>(row, i);
+        case T_IQ2_S: return elem_via_dequant4<T_IQ2_S>(row, i);
+        case T_IQ3_S: return elem_via_dequant4<T_IQ3_S>(row, i);
+        case T_IQ1_M: return elem_via_dequant4<T_IQ1_M>(row, i);
+        case T_TQ1_0: return elem_via_dequant4<T_TQ1_0>(row, i);
+        case T_TQ2_0: return elem_via_dequant4<T_TQ2_0>(row, i);
         default: return __int_as_float(0x7fc00000);          // unreachable (ggml_b200_op_get_rows rejects unknown types): NaN, never a silent 0
     }
 }

@@ -29,13 +29,15 @@ F32, F16, Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q8_1 = 0, 1, 2, 3, 6, 7, 8, 9
 Q2_K, Q3_K, Q4_K, Q5_K, Q6_K, Q8_K = 10, 11, 12, 13, 14, 15
 IQ4_NL, IQ4_XS = 20, 23
 IQ2_XXS, IQ3_XXS, IQ1_S = 16, 18, 19
+IQ2_XS, IQ3_S, IQ2_S, IQ1_M, TQ1_0, TQ2_0 = 17, 21, 22, 29, 34, 35
 TYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q4_1: "q4_1", Q5_0: "q5_0", Q5_1: "q5_1", Q8_0: "q8_0", Q8_1: "q8_1",
-              Q2_K: "q2_K", Q3_K: "q3_K", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K", IQ4_NL: "iq4_nl", IQ4_XS: "iq4_xs", IQ2_XXS: "iq2_xxs", IQ3_XXS: "iq3_xxs", IQ1_S: "iq1_s"}
+              Q2_K: "q2_K", Q3_K: "q3_K", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K", IQ4_NL: "iq4_nl", IQ4_XS: "iq4_xs", IQ2_XXS: "iq2_xxs", IQ3_XXS: "iq3_xxs", IQ1_S: "iq1_s",
+              IQ2_XS: "iq2_xs", IQ3_S: "iq3_s", IQ2_S: "iq2_s", IQ1_M: "iq1_m", TQ1_0: "tq1_0", TQ2_0: "tq2_0"}
 HOT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
 # the next weight formats; oracle pinned this round, CUDA kernels follow
 NEXT_TYPES = (Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS)
 # the grid-codebook i-quants (round 2): generic mat-vec / MUL_MAT_ID / dequantize kernels
-IQ_TYPES = (IQ2_XXS, IQ3_XXS, IQ1_S)
+IQ_TYPES = (IQ2_XXS, IQ3_XXS, IQ1_S, IQ2_XS, IQ2_S, IQ3_S, IQ1_M, TQ1_0, TQ2_0)
 
 
 def build(ref: bool = True) -> None:
@@ -306,7 +308,7 @@ def random_blocks(t: int, nblocks: int, rng: np.random.Generator, scale: float =
     """Arbitrary-but-valid packed blocks: uniformly random code bytes (every nibble / 6-bit scale /
     high-bit pattern occurs) with finite fp16 scales of magnitude ~`scale`."""
     ts = {Q4_0: 18, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q4_1: 20, Q5_0: 22, Q5_1: 24, Q2_K: 84, Q3_K: 110, IQ4_NL: 18, IQ4_XS: 136,
-          IQ2_XXS: 66, IQ3_XXS: 98, IQ1_S: 50}[t]
+          IQ2_XXS: 66, IQ3_XXS: 98, IQ1_S: 50, IQ2_XS: 74, IQ2_S: 82, IQ3_S: 110, IQ1_M: 56, TQ1_0: 54, TQ2_0: 66}[t]
     b = rng.integers(0, 256, size=(nblocks, ts), dtype=np.uint8)
 
     def put_half(col, vals):
@@ -333,8 +335,20 @@ def random_blocks(t: int, nblocks: int, rng: np.random.Generator, scale: float =
         put_half(108, rng.uniform(-scale / 32, scale / 32, nblocks))
     elif t == IQ4_XS:
         put_half(0, rng.uniform(-scale / 256, scale / 256, nblocks))
-    elif t in (IQ2_XXS, IQ3_XXS, IQ1_S):
+    elif t in (IQ2_XXS, IQ3_XXS, IQ1_S, IQ2_XS, IQ2_S, IQ3_S):
         put_half(0, rng.uniform(-scale / 16, scale / 16, nblocks))
+    elif t == IQ1_M:                                       # the f16 super-scale lives in the top nibbles of the four u16 scale words
+        h = rng.uniform(-scale / 16, scale / 16, nblocks).astype(np.float16).view(np.uint16).astype(np.uint32)
+        for i in range(4):
+            b[:, 49 + 2 * i] = (b[:, 49 + 2 * i] & 0x0F) | (((h >> (4 * i)) & 0xF) << 4).astype(np.uint8)
+    elif t in (TQ1_0, TQ2_0):
+        put_half(52 if t == TQ1_0 else 64, rng.uniform(-scale, scale, nblocks))
+        if t == TQ1_0:                                     # valid base-3 bytes: 5 trits -> ceil(v * 256 / 243), 4 trits (qh) likewise
+            v5 = rng.integers(0, 243, size=(nblocks, 48)); b[:, 0:48] = ((v5 * 256 + 242) // 243).astype(np.uint8)
+            v4 = rng.integers(0, 81, size=(nblocks, 4)) * 3; b[:, 48:52] = ((v4 * 256 + 242) // 243).astype(np.uint8)
+        else:                                              # 2-bit codes 0..2 only
+            c = rng.integers(0, 3, size=(nblocks, 64, 4))
+            b[:, 0:64] = (c[..., 0] | (c[..., 1] << 2) | (c[..., 2] << 4) | (c[..., 3] << 6)).astype(np.uint8)
     return b.reshape(-1)
 
 

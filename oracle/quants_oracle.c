@@ -96,7 +96,7 @@ int64_t oq_blck_size(int type) {
         case OQ_F32: case OQ_F16: return 1;
         case OQ_Q4_0: case OQ_Q8_0: case OQ_Q4_1: case OQ_Q5_0: case OQ_Q5_1: case OQ_Q8_1: case OQ_IQ4_NL: return 32;
         case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q8_K: case OQ_Q2_K: case OQ_Q3_K: case OQ_IQ4_XS: return 256;
-        case OQ_IQ2_XXS: case OQ_IQ3_XXS: case OQ_IQ1_S: return 256;
+        case OQ_IQ2_XXS: case OQ_IQ3_XXS: case OQ_IQ1_S: case OQ_IQ2_XS: case OQ_IQ2_S: case OQ_IQ3_S: case OQ_IQ1_M: case OQ_TQ1_0: case OQ_TQ2_0: return 256;
         default: return 0;
     }
 }
@@ -108,6 +108,7 @@ size_t oq_type_size(int type) {
         case OQ_Q2_K: return 84; case OQ_Q3_K: return 110; case OQ_IQ4_NL: return 18; case OQ_IQ4_XS: return 136;
         case OQ_Q4_K: return 144; case OQ_Q5_K: return 176; case OQ_Q6_K: return 210; case OQ_Q8_K: return 292;
         case OQ_IQ2_XXS: return 66; case OQ_IQ3_XXS: return 98; case OQ_IQ1_S: return 50;
+        case OQ_IQ2_XS: return 74; case OQ_IQ2_S: return 82; case OQ_IQ3_S: return 110; case OQ_IQ1_M: return 56; case OQ_TQ1_0: return 54; case OQ_TQ2_0: return 66;
         default: return 0;
     }
 }
@@ -340,6 +341,91 @@ static void deq_iq1_s(const uint8_t * b, float * y, int64_t k) {
     }
 }
 
+/* ---- IQ2_XS / IQ2_S / IQ3_S / IQ1_M and the ternary TQ1_0 / TQ2_0 (layouts: src/ggml-common.h:226-240, 338-396).  One helper per format yields the
+ * eight signed integer codes of group l (0..3) of sub-block ib (0..7); dequantize_row_* (src/ggml-quants.c:2061-2120, 2218-2420) and the
+ * generic ggml_vec_dot_*_q8_K branches are stated on top of it. */
+static void iq2_xs_codes(const uint8_t * b, int ib, int l, int * c) {
+    const uint32_t q = rd16(b + 2 + 8 * ib + 2 * l);
+    const uint8_t * grid = (const uint8_t *)(iq2xs_grid + (q & 511));
+    const int signs = ksigns_iq2xs[q >> 9];
+    for (int j = 0; j < 8; ++j) c[j] = (int)grid[j] * ((signs & kmask_iq2xs[j]) ? -1 : 1);
+}
+static void iq2_s_codes(const uint8_t * b, int ib, int l, int * c) {
+    const uint8_t * grid = (const uint8_t *)(iq2s_grid + (b[2 + 4 * ib + l] | ((b[66 + ib] << (8 - 2 * l)) & 0x300)));
+    const int signs = b[34 + 4 * ib + l];
+    for (int j = 0; j < 8; ++j) c[j] = (int)grid[j] * ((signs & kmask_iq2xs[j]) ? -1 : 1);
+}
+static void iq3_s_codes(const uint8_t * b, int ib, int l, int * c) {
+    const uint32_t qh = b[66 + ib];
+    const uint8_t * g1 = (const uint8_t *)(iq3s_grid + (b[2 + 8 * ib + 2 * l] | ((qh << (8 - 2 * l)) & 256)));
+    const uint8_t * g2 = (const uint8_t *)(iq3s_grid + (b[2 + 8 * ib + 2 * l + 1] | ((qh << (7 - 2 * l)) & 256)));
+    const int signs = b[74 + 4 * ib + l];
+    for (int j = 0; j < 4; ++j) { c[j] = (int)g1[j] * ((signs & kmask_iq2xs[j]) ? -1 : 1); c[j + 4] = (int)g2[j] * ((signs & kmask_iq2xs[j + 4]) ? -1 : 1); }
+}
+static void iq1_m_codes(const uint8_t * b, int ib, int l, int * c) {
+    const uint32_t qh = b[32 + 2 * ib + (l >> 1)];
+    const int8_t * grid = (const int8_t *)(iq1s_grid + (b[4 * ib + l] | ((qh << (8 - 4 * (l & 1))) & 0x700)));
+    for (int j = 0; j < 8; ++j) c[j] = grid[j];
+}
+static inline int iq1_m_delta(const uint8_t * b, int ib, int l) { return (b[32 + 2 * ib + (l >> 1)] & (0x08 << (4 * (l & 1)))) ? -1 : 1; }
+static inline int iq1_m_ls(const uint8_t * b, int ib, int l) { return 2 * ((rd16(b + 48 + 2 * (ib >> 1)) >> (6 * (ib & 1) + 3 * (l >> 1))) & 7) + 1; }
+static inline float iq1_m_d(const uint8_t * b) {
+    const uint32_t s0 = rd16(b + 48), s1 = rd16(b + 50), s2 = rd16(b + 52), s3 = rd16(b + 54);
+    return oq_fp16_to_fp32((uint16_t)((s0 >> 12) | ((s1 >> 8) & 0x00F0) | ((s2 >> 4) & 0x0F00) | (s3 & 0xF000)));
+}
+static inline int tq1_code(const uint8_t * b, int e) {                   /* element e of a TQ1_0 block, in { 0, 1, 2 } */
+    static const uint8_t pow3[5] = { 1, 3, 9, 27, 81 };
+    uint8_t byte; int n;
+    if (e < 160) { byte = b[e & 31]; n = e >> 5; }
+    else if (e < 240) { byte = b[32 + ((e - 160) & 15)]; n = (e - 160) >> 4; }
+    else { byte = b[48 + ((e - 240) & 3)]; n = (e - 240) >> 2; }
+    const uint8_t q = (uint8_t)(byte * pow3[n]);
+    return (int)(((uint16_t)q * 3) >> 8);
+}
+static inline int tq2_code(const uint8_t * b, int e) { return (b[32 * (e >> 7) + (e & 31)] >> (2 * ((e >> 5) & 3))) & 3; }
+
+static void deq_iq2_xs_s(int type, const uint8_t * b, float * y, int64_t k) {
+    const int bytes = type == OQ_IQ2_XS ? 74 : 82, so = type == OQ_IQ2_XS ? 66 : 74;
+    for (int64_t i = 0; i < k / 256; ++i, b += bytes) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int ib = 0; ib < 8; ++ib) {
+            const float db[2] = { d * (0.5f + (float)(b[so + ib] & 0xF)) * 0.25f, d * (0.5f + (float)(b[so + ib] >> 4)) * 0.25f };
+            for (int l = 0; l < 4; ++l) {
+                int c[8];
+                if (type == OQ_IQ2_XS) iq2_xs_codes(b, ib, l, c); else iq2_s_codes(b, ib, l, c);
+                for (int j = 0; j < 8; ++j) *y++ = db[l / 2] * (float)c[j];          /* = db * grid * (+-1) exactly */
+            }
+        }
+    }
+}
+static void deq_iq3_s(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 110) {
+        const float d = oq_fp16_to_fp32(rd16(b));
+        for (int ib = 0; ib < 8; ++ib) {
+            const float db = d * (float)(1 + 2 * ((b[106 + (ib >> 1)] >> (4 * (ib & 1))) & 0xF));
+            for (int l = 0; l < 4; ++l) { int c[8]; iq3_s_codes(b, ib, l, c); for (int j = 0; j < 8; ++j) *y++ = db * (float)c[j]; }
+        }
+    }
+}
+static void deq_iq1_m(const uint8_t * b, float * y, int64_t k) {
+    for (int64_t i = 0; i < k / 256; ++i, b += 56) {
+        const float d = iq1_m_d(b);
+        for (int ib = 0; ib < 8; ++ib)
+            for (int l = 0; l < 4; ++l) {
+                int c[8]; iq1_m_codes(b, ib, l, c);
+                const float dl = d * (float)iq1_m_ls(b, ib, l), delta = iq1_m_delta(b, ib, l) < 0 ? -OQ_IQ1S_DELTA : OQ_IQ1S_DELTA;
+                for (int j = 0; j < 8; ++j) *y++ = dl * ((float)c[j] + delta);
+            }
+    }
+}
+static void deq_tq(int type, const uint8_t * b, float * y, int64_t k) {
+    const int bytes = type == OQ_TQ1_0 ? 54 : 66;
+    for (int64_t i = 0; i < k / 256; ++i, b += bytes) {
+        const float d = oq_fp16_to_fp32(rd16(b + bytes - 2));
+        for (int e = 0; e < 256; ++e) *y++ = (float)((type == OQ_TQ1_0 ? tq1_code(b, e) : tq2_code(b, e)) - 1) * d;
+    }
+}
+
 static void deq_q8_K(const uint8_t * b, float * y, int64_t k) {
     for (int64_t i = 0; i < k / 256; ++i, b += 292, y += 256) {
         float d; memcpy(&d, b, 4);
@@ -368,6 +454,10 @@ int oq_dequantize_row(int type, const void * src, float * dst, int64_t k) {
         case OQ_IQ2_XXS: deq_iq2_xxs(b, dst, k); return 0;
         case OQ_IQ3_XXS: deq_iq3_xxs(b, dst, k); return 0;
         case OQ_IQ1_S: deq_iq1_s(b, dst, k); return 0;
+        case OQ_IQ2_XS: case OQ_IQ2_S: deq_iq2_xs_s(type, b, dst, k); return 0;
+        case OQ_IQ3_S: deq_iq3_s(b, dst, k); return 0;
+        case OQ_IQ1_M: deq_iq1_m(b, dst, k); return 0;
+        case OQ_TQ1_0: case OQ_TQ2_0: deq_tq(type, b, dst, k); return 0;
         default: return -1;
     }
 }
@@ -466,7 +556,7 @@ int oq_vec_dot_type(int type) {
         case OQ_Q4_0: case OQ_Q8_0: case OQ_Q5_0: case OQ_IQ4_NL: return OQ_Q8_0;
         case OQ_Q4_1: case OQ_Q5_1: return OQ_Q8_1;
         case OQ_Q4_K: case OQ_Q5_K: case OQ_Q6_K: case OQ_Q2_K: case OQ_Q3_K: case OQ_IQ4_XS: return OQ_Q8_K;
-        case OQ_IQ2_XXS: case OQ_IQ3_XXS: case OQ_IQ1_S: return OQ_Q8_K;
+        case OQ_IQ2_XXS: case OQ_IQ3_XXS: case OQ_IQ1_S: case OQ_IQ2_XS: case OQ_IQ2_S: case OQ_IQ3_S: case OQ_IQ1_M: case OQ_TQ1_0: case OQ_TQ2_0: return OQ_Q8_K;
         default: return -1;
     }
 }
@@ -709,6 +799,38 @@ static float dot_iq1_s_q8_K(int64_t k, const uint8_t * w, const uint8_t * y) {
     return sumf;
 }
 
+/* ggml_vec_dot_iq2_xs / iq2_s / iq3_s / iq1_m / tq1_0 / tq2_0 _q8_K, generic branches (src/ggml-cpu/ggml-cpu-quants.c) */
+static float dot_iq_more_q8_K(int type, int64_t k, const uint8_t * w, const uint8_t * y) {
+    const int bytes = (int)oq_type_size(type);
+    float sumf = 0.0f;
+    for (int64_t i = 0; i < k / 256; ++i, w += bytes, y += 292) {
+        float yd; memcpy(&yd, y, 4);
+        const int8_t * q8 = (const int8_t *)(y + 4);
+        int bsum = 0, bsum2 = 0;
+        for (int ib = 0; ib < 8; ++ib)
+            for (int l = 0; l < 4; ++l) {
+                int c[8], s = 0, s2 = 0, ls = 1;
+                switch (type) {
+                    case OQ_IQ2_XS: iq2_xs_codes(w, ib, l, c); ls = 2 * ((w[66 + ib] >> (4 * (l >> 1))) & 0xF) + 1; break;
+                    case OQ_IQ2_S:  iq2_s_codes(w, ib, l, c);  ls = 2 * ((w[74 + ib] >> (4 * (l >> 1))) & 0xF) + 1; break;
+                    case OQ_IQ3_S:  iq3_s_codes(w, ib, l, c);  ls = 2 * ((w[106 + (ib >> 1)] >> (4 * (ib & 1))) & 0xF) + 1; break;
+                    case OQ_IQ1_M:  iq1_m_codes(w, ib, l, c);  ls = iq1_m_ls(w, ib, l); break;
+                    case OQ_TQ1_0:  for (int j = 0; j < 8; ++j) c[j] = tq1_code(w, 32 * ib + 8 * l + j) - 1; break;
+                    default:        for (int j = 0; j < 8; ++j) c[j] = tq2_code(w, 32 * ib + 8 * l + j) - 1; break;
+                }
+                for (int j = 0; j < 8; ++j) { s += c[j] * (int)q8[32 * ib + 8 * l + j]; s2 += (int)q8[32 * ib + 8 * l + j]; }
+                bsum += ls * s;
+                if (type == OQ_IQ1_M) bsum2 += ls * iq1_m_delta(w, ib, l) * s2;
+            }
+        switch (type) {
+            case OQ_IQ1_M: sumf += iq1_m_d(w) * yd * ((float)bsum + OQ_IQ1S_DELTA * (float)bsum2); break;
+            case OQ_TQ1_0: case OQ_TQ2_0: sumf += (float)bsum * (oq_fp16_to_fp32(rd16(w + bytes - 2)) * yd); break;
+            default: sumf += (oq_fp16_to_fp32(rd16(w)) * yd) * (float)bsum; break;
+        }
+    }
+    return (type == OQ_IQ2_XS || type == OQ_IQ2_S) ? 0.125f * sumf : sumf;
+}
+
 float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
     const uint8_t * w = (const uint8_t *)wrow, * y = (const uint8_t *)yq;
     switch (type) {
@@ -727,6 +849,7 @@ float oq_vec_dot(int type, int64_t k, const void * wrow, const void * yq) {
         case OQ_IQ2_XXS: return dot_iq2_xxs_q8_K(k, w, y);
         case OQ_IQ3_XXS: return dot_iq3_xxs_q8_K(k, w, y);
         case OQ_IQ1_S: return dot_iq1_s_q8_K(k, w, y);
+        case OQ_IQ2_XS: case OQ_IQ2_S: case OQ_IQ3_S: case OQ_IQ1_M: case OQ_TQ1_0: case OQ_TQ2_0: return dot_iq_more_q8_K(type, k, w, y);
         default: return NAN;
     }
 }

@@ -11,7 +11,7 @@ extern "C" {
 /* type ids = enum ggml_type (reference include/ggml.h:351-390) */
 enum {
     OQ_F32 = 0, OQ_F16 = 1, OQ_Q4_0 = 2, OQ_Q4_1 = 3, OQ_Q5_0 = 6, OQ_Q5_1 = 7, OQ_Q8_0 = 8, OQ_Q8_1 = 9,
-    OQ_Q2_K = 10, OQ_Q3_K = 11, OQ_Q4_K = 12, OQ_Q5_K = 13, OQ_Q6_K = 14, OQ_Q8_K = 15, OQ_IQ4_NL = 20, OQ_IQ4_XS = 23, OQ_IQ2_XXS = 16, OQ_IQ3_XXS = 18, OQ_IQ1_S = 19,
+    OQ_Q2_K = 10, OQ_Q3_K = 11, OQ_Q4_K = 12, OQ_Q5_K = 13, OQ_Q6_K = 14, OQ_Q8_K = 15, OQ_IQ4_NL = 20, OQ_IQ4_XS = 23, OQ_IQ2_XXS = 16, OQ_IQ3_XXS = 18, OQ_IQ1_S = 19, OQ_IQ2_XS = 17, OQ_IQ3_S = 21, OQ_IQ2_S = 22, OQ_IQ1_M = 29, OQ_TQ1_0 = 34, OQ_TQ2_0 = 35,
 };
 
 float    oq_fp16_to_fp32(uint16_t h);

@@ -28,7 +28,7 @@ template <int T> static void dequant_all(const uint8_t * src, float * dst, int64
     for (int64_t e = 0; e < n; e += 4) { float o[4]; dequant4<T>(src, e, o); for (int i = 0; i < 4; ++i) dst[e + i] = o[i]; }
 }
 
-#define FOR_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_Q2_K) X(T_Q3_K) X(T_IQ4_NL) X(T_IQ4_XS) X(T_IQ2_XXS) X(T_IQ3_XXS) X(T_IQ1_S)
+#define FOR_TYPES(X) X(T_Q4_0) X(T_Q8_0) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_Q2_K) X(T_Q3_K) X(T_IQ4_NL) X(T_IQ4_XS) X(T_IQ2_XXS) X(T_IQ3_XXS) X(T_IQ1_S) X(T_IQ2_XS) X(T_IQ2_S) X(T_IQ3_S) X(T_IQ1_M) X(T_TQ1_0) X(T_TQ2_0)
 
 // tcgen05 GEMM operand preparation: one W row -> K fp16 values (swizzle key 0: the 8 chunks of a K-step land in order)
 template <int T> static void tc_row(const uint8_t * row, int64_t K, uint16_t * out) {

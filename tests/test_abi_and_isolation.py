@@ -55,7 +55,7 @@ def test_shim_validates_arguments_without_a_device():
     assert L.ggml_b200_row_size(g.Q2_K, 512) == 168 and L.ggml_b200_row_size(g.Q3_K, 512) == 220
     assert L.ggml_b200_row_size(g.Q4_0, 4096) == 2304 and L.ggml_b200_row_size(g.Q8_0, 4096) == 4352 and L.ggml_b200_row_size(g.Q5_K, 256) == 176
     a = g.MulMatArgs()
-    a.type, a.K, a.M, a.N = 17, 4096, 16, 1                 # IQ2_XS: not implemented -> explicit error, not a fallback
+    a.type, a.K, a.M, a.N = 30, 4096, 16, 1                 # BF16 weights: not implemented -> explicit error, not a fallback
     a.ne02 = a.ne03 = a.ne12 = a.ne13 = 1
     assert L.ggml_b200_mul_mat_plan(C.byref(a)) == -1
     a.type, a.K = g.Q4_K, 100                               # K not a multiple of the block size
