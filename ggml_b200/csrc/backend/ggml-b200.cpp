@@ -516,6 +516,14 @@ bool device_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
             return true;
         case GGML_OP_MUL_MAT:    return supports_mul_mat(op) || supports_mul_mat_float(op);
         case GGML_OP_MUL_MAT_ID: return supports_mul_mat_id(op);
+        case GGML_OP_FLASH_ATTN_EXT: {
+            const ggml_tensor * q = op->src[0], * k = op->src[1], * v = op->src[2], * mask = op->src[3];
+            auto kv_ok = [](const ggml_tensor * t) { return (t->type == GGML_TYPE_F16 || t->type == GGML_TYPE_F32 || is_b200_weight_type(t->type)) && t->nb[0] == ggml_type_size(t->type); };
+            if (q->type != GGML_TYPE_F32 || op->type != GGML_TYPE_F32 || q->nb[0] != sizeof(float) || op->nb[0] != sizeof(float)) return false;
+            if (!kv_ok(k) || !kv_ok(v) || q->ne[0] > 256 || k->ne[0] != q->ne[0] || v->ne[0] != q->ne[0]) return false;
+            if (mask && (mask->type != GGML_TYPE_F16 || mask->nb[0] != sizeof(ggml_fp16_t))) return false;
+            return q->ne[2] <= 65535 && q->ne[3] <= 65535;
+        }
         default: return supports_small_op(op);
     }
 }
@@ -966,6 +974,13 @@ void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
                 } else { auto x = desc(node->src[0]), y = desc(node->src[1]), d = desc(node); SHIM_OK(ggml_b200_op_mul_mat_f(&x, &y, &d, ctx->stream)); }
                 break;
             case GGML_OP_MUL_MAT_ID: compute_mul_mat_id(ctx, node); break;
+            case GGML_OP_FLASH_ATTN_EXT: {
+                auto q = desc(node->src[0]), k = desc(node->src[1]), v = desc(node->src[2]), d = desc(node);
+                ggml_b200_tensor m{};
+                if (node->src[3]) m = desc(node->src[3]);
+                SHIM_OK(ggml_b200_op_flash_attn_ext(&q, &k, &v, node->src[3] ? &m : nullptr, &d, ggml_get_op_params_f32(node, 0), ggml_get_op_params_f32(node, 1),
+                                                    ggml_get_op_params_f32(node, 2), ctx->stream));
+            } break;
             case GGML_OP_NORM: case GGML_OP_RMS_NORM: {
                 const int extra = fuse ? try_fuse_norm(ctx, cgraph, i) : 0;
                 if (extra > 0) i += extra; else compute_small_op(ctx, node);

@@ -348,6 +348,79 @@ __global__ void __launch_bounds__(128) mul_mat_f_kernel(tdesc a, tdesc b, tdesc 
     if (lane == 0) *(float *)(d.data + m * d.nb[0] + n * d.nb[1] + i12 * d.nb[2] + i13 * d.nb[3]) = acc;
 }
 
+// ------------------------------------------------------------------ FLASH_ATTN_EXT (f32 Q; f16 / f32 / block-quantized K and V; f16 mask)
+// What ggml_compute_forward_flash_attn_ext_f16 computes (src/ggml-cpu/ggml-cpu.c:10805-10990): per (query row, head, batch) an online-softmax
+// pass over the KV positions, dst[d, head, q, b] = sum_kv softmax(scale * K.q [softcap] + slope * mask) V.  One CTA per query row and head;
+// its four warps take the KV positions round-robin, each lane owns the elements lane, lane + 32, ... of the head dimension (<= 256), K and V
+// rows are decoded on the fly (any advertised block format: quantized KV caches), the four partial (max, sum, accumulator) triples are
+// merged through shared memory.  Accumulation is f32 (the CPU keeps an f16 accumulator for f16 V; the reference's own gate is NMSE 5e-4).
+// Replaces src/ggml-cuda/fattn*.cu for correctness; this is the bandwidth-shaped decode form, not a tensor-core prefill kernel.
+struct fa_params {
+    tdesc q, k, v, mask, dst;
+    float scale, max_bias, softcap, m0, m1;
+    uint32_t n_head_log2;
+};
+__global__ void __launch_bounds__(128) flash_attn_ext_kernel(fa_params p) {
+    pdl_trigger();
+    __shared__ float s_m[4], s_s[4], s_acc[4][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t iq1 = blockIdx.x, iq2 = blockIdx.y, iq3 = blockIdx.z;
+    const int D = (int)p.q.ne[0];
+    const int64_t nkv = p.k.ne[1];
+    const int64_t ik2 = iq2 / (p.q.ne[2] / p.k.ne[2]), ik3 = iq3 / (p.q.ne[3] / p.k.ne[3]);
+    const int64_t iv2 = iq2 / (p.q.ne[2] / p.v.ne[2]), iv3 = iq3 / (p.q.ne[3] / p.v.ne[3]);
+    const float * pq = (const float *)(p.q.data + iq1 * p.q.nb[1] + iq2 * p.q.nb[2] + iq3 * p.q.nb[3]);
+    float qv[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int d = lane + 32 * i; qv[i] = d < D ? pq[d] : 0.0f; acc[i] = 0.0f; }
+    float slope = 1.0f;
+    if (p.max_bias > 0.0f) {
+        const uint32_t h = (uint32_t)iq2;
+        slope = h < p.n_head_log2 ? powf(p.m0, (float)(h + 1)) : powf(p.m1, (float)(2 * (h - p.n_head_log2) + 1));
+    }
+    const __half * mp = p.mask.data ? (const __half *)(p.mask.data + iq1 * p.mask.nb[1]) : nullptr;
+    float M = -INFINITY, S = 0.0f;
+    for (int64_t ic = warp; ic < nkv; ic += 4) {
+        const float mv = mp ? slope * __half2float(mp[ic]) : 0.0f;
+        if (mv == -INFINITY) continue;                                          // warp-uniform
+        const uint8_t * krow = p.k.data + ic * p.k.nb[1] + ik2 * p.k.nb[2] + ik3 * p.k.nb[3];
+        float part = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int d = lane + 32 * i; if (d < D) part += qv[i] * load_elem(krow, p.k.type, d); }
+        float sc = warp_sum_f(part) * p.scale;
+        if (p.softcap != 0.0f) sc = p.softcap * tanhf(sc);
+        sc += mv;
+        float vs = 1.0f;
+        if (sc > M) {
+            const float ms = expf(M - sc);                                      // 0 on the first position (M = -inf)
+            M = sc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] *= ms;
+            S = S * ms + 1.0f;
+        } else {
+            vs = expf(sc - M);
+            S += vs;
+        }
+        const uint8_t * vrow = p.v.data + ic * p.v.nb[1] + iv2 * p.v.nb[2] + iv3 * p.v.nb[3];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int d = lane + 32 * i; if (d < D) acc[i] += vs * load_elem(vrow, p.v.type, d); }
+    }
+    if (lane == 0) { s_m[warp] = M; s_s[warp] = S; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int d = lane + 32 * i; if (d < D) s_acc[warp][d] = acc[i]; }
+    __syncthreads();
+    if (warp == 0) {
+        const float Mx = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+        float f[4], St = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { f[w] = s_m[w] == -INFINITY ? 0.0f : expf(s_m[w] - Mx); St += s_s[w] * f[w]; }
+        const float inv = 1.0f / St;
+        float * out = (float *)(p.dst.data + iq2 * p.dst.nb[1] + iq1 * p.dst.nb[2] + iq3 * p.dst.nb[3]);
+        for (int d = lane; d < D; d += 32)
+            out[d] = (s_acc[0][d] * f[0] + s_acc[1][d] * f[1] + s_acc[2][d] * f[2] + s_acc[3][d] * f[3]) * inv;
+    }
+}
+
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 } // namespace b200
@@ -483,6 +556,30 @@ int ggml_b200_op_cpy2(const ggml_b200_tensor * src_a, const ggml_b200_tensor * d
     if (!(fl(s) && fl(d) && fl(s2) && fl(d2))) { set_error("cpy2: float tensors only"); return GGML_B200_EUNSUPPORTED; }
     if (n == 0) return GGML_B200_OK;
     B200_CUDA_TRY(launch_pdl(cpy_kernel, dim3(blocks_for(n, 256), 2), dim3(256), (cudaStream_t)stream, s, d, s2, d2, n));
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int ggml_b200_op_flash_attn_ext(const ggml_b200_tensor * q, const ggml_b200_tensor * k, const ggml_b200_tensor * v, const ggml_b200_tensor * mask,
+                                const ggml_b200_tensor * dst, float scale, float max_bias, float logit_softcap, void * stream) {
+    fa_params p;
+    p.q = T(q); p.k = T(k); p.v = T(v); p.dst = T(dst);
+    if (mask) p.mask = T(mask); else { p.mask = tdesc{}; p.mask.data = nullptr; }
+    auto decodable = [](int t) { return t == T_F32 || t == T_F16 || type_bytes(t) != 0; };
+    REQUIRE(p.q.type == T_F32 && p.dst.type == T_F32 && p.q.nb[0] == 4 && p.dst.nb[0] == 4, "q and dst must be f32 rows");
+    REQUIRE(decodable(p.k.type) && decodable(p.v.type), "unsupported K / V type");
+    REQUIRE(p.q.ne[0] >= 1 && p.q.ne[0] <= 256 && p.k.ne[0] == p.q.ne[0] && p.v.ne[0] == p.q.ne[0] && p.v.ne[1] == p.k.ne[1], "head size must be <= 256 and agree");
+    REQUIRE(p.k.ne[2] > 0 && p.q.ne[2] % p.k.ne[2] == 0 && p.q.ne[3] % p.k.ne[3] == 0 && p.q.ne[2] % p.v.ne[2] == 0 && p.q.ne[3] % p.v.ne[3] == 0, "heads do not broadcast");
+    REQUIRE(!mask || (p.mask.type == T_F16 && p.mask.nb[0] == 2 && p.mask.ne[0] >= p.k.ne[1] && p.mask.ne[1] >= p.q.ne[1]), "mask must be f16 [n_kv, >= n_q]");
+    if (p.q.ne[1] == 0 || p.q.ne[2] == 0 || p.q.ne[3] == 0) return GGML_B200_OK;
+    REQUIRE(p.q.ne[2] <= 65535 && p.q.ne[3] <= 65535, "too many heads / batches for one grid");
+    p.scale = scale; p.max_bias = max_bias; p.softcap = logit_softcap;
+    if (logit_softcap != 0.0f) p.scale /= logit_softcap;
+    const uint32_t n_head = (uint32_t)p.q.ne[2];
+    uint32_t n_head_log2 = 1; while (n_head_log2 * 2 <= n_head) n_head_log2 *= 2;
+    p.n_head_log2 = n_head_log2;
+    p.m0 = powf(2.0f, -(max_bias) / n_head_log2); p.m1 = powf(2.0f, -(max_bias / 2.0f) / n_head_log2);
+    B200_CUDA_TRY(launch_pdl(flash_attn_ext_kernel, dim3((unsigned)p.q.ne[1], (unsigned)p.q.ne[2], (unsigned)p.q.ne[3]), dim3(128), (cudaStream_t)stream, p));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }

@@ -223,6 +223,10 @@ GGML_B200_API int ggml_b200_op_soft_max_diag(const float * src, const void * mas
 GGML_B200_API int ggml_b200_op_cpy(const ggml_b200_tensor * src, const ggml_b200_tensor * dst, void * stream);
 /* two independent float copies of the same element count in one launch (the K and V cache updates of a layer) */
 GGML_B200_API int ggml_b200_op_cpy2(const ggml_b200_tensor * src_a, const ggml_b200_tensor * dst_a, const ggml_b200_tensor * src_b, const ggml_b200_tensor * dst_b, void * stream);
+/* GGML_OP_FLASH_ATTN_EXT (include/ggml.h:1785-1800): q f32 [d, n_q, n_head, b], k / v [d, n_kv, n_head_kv, b] in f16, f32 or any block format this
+ * library decodes (quantized KV caches), mask f16 [n_kv, >= n_q] or NULL -> dst f32 [d, n_head, n_q, b]; d <= 256.  Replaces src/ggml-cuda/fattn*.cu. */
+GGML_B200_API int ggml_b200_op_flash_attn_ext(const ggml_b200_tensor * q, const ggml_b200_tensor * k, const ggml_b200_tensor * v, const ggml_b200_tensor * mask,
+                                              const ggml_b200_tensor * dst, float scale, float max_bias, float logit_softcap, void * stream);
 /* float mat-mul: src0 f32/f16 [K, M, ne02, ne03] (any strides) x src1 f32 [K, N, ne12, ne13] -> dst f32 */
 GGML_B200_API int ggml_b200_op_mul_mat_f(const ggml_b200_tensor * src0, const ggml_b200_tensor * src1, const ggml_b200_tensor * dst, void * stream);
 

@@ -60,7 +60,7 @@ def test_plugin_vs_cpu_backend_large(plugin):
         assert O.nmse(Yg, Yc) < 1e-10, (O.TYPE_NAMES[t], M, N, K)
 
 
-@pytest.mark.parametrize("op", ["GET_ROWS", "ADD", "MUL", "NORM", "RMS_NORM", "SCALE", "DIAG_MASK_INF", "SOFT_MAX", "GELU", "SILU", "CPY", "CONT", "DUP"])
+@pytest.mark.parametrize("op", ["GET_ROWS", "ADD", "MUL", "NORM", "RMS_NORM", "SCALE", "DIAG_MASK_INF", "SOFT_MAX", "GELU", "SILU", "CPY", "CONT", "DUP", "FLASH_ATTN_EXT"])
 def test_reference_test_backend_ops_small_ops(plugin, op):
     """the ops either side of the mat-mul in the gpt-2 graph, gated by the reference's own
     per-op tolerances (default NMSE 1e-7; CPY/SOFT_MAX 1e-6)"""
