@@ -207,6 +207,8 @@ class Ref:
         L.probe_mul_mat_sweep.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_int] * 5
         L.probe_mul_mat_split.restype = C.c_double
         L.probe_mul_mat_split.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_int]
+        L.probe_gguf_mul_mat.restype = C.c_double
+        L.probe_gguf_mul_mat.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 3
         L.probe_mul_mat_id.restype = C.c_double
         L.probe_mul_mat_id.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_int] * 2
 
@@ -290,6 +292,17 @@ class Ref:
         if s < 0:
             raise RuntimeError(f"probe_mul_mat_split({dev}) failed: {s}")
         return Y, float(s)
+
+    def gguf_mul_mat(self, t, W, X, M, N, K, dev, path):
+        """W -> GGUF file (reference writer) -> reference loader -> device buffer via the pinned host buffer type + async upload -> MUL_MAT.
+        Returns (Y[N, M], pinned: bool)"""
+        W = np.ascontiguousarray(W, dtype=np.uint8)
+        X = _f32(X)
+        Y = np.empty((N, M), dtype=np.float32)
+        rc = self.lib.probe_gguf_mul_mat(dev.encode(), str(path).encode(), t, _p(W), _p(X), _p(Y), M, N, K)
+        if rc < 0:
+            raise RuntimeError(f"probe_gguf_mul_mat({dev}) failed: {rc}")
+        return Y, rc == 0.0
 
     def mul_mat_id(self, t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok, dev="CPU", threads=0, iters=1):
         W = np.ascontiguousarray(W, dtype=np.uint8)

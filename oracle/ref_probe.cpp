@@ -14,6 +14,7 @@
 #include "ggml-alloc.h"
 #include "ggml-backend.h"
 #include "ggml-cpu.h"
+#include "gguf.h"
 
 #include <chrono>
 #include <cstdio>
@@ -242,6 +243,72 @@ double probe_mul_mat_split(const char * dev, int main_device, const float * tens
     ggml_backend_buffer_free(bc);
     ggml_backend_buffer_free(bw);
     ggml_free(cc); ggml_free(cw);
+    return out;
+}
+
+// The on-disk format either side of the path: write W (quantized, given) as a GGUF file with the reference's own writer, read
+// it back with the reference's own loader (gguf_init_from_file, no_alloc = true: metadata only), then do what a model loader does --
+// allocate the tensors in the device's default buffer, stage the file's data section through the device's PINNED host buffer type
+// (ggml_backend_dev_host_buffer_type) and upload with ggml_backend_tensor_set_async -- and run MUL_MAT on it.  Returns 0 and fills Y, or < 0.
+double probe_gguf_mul_mat(const char * dev, const char * path, int type_a, const void * W, const float * X, float * Y, int64_t M, int64_t N, int64_t K) {
+    {   // ---- write
+        ggml_init_params ip = { ggml_tensor_overhead() * 4, nullptr, true };
+        ggml_context * c = ggml_init(ip);
+        ggml_tensor * a = ggml_new_tensor_2d(c, (ggml_type) type_a, K, M);
+        ggml_set_name(a, "blk.0.ffn_up.weight");
+        gguf_context * g = gguf_init_empty();
+        gguf_set_val_str(g, "general.architecture", "probe");
+        gguf_set_val_u32(g, "probe.rows", (uint32_t) M);
+        gguf_add_tensor(g, a);
+        gguf_set_tensor_data(g, "blk.0.ffn_up.weight", W);
+        const bool ok = gguf_write_to_file(g, path, false);
+        gguf_free(g); ggml_free(c);
+        if (!ok) return -6.0;
+    }
+    backend_holder h;
+    if (!open_backend(h, dev, 0)) return -1.0;
+    ggml_context * cmeta = nullptr;
+    gguf_init_params gp = { /* no_alloc = */ true, /* ctx = */ &cmeta };
+    gguf_context * g = gguf_init_from_file(path, gp);
+    if (!g || !cmeta) return -7.0;
+    double out = -2.0;
+    ggml_tensor * a = ggml_get_tensor(cmeta, "blk.0.ffn_up.weight");
+    const int64_t tid = gguf_find_tensor(g, "blk.0.ffn_up.weight");
+    if (a && tid >= 0 && gguf_get_val_u32(g, gguf_find_key(g, "probe.rows")) == (uint32_t) M && a->type == (ggml_type) type_a && a->ne[0] == K && a->ne[1] == M) {
+        ggml_backend_buffer_t bw = ggml_backend_alloc_ctx_tensors(cmeta, h.be);          // weights in device memory
+        ggml_init_params ipc = { ggml_tensor_overhead() * 8 + ggml_graph_overhead(), nullptr, true };
+        ggml_context * cc = ggml_init(ipc);
+        ggml_tensor * b = ggml_new_tensor_2d(cc, GGML_TYPE_F32, K, N);
+        ggml_tensor * c = ggml_mul_mat(cc, a, b);
+        ggml_cgraph * gf = ggml_new_graph(cc);
+        ggml_build_forward_expand(gf, c);
+        ggml_backend_buffer_t bc = ggml_backend_alloc_ctx_tensors(cc, h.be);
+        if (bw && bc && ggml_backend_supports_op(h.be, c)) {
+            // stage the tensor's bytes from the file through pinned host memory, upload asynchronously
+            const size_t nbytes = ggml_nbytes(a), off = gguf_get_data_offset(g) + gguf_get_tensor_offset(g, tid);
+            ggml_backend_buffer_type_t hbt = ggml_backend_dev_host_buffer_type(ggml_backend_get_device(h.be));
+            ggml_backend_buffer_t hb = hbt ? ggml_backend_buft_alloc_buffer(hbt, nbytes) : nullptr;
+            std::vector<char> pageable;
+            void * stage = hb ? ggml_backend_buffer_get_base(hb) : (pageable.resize(nbytes), (void *) pageable.data());
+            FILE * f = fopen(path, "rb");
+            const bool rd = f && fseek(f, (long) off, SEEK_SET) == 0 && fread(stage, 1, nbytes, f) == nbytes;
+            if (f) fclose(f);
+            if (rd) {
+                ggml_backend_tensor_set_async(h.be, a, stage, 0, nbytes);
+                ggml_backend_tensor_set_async(h.be, b, X, 0, ggml_nbytes(b));
+                ggml_backend_graph_compute_async(h.be, gf);
+                ggml_backend_tensor_get_async(h.be, c, Y, 0, ggml_nbytes(c));
+                ggml_backend_synchronize(h.be);
+                out = hb ? 0.0 : 1.0;                              // 1: the device offers no pinned host buffer type (pageable staging)
+            } else out = -8.0;
+            if (hb) ggml_backend_buffer_free(hb);
+        }
+        if (bc) ggml_backend_buffer_free(bc);
+        if (bw) ggml_backend_buffer_free(bw);
+        ggml_free(cc);
+    } else out = -9.0;
+    gguf_free(g);
+    ggml_free(cmeta);
     return out;
 }
 

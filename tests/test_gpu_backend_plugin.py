@@ -114,3 +114,21 @@ def test_split_buffer_mul_mat(plugin):
         # a non-main device as the main device
         Ys, _ = ref.mul_mat_split(O.Q4_K, W, X, M, N, K, dev="B2001", main_device=1)
         assert np.array_equal(Ys, Y1[0, 0])
+
+
+def test_gguf_file_to_device_through_pinned_host_buffer(plugin, tmp_path):
+    """GGUF file (reference writer) -> reference loader -> device buffer, staged through the backend's pinned host buffer type and
+    uploaded with set_tensor_async -> MUL_MAT on the device == the oracle, for hot-path, next and i-quant formats"""
+    ref = O.Ref()
+    assert ref.load_backend(plugin)
+    orc = O.Oracle()
+    rng = np.random.default_rng(55)
+    for t, M, N, K in [(O.Q4_K, 11008, 1, 4096), (O.Q8_0, 4096, 4, 4096), (O.Q6_K, 1000, 1, 2048), (O.IQ2_XXS, 512, 2, 1024), (O.Q4_0, 4096, 64, 4096)]:
+        W = O.random_blocks(t, M * K // orc.blck_size(t), rng)
+        X = rng.uniform(-1, 1, N * K).astype(np.float32)
+        Y, pinned = ref.gguf_mul_mat(t, W, X, M, N, K, "B2000", tmp_path / "w.gguf")
+        assert pinned, "the device must offer a pinned host buffer type"
+        rows = rng.choice(M, 64, replace=False)
+        rb = orc.row_size(t, K)
+        want = orc.mul_mat(t, np.concatenate([W[r * rb:(r + 1) * rb] for r in rows]), X, 64, N, K)
+        assert O.nmse(Y[:, rows], want) < (1e-10 if N <= 8 else 1e-4), (O.TYPE_NAMES[t], M, N, K)

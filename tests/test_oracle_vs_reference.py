@@ -136,3 +136,14 @@ def test_mul_mat_id_matches_cpu_backend(t, cfg, oracle, ref):
     Yr, _ = ref.mul_mat_id(t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok, threads=2)
     Yo = oracle.mul_mat_id(t, W, X, ids, M, K, n_expert, n_used, nb1, n_tok)
     assert O.nmse(Yo, Yr) < 1e-12
+
+
+def test_gguf_file_round_trip_cpu(oracle, ref, tmp_path):
+    """the on-disk format next to the path, with the reference's unmodified writer and loader: quantized weights written to a
+    GGUF file, read back, MUL_MAT on the CPU backend == the oracle (the same probe drives the B200 backend in tests/test_gpu_backend_plugin.py)"""
+    rng = np.random.default_rng(5)
+    for t, M, N, K in [(O.Q4_K, 64, 2, 512), (O.Q8_0, 33, 1, 256), (O.IQ3_S, 16, 3, 256)]:
+        W = O.random_blocks(t, M * K // oracle.blck_size(t), rng)
+        X = rng.uniform(-1, 1, N * K).astype(np.float32)
+        Y, _ = ref.gguf_mul_mat(t, W, X, M, N, K, "CPU", tmp_path / "w.gguf")
+        assert O.nmse(Y, oracle.mul_mat(t, W, X, M, N, K)) < 1e-12, O.TYPE_NAMES[t]
