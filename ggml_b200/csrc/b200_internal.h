@@ -61,6 +61,10 @@ int    launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st);
 bool   mmq_tc2_eligible(const ggml_b200_mul_mat_args & a);
 size_t mmq_tc2_workspace(const ggml_b200_mul_mat_args & a);
 int    launch_mmq_tc2(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+// expert-grouped MUL_MAT_ID on the pair kernel (mmq_tc2.cu)
+bool   mmid_grouped_eligible(const ggml_b200_mul_mat_id_args & a);
+size_t mmid_grouped_workspace(const ggml_b200_mul_mat_id_args & a);
+int    launch_mmid_grouped(const ggml_b200_mul_mat_id_args & a, cudaStream_t st);
 unsigned int * tc_flag_slot();   // a zeroed, self-cleaning block of split-K flags from the device's control block (nullptr on error)
 int    tc_prepare_device();
 

@@ -59,6 +59,7 @@ extern "C" {
 
 size_t ggml_b200_mul_mat_id_workspace_size(const ggml_b200_mul_mat_id_args * a) {
     if (!a || type_bytes(a->type) == 0 || a->K <= 0) return 0;
+    if (mmid_grouped_eligible(*a)) return mmid_grouped_workspace(*a);
     return (size_t)make_act_layout(a->K, type_is_kquant(a->type)).bytes * (size_t)(a->nb1cols * a->n_tok) + 64;
 }
 
@@ -73,6 +74,7 @@ int ggml_b200_mul_mat_id(const ggml_b200_mul_mat_id_args * a, void * stream) {
     const size_t need = ggml_b200_mul_mat_id_workspace_size(a);
     if (!a->workspace || a->workspace_size < need) { set_error("mul_mat_id: workspace %zu < %zu", a->workspace_size, need); return GGML_B200_EWORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (mmid_grouped_eligible(*a)) return launch_mmid_grouped(*a, st);      // batched tokens: rows grouped per expert on the device, tensor cores
     // b[K, nb1cols, n_tok] -> records indexed t * nb1cols + c
     int rc = launch_quantize_activations(a->type, a->src1, a->K, a->nb1cols, a->n_tok, 1, a->nb11, a->nb12, 0, a->workspace, st);
     if (rc != GGML_B200_OK) return rc;

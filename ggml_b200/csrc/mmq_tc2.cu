@@ -40,6 +40,11 @@ struct tc2_params {
     float * y; float * partials; unsigned int * flags; const float * inv_scale;
     int64_t M, N;
     int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, w_static;
+    // grouped mode (MUL_MAT_ID, expert-grouped): the activation rows are SORTED by expert (position -> (token, slot) pair in `perm`), n-tiles are
+    // enumerated per expert (tile_base: prefix of tiles per expert, off: prefix of positions per expert, both n_expert + 1 long, device-resident:
+    // no host synchronisation); W is the [n_expert x M] row stack; y rows are scattered back through perm
+    const int32_t * g_off; const int32_t * g_tile_base; const int32_t * g_perm;
+    int32_t n_expert;
 };
 
 template <int T, int KS>
@@ -53,7 +58,7 @@ __device__ __forceinline__ void tc2_dequant_step(int nstages, int step, bool val
     if (lane == 0) { if (rank == 0) tc_arrive(&full[s]); else tc_arrive_cluster(&full[s], 0); }
 }
 
-template <int T>
+template <int T, bool GROUPED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const tc2_params p) {
     constexpr int RAW = tcfmt<T>::RAW, UK = tcfmt<T>::UNIT_KSTEPS;
@@ -77,8 +82,21 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int tile = pair % tiles, tm = tile % p.m_tiles, tn = tile / p.m_tiles;
     const int ubeg = (int)((int64_t)p.units_total * ks / p.splitk), uend = (int)((int64_t)p.units_total * (ks + 1) / p.splitk);
     const int nunits = uend - ubeg, nsteps = UK * nunits;
-    const int64_t row_base = (int64_t)tm * (2 * T2_BM) + (int64_t)rank * T2_BM;     // first W row of this CTA
+    // grouped mode: n-tile tn of the enumeration belongs to expert gx, covers sorted positions [gn0, gn0 + gcols); tiles past the last one
+    // (the grid is sized for the worst case) retire at once -- both CTAs of the pair see the same table, so the exit is pair-uniform
+    int gx = 0, gn0 = 0, gcols = 0;
+    if constexpr (GROUPED) {
+        if (tn >= p.g_tile_base[p.n_expert]) return;
+        int lo = 0, hi = p.n_expert;                              // largest x with tile_base[x] <= tn
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (p.g_tile_base[mid] <= tn) lo = mid; else hi = mid; }
+        gx = lo;
+        gn0 = p.g_off[gx] + (tn - p.g_tile_base[gx]) * p.BN;
+        gcols = min(p.BN, p.g_off[gx + 1] - gn0);
+    }
+    const int64_t row_base = (int64_t)tm * (2 * T2_BM) + (int64_t)rank * T2_BM;     // first W row of this CTA (within the expert's matrix)
     const int64_t rows_left = p.M - row_base;                     // may be <= 0 for the second CTA of the last tile
+    const int64_t w_row0 = GROUPED ? (int64_t)gx * p.M + row_base : row_base;       // row in the [n_expert x M] stack
+    const int x_row0 = GROUPED ? gn0 + (int)rank * (p.BN / 2) : tn * p.BN + (int)rank * (p.BN / 2);
 
     if (tid == 0) {
         // leader's stage barrier: 4 dequantizer warps of each CTA (the group that owns the K-step) + the leader's producer (expect_tx
@@ -108,13 +126,13 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 int coord;                                        // first 4-byte word of the box: 16-byte aligned start at or below the unit
                 if constexpr (tcfmt<T>::LOAD_BYTES == 2) coord = (((ubeg + u) * tcfmt<T>::UNIT_BYTES) & ~15) >> 2;
                 else                       coord = (ubeg + u) * tcfmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tcfmt<T>::ODD_BACK_WORDS;
-                tc_tma_2d(raw + rs * T2_BM * RAW, &map_w, coord, (int)row_base, &raw_full[rs]);
+                tc_tma_2d(raw + rs * T2_BM * RAW, &map_w, coord, (int)w_row0, &raw_full[rs]);
                 if (!x_ready) { tc_pdl_wait(); x_ready = true; }
                 for (int q = 0; q < UK; ++q) {
                     const int step = UK * u + q, s = step % p.nstages;
                     if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
                     if (rank == 0) tc_expect_tx(&full[s], (uint32_t)(2 * b_bytes));
-                    tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, ((ubeg + u) * UK + q) * T2_BK, tn * p.BN + (int)rank * (p.BN / 2), tc_cluster_addr(&full[s], 0));
+                    tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, ((ubeg + u) * UK + q) * T2_BK, x_row0, tc_cluster_addr(&full[s], 0));
                 }
             }
         }
@@ -207,8 +225,16 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                     for (int i = 0; i < 32; ++i) v[i] += __ldcg(&src[(size_t)(col0 + c0 + i) * T2_BM + mloc]);
                 }
                 if (m < p.M) {
+                    if constexpr (GROUPED) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { const int64_t n = n_base + c0 + i; if (n < p.N) p.y[(size_t)n * p.M + m] = v[i] * __ldcg(p.inv_scale + n); }
+                        for (int i = 0; i < 32; ++i) {
+                            const int col = col0 + c0 + i;                       // column of the tile = sorted position gn0 + col
+                            if (col < gcols) p.y[(size_t)__ldg(p.g_perm + gn0 + col) * p.M + m] = v[i] * __ldcg(p.inv_scale + gn0 + col);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { const int64_t n = n_base + c0 + i; if (n < p.N) p.y[(size_t)n * p.M + m] = v[i] * __ldcg(p.inv_scale + n); }
+                    }
                 }
             }
             if (p.splitk > 1) {
@@ -385,6 +411,176 @@ int launch_mmq_tc2(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q2_K:   return launch_tc2<T_Q2_K>(a, pl, st);
         case T_Q3_K:   return launch_tc2<T_Q3_K>(a, pl, st);
         default: set_error("mul_mat: unsupported weight type %d for the tcgen05 kernel", a.type); return GGML_B200_EUNSUPPORTED;
+    }
+}
+
+// ----------------------------------------------------------------------------- MUL_MAT_ID, expert-grouped (batched tokens)
+// The reference groups the rows per expert on the HOST (ids copied back, stream synchronised: src/ggml-cuda/ggml-cuda.cu:1975-2090; the CPU
+// backend builds matrix_rows the same way, src/ggml-cpu/ggml-cpu.c:7679-7694).  Here the grouping stays on the device: one small kernel counts
+// the (token, slot) pairs per expert, scans, and scatters the pair indices into a position list sorted by expert; the activation conversion
+// writes row `position`; the pair GEMM runs over a worst-case tile grid whose tiles look their expert / position range up in the device
+// tables, streaming every expert's weights once per 256-row tile instead of once per pair.  No host synchronisation anywhere.
+constexpr int MMID_MAX_EXPERTS = 1024;
+__global__ void __launch_bounds__(1024) mmid_group_kernel(const uint8_t * ids, size_t ids_nb1, int n_tok, int n_used, int n_expert, int BN,
+                                                          int32_t * off, int32_t * tile_base, int32_t * perm) {
+    __shared__ int hist[MMID_MAX_EXPERTS], cursor[MMID_MAX_EXPERTS];
+    const int n_pairs = n_tok * n_used;
+    for (int x = threadIdx.x; x < n_expert; x += blockDim.x) { hist[x] = 0; cursor[x] = 0; }
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < n_pairs; pr += blockDim.x) {
+        const int x = *(const int32_t *)(ids + (size_t)(pr / n_used) * ids_nb1 + (size_t)(pr % n_used) * 4);
+        if (x >= 0 && x < n_expert) atomicAdd(&hist[x], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0, tb = 0;
+        for (int x = 0; x < n_expert; ++x) { off[x] = o; tile_base[x] = tb; o += hist[x]; tb += (hist[x] + BN - 1) / BN; }
+        off[n_expert] = o; tile_base[n_expert] = tb;
+    }
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < n_pairs; pr += blockDim.x) {
+        const int x = *(const int32_t *)(ids + (size_t)(pr / n_used) * ids_nb1 + (size_t)(pr % n_used) * 4);
+        if (x >= 0 && x < n_expert) perm[off[x] + atomicAdd(&cursor[x], 1)] = pr;
+    }
+}
+
+// activation row of sorted position `pos` = b[t][e % nb1cols] of pair perm[pos] -> fp16 row pos with its exact power-of-two scale
+__global__ void __launch_bounds__(256) mmid_x_to_f16_kernel(const uint8_t * __restrict__ b, size_t nb11, size_t nb12, int n_used, int nb1cols, const int32_t * __restrict__ off,
+                                                            const int32_t * __restrict__ perm, int n_expert, __half * __restrict__ xh, float * __restrict__ inv_scale, int64_t K) {
+    const int pos = blockIdx.x;
+    if (pos >= off[n_expert]) return;                            // positions past the valid pairs (invalid expert ids) stay unused
+    const int pr = perm[pos], t = pr / n_used, e = pr % n_used;
+    const float * xr = (const float *)(b + (size_t)t * nb12 + (size_t)(e % nb1cols) * nb11);
+    __shared__ float s_max[8];
+    float amax = 0.0f;
+    for (int64_t k = (int64_t)threadIdx.x * 8; k < K; k += 256 * 8) {
+        const float4 a = load_f4(xr + k), c = load_f4(xr + k + 4);
+        amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = s_max[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, s_max[i]);
+    int ex = 0;
+    if (amax > 0.0f && amax <= 3.0e38f) ex = max(-100, min(100, (int)((__float_as_uint(amax) >> 23) & 0xFF) - 127 - 13));
+    const float sc = __uint_as_float((uint32_t)(127 - ex) << 23);
+    if (threadIdx.x == 0) inv_scale[pos] = __uint_as_float((uint32_t)(127 + ex) << 23);
+    for (int64_t k = (int64_t)threadIdx.x * 8; k < K; k += 256 * 8) {
+        const float4 a = load_f4(xr + k), c = load_f4(xr + k + 4);
+        __half2 h0 = __floats2half2_rn(a.x * sc, a.y * sc), h1 = __floats2half2_rn(a.z * sc, a.w * sc);
+        __half2 h2 = __floats2half2_rn(c.x * sc, c.y * sc), h3 = __floats2half2_rn(c.z * sc, c.w * sc);
+        uint4 o; o.x = h2u(h0); o.y = h2u(h1); o.z = h2u(h2); o.w = h2u(h3);
+        *(uint4 *)(xh + (size_t)pos * K + k) = o;
+    }
+}
+
+struct mmid_g_plan { int BN, m_tiles, max_tiles, chunks, nstages, smem; size_t xb_bytes, scale_bytes, tab_bytes, perm_bytes; int64_t n_pairs; };
+
+static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & pl) {
+    static const int env_on = getenv("GGML_B200_MMID_GROUPED") ? atoi(getenv("GGML_B200_MMID_GROUPED")) : 0;      // opt-in until validated on a B200
+    if (!env_on) return false;
+    switch (a.type) {
+        case T_Q4_0: case T_Q8_0: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_IQ4_NL: case T_IQ4_XS: case T_Q2_K: case T_Q3_K: break;
+        default: return false;
+    }
+    const int64_t n_pairs = a.n_used * a.n_tok;
+    if (n_pairs < 32 || a.n_expert > MMID_MAX_EXPERTS || a.M < 128 || a.K % 256 != 0 || a.K < 256) return false;
+    const size_t rb = row_bytes(a.type, a.K);
+    if (a.nb01 != rb || a.nb02 != rb * (size_t)a.M || (rb % 16) != 0 || ((uintptr_t)a.src0 & 15) != 0) return false;
+    if ((a.nb11 & 15) != 0 || (a.nb12 & 15) != 0 || ((uintptr_t)a.src1 & 15) != 0) return false;                 // 16-byte row loads in the conversion kernel
+    if (a.n_expert * a.M >= (1ll << 31) || n_pairs >= (1ll << 30) || !tc_get_encode()) return false;
+    // tile width: the average group size decides (Mixtral-like 8 x 2 at 512 tokens -> 128 per expert)
+    const int64_t avg = n_pairs / (a.n_expert > 0 ? a.n_expert : 1);
+    pl.BN = avg > 160 ? 256 : avg > 80 ? 128 : 64;
+    pl.m_tiles = (int)((a.M + 2 * T2_BM - 1) / (2 * T2_BM));
+    pl.max_tiles = (int)((n_pairs + pl.BN - 1) / pl.BN + a.n_expert);
+    pl.chunks = (int)(a.K / (a.type == T_Q8_0 ? 128 : 256));
+    const int raw = tc2_raw_bytes(a.type);
+    auto smem_of = [&](int ns) { return ns * (T2_BM * T2_BK * 2 + (pl.BN / 2) * T2_BK * 2) + 2 * T2_BM * raw + 256 + 1024; };
+    int nstages = T2_MAX_STAGES;
+    while (nstages > 2 && smem_of(nstages) > 227 * 1024) nstages--;
+    if (smem_of(nstages) > 227 * 1024) return false;
+    pl.nstages = nstages; pl.smem = smem_of(nstages);
+    if ((int64_t)pl.m_tiles * pl.max_tiles * 2 > 0x7fffffffLL) return false;
+    pl.n_pairs = n_pairs;
+    pl.xb_bytes = ((size_t)(n_pairs + pl.BN) * a.K * 2 + 255) & ~(size_t)255;        // + one tile of slack rows (read past the last position, never used)
+    pl.scale_bytes = ((size_t)(n_pairs + pl.BN) * 4 + 255) & ~(size_t)255;
+    pl.tab_bytes = ((size_t)(2 * (a.n_expert + 1)) * 4 + 255) & ~(size_t)255;
+    pl.perm_bytes = ((size_t)(n_pairs + pl.BN) * 4 + 255) & ~(size_t)255;
+    return true;
+}
+
+bool mmid_grouped_eligible(const ggml_b200_mul_mat_id_args & a) { mmid_g_plan pl; return make_mmid_g_plan(a, pl); }
+size_t mmid_grouped_workspace(const ggml_b200_mul_mat_id_args & a) {
+    mmid_g_plan pl;
+    if (!make_mmid_g_plan(a, pl)) return 0;
+    return pl.xb_bytes + pl.scale_bytes + pl.tab_bytes + pl.perm_bytes + 1024;
+}
+
+template <int T> static int launch_mmid_g(const ggml_b200_mul_mat_id_args & a, const mmid_g_plan & pl, cudaStream_t st) {
+    const size_t need = pl.xb_bytes + pl.scale_bytes + pl.tab_bytes + pl.perm_bytes + 1024;
+    if (!a.workspace || a.workspace_size < need) { set_error("mul_mat_id: workspace %zu < %zu", a.workspace_size, need); return GGML_B200_EWORKSPACE; }
+    uint8_t * ws = (uint8_t *)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
+    __half * xb = (__half *)ws;
+    float * inv_scale = (float *)(ws + pl.xb_bytes);
+    int32_t * off = (int32_t *)(ws + pl.xb_bytes + pl.scale_bytes), * tile_base = off + (a.n_expert + 1);
+    int32_t * perm = (int32_t *)(ws + pl.xb_bytes + pl.scale_bytes + pl.tab_bytes);
+    mmid_group_kernel<<<1, 1024, 0, st>>>((const uint8_t *)a.ids, a.ids_nb1, (int)a.n_tok, (int)a.n_used, (int)a.n_expert, pl.BN, off, tile_base, perm);
+    B200_LAUNCH_CHECK();
+    mmid_x_to_f16_kernel<<<(unsigned)pl.n_pairs, 256, 0, st>>>((const uint8_t *)a.src1, a.nb11, a.nb12, (int)a.n_used, (int)a.nb1cols, off, perm, (int)a.n_expert, xb, inv_scale, a.K);
+    B200_LAUNCH_CHECK();
+    const size_t rb = row_bytes(a.type, a.K);
+    alignas(64) CUtensorMap map_w, map_x;
+    {
+        const cuuint64_t dims[2] = { (cuuint64_t)(rb / 4), (cuuint64_t)(a.n_expert * a.M) };
+        const cuuint64_t strides[1] = { (cuuint64_t)rb };
+        const cuuint32_t box[2] = { (cuuint32_t)(tcfmt<T>::RAW / 4), (cuuint32_t)T2_BM };
+        const cuuint32_t es[2] = { 1, 1 };
+        CUresult r = tc_get_encode()(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)a.src0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(W experts) failed: %d", (int)r); return GGML_B200_ECUDA; }
+    }
+    {
+        const cuuint64_t dims[2] = { (cuuint64_t)a.K, (cuuint64_t)(pl.n_pairs + pl.BN) };
+        const cuuint64_t strides[1] = { (cuuint64_t)a.K * 2 };
+        const cuuint32_t box[2] = { (cuuint32_t)T2_BK, (cuuint32_t)(pl.BN / 2) };
+        const cuuint32_t es[2] = { 1, 1 };
+        CUresult r = tc_get_encode()(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)xb, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(X sorted) failed: %d", (int)r); return GGML_B200_ECUDA; }
+    }
+    tc2_params p{};
+    p.y = a.dst; p.partials = nullptr; p.flags = nullptr; p.inv_scale = inv_scale; p.M = a.M; p.N = pl.n_pairs;
+    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.w_static = 0;
+    p.g_off = off; p.g_tile_base = tile_base; p.g_perm = perm; p.n_expert = (int32_t)a.n_expert;
+    static per_device_flag attr_set;
+    if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
+    // plain launch (no programmatic dependency): the tile tables are read at kernel entry and must be complete
+    mmq_tc2_kernel<T, true><<<(unsigned)(2 * pl.m_tiles * pl.max_tiles), T2_THREADS, (size_t)pl.smem, st>>>(map_w, map_x, p);
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+int launch_mmid_grouped(const ggml_b200_mul_mat_id_args & a, cudaStream_t st) {
+    mmid_g_plan pl;
+    if (!make_mmid_g_plan(a, pl)) { set_error("mul_mat_id: shape not eligible for the grouped tensor-core path"); return GGML_B200_EUNSUPPORTED; }
+    switch (a.type) {
+        case T_Q4_0:   return launch_mmid_g<T_Q4_0>(a, pl, st);
+        case T_Q8_0:   return launch_mmid_g<T_Q8_0>(a, pl, st);
+        case T_Q4_K:   return launch_mmid_g<T_Q4_K>(a, pl, st);
+        case T_Q5_K:   return launch_mmid_g<T_Q5_K>(a, pl, st);
+        case T_Q6_K:   return launch_mmid_g<T_Q6_K>(a, pl, st);
+        case T_Q4_1:   return launch_mmid_g<T_Q4_1>(a, pl, st);
+        case T_Q5_0:   return launch_mmid_g<T_Q5_0>(a, pl, st);
+        case T_Q5_1:   return launch_mmid_g<T_Q5_1>(a, pl, st);
+        case T_IQ4_NL: return launch_mmid_g<T_IQ4_NL>(a, pl, st);
+        case T_IQ4_XS: return launch_mmid_g<T_IQ4_XS>(a, pl, st);
+        case T_Q2_K:   return launch_mmid_g<T_Q2_K>(a, pl, st);
+        case T_Q3_K:   return launch_mmid_g<T_Q3_K>(a, pl, st);
+        default: return GGML_B200_EUNSUPPORTED;
     }
 }
 

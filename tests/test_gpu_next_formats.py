@@ -24,3 +24,13 @@ def test_q6k_gemm_subprocess():
     p = subprocess.run([sys.executable, str(ROOT / "tests" / "gpu_q6k_gemm_check.py")], capture_output=True, text=True, timeout=200)
     print(p.stdout[-2000:])
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+
+
+def test_mul_mat_id_expert_grouped_subprocess():
+    """MUL_MAT_ID with the rows grouped per expert on the device and multiplied on the CTA-pair tcgen05 kernel (opt-in GGML_B200_MMID_GROUPED=1
+    until this check has passed on hardware), in its own process"""
+    import os
+    env = dict(os.environ, GGML_B200_MMID_GROUPED="1")
+    p = subprocess.run([sys.executable, str(ROOT / "tests" / "gpu_mmid_grouped_check.py"), "--time"], capture_output=True, text=True, timeout=300, env=env)
+    print(p.stdout[-2000:])
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
