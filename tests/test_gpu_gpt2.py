@@ -73,9 +73,10 @@ def test_gpt2_logits_track_cpu_step_by_step(model, kernels):
             pytest.fail(f"oracle/_ref/{exe} missing (make -C oracle b200bins in the build container)")
     env = {"GGML_B200_FORCE_GENERIC": "1"} if kernels == "generic" else None
     cpu_text, cpu_logits, _ = run_dump("gpt-2-backend-dump", model, N_STEPS, TMP / "cpu.logits")
-    ctoks = [int(t) for t in re.findall(r"<(\d+)>", cpu_text)]
-    assert cpu_logits.shape[0] == N_STEPS and len(ctoks) == N_STEPS, (cpu_logits.shape, len(ctoks))
-    assert list(cpu_logits.argmax(1)) == ctoks                                  # the dump is what the sampler saw
+    assert cpu_logits.shape[0] == N_STEPS, cpu_logits.shape
+    ctoks = [int(v) for v in cpu_logits.argmax(1)]                              # greedy (--top_k 1): the sampled token is the arg-max of the dumped logits
+    printed = [int(t) for t in re.findall(r"<(\d+)>", cpu_text)]                # ids outside the printable range are echoed as <id>
+    assert all(t in ctoks for t in printed), (printed, ctoks)
     np.array(ctoks, dtype=np.int32).tofile(TMP / "force.bin")
     _, gpu_logits, out = run_dump("gpt-2-backend-b200-dump", model, N_STEPS, TMP / f"b200_{kernels}.logits", force=TMP / "force.bin", extra=("-ngl", "12"), env_extra=env)
     assert "using CUDA backend" in out, out[-1500:]
@@ -94,8 +95,8 @@ def test_gpt2_logits_track_cpu_step_by_step(model, kernels):
             ties.append((i, margin, noise))
             assert margin <= 4 * noise, f"{kernels}: step {i}: argmax differs although the CPU margin {margin:.3e} exceeds 4 x the logit noise {noise:.3e}"
     # free-running generation: identical to the CPU until the first tie (if any)
-    free_text, _, _ = run("gpt-2-backend-b200", model, n=N_STEPS, extra=("-ngl", "12"), env_extra=env)
-    ftoks = [int(t) for t in re.findall(r"<(\d+)>", free_text)]
+    _, free_logits, _ = run_dump("gpt-2-backend-b200-dump", model, N_STEPS, TMP / f"b200_{kernels}_free.logits", extra=("-ngl", "12"), env_extra=env)
+    ftoks = [int(v) for v in free_logits.argmax(1)]
     first_tie = ties[0][0] if ties else N_STEPS
     assert ftoks[:first_tie] == ctoks[:first_tie], f"\ncpu: {ctoks}\ngpu: {ftoks}\nties: {ties}"
     print(f"gpt-2 117M q4_0 [{kernels} kernels]: {N_STEPS} teacher-forced steps, worst logits NMSE {worst_nmse:.2e}, worst noise/margin {worst_ratio:.2e}, "
