@@ -176,14 +176,24 @@ double probe_mul_mat_sweep(const char * dev, int type_a, const void * W, const f
     // e2e == 1: synchronous public calls (tensor_set, graph_compute, one tensor_get per output);
     // e2e == 2: the asynchronous public calls a pipelined application uses (tensor_set_async, graph_compute_async, tensor_get_async
     //           per output into distinct host rows, one synchronize per iteration); identical to mode 1 on backends without async copies
-    std::vector<float> host_out;
-    if (e2e == 2) host_out.resize((size_t) nw * M * N);
+    // results land in the device's pinned host buffer type when it offers one (what an application that cares about async copies uses)
+    std::vector<float> host_vec;
+    ggml_backend_buffer_t host_buf = nullptr;
+    float * host_out_p = nullptr;
+    if (e2e == 2) {
+        ggml_backend_buffer_type_t hbt = ggml_backend_dev_host_buffer_type(ggml_backend_get_device(h.be));
+        if (hbt) host_buf = ggml_backend_buft_alloc_buffer(hbt, (size_t) nw * M * N * sizeof(float) + K * N * sizeof(float));
+        if (host_buf) host_out_p = (float *) ggml_backend_buffer_get_base(host_buf);
+        else { host_vec.resize((size_t) nw * M * N + (size_t) K * N); host_out_p = host_vec.data(); }
+        memcpy(host_out_p + (size_t) nw * M * N, X, (size_t) K * N * sizeof(float));      // x staged in the same (pinned) buffer
+    }
+    const float * host_x = e2e == 2 ? host_out_p + (size_t) nw * M * N : X;
     double t0 = now_s();
     for (int i = 0; i < iters; ++i) {
         if (e2e == 2) {
-            ggml_backend_tensor_set_async(h.be, b, X, 0, ggml_nbytes(b));
+            ggml_backend_tensor_set_async(h.be, b, host_x, 0, ggml_nbytes(b));
             ggml_backend_graph_compute_async(h.be, gf);
-            for (int r = 0; r < nw; ++r) ggml_backend_tensor_get_async(h.be, outs[r], host_out.data() + (size_t) r * M * N, 0, ggml_nbytes(outs[r]));
+            for (int r = 0; r < nw; ++r) ggml_backend_tensor_get_async(h.be, outs[r], host_out_p + (size_t) r * M * N, 0, ggml_nbytes(outs[r]));
             ggml_backend_synchronize(h.be);
             continue;
         }
@@ -194,6 +204,7 @@ double probe_mul_mat_sweep(const char * dev, int type_a, const void * W, const f
     ggml_backend_synchronize(h.be);
     double t1 = now_s();
     ggml_backend_tensor_get(outs.back(), Y, 0, ggml_nbytes(outs.back()));
+    if (host_buf) ggml_backend_buffer_free(host_buf);
     ggml_backend_buffer_free(buf);
     ggml_free(ctx);
     return (t1 - t0) / ((double) (iters > 0 ? iters : 1) * nw);

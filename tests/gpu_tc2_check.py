@@ -24,10 +24,10 @@ def main():
     orc = O.Oracle()
     rng = np.random.default_rng(22)
     cases = [(O.Q8_0, 256, 64, 256), (O.Q8_0, 512, 512, 1024), (O.Q4_K, 4096, 512, 4096), (O.Q4_0, 300, 100, 512), (O.Q5_K, 1000, 257, 2048),
-             (O.Q6_K, 640, 130, 2048), (O.Q8_0, 200, 40, 768), (O.Q4_K, 11008, 96, 1024), (O.Q3_K, 520, 70, 1024), (O.Q5_0, 260, 33, 512),
+             (O.Q6_K, 640, 130, 2048), (O.Q8_0, 200, 40, 768), (O.Q4_K, 11008, 96, 1024), (O.Q3_K, 520, 70, 2048), (O.Q5_0, 260, 33, 512),
              (O.Q8_0, 4096, 512, 4096)]
     for (t, M, N, K) in cases:
-        assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMM, (M, N, K)
+        assert g.mul_mat_plan(t, M, N, K) == g.MM_GEMM, (O.TYPE_NAMES[t], M, N, K)     # (rows must be 16-byte multiples: Q3_K / Q6_K need K % 2048 == 0)
         W = O.random_blocks(t, M * K // orc.blck_size(t), rng)
         X = rng.uniform(-1, 1, N * K).astype(np.float32)
         Wd, Xd = dev(W), dev(X)
