@@ -3,6 +3,7 @@
 #include "b200_internal.h"
 #include "b200_quants.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -115,8 +116,30 @@ int ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream) {
     cudaStream_t st = (cudaStream_t)stream;
     switch (plan(*args)) {
         case GGML_B200_MM_FORCE_GEMV:
-            // n = 1: one-lane-per-256-weights kernel (mmvq_sb.cu); 2..8 columns: unit kernel (mmvq.cu)
-            if (!(args->flags & GGML_B200_MM_GEMV_V1) && mmvq_sb_eligible(*args)) return launch_mmvq_sb(*args, st);
+            // the superblock kernel (mmvq_sb.cu) for 1 <= n <= 8; the first-generation unit kernel (mmvq.cu) on request or as the last resort
+            if (!(args->flags & GGML_B200_MM_GEMV_V1)) {
+                if (mmvq_sb_eligible(*args)) return launch_mmvq_sb(*args, st);
+                // long rows x many columns: the activation records of all columns do not fit next to the weight stages.  Column groups of
+                // 4 / 2 / 1 on the same kernel re-stream W per group, which is far cheaper than leaving the bandwidth kernel
+                // (columns are independent: results are bit-identical to the one-launch form)
+                if (args->N > 1 && args->ne02 == 1 && args->ne03 == 1 && args->ne12 == 1 && args->ne13 == 1) {
+                    for (int64_t g = 4; g >= 1; g >>= 1) {
+                        if (g >= args->N) continue;
+                        ggml_b200_mul_mat_args sub = *args;
+                        sub.N = g;
+                        if (!mmvq_sb_eligible(sub)) continue;
+                        for (int64_t c0 = 0; c0 < args->N; c0 += g) {
+                            sub.N = std::min<int64_t>(g, args->N - c0);
+                            sub.src1 = (const float *)((const char *)args->src1 + (size_t)c0 * args->nb11);
+                            sub.dst = args->dst + (size_t)c0 * args->M;
+                            if (!mmvq_sb_eligible(sub)) { set_error("mul_mat: column group not eligible"); return GGML_B200_EUNSUPPORTED; }
+                            rc = launch_mmvq_sb(sub, st);
+                            if (rc != GGML_B200_OK) return rc;
+                        }
+                        return GGML_B200_OK;
+                    }
+                }
+            }
             return launch_mmvq_tma(*args, st);
         case GGML_B200_MM_FORCE_GEMM:    return launch_mmq_tc(*args, st);
         case GGML_B200_MM_FORCE_GENERIC: return launch_mmvq_generic(*args, st);

@@ -355,9 +355,11 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     const int SB_CONSUMER_WARPS = (env_warps == 4 && nc == 1) ? 4 : 8;
     pl.nw = SB_CONSUMER_WARPS;
     constexpr int RPW = 32 / F::LPR;
-    // experiment (GGML_B200_SB_TWOROW=1): two rows per lane group sharing the activation loads (Q4_K / Q5_K, n = 1)
-    static const int e_two = getenv("GGML_B200_SB_TWOROW") ? atoi(getenv("GGML_B200_SB_TWOROW")) : 0;
-    pl.two = nc == 1 && (T == T_Q4_K || T == T_Q5_K) && (e_two == 1 || (e_two == 2 && !ind));
+    // two rows per lane group sharing the activation loads (Q4_K / Q5_K, n = 1): measured on the dependent chain of the headline shape
+    // 8.0 -> 6.6 us (the consume phase is bounded by shared-memory traffic, 60 % of which are activation reads), but 4.43 -> 4.83 us for
+    // independent launches (fewer co-resident CTAs): default for DEPENDENT launches with enough tasks per row.  GGML_B200_SB_TWOROW = 0 off, 1 always
+    static const int e_two = getenv("GGML_B200_SB_TWOROW") ? atoi(getenv("GGML_B200_SB_TWOROW")) : 2;
+    pl.two = nc == 1 && (T == T_Q4_K || T == T_Q5_K) && (e_two == 1 || (e_two == 2 && !ind && a.K >= 2048 && a.M >= 2048 && (size_t)(SB_CONSUMER_WARPS * RPW * 2) * rb <= 100 * 1024));
     int granule = 1; while ((granule * rb) % 16 != 0) granule *= 2;
     int step = SB_CONSUMER_WARPS * RPW * (pl.two ? 2 : 1); while (step % granule != 0) step *= 2;
     int rpc = (int)(((size_t)env_stage_kb * 1024) / rb) / step * step; if (rpc < step) rpc = step;
