@@ -58,15 +58,64 @@ def run_dump(exe, model, n, dump, force=None, extra=(), env_extra=None):
 N_STEPS = 48
 
 
+def run_compare(model, mode, n_prompt=5, dev="B2000"):
+    """oracle/_ref/gpt2-compare: the example's own graph (main-backend.cpp included unmodified) evaluated node by node on ggml-cpu and on `dev` with
+    the reference's ggml_backend_compare_graph_backend; returns {phase: (nodes over 1e-9, worst NMSE, first node over, its op)} and the per-node lines"""
+    import ggml_b200
+    exe = O.REF_DIR / "gpt2-compare"
+    if not exe.exists():
+        pytest.fail("oracle/_ref/gpt2-compare missing (make -C oracle b200bins in the build container)")
+    env = O.ref_env()
+    env["GGML_BACKEND_PATH"] = str(ggml_b200.BACKEND_SO)
+    cmd = [str(exe), str(model), dev, str(n_prompt)] + (["sync"] if mode == "sync" else [])
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    out = {}
+    for l in p.stdout.splitlines():
+        f = l.split()
+        if f and f[0] == "summary":
+            out[f[1]] = (int(f[4]), float(f[6]), int(f[8]), f[9])
+    nodes = [l.split() for l in p.stdout.splitlines() if l.startswith("node ")]
+    return out, nodes
+
+
+def test_gpt2_graph_every_node_matches_cpu_on_identical_inputs(model):
+    """Per-op parity on the REAL token graph (prompt batch of 5 and one decode step, 487 nodes each): every node evaluated on the B200 backend
+    with exactly the inputs the CPU backend had (the device copy of each result is replaced by the CPU's after the comparison) must agree
+    with ggml-cpu to NMSE <= 1e-9 -- quantized mat-muls, float mat-muls over the KV cache, norms, soft-max, GELU, copies, adds."""
+    out, nodes = run_compare(model, "sync")
+    assert set(out) == {"prompt", "decode"}, out
+    for phase, (n_over, worst, first, op) in out.items():
+        assert n_over == 0 and worst <= 1e-9, (phase, n_over, worst, first, op)
+    assert len(nodes) > 500
+    print(f"gpt-2 graph, identical inputs per node: worst NMSE prompt {out['prompt'][1]:.2e}, decode {out['decode'][1]:.2e} over {len(nodes)} compared nodes")
+
+
+def test_gpt2_graph_free_running_deviation_starts_at_a_discontinuity(model):
+    """Free-running (the device consumes its own intermediate results, as in a real run) the deviation from ggml-cpu is NOT 1e-7: the
+    reference algorithm contains discontinuous steps -- GELU through an f16 -> f16 table (ggml-cpu.c:1355 ff.) and the int8 quantization of
+    the activations in front of every quantized mat-mul (ggml-cpu.c:7490-7509) -- which turn a 1e-7 difference in f32 summation order into an
+    occasional jump of one f16 ulp (5e-4) or one int8 code (1e-2) on single elements, and those cascade from layer to layer to ~1e-4 NMSE on
+    the logits.  Asserted: wherever a deviation above 1e-9 first appears it is at such a node (GELU, or a MUL_MAT fed by one), everything
+    before it is below 1e-9, and the accumulated deviation stays bounded (<= 5e-3)."""
+    out, nodes = run_compare(model, "free")
+    for phase, (n_over, worst, first, op) in out.items():
+        assert worst <= 5e-3, (phase, worst)
+        if n_over:
+            assert op in ("GELU", "MUL_MAT"), (phase, first, op)
+    print("gpt-2 graph, free-running: " + ", ".join(f"{ph}: {v[0]} nodes over 1e-9, worst {v[1]:.2e}, first at node {v[2]} ({v[3]})" for ph, v in out.items()))
+
+
 @pytest.mark.parametrize("kernels", ["fast", "generic"])
 def test_gpt2_logits_track_cpu_step_by_step(model, kernels):
-    """End-to-end parity of the whole token graph, QUANTIFIED: ggml-cpu generates N_STEPS greedy tokens and dumps its logits; the B200
-    backend is then teacher-forced along the SAME trajectory (so step i sees the identical context on both sides) and its logits are
-    compared step by step.  Asserted, for the default (superblock / fused) kernels and for the generic kernels:
-      * NMSE(logits_b200, logits_cpu) <= 1e-6 at every step (the reference's own per-op gates are 1e-7 .. 5e-4);
-      * the greedy token is IDENTICAL whenever the CPU's top-2 margin exceeds the measured logit noise of that step (4 x the largest
-        absolute deviation) -- i.e. any token difference is a genuine tie inside the f32 summation-order noise, not a bug;
-      * free-running (unforced) generation matches the CPU up to the first such tie."""
+    """End-to-end, QUANTIFIED: ggml-cpu generates N_STEPS greedy tokens and dumps its logits; the B200 backend is teacher-forced along the SAME
+    trajectory (step i sees the identical context on both sides) and its logits are compared step by step.  Asserted, for the default
+    (superblock / fused) kernels and for the generic kernels:
+      * NMSE(logits_b200, logits_cpu) <= 5e-3 at every step -- the bound of the cascade through the reference's discontinuous steps (see
+        test_gpt2_graph_free_running_deviation_starts_at_a_discontinuity; per-op parity on identical inputs is <= 1e-9);
+      * the greedy token is IDENTICAL whenever the CPU's top-2 margin exceeds 6 x the RMS logit deviation of that step, i.e. every token
+        difference is a near-tie inside the measured noise, not a wrong computation;
+      * free-running (unforced) generation matches the CPU up to the first such near-tie."""
     import numpy as np
     for exe in ("gpt-2-backend-dump", "gpt-2-backend-b200-dump"):
         if not (O.REF_DIR / exe).exists():
@@ -81,26 +130,28 @@ def test_gpt2_logits_track_cpu_step_by_step(model, kernels):
     _, gpu_logits, out = run_dump("gpt-2-backend-b200-dump", model, N_STEPS, TMP / f"b200_{kernels}.logits", force=TMP / "force.bin", extra=("-ngl", "12"), env_extra=env)
     assert "using CUDA backend" in out, out[-1500:]
     assert gpu_logits.shape == cpu_logits.shape
-    ties, worst_nmse, worst_ratio = [], 0.0, 0.0
+    ties, worst_nmse, n_same = [], 0.0, 0
     for i in range(N_STEPS):
-        c, g_ = cpu_logits[i], gpu_logits[i]
-        nm = O.nmse(g_, c)
+        c, g_ = cpu_logits[i].astype(np.float64), gpu_logits[i].astype(np.float64)
+        nm = O.nmse(gpu_logits[i], cpu_logits[i])
         worst_nmse = max(worst_nmse, nm)
-        assert nm <= 1e-6, (kernels, i, nm)
-        noise = float(np.abs(g_ - c).max())
+        assert nm <= 5e-3, (kernels, i, nm)
+        rms = float(np.sqrt(np.mean((g_ - c) ** 2)))
         top2 = np.sort(c)[-2:]
         margin = float(top2[1] - top2[0])
-        worst_ratio = max(worst_ratio, noise / max(margin, 1e-30))
         if int(g_.argmax()) != int(c.argmax()):
-            ties.append((i, margin, noise))
-            assert margin <= 4 * noise, f"{kernels}: step {i}: argmax differs although the CPU margin {margin:.3e} exceeds 4 x the logit noise {noise:.3e}"
-    # free-running generation: identical to the CPU until the first tie (if any)
+            ties.append((i, margin, rms))
+            assert margin <= 6 * rms, f"{kernels}: step {i}: argmax differs although the CPU margin {margin:.3e} exceeds 6 x the RMS logit deviation {rms:.3e}"
+        else:
+            n_same += 1
+    # free-running generation: identical to the CPU until the first near-tie (if any)
     _, free_logits, _ = run_dump("gpt-2-backend-b200-dump", model, N_STEPS, TMP / f"b200_{kernels}_free.logits", extra=("-ngl", "12"), env_extra=env)
     ftoks = [int(v) for v in free_logits.argmax(1)]
     first_tie = ties[0][0] if ties else N_STEPS
     assert ftoks[:first_tie] == ctoks[:first_tie], f"\ncpu: {ctoks}\ngpu: {ftoks}\nties: {ties}"
-    print(f"gpt-2 117M q4_0 [{kernels} kernels]: {N_STEPS} teacher-forced steps, worst logits NMSE {worst_nmse:.2e}, worst noise/margin {worst_ratio:.2e}, "
-          f"argmax differs at {len(ties)} steps (all inside the noise): {ties[:4]}; free-running prefix identical for {first_tie} tokens")
+    assert n_same >= N_STEPS // 2, (n_same, ties)
+    print(f"gpt-2 117M q4_0 [{kernels} kernels]: {N_STEPS} teacher-forced steps, worst logits NMSE {worst_nmse:.2e}, same greedy token at {n_same}/{N_STEPS} steps, "
+          f"differences only at near-ties (margin, rms): {[(i, round(m, 4), round(r, 4)) for i, m, r in ties[:5]]}; free-running prefix identical for {first_tie} tokens")
 
 
 def test_gpt2_graph_fusions_are_bit_exact(model):
