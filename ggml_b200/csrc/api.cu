@@ -72,6 +72,7 @@ const char * ggml_b200_version(void) { return "ggml-b200 0.1 (sm_100a)"; }
 uint64_t ggml_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int ggml_b200_sm_count(void) { return sm_count(); }
 int ggml_b200_prepare(void) { const int rc = prepare_device(); return rc != GGML_B200_OK ? rc : tc_prepare_device(); }
+int ggml_b200_debug_gemm_trace(uint64_t * host_dst, int32_t max_ctas) { return tc2_trace_read((unsigned long long *)host_dst, max_ctas); }
 int ggml_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -67,5 +67,6 @@ size_t mmid_grouped_workspace(const ggml_b200_mul_mat_id_args & a);
 int    launch_mmid_grouped(const ggml_b200_mul_mat_id_args & a, cudaStream_t st);
 unsigned int * tc_flag_slot();   // a zeroed, self-cleaning block of split-K flags from the device's control block (nullptr on error)
 int    tc_prepare_device();
+int tc2_trace_read(unsigned long long * host_dst, int max_ctas);   // developer trace of the CTA-pair GEMM (mmq_tc2.cu)
 
 } // namespace b200

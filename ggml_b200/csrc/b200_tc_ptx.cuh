@@ -28,6 +28,13 @@ __device__ __forceinline__ void tc_wait_cluster(uint64_t * b, uint32_t parity) {
 __device__ __forceinline__ void tc_arrive_cluster(uint64_t * b, uint32_t cta_rank) {    // same barrier offset in CTA `cta_rank` of the cluster
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(tc_smem(b)), "r"(cta_rank));
+    // default semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): the data this orders lives in the arriving
+    // CTA's own shared memory and is read by its own SM's tensor core; a cluster-scope release costs a MEMBAR.GPU per stage for nothing
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tc_arrive_cluster_release(uint64_t * b, uint32_t cta_rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(tc_smem(b)), "r"(cta_rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }

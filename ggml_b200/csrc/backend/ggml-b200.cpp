@@ -25,6 +25,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +88,8 @@ struct backend_ctx {
     bool            capturing = false;
     std::unordered_set<const ggml_tensor *> written;   // roots whose memory some node of the current cgraph writes through a view
     bool            first_real_node = true;
+    // GGML_B200_PROFILE=1: host time spent in graph_compute per mode (printed when the backend is freed)
+    struct host_profile { uint64_t calls[4] = {0,0,0,0}; double us[4] = {0,0,0,0}; uint64_t nodes[4] = {0,0,0,0}; } prof;   // 0 replay, 1 capture+update, 2 eager, 3 small/first
     // split-buffer mat-muls: one auxiliary stream per other device (+ staging for the activations, the n > 1 result, kernel scratch)
     struct split_peer {
         cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
@@ -754,6 +757,13 @@ const char * backend_get_name(ggml_backend_t backend) { return ((backend_ctx *) 
 
 void backend_free(ggml_backend_t backend) {
     backend_ctx * ctx = (backend_ctx *) backend->context;
+    if (ctx->prof.calls[0] + ctx->prof.calls[1] + ctx->prof.calls[2] + ctx->prof.calls[3]) {
+        static const char * mode_name[4] = { "replay", "capture+update", "eager", "uncached" };
+        for (int m = 0; m < 4; ++m)
+            if (ctx->prof.calls[m])
+                fprintf(stderr, "ggml-b200 profile [%s] %-14s: %llu graph_compute calls, %.1f us host time per call, %.1f nodes per call\n", ctx->name.c_str(), mode_name[m],
+                        (unsigned long long) ctx->prof.calls[m], ctx->prof.us[m] / (double) ctx->prof.calls[m], (double) ctx->prof.nodes[m] / (double) ctx->prof.calls[m]);
+    }
     {
         scoped_device sd(ctx->device);
         cudaStreamSynchronize(ctx->stream);
@@ -1024,9 +1034,7 @@ void graph_signature(const ggml_cgraph * cgraph, std::vector<uint64_t> & sig) {
     }
 }
 
-ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
-    backend_ctx * ctx = (backend_ctx *) backend->context;
-    scoped_device sd(ctx->device);
+static ggml_status graph_compute_impl(backend_ctx * ctx, ggml_cgraph * cgraph, int & mode, int & n_real_out) {
     static const bool graphs_off = getenv("GGML_B200_DISABLE_GRAPHS") && atoi(getenv("GGML_B200_DISABLE_GRAPHS")) != 0;
     int n_real = 0;
     bool has_split = false;        // multi-device work is not captured (the reference disables CUDA graphs for split buffers too, ggml-cuda.cu:2620)
@@ -1034,8 +1042,10 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
         n_real += !is_noop(cgraph->nodes[i]->op);
         has_split = has_split || tensor_in_split_buffer(cgraph->nodes[i]->src[0]);
     }
+    n_real_out = n_real;
     const bool use_graph = !graphs_off && !has_split && n_real >= 8 && ctx->graph_calls++ > 0;
     if (!use_graph) {
+        mode = 3;
         compute_nodes(ctx, cgraph);
         return GGML_STATUS_SUCCESS;
     }
@@ -1048,6 +1058,7 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
             g.last_use = ctx->graph_clock;
             ctx->consecutive_updates = 0;
             ctx->last_sig = sig;
+            mode = 0;
             CUDA_OK(cudaGraphLaunch(g.exec, ctx->stream));
             return GGML_STATUS_SUCCESS;
         }
@@ -1057,9 +1068,11 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
     ctx->last_sig = sig;
     if (repeated) ctx->consecutive_updates = 0;
     else if (++ctx->consecutive_updates > max_updates) {
+        mode = 2;
         compute_nodes(ctx, cgraph);                                // ever-changing graph: direct launches
         return GGML_STATUS_SUCCESS;
     }
+    mode = 1;
     // size the scratch pool before capturing (allocation is not part of the graph)
     size_t need = 0;
     for (int i = 0; i < cgraph->n_nodes; ++i) { const size_t n = node_scratch_need(cgraph->nodes[i]); if (n > need) need = n; }
@@ -1091,6 +1104,19 @@ ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) 
     slot->last_use = ctx->graph_clock;
     CUDA_OK(cudaGraphLaunch(slot->exec, ctx->stream));
     return GGML_STATUS_SUCCESS;
+}
+
+ggml_status backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
+    backend_ctx * ctx = (backend_ctx *) backend->context;
+    scoped_device sd(ctx->device);
+    static const bool profile = getenv("GGML_B200_PROFILE") && atoi(getenv("GGML_B200_PROFILE")) != 0;
+    int mode = 3, n_real = 0;
+    if (!profile) return graph_compute_impl(ctx, cgraph, mode, n_real);
+    const auto t0 = std::chrono::steady_clock::now();
+    const ggml_status st = graph_compute_impl(ctx, cgraph, mode, n_real);
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    ctx->prof.calls[mode]++; ctx->prof.us[mode] += us; ctx->prof.nodes[mode] += (uint64_t) n_real;
+    return st;
 }
 
 void backend_event_record(ggml_backend_t backend, ggml_backend_event_t event) {

@@ -57,8 +57,7 @@ __device__ __forceinline__ void tc_dequant_step(int nstages, int step, bool vali
     if (step >= nstages) tc_wait(&empty[s], (uint32_t)((step / nstages) - 1) & 1u);
     if (valid) dq64<T, KS>(u, a_ring + s * stage_bytes + a_row_off, sw);
     tc_fence_async_smem();
-    __syncwarp();
-    if (lane == 0) tc_arrive(&full[s]);
+    tc_arrive(&full[s]);        // every writer arrives for itself after its own proxy fence (an elected lane after __syncwarp() lost rows in the pair kernel: mmq_tc2.cu)
 }
 
 template <int T, int HALVES>
@@ -86,8 +85,8 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
     const bool two_halves = HALVES == 2 && rows_left > TC_BM;    // the second 128-row sub-tile exists
 
     if (tid == 0) {
-        // a stage's A part is written by all 8 dequantizer warps (HALVES = 2) or by the 4 that own its K-step (HALVES = 1); + the B TMA
-        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], (HALVES == 2 ? TC_DQ_WARPS : TC_DQ_WARPS / 2) + 1); tc_mbar_init(&empty[s], 1); }
+        // a stage's A part is written by all 8 dequantizer warps (HALVES = 2) or by the 4 that own its K-step (HALVES = 1), every thread arrives; + the B TMA
+        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], (HALVES == 2 ? TC_DQ_WARPS : TC_DQ_WARPS / 2) * 32 + 1); tc_mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], TC_DQ_WARPS); }
         tc_mbar_init(acc_full, 1);
         tc_fence_init();

@@ -33,13 +33,16 @@ namespace b200 {
 
 constexpr int T2_BM = 128;                    // W rows per CTA (256 per pair)
 constexpr int T2_BK = 64;
-constexpr int T2_DQ_WARPS = 8, T2_THREADS = (2 + T2_DQ_WARPS) * 32;
-constexpr int T2_MAX_STAGES = 8;
+constexpr int T2_DQ_WARPS = 8, T2_THREADS = (3 + T2_DQ_WARPS) * 32;
+constexpr int T2_MAX_STAGES = 8, T2_MAX_RAW = 8;
+constexpr int T2_TRACE_CTAS = 4096;
 
 struct tc2_params {
     float * y; float * partials; unsigned int * flags; const float * inv_scale;
+    const uint8_t * w_dbg; int64_t rb_dbg;       // developer aid (dbg & 32): the weight matrix, to cross-check the raw ring against global memory
+    unsigned long long * trace;                 // developer aid (GGML_B200_TC2_TRACE=1): 8 globaltimer stamps per CTA, else nullptr
     int64_t M, N;
-    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, w_static;
+    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, dbg;
     // grouped mode (MUL_MAT_ID, expert-grouped): the activation rows are SORTED by expert (position -> (token, slot) pair in `perm`), n-tiles are
     // enumerated per expert (tile_base: prefix of tiles per expert, off: prefix of positions per expert, both n_expert + 1 long, device-resident:
     // no host synchronisation); W is the [n_expert x M] row stack; y rows are scattered back through perm
@@ -47,15 +50,28 @@ struct tc2_params {
     int32_t n_expert;
 };
 
+__device__ __forceinline__ void tc2_stamp(unsigned long long * trace, int ev) {
+    if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)blockIdx.x * 8 + ev] = t; }
+}
+
 template <int T, int KS>
 __device__ __forceinline__ void tc2_dequant_step(int nstages, int step, bool valid, const uint32_t (&u)[tcfmt<T>::UNIT_WORDS], uint8_t * ring, int stage_bytes, int a_row_off,
-                                                 uint32_t sw, int lane, uint32_t rank, uint64_t * full, uint64_t * empty) {
+                                                 uint32_t sw, int lane, uint32_t rank, uint64_t * full, uint64_t * empty, int dbg, long long * acct) {
     const int s = step % nstages;
+    long long t0 = 0;
+    if (acct) t0 = clock64();
     if (step >= nstages) tc_wait(&empty[s], (uint32_t)((step / nstages) - 1) & 1u);
+    if (acct) { const long long t1 = clock64(); acct[1] += t1 - t0; }
     if (valid) dq64<T, KS>(u, ring + s * stage_bytes + a_row_off, sw);
-    tc_fence_async_all();                      // generic-proxy stores -> visible to the tensor core (async proxy), also from the peer SM
+    // generic-proxy stores to THIS CTA's shared memory -> visible to the async proxy (each SM's tensor core reads its own half of A);
+    // the arrival on the leader's barrier orders them before the MMA the leader issues for both SMs
+    if (dbg & 2) tc_fence_async_all(); else tc_fence_async_smem();
+    // EVERY writer arrives for itself, right after its own proxy fence.  An elected lane arriving for the warp after __syncwarp() lost rows
+    // when the MMA was issued the moment the barrier completed (tests/gpu_tc2_stress.py; profiles/r02_gemm_pair_v2.md): rows 0..31 of a
+    // stage, a few times per thousand launches, once the tensor pipe was waiting for the dequantizers instead of the other way round
+    if (!(dbg & 16)) { if (rank == 0) tc_arrive(&full[s]); else tc_arrive_cluster(&full[s], 0); return; }
     __syncwarp();
-    if (lane == 0) { if (rank == 0) tc_arrive(&full[s]); else tc_arrive_cluster(&full[s], 0); }
+    if (lane == 0) { if (rank == 0) tc_arrive(&full[s]); else if (dbg & 1) tc_arrive_cluster_release(&full[s], 0); else tc_arrive_cluster(&full[s], 0); }
 }
 
 template <int T, bool GROUPED = false>
@@ -63,17 +79,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const tc2_params p) {
     constexpr int RAW = tcfmt<T>::RAW, UK = tcfmt<T>::UNIT_KSTEPS;
     extern __shared__ __align__(1024) uint8_t smem[];
-    // identical layout in both CTAs: [ring: nstages x (A 16 KB | B half BN/2 x 128 B)][raw: 2 x 128 x RAW][barriers][tmem slot]
+    // identical layout in both CTAs: [ring: nstages x (A 16 KB | B half BN/2 x 128 B)][raw: nraw x 128 x RAW][barriers][tmem slot][inv_scale tile]
     constexpr int a_bytes = T2_BM * T2_BK * 2;
     const int b_bytes = (p.BN / 2) * T2_BK * 2, stage_bytes = a_bytes + b_bytes;
     uint8_t * ring = smem;
     uint8_t * raw  = ring + p.nstages * stage_bytes;
-    uint64_t * bars = (uint64_t *)(raw + 2 * T2_BM * RAW);
-    uint64_t * full = bars, * empty = bars + T2_MAX_STAGES, * raw_full = bars + 2 * T2_MAX_STAGES, * raw_empty = raw_full + 2, * acc_full = raw_empty + 2;
+    uint64_t * bars = (uint64_t *)(raw + p.nraw * T2_BM * RAW);
+    uint64_t * full = bars, * empty = bars + T2_MAX_STAGES, * raw_full = bars + 2 * T2_MAX_STAGES, * raw_empty = raw_full + T2_MAX_RAW, * acc_full = raw_empty + T2_MAX_RAW;
     uint32_t * tmem_slot = (uint32_t *)(acc_full + 1);
+    float * s_inv = (float *)(tmem_slot + 2);                     // inv_scale of the tile's BN columns (epilogue)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = tc_cluster_ctarank();                   // 0 = leader
+    if (tid == 0) tc2_stamp(p.trace, 0);
     tc_pdl_launch_dependents();
     // work item of the pair: partial producers (ks > 0) first, tile owners (ks == 0) last
     const int pair = (int)blockIdx.x >> 1;
@@ -99,10 +117,10 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int x_row0 = GROUPED ? gn0 + (int)rank * (p.BN / 2) : tn * p.BN + (int)rank * (p.BN / 2);
 
     if (tid == 0) {
-        // leader's stage barrier: 4 dequantizer warps of each CTA (the group that owns the K-step) + the leader's producer (expect_tx
+        // leader's stage barrier: the 128 dequantizer threads of each CTA that own the K-step + the leader's activation producer (expect_tx
         // for both activation halves); the non-leader's copy of it is unused.  empty / acc_full: one multicast commit each.
-        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 2 + 1); tc_mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], T2_DQ_WARPS); }
+        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], (p.dbg & 16) ? T2_DQ_WARPS / 2 * 2 + 1 : T2_DQ_WARPS * 32 + 1); tc_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.nraw; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], T2_DQ_WARPS); }
         tc_mbar_init(acc_full, 1);
         tc_fence_init();
         tc_prefetch_map(&map_w); tc_prefetch_map(&map_x);
@@ -113,39 +131,54 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     tc_cluster_sync();                                            // the peer's barriers exist before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (tid == 0) tc2_stamp(p.trace, 1);
 
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs)
+        // ===================== raw W producer (both CTAs): the packed units of the own 128 rows, nraw units ahead of the dequantizers
         if (lane == 0) {
             if (!p.w_static) tc_pdl_wait();                       // W produced by the preceding kernel: nothing may be read before it is done
-            bool x_ready = !p.w_static ? true : false;            // the fp16 activations are written by the conversion kernel just before this one
             for (int u = 0; u < nunits; ++u) {
-                const int rs = u & 1;
-                if (u >= 2) tc_wait(&raw_empty[rs], (uint32_t)((u >> 1) - 1) & 1u);
+                const int rs = u % p.nraw;
+                if (u >= p.nraw) tc_wait(&raw_empty[rs], (uint32_t)((u / p.nraw) - 1) & 1u);
                 tc_expect_tx(&raw_full[rs], T2_BM * RAW);
                 int coord;                                        // first 4-byte word of the box: 16-byte aligned start at or below the unit
                 if constexpr (tcfmt<T>::LOAD_BYTES == 2) coord = (((ubeg + u) * tcfmt<T>::UNIT_BYTES) & ~15) >> 2;
                 else                       coord = (ubeg + u) * tcfmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tcfmt<T>::ODD_BACK_WORDS;
                 tc_tma_2d(raw + rs * T2_BM * RAW, &map_w, coord, (int)w_row0, &raw_full[rs]);
-                if (!x_ready) { tc_pdl_wait(); x_ready = true; }
-                for (int q = 0; q < UK; ++q) {
-                    const int step = UK * u + q, s = step % p.nstages;
-                    if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
-                    if (rank == 0) tc_expect_tx(&full[s], (uint32_t)(2 * b_bytes));
-                    tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, ((ubeg + u) * UK + q) * T2_BK, x_row0, tc_cluster_addr(&full[s], 0));
-                }
             }
+        }
+    } else if (warp == 2 + T2_DQ_WARPS) {
+        // ===================== activation producer (both CTAs): the own half of every stage's B tile, signalled on the LEADER's stage barrier
+        if (lane == 0) {
+            tc_pdl_wait();                                        // the fp16 activations are written by the conversion kernel just before this one
+            tc2_stamp(p.trace, 2);
+            const uint32_t full0 = tc_cluster_addr(&full[0], 0);
+            long long bwait = 0;
+            for (int step = 0; step < nsteps; ++step) {
+                const int s = step % p.nstages;
+                const long long t0 = p.trace ? clock64() : 0;
+                if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
+                if (p.trace) bwait += clock64() - t0;
+                if (rank == 0) tc_expect_tx(&full[s], (uint32_t)(2 * b_bytes));
+                tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, (ubeg * UK + step) * T2_BK, x_row0, full0 + (uint32_t)(s * 8));
+            }
+            if (p.trace && (int)blockIdx.x < T2_TRACE_CTAS / 2) p.trace[((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + 7] = (unsigned long long)bwait;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only)
         if (rank == 0) {
             // instruction descriptor: D = f32 (bit 4), A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 with M = 256 (the pair)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((2 * T2_BM) >> 4) << 24);
+            long long mma_wait = 0;
             for (int step = 0; step < nsteps; ++step) {
                 const int s = step % p.nstages;
-                tc_wait_cluster(&full[s], (uint32_t)(step / p.nstages) & 1u);
+                const long long t0 = p.trace ? clock64() : 0;
+                if (p.dbg & 4) tc_wait_cluster(&full[s], (uint32_t)(step / p.nstages) & 1u); else tc_wait(&full[s], (uint32_t)(step / p.nstages) & 1u);
+                if (p.trace) mma_wait += clock64() - t0;
+                if (p.dbg & 8) __nanosleep(300);
                 tc_fence_after();
                 if (lane == 0) {
+                    if (step == 0) tc2_stamp(p.trace, 3);
                     const uint64_t ad = tc_smem_desc(tc_smem(ring + s * stage_bytes));
                     const uint64_t bd = tc_smem_desc(tc_smem(ring + s * stage_bytes + a_bytes));
 #pragma unroll
@@ -156,6 +189,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 }
                 __syncwarp();
             }
+            if (p.trace && lane == 0 && (int)blockIdx.x < T2_TRACE_CTAS / 2) p.trace[((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + 3] = (unsigned long long)mma_wait;
         }
     } else {
         // ===================== dequantizers: two threads per row (warps 2-5 / 6-9), each half of the unit's K-steps
@@ -165,31 +199,54 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const uint32_t sw = (uint32_t)(row & 7);
         const int a_row_off = (row >> 3) * 1024 + (row & 7) * 128;
         uint32_t ub[tcfmt<T>::UNIT_WORDS];
+        // developer accounting (trace on): lane 0 of the first warp of each group sums its cycles waiting for raw units [0] / free stages [1]
+        long long acct_store[2] = { 0, 0 };
+        long long * acct = (p.trace && lane == 0 && (dwarp & 3) == 0) ? acct_store : nullptr;
+        const long long loop_t0 = acct ? clock64() : 0;
         for (int u = 0; u < nunits; ++u) {
-            const int rs = u & 1;
-            tc_wait(&raw_full[rs], (uint32_t)(u >> 1) & 1u);
+            const int rs = u % p.nraw;
+            { const long long t0 = acct ? clock64() : 0;
+              tc_wait(&raw_full[rs], (uint32_t)(u / p.nraw) & 1u);
+              if (acct) acct[0] += clock64() - t0; }
             int lead;                                             // bytes between the box start and the unit's first byte
             if constexpr (tcfmt<T>::LOAD_BYTES == 2) lead = ((ubeg + u) * tcfmt<T>::UNIT_BYTES) & 15;
             else                       lead = ((ubeg + u) & 1) * (4 * tcfmt<T>::ODD_BACK_WORDS);
             tc_load_unit<T>(raw + rs * T2_BM * RAW + row * RAW + lead, ub);
+            if ((p.dbg & 32) && valid && p.trace) {
+                // cross-check: the same unit straight from global memory
+                uint32_t ug[tcfmt<T>::UNIT_WORDS];
+                size_t off;
+                if constexpr (tcfmt<T>::LOAD_BYTES == 2) off = (size_t)(ubeg + u) * tcfmt<T>::UNIT_BYTES;
+                else                       off = (size_t)(ubeg + u) * tcfmt<T>::STRIDE_WORDS * 4;
+                tc_load_unit<T>(p.w_dbg + (size_t)(w_row0 + row) * p.rb_dbg + off, ug);
+                bool bad = false;
+#pragma unroll
+                for (int i = 0; i < tcfmt<T>::UNIT_WORDS; ++i) bad = bad || (ug[i] != ub[i]);
+                if (bad) atomicAdd(p.trace + (size_t)T2_TRACE_CTAS * 8 - 1, 1ull);
+            }
             __syncwarp();
             if (lane == 0) tc_arrive(&raw_empty[rs]);            // the unit is in registers: the buffer can be refilled
             if constexpr (UK == 4) {
                 if (ksel == 0) {
-                    tc2_dequant_step<T, 0>(p.nstages, UK * u + 0, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty);
-                    tc2_dequant_step<T, 1>(p.nstages, UK * u + 1, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty);
+                    tc2_dequant_step<T, 0>(p.nstages, UK * u + 0, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
+                    tc2_dequant_step<T, 1>(p.nstages, UK * u + 1, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
                 } else {
-                    tc2_dequant_step<T, 2>(p.nstages, UK * u + 2, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty);
-                    tc2_dequant_step<T, 3>(p.nstages, UK * u + 3, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty);
+                    tc2_dequant_step<T, 2>(p.nstages, UK * u + 2, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
+                    tc2_dequant_step<T, 3>(p.nstages, UK * u + 3, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
                 }
             } else {
-                if (ksel == 0) tc2_dequant_step<T, 0>(p.nstages, UK * u + 0, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty);
-                else           tc2_dequant_step<T, 1>(p.nstages, UK * u + 1, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty);
+                if (ksel == 0) tc2_dequant_step<T, 0>(p.nstages, UK * u + 0, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
+                else           tc2_dequant_step<T, 1>(p.nstages, UK * u + 1, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
             }
+        }
+        if (acct && (int)blockIdx.x < T2_TRACE_CTAS / 2) {
+            unsigned long long * w = p.trace + ((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + (ksel ? 4 : 0);
+            w[0] = (unsigned long long)acct[0]; w[1] = (unsigned long long)acct[1]; w[2] = (unsigned long long)(clock64() - loop_t0);
         }
         // ===================== epilogue: this CTA's 128 accumulator lanes x BN columns
         tc_wait(acc_full, 0);
         tc_fence_after();
+        if (dq == 0) tc2_stamp(p.trace, 4);
         // each warp owns its TMEM lane quarter (hardware: warp id % 4) and one half of the columns
         const int lg = warp & 3, grp = dwarp >> 2;
         const int ncol = p.BN / 2, col0 = grp * ncol;
@@ -212,10 +269,14 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             asm volatile("bar.sync 1, %0;" ::"n"(T2_DQ_WARPS * 32) : "memory");
             if (dq == 0) atomicAdd(&p.flags[fidx], 1u);
         } else {
-            if (p.splitk > 1) {
-                if (dq == 0) { while (atomicAdd(&p.flags[fidx], 0u) < (unsigned)(p.splitk - 1)) __nanosleep(64); __threadfence(); }
-                asm volatile("bar.sync 1, %0;" ::"n"(T2_DQ_WARPS * 32) : "memory");
+            // inv_scale of the tile's columns -> shared memory: one L2 round trip for the tile instead of one in front of every store
+            for (int c = dq; c < p.BN; c += T2_DQ_WARPS * 32) {
+                const int64_t n = GROUPED ? (int64_t)gn0 + c : (int64_t)tn * p.BN + c;
+                s_inv[c] = (GROUPED ? c < gcols : n < p.N) ? __ldcg(p.inv_scale + n) : 0.0f;
             }
+            if (p.splitk > 1 && dq == 0) { while (atomicAdd(&p.flags[fidx], 0u) < (unsigned)(p.splitk - 1)) __nanosleep(64); __threadfence(); }
+            asm volatile("bar.sync 1, %0;" ::"n"(T2_DQ_WARPS * 32) : "memory");
+            if (dq == 0) tc2_stamp(p.trace, 5);
             for (int c0 = 0; c0 < ncol; c0 += 32) {
                 float v[32];
                 tc_ld32(tacc + (uint32_t)c0, v);
@@ -226,14 +287,14 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 }
                 if (m < p.M) {
                     if constexpr (GROUPED) {
+                        int prm[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int col = col0 + c0 + i;                       // column of the tile = sorted position gn0 + col
-                            if (col < gcols) p.y[(size_t)__ldg(p.g_perm + gn0 + col) * p.M + m] = v[i] * __ldcg(p.inv_scale + gn0 + col);
-                        }
+                        for (int i = 0; i < 32; ++i) prm[i] = (col0 + c0 + i) < gcols ? __ldg(p.g_perm + gn0 + col0 + c0 + i) : -1;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (prm[i] >= 0) p.y[(size_t)prm[i] * p.M + m] = v[i] * s_inv[col0 + c0 + i];
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { const int64_t n = n_base + c0 + i; if (n < p.N) p.y[(size_t)n * p.M + m] = v[i] * __ldcg(p.inv_scale + n); }
+                        for (int i = 0; i < 32; ++i) { const int64_t n = n_base + c0 + i; if (n < p.N) p.y[(size_t)n * p.M + m] = v[i] * s_inv[col0 + c0 + i]; }
                     }
                 }
             }
@@ -242,11 +303,13 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 if (dq == 0) p.flags[fidx] = 0;                  // leave the flag clean for the next launch that gets this slot
             }
         }
+        if (dq == 0) tc2_stamp(p.trace, 6);
         tc_fence_before();
     }
     __syncthreads();
     tc_cluster_sync();                                            // neither CTA retires (nor frees TMEM) while the pair still works
     if (warp == 1) { tc_fence_after(); tc_tmem_dealloc_pair(tmem, tc_tmem_cols(p.BN)); }
+    if (tid == 0) tc2_stamp(p.trace, 7);
 }
 
 // ----------------------------------------------------------------------------- split-K flags: persistent, zero-initialised, self-cleaning
@@ -276,9 +339,27 @@ unsigned int * tc_flag_slot() {
     return b + (size_t)(seq.fetch_add(1, std::memory_order_relaxed) % T2_FLAG_SLOTS) * T2_FLAGS_PER_SLOT;
 }
 
+// ----------------------------------------------------------------------------- developer trace (GGML_B200_TC2_TRACE=1): the last launch's per-CTA stamps
+static unsigned long long * tc2_trace_buf() {
+    static const bool on = getenv("GGML_B200_TC2_TRACE") && atoi(getenv("GGML_B200_TC2_TRACE")) != 0;
+    if (!on) return nullptr;
+    static unsigned long long * buf = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!buf) { if (cudaMalloc(&buf, (size_t)T2_TRACE_CTAS * 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); buf = nullptr; } else cudaMemset(buf, 0, (size_t)T2_TRACE_CTAS * 8 * sizeof(unsigned long long)); }
+    return buf;
+}
+int tc2_trace_read(unsigned long long * host_dst, int max_ctas) {
+    unsigned long long * b = tc2_trace_buf();
+    if (!b) return 0;
+    const int n = max_ctas < T2_TRACE_CTAS ? max_ctas : T2_TRACE_CTAS;
+    if (cudaMemcpy(host_dst, b, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 // ----------------------------------------------------------------------------- host side
 struct tc2_plan {
-    int BN, m_tiles, n_tiles, splitk, chunks, nstages, smem, grid;
+    int BN, m_tiles, n_tiles, splitk, chunks, nstages, nraw, smem, grid;
     size_t xb_bytes, partial_bytes, scale_bytes;
 };
 
@@ -292,6 +373,28 @@ static int tc2_raw_bytes(int type) {
         case T_Q3_K: return 128;
         default: return 144;                                         // Q4_0, Q8_0 (half units), Q4_K, IQ4_NL, IQ4_XS
     }
+}
+
+// shared-memory split: the operand ring only has to cover the dequantize -> MMA hand-over and the L2 latency of the activation tiles; what is
+// left goes to the raw W ring, which covers the HBM latency of the weight stream (profiles/r02_gemm_pair.md: with 2 raw units in flight the
+// dequantizers spent a quarter of their time waiting for the next unit)
+static bool tc2_smem_plan(int BN, int raw, int & nstages, int & nraw, int & smem) {
+    static const int env_stages = getenv("GGML_B200_TC2_STAGES") ? atoi(getenv("GGML_B200_TC2_STAGES")) : 0;
+    static const int env_raw = getenv("GGML_B200_TC2_RAW") ? atoi(getenv("GGML_B200_TC2_RAW")) : 0;
+    const int stage = T2_BM * T2_BK * 2 + (BN / 2) * T2_BK * 2, tail = 2 * (T2_MAX_STAGES + T2_MAX_RAW) * 8 + 64 + 256 * 4 + 1024;
+    const int budget = 227 * 1024 - tail;
+    // at least 3 stages: a dequantizer group revisits the ring every <= 3 K-steps, and the parity wait on a stage's "empty" barrier is only
+    // unambiguous while the barrier is at most one phase behind the waiter (2 stages fault: the wait returns on the previous phase)
+    int ns = env_stages >= 3 && env_stages <= T2_MAX_STAGES ? env_stages : 4;
+    while (ns > 3 && ns * stage + 2 * T2_BM * raw > budget) ns--;
+    if (ns * stage + 2 * T2_BM * raw > budget) return false;
+    int nr = (budget - ns * stage) / (T2_BM * raw);
+    if (nr > T2_MAX_RAW) nr = T2_MAX_RAW;
+    if (env_raw >= 2 && env_raw < nr) nr = env_raw;
+    // leftover after a full raw ring: deepen the operand ring
+    if (!(env_stages >= 3)) while (ns < T2_MAX_STAGES && (ns + 1) * stage + nr * T2_BM * raw <= budget) ns++;
+    nstages = ns; nraw = nr; smem = ns * stage + nr * T2_BM * raw + tail;
+    return true;
 }
 
 static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
@@ -324,13 +427,7 @@ static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     if (env_splitk > 0 && env_splitk <= pl.chunks) splitk = env_splitk;
     if (splitk > 1 && tiles * 2 > T2_FLAGS_PER_SLOT) splitk = 1;
     pl.splitk = splitk;
-    const int raw = tc2_raw_bytes(a.type);
-    auto smem_of = [&](int ns) { return ns * (T2_BM * T2_BK * 2 + (BN / 2) * T2_BK * 2) + 2 * T2_BM * raw + 256 + 1024; };
-    static const int env_stages = getenv("GGML_B200_TC2_STAGES") ? atoi(getenv("GGML_B200_TC2_STAGES")) : 0;
-    int nstages = env_stages >= 2 && env_stages <= T2_MAX_STAGES ? env_stages : T2_MAX_STAGES;
-    while (nstages > 2 && smem_of(nstages) > 227 * 1024) nstages--;
-    if (smem_of(nstages) > 227 * 1024) return false;
-    pl.nstages = nstages; pl.smem = smem_of(nstages);
+    if (!tc2_smem_plan(BN, tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
     pl.grid = 2 * tiles * splitk;
     pl.xb_bytes = ((size_t)a.N * a.K * 2 + 255) & ~(size_t)255;
     pl.partial_bytes = splitk > 1 ? (size_t)tiles * 2 * (splitk - 1) * BN * T2_BM * 4 : 0;
@@ -379,8 +476,12 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
     }
     tc2_params p;
     p.y = a.dst; p.partials = partials; p.flags = flags; p.inv_scale = inv_scale; p.M = a.M; p.N = a.N;
-    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages;
+    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw;
     p.w_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
+    static const int env_dbg = getenv("GGML_B200_TC2_DBG") ? atoi(getenv("GGML_B200_TC2_DBG")) : 0;      // developer switch: 1 cluster-scope release on the remote arrive, 2 full proxy fence, 4 cluster-scope acquire in the MMA issuer
+    p.dbg = env_dbg;
+    p.trace = pl.grid < T2_TRACE_CTAS / 2 ? tc2_trace_buf() : nullptr;
+    p.w_dbg = (const uint8_t *)a.src0; p.rb_dbg = (int64_t)rb;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
     cudaLaunchConfig_t cfg = {};
@@ -477,7 +578,7 @@ __global__ void __launch_bounds__(256) mmid_x_to_f16_kernel(const uint8_t * __re
     }
 }
 
-struct mmid_g_plan { int BN, m_tiles, max_tiles, chunks, nstages, smem; size_t xb_bytes, scale_bytes, tab_bytes, perm_bytes; int64_t n_pairs; };
+struct mmid_g_plan { int BN, m_tiles, max_tiles, chunks, nstages, nraw, smem; size_t xb_bytes, scale_bytes, tab_bytes, perm_bytes; int64_t n_pairs; };
 
 static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & pl) {
     static const int env_on = getenv("GGML_B200_MMID_GROUPED") ? atoi(getenv("GGML_B200_MMID_GROUPED")) : 0;      // opt-in until validated on a B200
@@ -498,12 +599,7 @@ static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & 
     pl.m_tiles = (int)((a.M + 2 * T2_BM - 1) / (2 * T2_BM));
     pl.max_tiles = (int)((n_pairs + pl.BN - 1) / pl.BN + a.n_expert);
     pl.chunks = (int)(a.K / (a.type == T_Q8_0 ? 128 : 256));
-    const int raw = tc2_raw_bytes(a.type);
-    auto smem_of = [&](int ns) { return ns * (T2_BM * T2_BK * 2 + (pl.BN / 2) * T2_BK * 2) + 2 * T2_BM * raw + 256 + 1024; };
-    int nstages = T2_MAX_STAGES;
-    while (nstages > 2 && smem_of(nstages) > 227 * 1024) nstages--;
-    if (smem_of(nstages) > 227 * 1024) return false;
-    pl.nstages = nstages; pl.smem = smem_of(nstages);
+    if (!tc2_smem_plan(pl.BN, tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
     if ((int64_t)pl.m_tiles * pl.max_tiles * 2 > 0x7fffffffLL) return false;
     pl.n_pairs = n_pairs;
     pl.xb_bytes = ((size_t)(n_pairs + pl.BN) * a.K * 2 + 255) & ~(size_t)255;        // + one tile of slack rows (read past the last position, never used)
@@ -554,7 +650,7 @@ template <int T> static int launch_mmid_g(const ggml_b200_mul_mat_id_args & a, c
     }
     tc2_params p{};
     p.y = a.dst; p.partials = nullptr; p.flags = nullptr; p.inv_scale = inv_scale; p.M = a.M; p.N = pl.n_pairs;
-    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.w_static = 0;
+    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.dbg = 0;
     p.g_off = off; p.g_tile_base = tile_base; p.g_perm = perm; p.n_expert = (int32_t)a.n_expert;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }

@@ -241,6 +241,9 @@ GGML_B200_API int          ggml_b200_sm_count(void);
 GGML_B200_API int          ggml_b200_prepare(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 GGML_B200_API uint64_t     ggml_b200_launch_count(void);
+/* developer diagnostic (env GGML_B200_TC2_TRACE=1, else returns 0): copies the per-CTA %globaltimer stamps of the LAST CTA-pair GEMM launch
+   (8 per CTA: entry, prologue done, activations ready, first MMA, accumulator ready, split-K hand-over, epilogue done, exit) */
+GGML_B200_API int          ggml_b200_debug_gemm_trace(uint64_t * host_dst, int32_t max_ctas);
 GGML_B200_API const char * ggml_b200_version(void);
 /* developer aid (GGML_B200_SB_DEBUG=1): %globaltimer stamps of CTA 0 for the last 32 mat-vec launches, 8 per launch */
 GGML_B200_API int          ggml_b200_debug_trace(unsigned long long * out256);
