@@ -66,7 +66,7 @@ __device__ __forceinline__ void codes4_affine(uint32_t w, __half2 d, __half2 m, 
 // 8 chunks of 8 halves (16 bytes), chunk c = k 8c..8c+7, each stored as soon as it is computed to its SWIZZLE_128B position
 // (chunk index XOR row % 8) in the row's 128-byte line of the A stage.  Every index below is a compile-time constant.
 #define TC_OUT(idx, r) (*(uint4 *)(a_row + (((uint32_t)(idx) ^ sw) << 4)) = (r))
-template <int T, int KS> __device__ __forceinline__ void dq64(const uint32_t (&u)[tcfmt<T>::UNIT_WORDS], uint8_t * a_row, uint32_t sw) {
+template <int T, int KS, int UW = tcfmt<T>::UNIT_WORDS> __device__ __forceinline__ void dq64(const uint32_t (&u)[UW], uint8_t * a_row, uint32_t sw) {   // UW deduced: the pair kernel's Q8_0 unit is 8 blocks wide
     if constexpr (T == T_Q8_0) {
         // blocks 2KS, 2KS+1 of the unit: block b starts at byte 34 b = word 8.5 b; block 2KS at word 17 KS
         constexpr int o = 17 * KS;

@@ -58,6 +58,16 @@ __device__ __forceinline__ void tc_tma_2d_pair(void * dst, const CUtensorMap * m
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(tc_smem(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
+// shared -> global bulk stores (async proxy; the smem source must have been fenced with fence.proxy.async by its writers)
+__device__ __forceinline__ void tc_tma_store_2d(const CUtensorMap * map, const void * src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(tc_smem(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_store_1d(void * gdst, const void * src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(tc_smem(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tc_bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tc_prefetch_map(const CUtensorMap * map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }

@@ -37,12 +37,25 @@ constexpr int T2_DQ_WARPS = 8, T2_THREADS = (3 + T2_DQ_WARPS) * 32;
 constexpr int T2_MAX_STAGES = 8, T2_MAX_RAW = 8;
 constexpr int T2_TRACE_CTAS = 4096;
 
+// raw-unit geometry of this kernel: mmq_tc.cu's, except Q8_0, whose unit is 8 blocks (272 B = 17 x 16: always 16-byte aligned, no lead) so that,
+// like every other format, a dequantizer group owns two consecutive K-steps per unit (one unit load, one proxy fence per two stages) and the
+// row pitch of the raw box (272 = 16 mod 128) keeps the 128-bit shared-memory loads conflict-free
+template <int T> struct tc2fmt : tcfmt<T> {};
+template <> struct tc2fmt<T_Q8_0> { static constexpr int RAW = 272, STRIDE_WORDS = 68, UNIT_WORDS = 68, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
+template <int T> __device__ __forceinline__ void tc2_load_unit(const uint8_t * g, uint32_t (&u)[tc2fmt<T>::UNIT_WORDS]) {     // g: the unit in shared memory
+    if constexpr (T == T_Q8_0) {
+#pragma unroll
+        for (int i = 0; i < 17; ++i) { const uint4 v = *((const uint4 *)g + i); u[4 * i] = v.x; u[4 * i + 1] = v.y; u[4 * i + 2] = v.z; u[4 * i + 3] = v.w; }
+    } else {
+        tc_load_unit<T>(g, u);
+    }
+}
+
 struct tc2_params {
     float * y; float * partials; unsigned int * flags; const float * inv_scale;
-    const uint8_t * w_dbg; int64_t rb_dbg;       // developer aid (dbg & 32): the weight matrix, to cross-check the raw ring against global memory
     unsigned long long * trace;                 // developer aid (GGML_B200_TC2_TRACE=1): 8 globaltimer stamps per CTA, else nullptr
     int64_t M, N;
-    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, dbg;
+    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, tma_epi;
     // grouped mode (MUL_MAT_ID, expert-grouped): the activation rows are SORTED by expert (position -> (token, slot) pair in `perm`), n-tiles are
     // enumerated per expert (tile_base: prefix of tiles per expert, off: prefix of positions per expert, both n_expert + 1 long, device-resident:
     // no host synchronisation); W is the [n_expert x M] row stack; y rows are scattered back through perm
@@ -54,30 +67,36 @@ __device__ __forceinline__ void tc2_stamp(unsigned long long * trace, int ev) {
     if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)blockIdx.x * 8 + ev] = t; }
 }
 
+// position in a ring of n slots without run-time division: slot index + parity of the round
+struct tc2_ring_pos {
+    int s; uint32_t par; bool first;
+    __device__ __forceinline__ void advance(int d, int n) { s += d; if (s >= n) { s -= n; par ^= 1u; first = false; } }     // d <= n
+};
+
+// one K-step of A: wait for the stage to be free, dequantize the thread's 64 weights into its swizzled row
 template <int T, int KS>
-__device__ __forceinline__ void tc2_dequant_step(int nstages, int step, bool valid, const uint32_t (&u)[tcfmt<T>::UNIT_WORDS], uint8_t * ring, int stage_bytes, int a_row_off,
-                                                 uint32_t sw, int lane, uint32_t rank, uint64_t * full, uint64_t * empty, int dbg, long long * acct) {
-    const int s = step % nstages;
+__device__ __forceinline__ void tc2_dequant_write(const tc2_ring_pos & pos, bool valid, const uint32_t (&u)[tc2fmt<T>::UNIT_WORDS], uint8_t * ring, int stage_bytes, int a_row_off,
+                                                  uint32_t sw, uint64_t * empty, long long * acct) {
     long long t0 = 0;
     if (acct) t0 = clock64();
-    if (step >= nstages) tc_wait(&empty[s], (uint32_t)((step / nstages) - 1) & 1u);
+    if (!pos.first) tc_wait(&empty[pos.s], pos.par ^ 1u);
     if (acct) { const long long t1 = clock64(); acct[1] += t1 - t0; }
-    if (valid) dq64<T, KS>(u, ring + s * stage_bytes + a_row_off, sw);
-    // generic-proxy stores to THIS CTA's shared memory -> visible to the async proxy (each SM's tensor core reads its own half of A);
-    // the arrival on the leader's barrier orders them before the MMA the leader issues for both SMs
-    if (dbg & 2) tc_fence_async_all(); else tc_fence_async_smem();
-    // EVERY writer arrives for itself, right after its own proxy fence.  An elected lane arriving for the warp after __syncwarp() lost rows
-    // when the MMA was issued the moment the barrier completed (tests/gpu_tc2_stress.py; profiles/r02_gemm_pair_v2.md): rows 0..31 of a
-    // stage, a few times per thousand launches, once the tensor pipe was waiting for the dequantizers instead of the other way round
-    if (!(dbg & 16)) { if (rank == 0) tc_arrive(&full[s]); else tc_arrive_cluster(&full[s], 0); return; }
-    __syncwarp();
-    if (lane == 0) { if (rank == 0) tc_arrive(&full[s]); else if (dbg & 1) tc_arrive_cluster_release(&full[s], 0); else tc_arrive_cluster(&full[s], 0); }
+    if (valid) dq64<T, KS>(u, ring + pos.s * stage_bytes + a_row_off, sw);
 }
+// Hand-over of a dequantized stage to the tensor core, as it has to be for a CTA pair:
+//   * EVERY writer arrives for itself, after its own proxy fence (generic-proxy stores -> visible to the async proxy), on the stage barrier
+//     of ITS OWN CTA (release at CTA scope).  An elected lane arriving for the warp after __syncwarp() lost rows when the MMA was issued the
+//     moment the barrier completed (tests/gpu_tc2_stress.py, profiles/r02_gemm_pair_v2.md);
+//   * in the non-leader CTA the otherwise idle warp 1 waits for that local barrier and RELAYS it to the leader's stage barrier with one
+//     cluster-scope release (cumulative over the 128 writers it has acquired); the leader's MMA issuer acquires at cluster scope.  A CTA-scope
+//     release sent straight to the leader's barrier by every writer of the peer still lost a row once per ~50 launches when the tensor pipe
+//     was waiting for the dequantizers (BN <= 128), and a cluster-scope release per writer costs a GPU-scope memory barrier per thread.
+__device__ __forceinline__ void tc2_stage_arrive(int s, uint64_t * full) { tc_arrive(&full[s]); }
 
 template <int T, bool GROUPED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
-mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const tc2_params p) {
-    constexpr int RAW = tcfmt<T>::RAW, UK = tcfmt<T>::UNIT_KSTEPS;
+mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const tc2_params p) {
+    constexpr int RAW = tc2fmt<T>::RAW, UK = tc2fmt<T>::UNIT_KSTEPS;
     extern __shared__ __align__(1024) uint8_t smem[];
     // identical layout in both CTAs: [ring: nstages x (A 16 KB | B half BN/2 x 128 B)][raw: nraw x 128 x RAW][barriers][tmem slot][inv_scale tile]
     constexpr int a_bytes = T2_BM * T2_BK * 2;
@@ -117,17 +136,31 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int x_row0 = GROUPED ? gn0 + (int)rank * (p.BN / 2) : tn * p.BN + (int)rank * (p.BN / 2);
 
     if (tid == 0) {
-        // leader's stage barrier: the 128 dequantizer threads of each CTA that own the K-step + the leader's activation producer (expect_tx
-        // for both activation halves); the non-leader's copy of it is unused.  empty / acc_full: one multicast commit each.
-        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], (p.dbg & 16) ? T2_DQ_WARPS / 2 * 2 + 1 : T2_DQ_WARPS * 32 + 1); tc_mbar_init(&empty[s], 1); }
+        // stage barrier: the 128 dequantizer threads of this CTA that own the K-step; in the leader also its activation producer (expect_tx for
+        // both activation halves) and the non-leader's relay warp.  empty / acc_full: one multicast commit each.
+        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + (rank == 0 ? 2 : 0)); tc_mbar_init(&empty[s], 1); }
         for (int s = 0; s < p.nraw; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], T2_DQ_WARPS); }
         tc_mbar_init(acc_full, 1);
         tc_fence_init();
         tc_prefetch_map(&map_w); tc_prefetch_map(&map_x);
+        if (p.tma_epi) tc_prefetch_map(&map_y);
     }
     if (warp == 1) tc_tmem_alloc_pair(tmem_slot, tc_tmem_cols(p.BN));
     tc_fence_before();
     __syncthreads();
+    auto issue_raw = [&](int u, int rs) {
+        tc_expect_tx(&raw_full[rs], T2_BM * RAW);
+        int coord;                                                // first 4-byte word of the box: 16-byte aligned start at or below the unit
+        if constexpr (tc2fmt<T>::LOAD_BYTES == 2) coord = (((ubeg + u) * tc2fmt<T>::UNIT_BYTES) & ~15) >> 2;
+        else                        coord = (ubeg + u) * tc2fmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tc2fmt<T>::ODD_BACK_WORDS;
+        tc_tma_2d(raw + rs * T2_BM * RAW, &map_w, coord, (int)w_row0, &raw_full[rs]);
+    };
+    // the weight stream only involves this CTA's own barriers: its first requests leave before the cluster-wide sync (HBM latency overlaps it)
+    const int raw_issued = nunits < p.nraw ? nunits : p.nraw;     // (nraw < number of units of a ring round: advance() wraps at most once)
+    if (tid == 0) {
+        if (!p.w_static) tc_pdl_wait();                           // W produced by the preceding kernel: nothing may be read before it is done
+        for (int u = 0; u < raw_issued; ++u) issue_raw(u, u);
+    }
     tc_cluster_sync();                                            // the peer's barriers exist before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
@@ -136,15 +169,11 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     if (warp == 0) {
         // ===================== raw W producer (both CTAs): the packed units of the own 128 rows, nraw units ahead of the dequantizers
         if (lane == 0) {
-            if (!p.w_static) tc_pdl_wait();                       // W produced by the preceding kernel: nothing may be read before it is done
-            for (int u = 0; u < nunits; ++u) {
-                const int rs = u % p.nraw;
-                if (u >= p.nraw) tc_wait(&raw_empty[rs], (uint32_t)((u / p.nraw) - 1) & 1u);
-                tc_expect_tx(&raw_full[rs], T2_BM * RAW);
-                int coord;                                        // first 4-byte word of the box: 16-byte aligned start at or below the unit
-                if constexpr (tcfmt<T>::LOAD_BYTES == 2) coord = (((ubeg + u) * tcfmt<T>::UNIT_BYTES) & ~15) >> 2;
-                else                       coord = (ubeg + u) * tcfmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tcfmt<T>::ODD_BACK_WORDS;
-                tc_tma_2d(raw + rs * T2_BM * RAW, &map_w, coord, (int)w_row0, &raw_full[rs]);
+            tc2_ring_pos rpos{ 0, 0u, true };
+            rpos.advance(raw_issued, p.nraw);                     // the first units were requested before the cluster-wide sync
+            for (int u = raw_issued; u < nunits; ++u, rpos.advance(1, p.nraw)) {
+                if (!rpos.first) tc_wait(&raw_empty[rpos.s], rpos.par ^ 1u);
+                issue_raw(u, rpos.s);
             }
         }
     } else if (warp == 2 + T2_DQ_WARPS) {
@@ -154,10 +183,11 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             tc2_stamp(p.trace, 2);
             const uint32_t full0 = tc_cluster_addr(&full[0], 0);
             long long bwait = 0;
-            for (int step = 0; step < nsteps; ++step) {
-                const int s = step % p.nstages;
+            tc2_ring_pos pos{ 0, 0u, true };
+            for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
+                const int s = pos.s;
                 const long long t0 = p.trace ? clock64() : 0;
-                if (step >= p.nstages) tc_wait(&empty[s], (uint32_t)((step / p.nstages) - 1) & 1u);
+                if (!pos.first) tc_wait(&empty[s], pos.par ^ 1u);
                 if (p.trace) bwait += clock64() - t0;
                 if (rank == 0) tc_expect_tx(&full[s], (uint32_t)(2 * b_bytes));
                 tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, (ubeg * UK + step) * T2_BK, x_row0, full0 + (uint32_t)(s * 8));
@@ -170,12 +200,12 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             // instruction descriptor: D = f32 (bit 4), A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 with M = 256 (the pair)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((2 * T2_BM) >> 4) << 24);
             long long mma_wait = 0;
-            for (int step = 0; step < nsteps; ++step) {
-                const int s = step % p.nstages;
+            tc2_ring_pos pos{ 0, 0u, true };
+            for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
+                const int s = pos.s;
                 const long long t0 = p.trace ? clock64() : 0;
-                if (p.dbg & 4) tc_wait_cluster(&full[s], (uint32_t)(step / p.nstages) & 1u); else tc_wait(&full[s], (uint32_t)(step / p.nstages) & 1u);
+                tc_wait_cluster(&full[s], pos.par);
                 if (p.trace) mma_wait += clock64() - t0;
-                if (p.dbg & 8) __nanosleep(300);
                 tc_fence_after();
                 if (lane == 0) {
                     if (step == 0) tc2_stamp(p.trace, 3);
@@ -190,6 +220,13 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 __syncwarp();
             }
             if (p.trace && lane == 0 && (int)blockIdx.x < T2_TRACE_CTAS / 2) p.trace[((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + 3] = (unsigned long long)mma_wait;
+        } else if (lane == 0) {
+            // non-leader: relay "this CTA's half of stage s is written" to the leader's barrier
+            tc2_ring_pos pos{ 0, 0u, true };
+            for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
+                tc_wait(&full[pos.s], pos.par);
+                tc_arrive_cluster_release(&full[pos.s], 0);
+            }
         }
     } else {
         // ===================== dequantizers: two threads per row (warps 2-5 / 6-9), each half of the unit's K-steps
@@ -198,45 +235,46 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const bool valid = row < rows_left;                       // rows past M: the TMA box is zero-filled, nothing to convert
         const uint32_t sw = (uint32_t)(row & 7);
         const int a_row_off = (row >> 3) * 1024 + (row & 7) * 128;
-        uint32_t ub[tcfmt<T>::UNIT_WORDS];
+        uint32_t ub[tc2fmt<T>::UNIT_WORDS];
         // developer accounting (trace on): lane 0 of the first warp of each group sums its cycles waiting for raw units [0] / free stages [1]
         long long acct_store[2] = { 0, 0 };
         long long * acct = (p.trace && lane == 0 && (dwarp & 3) == 0) ? acct_store : nullptr;
         const long long loop_t0 = acct ? clock64() : 0;
+        // this group's K-steps: UK = 4: steps 4u + 2 ksel, + 1 (two consecutive stages, one proxy fence); UK = 2: step 2u + ksel
+        constexpr int PER = UK / 2;
+        tc2_ring_pos pos{ ksel * PER, 0u, true };                 // ring position of the group's next K-step (PER <= 2 < nstages)
+        tc2_ring_pos rpos{ 0, 0u, true };                         // raw ring
+        const uint8_t * my_raw = raw + row * RAW;
         for (int u = 0; u < nunits; ++u) {
-            const int rs = u % p.nraw;
             { const long long t0 = acct ? clock64() : 0;
-              tc_wait(&raw_full[rs], (uint32_t)(u / p.nraw) & 1u);
+              tc_wait(&raw_full[rpos.s], rpos.par);
               if (acct) acct[0] += clock64() - t0; }
             int lead;                                             // bytes between the box start and the unit's first byte
-            if constexpr (tcfmt<T>::LOAD_BYTES == 2) lead = ((ubeg + u) * tcfmt<T>::UNIT_BYTES) & 15;
-            else                       lead = ((ubeg + u) & 1) * (4 * tcfmt<T>::ODD_BACK_WORDS);
-            tc_load_unit<T>(raw + rs * T2_BM * RAW + row * RAW + lead, ub);
-            if ((p.dbg & 32) && valid && p.trace) {
-                // cross-check: the same unit straight from global memory
-                uint32_t ug[tcfmt<T>::UNIT_WORDS];
-                size_t off;
-                if constexpr (tcfmt<T>::LOAD_BYTES == 2) off = (size_t)(ubeg + u) * tcfmt<T>::UNIT_BYTES;
-                else                       off = (size_t)(ubeg + u) * tcfmt<T>::STRIDE_WORDS * 4;
-                tc_load_unit<T>(p.w_dbg + (size_t)(w_row0 + row) * p.rb_dbg + off, ug);
-                bool bad = false;
-#pragma unroll
-                for (int i = 0; i < tcfmt<T>::UNIT_WORDS; ++i) bad = bad || (ug[i] != ub[i]);
-                if (bad) atomicAdd(p.trace + (size_t)T2_TRACE_CTAS * 8 - 1, 1ull);
-            }
+            if constexpr (tc2fmt<T>::LOAD_BYTES == 2) lead = ((ubeg + u) * tc2fmt<T>::UNIT_BYTES) & 15;
+            else                       lead = ((ubeg + u) & 1) * (4 * tc2fmt<T>::ODD_BACK_WORDS);
+            tc2_load_unit<T>(my_raw + rpos.s * (T2_BM * RAW) + lead, ub);
             __syncwarp();
-            if (lane == 0) tc_arrive(&raw_empty[rs]);            // the unit is in registers: the buffer can be refilled
+            if (lane == 0) tc_arrive(&raw_empty[rpos.s]);        // the unit is in registers: the buffer can be refilled
+            rpos.advance(1, p.nraw);
             if constexpr (UK == 4) {
+                tc2_ring_pos pos2 = pos; pos2.advance(1, p.nstages);
                 if (ksel == 0) {
-                    tc2_dequant_step<T, 0>(p.nstages, UK * u + 0, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
-                    tc2_dequant_step<T, 1>(p.nstages, UK * u + 1, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
+                    tc2_dequant_write<T, 0>(pos,  valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
+                    tc2_dequant_write<T, 1>(pos2, valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
                 } else {
-                    tc2_dequant_step<T, 2>(p.nstages, UK * u + 2, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
-                    tc2_dequant_step<T, 3>(p.nstages, UK * u + 3, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
+                    tc2_dequant_write<T, 2>(pos,  valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
+                    tc2_dequant_write<T, 3>(pos2, valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
                 }
+                tc_fence_async_smem();
+                tc2_stage_arrive(pos.s, full);
+                tc2_stage_arrive(pos2.s, full);
+                pos = pos2; pos.advance(3, p.nstages);
             } else {
-                if (ksel == 0) tc2_dequant_step<T, 0>(p.nstages, UK * u + 0, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
-                else           tc2_dequant_step<T, 1>(p.nstages, UK * u + 1, valid, ub, ring, stage_bytes, a_row_off, sw, lane, rank, full, empty, p.dbg, acct);
+                if (ksel == 0) tc2_dequant_write<T, 0>(pos, valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
+                else           tc2_dequant_write<T, 1>(pos, valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
+                tc_fence_async_smem();
+                tc2_stage_arrive(pos.s, full);
+                pos.advance(2, p.nstages);
             }
         }
         if (acct && (int)blockIdx.x < T2_TRACE_CTAS / 2) {
@@ -256,15 +294,34 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const int mloc = lg * 32 + lane;
         const int fidx = tile * 2 + (int)rank;
         float * part = p.partials ? p.partials + ((size_t)fidx * (p.splitk - 1)) * (size_t)(p.BN * T2_BM) : nullptr;
+        // bulk-store epilogue (dense output): each column-half group (4 warps = the 128 accumulator lanes) stages a [32 columns][128 rows] slab in
+        // the now idle operand ring and one thread hands it to the TMA (2-D store into y, clipped at the M / N edges by the tensor map; 1-D 16 KB
+        // stores for split-K partials); two slabs per group alternate.  Replaces 32 scattered 128-byte warp stores per slab and thread.
+        const bool tma_epi = !GROUPED && p.tma_epi != 0;
+        float * slabs = (float *)ring + grp * (2 * 32 * T2_BM);
+        const int gtid = dq & 127;
+        auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); };
         if (ks > 0) {
             // split-K partial: [ks-1][n_local][m_local]
             float * dst = part + (size_t)(ks - 1) * (p.BN * T2_BM);
             for (int c0 = 0; c0 < ncol; c0 += 32) {
                 float v[32];
-                tc_ld32(tacc + (uint32_t)c0, v);
+                if (tma_epi) {
+                    float * buf = slabs + ((c0 >> 5) & 1) * (32 * T2_BM);
+                    if (c0 >= 64) { if (gtid == 0) tc_bulk_wait_read<1>(); group_sync(); }
+                    tc_ld32(tacc + (uint32_t)c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dst[(size_t)(col0 + c0 + i) * T2_BM + mloc] = v[i];
+                    for (int i = 0; i < 32; ++i) buf[i * T2_BM + mloc] = v[i];
+                    tc_fence_async_smem();
+                    group_sync();
+                    if (gtid == 0) { tc_bulk_store_1d(dst + (size_t)(col0 + c0) * T2_BM, buf, 32 * T2_BM * 4); tc_bulk_commit(); }
+                } else {
+                    tc_ld32(tacc + (uint32_t)c0, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) dst[(size_t)(col0 + c0 + i) * T2_BM + mloc] = v[i];
+                }
             }
+            if (tma_epi && gtid == 0) { tc_bulk_wait<0>(); tc_fence_async_all(); }     // the partial is in global memory before the flag goes up
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(T2_DQ_WARPS * 32) : "memory");
             if (dq == 0) atomicAdd(&p.flags[fidx], 1u);
@@ -279,13 +336,21 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             if (dq == 0) tc2_stamp(p.trace, 5);
             for (int c0 = 0; c0 < ncol; c0 += 32) {
                 float v[32];
+                float * buf = slabs + ((c0 >> 5) & 1) * (32 * T2_BM);
+                if (tma_epi && c0 >= 64) { if (gtid == 0) tc_bulk_wait_read<1>(); group_sync(); }
                 tc_ld32(tacc + (uint32_t)c0, v);
                 for (int j = 1; j < p.splitk; ++j) {
                     const float * src = part + (size_t)(j - 1) * (p.BN * T2_BM);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += __ldcg(&src[(size_t)(col0 + c0 + i) * T2_BM + mloc]);
                 }
-                if (m < p.M) {
+                if (tma_epi) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) buf[i * T2_BM + mloc] = v[i] * s_inv[col0 + c0 + i];
+                    tc_fence_async_smem();
+                    group_sync();
+                    if (gtid == 0 && rows_left > 0 && n_base + c0 < p.N) { tc_tma_store_2d(&map_y, buf, (int)row_base, (int)(n_base + c0)); tc_bulk_commit(); }
+                } else if (m < p.M) {
                     if constexpr (GROUPED) {
                         int prm[32];
 #pragma unroll
@@ -298,6 +363,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                     }
                 }
             }
+            if (tma_epi && gtid == 0) tc_bulk_wait_read<0>();        // the slabs are read out before the CTA gives its shared memory back
             if (p.splitk > 1) {
                 asm volatile("bar.sync 1, %0;" ::"n"(T2_DQ_WARPS * 32) : "memory");
                 if (dq == 0) p.flags[fidx] = 0;                  // leave the flag clean for the next launch that gets this slot
@@ -371,7 +437,8 @@ static int tc2_raw_bytes(int type) {
         case T_Q5_1: return 192;
         case T_Q2_K: return 96;
         case T_Q3_K: return 128;
-        default: return 144;                                         // Q4_0, Q8_0 (half units), Q4_K, IQ4_NL, IQ4_XS
+        case T_Q8_0: return 272;
+        default: return 144;                                         // Q4_0, Q4_K, IQ4_NL, IQ4_XS
     }
 }
 
@@ -419,7 +486,7 @@ static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     pl.BN = BN;
     pl.n_tiles = (int)((a.N + BN - 1) / BN);
     pl.m_tiles = (int)((a.M + 2 * T2_BM - 1) / (2 * T2_BM));
-    pl.chunks = (int)(a.K / (a.type == T_Q8_0 ? 128 : 256));     // raw units along K (tcfmt<T>::UNIT_KSTEPS x 64 weights each)
+    pl.chunks = (int)(a.K / 256);                                // raw units along K (4 K-steps of 64 weights each)
     const int tiles = pl.m_tiles * pl.n_tiles;
     const int pairs = sm_count() / 2;
     int splitk = pairs / tiles; if (splitk < 1) splitk = 1; if (splitk > 8) splitk = 8; if (splitk > pl.chunks) splitk = pl.chunks;
@@ -459,7 +526,7 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
     {
         const cuuint64_t dims[2] = { (cuuint64_t)(rb / 4), (cuuint64_t)a.M };
         const cuuint64_t strides[1] = { (cuuint64_t)rb };
-        const cuuint32_t box[2] = { (cuuint32_t)(tcfmt<T>::RAW / 4), (cuuint32_t)T2_BM };
+        const cuuint32_t box[2] = { (cuuint32_t)(tc2fmt<T>::RAW / 4), (cuuint32_t)T2_BM };
         const cuuint32_t es[2] = { 1, 1 };
         CUresult r = tc_get_encode()(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)a.src0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -474,14 +541,25 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(X) failed: %d", (int)r); return GGML_B200_ECUDA; }
     }
+    static const bool env_tma_epi_off = getenv("GGML_B200_TC2_TMA_EPI") && atoi(getenv("GGML_B200_TC2_TMA_EPI")) == 0;
+    const int stage_bytes_h = T2_BM * T2_BK * 2 + (pl.BN / 2) * T2_BK * 2;
+    const bool tma_epi = !env_tma_epi_off && (a.M % 4) == 0 && ((uintptr_t)a.dst & 15) == 0 && (size_t)pl.nstages * stage_bytes_h >= 2 * 2 * 32 * T2_BM * 4;
+    alignas(64) CUtensorMap map_y = map_x;                         // placeholder when the bulk-store epilogue is off
+    if (tma_epi) {
+        const cuuint64_t dims[2] = { (cuuint64_t)a.M, (cuuint64_t)a.N };
+        const cuuint64_t strides[1] = { (cuuint64_t)a.M * 4 };
+        const cuuint32_t box[2] = { (cuuint32_t)T2_BM, 32 };
+        const cuuint32_t es[2] = { 1, 1 };
+        CUresult r = tc_get_encode()(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)a.dst, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(Y) failed: %d", (int)r); return GGML_B200_ECUDA; }
+    }
     tc2_params p;
     p.y = a.dst; p.partials = partials; p.flags = flags; p.inv_scale = inv_scale; p.M = a.M; p.N = a.N;
     p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw;
     p.w_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
-    static const int env_dbg = getenv("GGML_B200_TC2_DBG") ? atoi(getenv("GGML_B200_TC2_DBG")) : 0;      // developer switch: 1 cluster-scope release on the remote arrive, 2 full proxy fence, 4 cluster-scope acquire in the MMA issuer
-    p.dbg = env_dbg;
+    p.tma_epi = tma_epi ? 1 : 0;
     p.trace = pl.grid < T2_TRACE_CTAS / 2 ? tc2_trace_buf() : nullptr;
-    p.w_dbg = (const uint8_t *)a.src0; p.rb_dbg = (int64_t)rb;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
     cudaLaunchConfig_t cfg = {};
@@ -490,7 +568,7 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;             // the cluster shape is compiled in (__cluster_dims__)
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_tc2_kernel<T>, map_w, map_x, p));
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_tc2_kernel<T>, map_w, map_x, map_y, p));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -598,7 +676,7 @@ static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & 
     pl.BN = avg > 160 ? 256 : avg > 80 ? 128 : 64;
     pl.m_tiles = (int)((a.M + 2 * T2_BM - 1) / (2 * T2_BM));
     pl.max_tiles = (int)((n_pairs + pl.BN - 1) / pl.BN + a.n_expert);
-    pl.chunks = (int)(a.K / (a.type == T_Q8_0 ? 128 : 256));
+    pl.chunks = (int)(a.K / 256);
     if (!tc2_smem_plan(pl.BN, tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
     if ((int64_t)pl.m_tiles * pl.max_tiles * 2 > 0x7fffffffLL) return false;
     pl.n_pairs = n_pairs;
@@ -633,7 +711,7 @@ template <int T> static int launch_mmid_g(const ggml_b200_mul_mat_id_args & a, c
     {
         const cuuint64_t dims[2] = { (cuuint64_t)(rb / 4), (cuuint64_t)(a.n_expert * a.M) };
         const cuuint64_t strides[1] = { (cuuint64_t)rb };
-        const cuuint32_t box[2] = { (cuuint32_t)(tcfmt<T>::RAW / 4), (cuuint32_t)T2_BM };
+        const cuuint32_t box[2] = { (cuuint32_t)(tc2fmt<T>::RAW / 4), (cuuint32_t)T2_BM };
         const cuuint32_t es[2] = { 1, 1 };
         CUresult r = tc_get_encode()(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)a.src0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -650,12 +728,12 @@ template <int T> static int launch_mmid_g(const ggml_b200_mul_mat_id_args & a, c
     }
     tc2_params p{};
     p.y = a.dst; p.partials = nullptr; p.flags = nullptr; p.inv_scale = inv_scale; p.M = a.M; p.N = pl.n_pairs;
-    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.dbg = 0;
+    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.tma_epi = 0;
     p.g_off = off; p.g_tile_base = tile_base; p.g_perm = perm; p.n_expert = (int32_t)a.n_expert;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
     // plain launch (no programmatic dependency): the tile tables are read at kernel entry and must be complete
-    mmq_tc2_kernel<T, true><<<(unsigned)(2 * pl.m_tiles * pl.max_tiles), T2_THREADS, (size_t)pl.smem, st>>>(map_w, map_x, p);
+    mmq_tc2_kernel<T, true><<<(unsigned)(2 * pl.m_tiles * pl.max_tiles), T2_THREADS, (size_t)pl.smem, st>>>(map_w, map_x, map_x, p);
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
