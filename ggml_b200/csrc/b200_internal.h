@@ -56,6 +56,7 @@ int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cud
 // mmq_tc.cu (tcgen05 GEMM)
 bool   mmq_tc_eligible(const ggml_b200_mul_mat_args & a);
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a);
+bool   mmq_tc_eligible_small(const ggml_b200_mul_mat_args & a);   // 5 <= n <= 8 on the tensor-core path (shapes the mat-vec kernel would have to split)
 int    launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st);
 // mmq_tc2.cu (tcgen05 GEMM on CTA pairs, cta_group::2)
 bool   mmq_tc2_eligible(const ggml_b200_mul_mat_args & a);

@@ -25,6 +25,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -151,15 +152,27 @@ void buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, ui
     CUDA_OK(cudaMemsetAsync((char *) tensor->data + offset, value, size, cudaStreamPerThread));
     CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
 }
+// GGML_B200_PROFILE=1: host time in the synchronous tensor transfers and in backend synchronize (printed with the graph_compute profile)
+struct io_profile { std::atomic<uint64_t> calls[3]; std::atomic<uint64_t> ns[3]; };      // 0 set_tensor, 1 get_tensor, 2 synchronize
+io_profile g_io_prof;
+bool profile_on() { static const bool on = getenv("GGML_B200_PROFILE") && atoi(getenv("GGML_B200_PROFILE")) != 0; return on; }
+struct io_timer {
+    int k; std::chrono::steady_clock::time_point t0;
+    explicit io_timer(int kind) : k(profile_on() ? kind : -1) { if (k >= 0) t0 = std::chrono::steady_clock::now(); }
+    ~io_timer() { if (k >= 0) { g_io_prof.calls[k]++; g_io_prof.ns[k] += (uint64_t) std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } }
+};
+
 void buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
     buffer_ctx * ctx = (buffer_ctx *) buffer->context;
     scoped_device sd(ctx->device);
+    io_timer tm(0);
     CUDA_OK(cudaMemcpyAsync((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice, cudaStreamPerThread));
     CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
 }
 void buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
     buffer_ctx * ctx = (buffer_ctx *) buffer->context;
     scoped_device sd(ctx->device);
+    io_timer tm(1);
     CUDA_OK(cudaMemcpyAsync(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost, cudaStreamPerThread));
     CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
 }
@@ -763,6 +776,11 @@ void backend_free(ggml_backend_t backend) {
             if (ctx->prof.calls[m])
                 fprintf(stderr, "ggml-b200 profile [%s] %-14s: %llu graph_compute calls, %.1f us host time per call, %.1f nodes per call\n", ctx->name.c_str(), mode_name[m],
                         (unsigned long long) ctx->prof.calls[m], ctx->prof.us[m] / (double) ctx->prof.calls[m], (double) ctx->prof.nodes[m] / (double) ctx->prof.calls[m]);
+        static const char * io_name[3] = { "set_tensor", "get_tensor", "synchronize" };
+        for (int k = 0; k < 3; ++k)
+            if (g_io_prof.calls[k])
+                fprintf(stderr, "ggml-b200 profile %-12s: %llu calls, %.1f us host time per call\n", io_name[k], (unsigned long long) g_io_prof.calls[k].load(),
+                        (double) g_io_prof.ns[k].load() / 1e3 / (double) g_io_prof.calls[k].load());
     }
     {
         scoped_device sd(ctx->device);
@@ -828,6 +846,7 @@ bool backend_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t backend
 void backend_synchronize(ggml_backend_t backend) {
     backend_ctx * ctx = (backend_ctx *) backend->context;
     scoped_device sd(ctx->device);
+    io_timer tm(2);
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 }
 

@@ -311,9 +311,10 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     const bool next_fmt = a.type == T_Q4_1 || a.type == T_Q5_0 || a.type == T_Q5_1 || a.type == T_IQ4_NL || a.type == T_IQ4_XS || a.type == T_Q2_K || a.type == T_Q3_K;
     if (a.type != T_Q4_0 && a.type != T_Q8_0 && a.type != T_Q4_K && a.type != T_Q5_K && !(a.type == T_Q6_K && !env_q6k_off) && !next_fmt) return false;
     if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
-    // n >= 9: every batch the mat-vec kernels do not take (the reference's mul_mat_q threshold, ggml-cuda.cu:1852-1875); columns
-    // beyond n in the 32-wide minimum tile are zero-filled by the TMA box and never stored
-    if (a.N < 9 || a.K % 256 != 0 || a.K < 256 || a.M < 1) return false;
+    // n >= 9: every batch the mat-vec kernels do not take (the reference's mul_mat_q threshold, ggml-cuda.cu:1852-1875); also 5 <= n <= 8
+    // when the mat-vec kernel cannot hold that many activation records next to its weight stages (very long rows: api.cu decides);
+    // columns beyond n in the 32-wide minimum tile are zero-filled by the TMA box and never stored
+    if (a.N < 5 || a.K % 256 != 0 || a.K < 256 || a.M < 1) return false;
     const size_t rb = row_bytes(a.type, a.K);
     if (a.nb01 != rb || (rb % 16) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0 || (a.nb11 & 3) != 0) return false;
     if (a.M >= (1ll << 31) || a.N >= (1ll << 31) || rb >= (1ull << 31)) return false;
@@ -361,7 +362,8 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     return true;
 }
 
-bool mmq_tc_eligible(const ggml_b200_mul_mat_args & a) { tc_plan pl; return make_tc_plan(a, pl); }
+bool mmq_tc_eligible(const ggml_b200_mul_mat_args & a) { tc_plan pl; return a.N >= 9 && make_tc_plan(a, pl); }
+bool mmq_tc_eligible_small(const ggml_b200_mul_mat_args & a) { tc_plan pl; return a.N >= 5 && make_tc_plan(a, pl); }
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a) {
     if (mmq_tc2_eligible(a)) return mmq_tc2_workspace(a);
     tc_plan pl;

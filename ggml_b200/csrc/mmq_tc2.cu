@@ -55,7 +55,7 @@ struct tc2_params {
     float * y; float * partials; unsigned int * flags; const float * inv_scale;
     unsigned long long * trace;                 // developer aid (GGML_B200_TC2_TRACE=1): 8 globaltimer stamps per CTA, else nullptr
     int64_t M, N;
-    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, tma_epi;
+    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, tma_epi, solo;
     // grouped mode (MUL_MAT_ID, expert-grouped): the activation rows are SORTED by expert (position -> (token, slot) pair in `perm`), n-tiles are
     // enumerated per expert (tile_base: prefix of tiles per expert, off: prefix of positions per expert, both n_expert + 1 long, device-resident:
     // no host synchronisation); W is the [n_expert x M] row stack; y rows are scattered back through perm
@@ -100,7 +100,8 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem[];
     // identical layout in both CTAs: [ring: nstages x (A 16 KB | B half BN/2 x 128 B)][raw: nraw x 128 x RAW][barriers][tmem slot][inv_scale tile]
     constexpr int a_bytes = T2_BM * T2_BK * 2;
-    const int b_bytes = (p.BN / 2) * T2_BK * 2, stage_bytes = a_bytes + b_bytes;
+    // pair mode: each CTA holds its HALF of the activation tile; solo mode: each CTA holds the WHOLE tile (its half + the peer's, by TMA multicast)
+    const int b_half = (p.BN / 2) * T2_BK * 2, b_bytes = p.solo ? 2 * b_half : b_half, stage_bytes = a_bytes + b_bytes;
     uint8_t * ring = smem;
     uint8_t * raw  = ring + p.nstages * stage_bytes;
     uint64_t * bars = (uint64_t *)(raw + p.nraw * T2_BM * RAW);
@@ -138,14 +139,17 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     if (tid == 0) {
         // stage barrier: the 128 dequantizer threads of this CTA that own the K-step; in the leader also its activation producer (expect_tx for
         // both activation halves) and the non-leader's relay warp.  empty / acc_full: one multicast commit each.
-        for (int s = 0; s < p.nstages; ++s) { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + (rank == 0 ? 2 : 0)); tc_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.nstages; ++s) {
+            if (p.solo) { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + 1); tc_mbar_init(&empty[s], 2); }      // own producer's expect_tx; both CTAs' MMAs release a stage
+            else        { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + (rank == 0 ? 2 : 0)); tc_mbar_init(&empty[s], 1); }
+        }
         for (int s = 0; s < p.nraw; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], T2_DQ_WARPS); }
         tc_mbar_init(acc_full, 1);
         tc_fence_init();
         tc_prefetch_map(&map_w); tc_prefetch_map(&map_x);
         if (p.tma_epi) tc_prefetch_map(&map_y);
     }
-    if (warp == 1) tc_tmem_alloc_pair(tmem_slot, tc_tmem_cols(p.BN));
+    if (warp == 1) { if (p.solo) tc_tmem_alloc(tmem_slot, tc_tmem_cols(p.BN)); else tc_tmem_alloc_pair(tmem_slot, tc_tmem_cols(p.BN)); }
     tc_fence_before();
     __syncthreads();
     auto issue_raw = [&](int u, int rs) {
@@ -155,13 +159,16 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         else                        coord = (ubeg + u) * tc2fmt<T>::STRIDE_WORDS - ((ubeg + u) & 1) * tc2fmt<T>::ODD_BACK_WORDS;
         tc_tma_2d(raw + rs * T2_BM * RAW, &map_w, coord, (int)w_row0, &raw_full[rs]);
     };
-    // the weight stream only involves this CTA's own barriers: its first requests leave before the cluster-wide sync (HBM latency overlaps it)
+    // the weight stream only involves this CTA's own barriers: its first requests leave between the two halves of the cluster-wide sync (the
+    // descriptor fetch and the HBM latency overlap the wait; issuing them before the arrive delayed the whole pair by 1.5 us)
     const int raw_issued = nunits < p.nraw ? nunits : p.nraw;     // (nraw < number of units of a ring round: advance() wraps at most once)
+    tc_cluster_arrive();
     if (tid == 0) {
         if (!p.w_static) tc_pdl_wait();                           // W produced by the preceding kernel: nothing may be read before it is done
         for (int u = 0; u < raw_issued; ++u) issue_raw(u, u);
     }
-    tc_cluster_sync();                                            // the peer's barriers exist before anything is signalled on them
+    __syncwarp();
+    tc_cluster_wait();                                            // the peer's barriers exist before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (tid == 0) tc2_stamp(p.trace, 1);
@@ -189,43 +196,58 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 const long long t0 = p.trace ? clock64() : 0;
                 if (!pos.first) tc_wait(&empty[s], pos.par ^ 1u);
                 if (p.trace) bwait += clock64() - t0;
-                if (rank == 0) tc_expect_tx(&full[s], (uint32_t)(2 * b_bytes));
-                tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, (ubeg * UK + step) * T2_BK, x_row0, full0 + (uint32_t)(s * 8));
+                if (p.solo) {
+                    // own half of the tile into BOTH CTAs (same offset), counted on each CTA's own stage barrier; this CTA expects both halves
+                    tc_expect_tx(&full[s], (uint32_t)(2 * b_half));
+                    tc_tma_2d_mc(ring + s * stage_bytes + a_bytes + (int)rank * b_half, &map_x, (ubeg * UK + step) * T2_BK, x_row0, &full[s], (uint16_t)3);
+                } else {
+                    if (rank == 0) tc_expect_tx(&full[s], (uint32_t)(2 * b_half));
+                    tc_tma_2d_pair(ring + s * stage_bytes + a_bytes, &map_x, (ubeg * UK + step) * T2_BK, x_row0, full0 + (uint32_t)(s * 8));
+                }
             }
             if (p.trace && (int)blockIdx.x < T2_TRACE_CTAS / 2) p.trace[((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + 7] = (unsigned long long)bwait;
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA only)
-        if (rank == 0) {
-            // instruction descriptor: D = f32 (bit 4), A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 with M = 256 (the pair)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((2 * T2_BM) >> 4) << 24);
+        // ===================== MMA issuer: the leader for the pair (cta_group::2), or every CTA for itself (solo, cta_group::1)
+        if (rank == 0 || p.solo) {
+            // instruction descriptor: D = f32 (bit 4), A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256: the pair; 128: solo)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(((p.solo ? 1 : 2) * T2_BM) >> 4) << 24);
             long long mma_wait = 0;
             tc2_ring_pos pos{ 0, 0u, true };
             for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
                 const int s = pos.s;
                 const long long t0 = p.trace ? clock64() : 0;
-                tc_wait_cluster(&full[s], pos.par);
+                if (p.solo) tc_wait(&full[s], pos.par); else tc_wait_cluster(&full[s], pos.par);
                 if (p.trace) mma_wait += clock64() - t0;
                 tc_fence_after();
                 if (lane == 0) {
                     if (step == 0) tc2_stamp(p.trace, 3);
                     const uint64_t ad = tc_smem_desc(tc_smem(ring + s * stage_bytes));
                     const uint64_t bd = tc_smem_desc(tc_smem(ring + s * stage_bytes + a_bytes));
+                    if (p.solo) {
 #pragma unroll
-                    for (int k = 0; k < T2_BK / 16; ++k)
-                        tc_mma_f16_pair(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (step | k) != 0 ? 1u : 0u);   // +32 bytes per K = 16
-                    tc_commit_pair(&empty[s]);
-                    if (step == nsteps - 1) tc_commit_pair(acc_full);
+                        for (int k = 0; k < T2_BK / 16; ++k)
+                            tc_mma_f16(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (step | k) != 0 ? 1u : 0u);
+                        tc_commit_mc(&empty[s], (uint16_t)3);        // the stage holds the peer's half too: both CTAs must be done with it
+                        if (step == nsteps - 1) tc_commit(acc_full);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < T2_BK / 16; ++k)
+                            tc_mma_f16_pair(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (step | k) != 0 ? 1u : 0u);   // +32 bytes per K = 16
+                        tc_commit_pair(&empty[s]);
+                        if (step == nsteps - 1) tc_commit_pair(acc_full);
+                    }
                 }
                 __syncwarp();
             }
             if (p.trace && lane == 0 && (int)blockIdx.x < T2_TRACE_CTAS / 2) p.trace[((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + 3] = (unsigned long long)mma_wait;
-        } else if (lane == 0) {
-            // non-leader: relay "this CTA's half of stage s is written" to the leader's barrier
-            tc2_ring_pos pos{ 0, 0u, true };
-            for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
-                tc_wait(&full[pos.s], pos.par);
-                tc_arrive_cluster_release(&full[pos.s], 0);
+        } else if (lane < p.nstages) {
+            // non-leader: relay "this CTA's half of stage s is written" to the leader's barrier.  One lane per stage slot: the cluster-scope
+            // release costs a GPU-scope memory barrier (~1 us), a single relay thread would serialize the ring on it
+            uint32_t par = 0;
+            for (int step = lane; step < nsteps; step += p.nstages, par ^= 1u) {
+                tc_wait(&full[lane], par);
+                tc_arrive_cluster_release(&full[lane], 0);
             }
         }
     } else {
@@ -374,7 +396,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
     __syncthreads();
     tc_cluster_sync();                                            // neither CTA retires (nor frees TMEM) while the pair still works
-    if (warp == 1) { tc_fence_after(); tc_tmem_dealloc_pair(tmem, tc_tmem_cols(p.BN)); }
+    if (warp == 1) { tc_fence_after(); if (p.solo) tc_tmem_dealloc(tmem, tc_tmem_cols(p.BN)); else tc_tmem_dealloc_pair(tmem, tc_tmem_cols(p.BN)); }
     if (tid == 0) tc2_stamp(p.trace, 7);
 }
 
@@ -445,10 +467,15 @@ static int tc2_raw_bytes(int type) {
 // shared-memory split: the operand ring only has to cover the dequantize -> MMA hand-over and the L2 latency of the activation tiles; what is
 // left goes to the raw W ring, which covers the HBM latency of the weight stream (profiles/r02_gemm_pair.md: with 2 raw units in flight the
 // dequantizers spent a quarter of their time waiting for the next unit)
+static bool tc2_solo_mode() {
+    // 1 (default): cta_group::1 MMAs per CTA, activation tile shared by TMA multicast; 0: cta_group::2 pair MMAs with the relayed hand-over
+    static const int env = getenv("GGML_B200_TC2_SOLO") ? atoi(getenv("GGML_B200_TC2_SOLO")) : 1;
+    return env != 0;
+}
 static bool tc2_smem_plan(int BN, int raw, int & nstages, int & nraw, int & smem) {
     static const int env_stages = getenv("GGML_B200_TC2_STAGES") ? atoi(getenv("GGML_B200_TC2_STAGES")) : 0;
     static const int env_raw = getenv("GGML_B200_TC2_RAW") ? atoi(getenv("GGML_B200_TC2_RAW")) : 0;
-    const int stage = T2_BM * T2_BK * 2 + (BN / 2) * T2_BK * 2, tail = 2 * (T2_MAX_STAGES + T2_MAX_RAW) * 8 + 64 + 256 * 4 + 1024;
+    const int stage = T2_BM * T2_BK * 2 + (tc2_solo_mode() ? BN : BN / 2) * T2_BK * 2, tail = 2 * (T2_MAX_STAGES + T2_MAX_RAW) * 8 + 64 + 256 * 4 + 1024;
     const int budget = 227 * 1024 - tail;
     // at least 3 stages: a dequantizer group revisits the ring every <= 3 K-steps, and the parity wait on a stage's "empty" barrier is only
     // unambiguous while the barrier is at most one phase behind the waiter (2 stages fault: the wait returns on the previous phase)
@@ -542,7 +569,7 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(X) failed: %d", (int)r); return GGML_B200_ECUDA; }
     }
     static const bool env_tma_epi_off = getenv("GGML_B200_TC2_TMA_EPI") && atoi(getenv("GGML_B200_TC2_TMA_EPI")) == 0;
-    const int stage_bytes_h = T2_BM * T2_BK * 2 + (pl.BN / 2) * T2_BK * 2;
+    const int stage_bytes_h = T2_BM * T2_BK * 2 + (tc2_solo_mode() ? pl.BN : pl.BN / 2) * T2_BK * 2;
     const bool tma_epi = !env_tma_epi_off && (a.M % 4) == 0 && ((uintptr_t)a.dst & 15) == 0 && (size_t)pl.nstages * stage_bytes_h >= 2 * 2 * 32 * T2_BM * 4;
     alignas(64) CUtensorMap map_y = map_x;                         // placeholder when the bulk-store epilogue is off
     if (tma_epi) {
@@ -559,6 +586,7 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
     p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw;
     p.w_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     p.tma_epi = tma_epi ? 1 : 0;
+    p.solo = tc2_solo_mode() ? 1 : 0;
     p.trace = pl.grid < T2_TRACE_CTAS / 2 ? tc2_trace_buf() : nullptr;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
@@ -728,7 +756,7 @@ template <int T> static int launch_mmid_g(const ggml_b200_mul_mat_id_args & a, c
     }
     tc2_params p{};
     p.y = a.dst; p.partials = nullptr; p.flags = nullptr; p.inv_scale = inv_scale; p.M = a.M; p.N = pl.n_pairs;
-    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.tma_epi = 0;
+    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.tma_epi = 0; p.solo = tc2_solo_mode() ? 1 : 0;
     p.g_off = off; p.g_tile_base = tile_base; p.g_perm = perm; p.n_expert = (int32_t)a.n_expert;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }

@@ -14,7 +14,7 @@ from oracle import oracle as O  # noqa: E402
 t = {v: k for k, v in g.TYPE_NAMES.items()}[sys.argv[1]]
 M, N, K = (int(v) for v in sys.argv[2:5])
 rng = np.random.default_rng(1)
-nbuf = 4
+nbuf = int(os.environ.get("GEMM_PROF_NBUF", "4"))      # 4 matrices stay L2-resident at 4096^2; bench.py rotates enough of them to stream from HBM
 Ws = [torch.from_numpy(O.random_blocks(t, M * K // O.Oracle().blck_size(t), rng)).cuda() for _ in range(nbuf)]
 X = torch.from_numpy(rng.uniform(-1, 1, N * K).astype(np.float32)).cuda()
 Ys = [torch.empty((1, 1, N, M), device="cuda") for _ in range(nbuf)]
