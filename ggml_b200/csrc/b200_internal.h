@@ -56,6 +56,11 @@ int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cud
 // mmq_tc.cu (tcgen05 GEMM)
 bool   mmq_tc_eligible(const ggml_b200_mul_mat_args & a);
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a);
+bool   mmq_dense_eligible(const ggml_b200_mul_mat_args & a);   // n >= 9, formats without an operand decoder: dequantize to fp16 + the same GEMM (mmq_tc2.cu)
+size_t mmq_dense_workspace(const ggml_b200_mul_mat_args & a);
+int    launch_mmq_dense(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+size_t mmq_f16w_workspace(int64_t M, int64_t N, int64_t K);         // dense fp16 weights, n >= 9 (0 = not eligible)
+int    launch_mmq_f16w(const void * w, size_t nb01, const float * x, size_t nb11, float * y, int64_t M, int64_t N, int64_t K, void * ws, size_t ws_size, uint32_t flags, cudaStream_t st);
 bool   mmq_tc_eligible_small(const ggml_b200_mul_mat_args & a);   // 5 <= n <= 8 on the tensor-core path (shapes the mat-vec kernel would have to split)
 int    launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st);
 // mmq_tc2.cu (tcgen05 GEMM on CTA pairs, cta_group::2)

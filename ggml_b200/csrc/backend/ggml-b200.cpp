@@ -850,6 +850,15 @@ void backend_synchronize(ggml_backend_t backend) {
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 }
 
+// dense f16 weights x f32 activations with a batch: the tensor-core kernel's fp16 path (plain 2-D operands, rows 16-byte aligned)
+bool f16_weights_on_tensor_cores(const ggml_tensor * node) {
+    const ggml_tensor * a = node->src[0], * b = node->src[1];
+    if (a->type != GGML_TYPE_F16 || b->type != GGML_TYPE_F32 || node->type != GGML_TYPE_F32) return false;
+    if (a->ne[2] != 1 || a->ne[3] != 1 || b->ne[2] != 1 || b->ne[3] != 1 || b->ne[1] < 9) return false;
+    if (a->nb[0] != 2 || b->nb[0] != 4 || (a->nb[1] % 16) != 0 || (b->nb[1] % 4) != 0 || ((uintptr_t) a->data % 16) != 0 || !ggml_is_contiguous(node)) return false;
+    return ggml_b200_mul_mat_f16_workspace_size(a->ne[1], b->ne[1], a->ne[0]) > 0;
+}
+
 size_t node_scratch_need(const ggml_tensor * node) {
     if (node->op == GGML_OP_MUL_MAT && is_b200_weight_type(node->src[0]->type)) {
         const ggml_tensor * a = node->src[0], * b = node->src[1];
@@ -862,6 +871,7 @@ size_t node_scratch_need(const ggml_tensor * node) {
         args.src0 = a->data; args.src1 = (const float *) b->data; args.dst = (float *) node->data;
         return ggml_b200_mul_mat_workspace_size(&args);
     }
+    if (node->op == GGML_OP_MUL_MAT && f16_weights_on_tensor_cores(node)) return ggml_b200_mul_mat_f16_workspace_size(node->src[0]->ne[1], node->src[1]->ne[1], node->src[0]->ne[0]);
     if (node->op == GGML_OP_MUL_MAT_ID) {
         const ggml_tensor * as = node->src[0], * b = node->src[1];
         ggml_b200_mul_mat_id_args args{};
@@ -1000,6 +1010,12 @@ void compute_nodes(backend_ctx * ctx, ggml_cgraph * cgraph) {
                 if (is_b200_weight_type(node->src[0]->type)) {
                     const int extra = fuse ? try_fuse_mul_mat(ctx, cgraph, i) : 0;
                     if (extra > 0) i += extra; else compute_mul_mat(ctx, node);
+                } else if (f16_weights_on_tensor_cores(node)) {
+                    const ggml_tensor * a = node->src[0], * b = node->src[1];
+                    const size_t need = ggml_b200_mul_mat_f16_workspace_size(a->ne[1], b->ne[1], a->ne[0]);
+                    void * ws = ctx->scratch(need);
+                    SHIM_OK(ggml_b200_mul_mat_f16(a->data, a->nb[1], (const float *) b->data, b->nb[1], (float *) node->data, a->ne[1], b->ne[1], a->ne[0], ws, ctx->workspace_size,
+                                                  src0_flags(ctx, node->src[0]), ctx->stream));
                 } else { auto x = desc(node->src[0]), y = desc(node->src[1]), d = desc(node); SHIM_OK(ggml_b200_op_mul_mat_f(&x, &y, &d, ctx->stream)); }
                 break;
             case GGML_OP_MUL_MAT_ID: compute_mul_mat_id(ctx, node); break;

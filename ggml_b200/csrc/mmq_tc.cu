@@ -362,9 +362,10 @@ static bool make_tc_plan(const ggml_b200_mul_mat_args & a, tc_plan & pl) {
     return true;
 }
 
-bool mmq_tc_eligible(const ggml_b200_mul_mat_args & a) { tc_plan pl; return a.N >= 9 && make_tc_plan(a, pl); }
+bool mmq_tc_eligible(const ggml_b200_mul_mat_args & a) { tc_plan pl; return a.N >= 9 && (make_tc_plan(a, pl) || mmq_dense_eligible(a)); }
 bool mmq_tc_eligible_small(const ggml_b200_mul_mat_args & a) { tc_plan pl; return a.N >= 5 && make_tc_plan(a, pl); }
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a) {
+    if (mmq_dense_eligible(a)) return mmq_dense_workspace(a);
     if (mmq_tc2_eligible(a)) return mmq_tc2_workspace(a);
     tc_plan pl;
     if (!make_tc_plan(a, pl)) return 0;
@@ -414,6 +415,7 @@ template <int T, int HALVES> static int launch_tc(const ggml_b200_mul_mat_args &
 }
 
 int launch_mmq_tc(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+    if (mmq_dense_eligible(a)) return launch_mmq_dense(a, st);             // formats without an operand decoder: fp16 copy + the same GEMM
     if (mmq_tc2_eligible(a)) return launch_mmq_tc2(a, st);              // CTA pairs (cta_group::2) where the problem is large enough
     tc_plan pl;
     if (!make_tc_plan(a, pl)) { set_error("mul_mat: shape not eligible for the tcgen05 kernel"); return GGML_B200_EUNSUPPORTED; }

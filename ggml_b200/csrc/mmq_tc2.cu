@@ -42,8 +42,13 @@ constexpr int T2_TRACE_CTAS = 4096;
 // row pitch of the raw box (272 = 16 mod 128) keeps the 128-bit shared-memory loads conflict-free
 template <int T> struct tc2fmt : tcfmt<T> {};
 template <> struct tc2fmt<T_Q8_0> { static constexpr int RAW = 272, STRIDE_WORDS = 68, UNIT_WORDS = 68, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
+// T_F16: the A operand already is fp16 (dense f16 weights, or a format without an operand decoder dequantized into the workspace first):
+// the weight producer copies every K-step's 128 x 64 tile straight into the operand ring (SWIZZLE_128B), no raw ring, no dequantizers
+template <> struct tc2fmt<T_F16> { static constexpr int RAW = 16, STRIDE_WORDS = 0, UNIT_WORDS = 1, UNIT_KSTEPS = 4, ODD_BACK_WORDS = 0, LOAD_BYTES = 16; };
 template <int T> __device__ __forceinline__ void tc2_load_unit(const uint8_t * g, uint32_t (&u)[tc2fmt<T>::UNIT_WORDS]) {     // g: the unit in shared memory
-    if constexpr (T == T_Q8_0) {
+    if constexpr (T == T_F16) {
+        u[0] = 0;
+    } else if constexpr (T == T_Q8_0) {
 #pragma unroll
         for (int i = 0; i < 17; ++i) { const uint4 v = *((const uint4 *)g + i); u[4 * i] = v.x; u[4 * i + 1] = v.y; u[4 * i + 2] = v.z; u[4 * i + 3] = v.w; }
     } else {
@@ -97,6 +102,7 @@ template <int T, bool GROUPED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const tc2_params p) {
     constexpr int RAW = tc2fmt<T>::RAW, UK = tc2fmt<T>::UNIT_KSTEPS;
+    constexpr bool DENSE = T == T_F16;                            // fp16 A tiles by TMA, solo mode only (the host guarantees p.solo)
     extern __shared__ __align__(1024) uint8_t smem[];
     // identical layout in both CTAs: [ring: nstages x (A 16 KB | B half BN/2 x 128 B)][raw: nraw x 128 x RAW][barriers][tmem slot][inv_scale tile]
     constexpr int a_bytes = T2_BM * T2_BK * 2;
@@ -140,7 +146,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         // stage barrier: the 128 dequantizer threads of this CTA that own the K-step; in the leader also its activation producer (expect_tx for
         // both activation halves) and the non-leader's relay warp.  empty / acc_full: one multicast commit each.
         for (int s = 0; s < p.nstages; ++s) {
-            if (p.solo) { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + 1); tc_mbar_init(&empty[s], 2); }      // own producer's expect_tx; both CTAs' MMAs release a stage
+            if (p.solo) { tc_mbar_init(&full[s], DENSE ? 2 : T2_DQ_WARPS / 2 * 32 + 1); tc_mbar_init(&empty[s], 2); }      // own producer's expect_tx; both CTAs' MMAs release a stage
             else        { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + (rank == 0 ? 2 : 0)); tc_mbar_init(&empty[s], 1); }
         }
         for (int s = 0; s < p.nraw; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], T2_DQ_WARPS); }
@@ -161,9 +167,9 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     };
     // the weight stream only involves this CTA's own barriers: its first requests leave between the two halves of the cluster-wide sync (the
     // descriptor fetch and the HBM latency overlap the wait; issuing them before the arrive delayed the whole pair by 1.5 us)
-    const int raw_issued = nunits < p.nraw ? nunits : p.nraw;     // (nraw < number of units of a ring round: advance() wraps at most once)
+    const int raw_issued = DENSE ? 0 : (nunits < p.nraw ? nunits : p.nraw);   // (nraw < number of units of a ring round: advance() wraps at most once)
     tc_cluster_arrive();
-    if (tid == 0) {
+    if (tid == 0 && !DENSE) {
         if (!p.w_static) tc_pdl_wait();                           // W produced by the preceding kernel: nothing may be read before it is done
         for (int u = 0; u < raw_issued; ++u) issue_raw(u, u);
     }
@@ -175,7 +181,16 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
     if (warp == 0) {
         // ===================== raw W producer (both CTAs): the packed units of the own 128 rows, nraw units ahead of the dequantizers
-        if (lane == 0) {
+        if (DENSE && lane == 0) {
+            // fp16 weights: the K-step's A tile goes straight into the operand ring
+            if (!p.w_static) tc_pdl_wait();
+            tc2_ring_pos pos{ 0, 0u, true };
+            for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
+                if (!pos.first) tc_wait(&empty[pos.s], pos.par ^ 1u);
+                tc_expect_tx(&full[pos.s], (uint32_t)a_bytes);
+                tc_tma_2d(ring + pos.s * stage_bytes, &map_w, (ubeg * UK + step) * T2_BK, (int)w_row0, &full[pos.s]);
+            }
+        } else if (lane == 0) {
             tc2_ring_pos rpos{ 0, 0u, true };
             rpos.advance(raw_issued, p.nraw);                     // the first units were requested before the cluster-wide sync
             for (int u = raw_issued; u < nunits; ++u, rpos.advance(1, p.nraw)) {
@@ -267,7 +282,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tc2_ring_pos pos{ ksel * PER, 0u, true };                 // ring position of the group's next K-step (PER <= 2 < nstages)
         tc2_ring_pos rpos{ 0, 0u, true };                         // raw ring
         const uint8_t * my_raw = raw + row * RAW;
-        for (int u = 0; u < nunits; ++u) {
+        for (int u = 0; u < (DENSE ? 0 : nunits); ++u) {
             { const long long t0 = acct ? clock64() : 0;
               tc_wait(&raw_full[rpos.s], rpos.par);
               if (acct) acct[0] += clock64() - t0; }
@@ -482,9 +497,9 @@ static bool tc2_smem_plan(int BN, int raw, int & nstages, int & nraw, int & smem
     int ns = env_stages >= 3 && env_stages <= T2_MAX_STAGES ? env_stages : 4;
     while (ns > 3 && ns * stage + 2 * T2_BM * raw > budget) ns--;
     if (ns * stage + 2 * T2_BM * raw > budget) return false;
-    int nr = (budget - ns * stage) / (T2_BM * raw);
+    int nr = raw > 0 ? (budget - ns * stage) / (T2_BM * raw) : 0;
     if (nr > T2_MAX_RAW) nr = T2_MAX_RAW;
-    if (env_raw >= 2 && env_raw < nr) nr = env_raw;
+    if (env_raw >= 2 && env_raw < nr && raw > 0) nr = env_raw;
     // leftover after a full raw ring: deepen the operand ring
     if (!(env_stages >= 3)) while (ns < T2_MAX_STAGES && (ns + 1) * stage + nr * T2_BM * raw <= budget) ns++;
     nstages = ns; nraw = nr; smem = ns * stage + nr * T2_BM * raw + tail;
@@ -495,16 +510,19 @@ static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     static const int env_mode = getenv("GGML_B200_TC_PAIR") ? atoi(getenv("GGML_B200_TC_PAIR")) : 1;     // 0 = off (one-CTA kernel everywhere)
     if (env_mode == 0) return false;
     static const bool env_q6k_off = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) == 0;
+    const bool dense = a.type == T_F16;                            // fp16 A tiles (launch_mmq_dense): needs the solo mode
     switch (a.type) {
         case T_Q4_0: case T_Q8_0: case T_Q4_K: case T_Q5_K: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_IQ4_NL: case T_IQ4_XS: case T_Q2_K: case T_Q3_K: break;
         case T_Q6_K: if (env_q6k_off) return false; break;
+        case T_F16: if (!tc2_solo_mode()) return false; break;
         default: return false;
     }
     if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
     // pairs pay off once a 256-row tile is mostly full and the batch fills at least a 64-column tile; smaller problems keep the one-CTA kernel
-    if (a.N < 33 || a.M < 192 || a.K % 256 != 0 || a.K < 256) return false;
-    const size_t rb = row_bytes(a.type, a.K);
-    if (a.nb01 != rb || (rb % 16) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0 || (a.nb11 & 3) != 0) return false;
+    // (the dense path has no other tensor-core kernel: it takes every n >= 9)
+    if (a.N < (dense ? 9 : 33) || a.M < (dense ? 1 : 192) || a.K % 256 != 0 || a.K < 256) return false;
+    const size_t rb = dense ? (size_t)a.K * 2 : row_bytes(a.type, a.K);
+    if ((dense ? (a.nb01 < rb || (a.nb01 % 16) != 0) : a.nb01 != rb) || (rb % 16) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 3) != 0 || (a.nb11 & 3) != 0) return false;
     if (a.M >= (1ll << 31) || a.N >= (1ll << 31) || rb >= (1ull << 31)) return false;
     if (!tc_get_encode()) return false;
     static const int env_bn = getenv("GGML_B200_TC2_BN") ? atoi(getenv("GGML_B200_TC2_BN")) : 0;
@@ -521,7 +539,7 @@ static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     if (env_splitk > 0 && env_splitk <= pl.chunks) splitk = env_splitk;
     if (splitk > 1 && tiles * 2 > T2_FLAGS_PER_SLOT) splitk = 1;
     pl.splitk = splitk;
-    if (!tc2_smem_plan(BN, tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
+    if (!tc2_smem_plan(BN, dense ? 0 : tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
     pl.grid = 2 * tiles * splitk;
     pl.xb_bytes = ((size_t)a.N * a.K * 2 + 255) & ~(size_t)255;
     pl.partial_bytes = splitk > 1 ? (size_t)tiles * 2 * (splitk - 1) * BN * T2_BM * 4 : 0;
@@ -548,9 +566,18 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
 
     { const int rc = tc_launch_x_to_f16(a.src1, a.nb11, xb, inv_scale, a.K, a.N, st, use_pdl); if (rc != GGML_B200_OK) return rc; }
-    const size_t rb = row_bytes(a.type, a.K);
+    const size_t rb = T == T_F16 ? (size_t)a.K * 2 : row_bytes(a.type, a.K);
     alignas(64) CUtensorMap map_w, map_x;
-    {
+    if constexpr (T == T_F16) {
+        // fp16 weights [M][K]: 128 x 64 tiles straight into the swizzled operand ring
+        const cuuint64_t dims[2] = { (cuuint64_t)a.K, (cuuint64_t)a.M };
+        const cuuint64_t strides[1] = { (cuuint64_t)a.nb01 };
+        const cuuint32_t box[2] = { (cuuint32_t)T2_BK, (cuuint32_t)T2_BM };
+        const cuuint32_t es[2] = { 1, 1 };
+        CUresult r = tc_get_encode()(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)a.src0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(W fp16) failed: %d", (int)r); return GGML_B200_ECUDA; }
+    } else {
         const cuuint64_t dims[2] = { (cuuint64_t)(rb / 4), (cuuint64_t)a.M };
         const cuuint64_t strides[1] = { (cuuint64_t)rb };
         const cuuint32_t box[2] = { (cuuint32_t)(tc2fmt<T>::RAW / 4), (cuuint32_t)T2_BM };
@@ -619,6 +646,72 @@ int launch_mmq_tc2(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q3_K:   return launch_tc2<T_Q3_K>(a, pl, st);
         default: set_error("mul_mat: unsupported weight type %d for the tcgen05 kernel", a.type); return GGML_B200_EUNSUPPORTED;
     }
+}
+
+// ----------------------------------------------------------------------------- formats without an operand decoder (grid i-quants, ternary): n >= 9
+// W is dequantized to fp16 into the workspace by the bit-exact conversion kernel (dequant.cu) and the same GEMM runs with plain fp16 A tiles.
+// One extra pass over W (2 bytes per weight written, then read N / BN times), against the generic kernel's one warp per output element:
+// 7.2-10.6 ms -> see profiles/r02_results.md at 4096 x 14336 x 512.  Replaces the reference's dequantize + cuBLAS route
+// (src/ggml-cuda/ggml-cuda.cu:1158-1300) for these formats.
+static bool dense_source_type(int t) {
+    switch (t) {
+        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ2_S: case T_IQ3_XXS: case T_IQ3_S: case T_IQ1_S: case T_IQ1_M: case T_TQ1_0: case T_TQ2_0: return true;
+        default: return false;
+    }
+}
+static bool make_dense_args(const ggml_b200_mul_mat_args & a, ggml_b200_mul_mat_args & b, size_t & wbytes) {
+    static const bool env_off = getenv("GGML_B200_TC_DENSE") && atoi(getenv("GGML_B200_TC_DENSE")) == 0;
+    if (env_off || !dense_source_type(a.type) || a.N < 9 || a.K % 256 != 0) return false;
+    if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1 || a.nb01 != row_bytes(a.type, a.K)) return false;
+    wbytes = ((size_t)a.M * (size_t)a.K * 2 + 255) & ~(size_t)255;
+    b = a;
+    b.type = T_F16; b.nb01 = (size_t)a.K * 2; b.nb02 = b.nb01 * (size_t)a.M; b.nb03 = b.nb02;
+    b.src0 = (const void *)(uintptr_t)256;                           // placeholder with the alignment of the real buffer (plan only looks at alignment)
+    b.flags &= ~(uint32_t)GGML_B200_MM_SRC0_STATIC;                   // the fp16 copy is produced by the kernel in front of the GEMM
+    return true;
+}
+bool mmq_dense_eligible(const ggml_b200_mul_mat_args & a) {
+    ggml_b200_mul_mat_args b; size_t wbytes; tc2_plan pl;
+    return make_dense_args(a, b, wbytes) && make_tc2_plan(b, pl);
+}
+size_t mmq_dense_workspace(const ggml_b200_mul_mat_args & a) {
+    ggml_b200_mul_mat_args b; size_t wbytes; tc2_plan pl;
+    if (!make_dense_args(a, b, wbytes) || !make_tc2_plan(b, pl)) return 0;
+    return wbytes + 256 + pl.xb_bytes + pl.partial_bytes + pl.scale_bytes + 1024;
+}
+int launch_mmq_dense(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+    ggml_b200_mul_mat_args b; size_t wbytes; tc2_plan pl;
+    if (!make_dense_args(a, b, wbytes) || !make_tc2_plan(b, pl)) { set_error("mul_mat: shape not eligible for the dequantize + fp16 tensor-core path"); return GGML_B200_EUNSUPPORTED; }
+    const size_t need = wbytes + 256 + pl.xb_bytes + pl.partial_bytes + pl.scale_bytes + 1024;
+    if (!a.workspace || a.workspace_size < need) { set_error("mul_mat: workspace %zu < %zu", a.workspace_size, need); return GGML_B200_EWORKSPACE; }
+    uint8_t * ws = (uint8_t *)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
+    const int rc = ggml_b200_dequantize(a.type, a.src0, ws, T_F16, a.M * a.K, (void *)st);
+    if (rc != GGML_B200_OK) return rc;
+    b.src0 = ws;
+    b.workspace = ws + wbytes;
+    b.workspace_size = a.workspace_size - (size_t)((ws + wbytes) - (uint8_t *)a.workspace);
+    return launch_tc2<T_F16>(b, pl, st);
+}
+
+// dense fp16 weights x f32 activations, n >= 9 (the reference: cuBLAS, ggml-cuda.cu:1158-1300): straight onto the fp16 A path
+static bool make_f16w_args(const void * w, size_t nb01, const float * x, size_t nb11, float * y, int64_t M, int64_t N, int64_t K, uint32_t flags, ggml_b200_mul_mat_args & b) {
+    b = ggml_b200_mul_mat_args{};
+    b.type = T_F16; b.M = M; b.N = N; b.K = K; b.ne02 = b.ne03 = b.ne12 = b.ne13 = 1;
+    b.nb01 = nb01; b.nb02 = nb01 * (size_t)M; b.nb03 = b.nb02; b.nb11 = nb11; b.nb12 = nb11 * (size_t)N; b.nb13 = b.nb12;
+    b.src0 = w; b.src1 = x; b.dst = y; b.flags = flags;
+    return w && x && y && M > 0 && N > 0 && K > 0;
+}
+size_t mmq_f16w_workspace(int64_t M, int64_t N, int64_t K) {
+    ggml_b200_mul_mat_args b; tc2_plan pl;
+    make_f16w_args((const void *)(uintptr_t)256, (size_t)K * 2, (const float *)(uintptr_t)256, (size_t)K * 4, (float *)(uintptr_t)256, M, N, K, 0, b);
+    if (!make_tc2_plan(b, pl)) return 0;
+    return pl.xb_bytes + pl.partial_bytes + pl.scale_bytes + 1024;
+}
+int launch_mmq_f16w(const void * w, size_t nb01, const float * x, size_t nb11, float * y, int64_t M, int64_t N, int64_t K, void * ws, size_t ws_size, uint32_t flags, cudaStream_t st) {
+    ggml_b200_mul_mat_args b; tc2_plan pl;
+    if (!make_f16w_args(w, nb01, x, nb11, y, M, N, K, flags, b) || !make_tc2_plan(b, pl)) { set_error("mul_mat_f16: shape not eligible for the tensor-core path"); return GGML_B200_EUNSUPPORTED; }
+    b.workspace = ws; b.workspace_size = ws_size;
+    return launch_tc2<T_F16>(b, pl, st);
 }
 
 // ----------------------------------------------------------------------------- MUL_MAT_ID, expert-grouped (batched tokens)

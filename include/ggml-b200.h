@@ -112,6 +112,11 @@ typedef struct ggml_b200_epilogue {
     float *       dst_unary;  /* [M] or NULL */
     const float * residual;   /* [M], unary == 2 only; may alias dst_unary */
 } ggml_b200_epilogue;
+/* dense fp16 weights [M][K] (row stride nb01 bytes, a multiple of 16) x f32 activations [N][K] -> f32 [N][M] on the tensor cores, n >= 9, K % 256 == 0
+   (the reference: cuBLAS GEMM, src/ggml-cuda/ggml-cuda.cu:1158-1300).  workspace_size = 0 from the size function: shape not eligible. */
+GGML_B200_API size_t ggml_b200_mul_mat_f16_workspace_size(int64_t M, int64_t N, int64_t K);
+GGML_B200_API int    ggml_b200_mul_mat_f16(const void * w, size_t nb01, const float * x, size_t nb11, float * y, int64_t M, int64_t N, int64_t K,
+                                           void * workspace, size_t workspace_size, uint32_t flags, void * stream);
 GGML_B200_API int    ggml_b200_mul_mat_fused(const ggml_b200_mul_mat_args * args, const ggml_b200_epilogue * epilogue, void * stream);
 
 /* MUL_MAT with HOST activations / results: copies src1 (host, contiguous [N][K]) to the device, runs
