@@ -60,7 +60,7 @@ struct tc2_params {
     float * y; float * partials; unsigned int * flags; const float * inv_scale;
     unsigned long long * trace;                 // developer aid (GGML_B200_TC2_TRACE=1): 8 globaltimer stamps per CTA, else nullptr
     int64_t M, N;
-    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, tma_epi, solo;
+    int32_t BN, m_tiles, n_tiles, splitk, units_total, nstages, nraw, w_static, tma_epi, solo, dbg;
     // grouped mode (MUL_MAT_ID, expert-grouped): the activation rows are SORTED by expert (position -> (token, slot) pair in `perm`), n-tiles are
     // enumerated per expert (tile_base: prefix of tiles per expert, off: prefix of positions per expert, both n_expert + 1 long, device-resident:
     // no host synchronisation); W is the [n_expert x M] row stack; y rows are scattered back through perm
@@ -102,7 +102,7 @@ template <int T, bool GROUPED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const tc2_params p) {
     constexpr int RAW = tc2fmt<T>::RAW, UK = tc2fmt<T>::UNIT_KSTEPS;
-    constexpr bool DENSE = T == T_F16;                            // fp16 A tiles by TMA, solo mode only (the host guarantees p.solo)
+    constexpr bool DENSE = T == T_F16;                            // fp16 A tiles by TMA: no dequantizers, no generic-proxy hand-over
     extern __shared__ __align__(1024) uint8_t smem[];
     // identical layout in both CTAs: [ring: nstages x (A 16 KB | B half BN/2 x 128 B)][raw: nraw x 128 x RAW][barriers][tmem slot][inv_scale tile]
     constexpr int a_bytes = T2_BM * T2_BK * 2;
@@ -146,10 +146,10 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         // stage barrier: the 128 dequantizer threads of this CTA that own the K-step; in the leader also its activation producer (expect_tx for
         // both activation halves) and the non-leader's relay warp.  empty / acc_full: one multicast commit each.
         for (int s = 0; s < p.nstages; ++s) {
-            if (p.solo) { tc_mbar_init(&full[s], DENSE ? 2 : T2_DQ_WARPS / 2 * 32 + 1); tc_mbar_init(&empty[s], 2); }      // own producer's expect_tx; both CTAs' MMAs release a stage
-            else        { tc_mbar_init(&full[s], T2_DQ_WARPS / 2 * 32 + (rank == 0 ? 2 : 0)); tc_mbar_init(&empty[s], 1); }
+            if (p.solo) { tc_mbar_init(&full[s], DENSE ? 2 : T2_DQ_WARPS / 2 * 32 + 1); tc_mbar_init(&empty[s], p.solo == 2 ? 1 : 2); }      // own producer's expect_tx; (multicast: both CTAs' MMAs release a stage)
+            else        { tc_mbar_init(&full[s], DENSE ? 2 : T2_DQ_WARPS / 2 * 32 + (rank == 0 ? 2 : 0)); tc_mbar_init(&empty[s], 1); }   // (DENSE: the leader's two expect_tx)
         }
-        for (int s = 0; s < p.nraw; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], T2_DQ_WARPS); }
+        for (int s = 0; s < p.nraw; ++s) { tc_mbar_init(&raw_full[s], 1); tc_mbar_init(&raw_empty[s], (p.dbg & 4) ? T2_DQ_WARPS * 32 : T2_DQ_WARPS); }
         tc_mbar_init(acc_full, 1);
         tc_fence_init();
         tc_prefetch_map(&map_w); tc_prefetch_map(&map_x);
@@ -167,7 +167,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     };
     // the weight stream only involves this CTA's own barriers: its first requests leave between the two halves of the cluster-wide sync (the
     // descriptor fetch and the HBM latency overlap the wait; issuing them before the arrive delayed the whole pair by 1.5 us)
-    const int raw_issued = DENSE ? 0 : (nunits < p.nraw ? nunits : p.nraw);   // (nraw < number of units of a ring round: advance() wraps at most once)
+    const int raw_issued = (DENSE || (p.dbg & 2)) ? 0 : (nunits < p.nraw ? nunits : p.nraw);   // (nraw < number of units of a ring round: advance() wraps at most once)
     tc_cluster_arrive();
     if (tid == 0 && !DENSE) {
         if (!p.w_static) tc_pdl_wait();                           // W produced by the preceding kernel: nothing may be read before it is done
@@ -187,8 +187,14 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             tc2_ring_pos pos{ 0, 0u, true };
             for (int step = 0; step < nsteps; ++step, pos.advance(1, p.nstages)) {
                 if (!pos.first) tc_wait(&empty[pos.s], pos.par ^ 1u);
-                tc_expect_tx(&full[pos.s], (uint32_t)a_bytes);
-                tc_tma_2d(ring + pos.s * stage_bytes, &map_w, (ubeg * UK + step) * T2_BK, (int)w_row0, &full[pos.s]);
+                if (p.solo) {
+                    tc_expect_tx(&full[pos.s], (uint32_t)a_bytes);
+                    tc_tma_2d(ring + pos.s * stage_bytes, &map_w, (ubeg * UK + step) * T2_BK, (int)w_row0, &full[pos.s]);
+                } else {
+                    // pair mode: both CTAs' A tiles are counted on the leader's stage barrier (everything on the async proxy: no relay needed)
+                    if (rank == 0) tc_expect_tx(&full[pos.s], (uint32_t)(2 * a_bytes));
+                    tc_tma_2d_pair(ring + pos.s * stage_bytes, &map_w, (ubeg * UK + step) * T2_BK, (int)w_row0, tc_cluster_addr(&full[pos.s], 0));
+                }
             }
         } else if (lane == 0) {
             tc2_ring_pos rpos{ 0, 0u, true };
@@ -211,7 +217,13 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 const long long t0 = p.trace ? clock64() : 0;
                 if (!pos.first) tc_wait(&empty[s], pos.par ^ 1u);
                 if (p.trace) bwait += clock64() - t0;
-                if (p.solo) {
+                if (p.solo == 2) {
+                    // independent CTAs: both halves of the activation tile by this CTA's own copies
+                    const int xr = x_row0 - (int)rank * (p.BN / 2);
+                    tc_expect_tx(&full[s], (uint32_t)(2 * b_half));
+                    tc_tma_2d(ring + s * stage_bytes + a_bytes, &map_x, (ubeg * UK + step) * T2_BK, xr, &full[s]);
+                    tc_tma_2d(ring + s * stage_bytes + a_bytes + b_half, &map_x, (ubeg * UK + step) * T2_BK, xr + p.BN / 2, &full[s]);
+                } else if (p.solo) {
                     // own half of the tile into BOTH CTAs (same offset), counted on each CTA's own stage barrier; this CTA expects both halves
                     tc_expect_tx(&full[s], (uint32_t)(2 * b_half));
                     tc_tma_2d_mc(ring + s * stage_bytes + a_bytes + (int)rank * b_half, &map_x, (ubeg * UK + step) * T2_BK, x_row0, &full[s], (uint16_t)3);
@@ -243,7 +255,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < T2_BK / 16; ++k)
                             tc_mma_f16(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (step | k) != 0 ? 1u : 0u);
-                        tc_commit_mc(&empty[s], (uint16_t)3);        // the stage holds the peer's half too: both CTAs must be done with it
+                        if (p.solo == 2) tc_commit(&empty[s]); else tc_commit_mc(&empty[s], (uint16_t)3);   // multicast: the stage holds the peer's half too, both CTAs must be done with it
                         if (step == nsteps - 1) tc_commit(acc_full);
                     } else {
 #pragma unroll
@@ -256,7 +268,7 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 __syncwarp();
             }
             if (p.trace && lane == 0 && (int)blockIdx.x < T2_TRACE_CTAS / 2) p.trace[((size_t)(T2_TRACE_CTAS / 2) + blockIdx.x) * 8 + 3] = (unsigned long long)mma_wait;
-        } else if (lane < p.nstages) {
+        } else if (!DENSE && lane < p.nstages) {
             // non-leader: relay "this CTA's half of stage s is written" to the leader's barrier.  One lane per stage slot: the cluster-scope
             // release costs a GPU-scope memory barrier (~1 us), a single relay thread would serialize the ring on it
             uint32_t par = 0;
@@ -290,20 +302,22 @@ mmq_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             if constexpr (tc2fmt<T>::LOAD_BYTES == 2) lead = ((ubeg + u) * tc2fmt<T>::UNIT_BYTES) & 15;
             else                       lead = ((ubeg + u) & 1) * (4 * tc2fmt<T>::ODD_BACK_WORDS);
             tc2_load_unit<T>(my_raw + rpos.s * (T2_BM * RAW) + lead, ub);
-            __syncwarp();
-            if (lane == 0) tc_arrive(&raw_empty[rpos.s]);        // the unit is in registers: the buffer can be refilled
+            if (p.dbg & 4) tc_arrive(&raw_empty[rpos.s]);
+            else { __syncwarp(); if (lane == 0) tc_arrive(&raw_empty[rpos.s]); }       // the unit is in registers: the buffer can be refilled
             rpos.advance(1, p.nraw);
             if constexpr (UK == 4) {
                 tc2_ring_pos pos2 = pos; pos2.advance(1, p.nstages);
                 if (ksel == 0) {
                     tc2_dequant_write<T, 0>(pos,  valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
+                    if (p.dbg & 1) { tc_fence_async_smem(); tc2_stage_arrive(pos.s, full); }
                     tc2_dequant_write<T, 1>(pos2, valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
                 } else {
                     tc2_dequant_write<T, 2>(pos,  valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
+                    if (p.dbg & 1) { tc_fence_async_smem(); tc2_stage_arrive(pos.s, full); }
                     tc2_dequant_write<T, 3>(pos2, valid, ub, ring, stage_bytes, a_row_off, sw, empty, acct);
                 }
                 tc_fence_async_smem();
-                tc2_stage_arrive(pos.s, full);
+                if (!(p.dbg & 1)) tc2_stage_arrive(pos.s, full);
                 tc2_stage_arrive(pos2.s, full);
                 pos = pos2; pos.advance(3, p.nstages);
             } else {
@@ -462,7 +476,7 @@ int tc2_trace_read(unsigned long long * host_dst, int max_ctas) {
 
 // ----------------------------------------------------------------------------- host side
 struct tc2_plan {
-    int BN, m_tiles, n_tiles, splitk, chunks, nstages, nraw, smem, grid;
+    int BN, m_tiles, n_tiles, splitk, chunks, nstages, nraw, smem, grid, mode;
     size_t xb_bytes, partial_bytes, scale_bytes;
 };
 
@@ -482,15 +496,20 @@ static int tc2_raw_bytes(int type) {
 // shared-memory split: the operand ring only has to cover the dequantize -> MMA hand-over and the L2 latency of the activation tiles; what is
 // left goes to the raw W ring, which covers the HBM latency of the weight stream (profiles/r02_gemm_pair.md: with 2 raw units in flight the
 // dequantizers spent a quarter of their time waiting for the next unit)
-static bool tc2_solo_mode() {
-    // 1 (default): cta_group::1 MMAs per CTA, activation tile shared by TMA multicast; 0: cta_group::2 pair MMAs with the relayed hand-over
-    static const int env = getenv("GGML_B200_TC2_SOLO") ? atoi(getenv("GGML_B200_TC2_SOLO")) : 1;
-    return env != 0;
+// MMA mode of a launch.  2 (quantized formats): cta_group::1, the two CTAs of a cluster work independently (each loads the whole activation tile):
+// the hand-over of a dequantized stage stays inside one CTA -- the only form that is both clean under tests/gpu_tc2_stress.py and at least as fast
+// as everything else measured (profiles/r02_gemm_pair_v2.md).  0 (fp16 A tiles): cta_group::2 pair MMAs, every operand arrives by TMA, so nothing
+// crosses a CTA boundary on the generic proxy; for quantized formats mode 0 needs the relayed hand-over (clean, 10-25 % slower).  1: cta_group::1
+// with the activation tile shared by TMA multicast -- loses rows under the stress test (not understood), kept only for study.
+static int tc2_mode_for(bool dense) {
+    static const int env = getenv("GGML_B200_TC2_SOLO") ? atoi(getenv("GGML_B200_TC2_SOLO")) : -1;
+    if (env >= 0 && env <= 2) return env;
+    return dense ? 0 : 2;
 }
-static bool tc2_smem_plan(int BN, int raw, int & nstages, int & nraw, int & smem) {
+static bool tc2_smem_plan(int BN, int raw, int mode, int & nstages, int & nraw, int & smem) {
     static const int env_stages = getenv("GGML_B200_TC2_STAGES") ? atoi(getenv("GGML_B200_TC2_STAGES")) : 0;
     static const int env_raw = getenv("GGML_B200_TC2_RAW") ? atoi(getenv("GGML_B200_TC2_RAW")) : 0;
-    const int stage = T2_BM * T2_BK * 2 + (tc2_solo_mode() ? BN : BN / 2) * T2_BK * 2, tail = 2 * (T2_MAX_STAGES + T2_MAX_RAW) * 8 + 64 + 256 * 4 + 1024;
+    const int stage = T2_BM * T2_BK * 2 + (mode != 0 ? BN : BN / 2) * T2_BK * 2, tail = 2 * (T2_MAX_STAGES + T2_MAX_RAW) * 8 + 64 + 256 * 4 + 1024;
     const int budget = 227 * 1024 - tail;
     // at least 3 stages: a dequantizer group revisits the ring every <= 3 K-steps, and the parity wait on a stage's "empty" barrier is only
     // unambiguous while the barrier is at most one phase behind the waiter (2 stages fault: the wait returns on the previous phase)
@@ -510,11 +529,11 @@ static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     static const int env_mode = getenv("GGML_B200_TC_PAIR") ? atoi(getenv("GGML_B200_TC_PAIR")) : 1;     // 0 = off (one-CTA kernel everywhere)
     if (env_mode == 0) return false;
     static const bool env_q6k_off = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) == 0;
-    const bool dense = a.type == T_F16;                            // fp16 A tiles (launch_mmq_dense): needs the solo mode
+    const bool dense = a.type == T_F16;                            // fp16 A tiles (launch_mmq_dense / launch_mmq_f16w)
     switch (a.type) {
         case T_Q4_0: case T_Q8_0: case T_Q4_K: case T_Q5_K: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_IQ4_NL: case T_IQ4_XS: case T_Q2_K: case T_Q3_K: break;
         case T_Q6_K: if (env_q6k_off) return false; break;
-        case T_F16: if (!tc2_solo_mode()) return false; break;
+        case T_F16: break;
         default: return false;
     }
     if (a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
@@ -539,7 +558,8 @@ static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     if (env_splitk > 0 && env_splitk <= pl.chunks) splitk = env_splitk;
     if (splitk > 1 && tiles * 2 > T2_FLAGS_PER_SLOT) splitk = 1;
     pl.splitk = splitk;
-    if (!tc2_smem_plan(BN, dense ? 0 : tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
+    pl.mode = tc2_mode_for(dense);
+    if (!tc2_smem_plan(BN, dense ? 0 : tc2_raw_bytes(a.type), pl.mode, pl.nstages, pl.nraw, pl.smem)) return false;
     pl.grid = 2 * tiles * splitk;
     pl.xb_bytes = ((size_t)a.N * a.K * 2 + 255) & ~(size_t)255;
     pl.partial_bytes = splitk > 1 ? (size_t)tiles * 2 * (splitk - 1) * BN * T2_BM * 4 : 0;
@@ -596,7 +616,7 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(X) failed: %d", (int)r); return GGML_B200_ECUDA; }
     }
     static const bool env_tma_epi_off = getenv("GGML_B200_TC2_TMA_EPI") && atoi(getenv("GGML_B200_TC2_TMA_EPI")) == 0;
-    const int stage_bytes_h = T2_BM * T2_BK * 2 + (tc2_solo_mode() ? pl.BN : pl.BN / 2) * T2_BK * 2;
+    const int stage_bytes_h = T2_BM * T2_BK * 2 + (pl.mode != 0 ? pl.BN : pl.BN / 2) * T2_BK * 2;
     const bool tma_epi = !env_tma_epi_off && (a.M % 4) == 0 && ((uintptr_t)a.dst & 15) == 0 && (size_t)pl.nstages * stage_bytes_h >= 2 * 2 * 32 * T2_BM * 4;
     alignas(64) CUtensorMap map_y = map_x;                         // placeholder when the bulk-store epilogue is off
     if (tma_epi) {
@@ -613,7 +633,9 @@ template <int T> static int launch_tc2(const ggml_b200_mul_mat_args & a, const t
     p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splitk = pl.splitk; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw;
     p.w_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     p.tma_epi = tma_epi ? 1 : 0;
-    p.solo = tc2_solo_mode() ? 1 : 0;
+    p.solo = pl.mode;
+    static const int env_dbg = getenv("GGML_B200_TC2_DBG") ? atoi(getenv("GGML_B200_TC2_DBG")) : 0;     // developer switches: 1 fence per stage, 2 no early weight requests, 4 per-thread raw release
+    p.dbg = env_dbg;
     p.trace = pl.grid < T2_TRACE_CTAS / 2 ? tc2_trace_buf() : nullptr;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
@@ -777,7 +799,7 @@ __global__ void __launch_bounds__(256) mmid_x_to_f16_kernel(const uint8_t * __re
     }
 }
 
-struct mmid_g_plan { int BN, m_tiles, max_tiles, chunks, nstages, nraw, smem; size_t xb_bytes, scale_bytes, tab_bytes, perm_bytes; int64_t n_pairs; };
+struct mmid_g_plan { int BN, m_tiles, max_tiles, chunks, nstages, nraw, smem, mode; size_t xb_bytes, scale_bytes, tab_bytes, perm_bytes; int64_t n_pairs; };
 
 static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & pl) {
     static const int env_on = getenv("GGML_B200_MMID_GROUPED") ? atoi(getenv("GGML_B200_MMID_GROUPED")) : 0;      // opt-in until validated on a B200
@@ -798,7 +820,8 @@ static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & 
     pl.m_tiles = (int)((a.M + 2 * T2_BM - 1) / (2 * T2_BM));
     pl.max_tiles = (int)((n_pairs + pl.BN - 1) / pl.BN + a.n_expert);
     pl.chunks = (int)(a.K / 256);
-    if (!tc2_smem_plan(pl.BN, tc2_raw_bytes(a.type), pl.nstages, pl.nraw, pl.smem)) return false;
+    pl.mode = tc2_mode_for(false);
+    if (!tc2_smem_plan(pl.BN, tc2_raw_bytes(a.type), pl.mode, pl.nstages, pl.nraw, pl.smem)) return false;
     if ((int64_t)pl.m_tiles * pl.max_tiles * 2 > 0x7fffffffLL) return false;
     pl.n_pairs = n_pairs;
     pl.xb_bytes = ((size_t)(n_pairs + pl.BN) * a.K * 2 + 255) & ~(size_t)255;        // + one tile of slack rows (read past the last position, never used)
@@ -849,7 +872,7 @@ template <int T> static int launch_mmid_g(const ggml_b200_mul_mat_id_args & a, c
     }
     tc2_params p{};
     p.y = a.dst; p.partials = nullptr; p.flags = nullptr; p.inv_scale = inv_scale; p.M = a.M; p.N = pl.n_pairs;
-    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.tma_epi = 0; p.solo = tc2_solo_mode() ? 1 : 0;
+    p.BN = pl.BN; p.m_tiles = pl.m_tiles; p.n_tiles = pl.max_tiles; p.splitk = 1; p.units_total = pl.chunks; p.nstages = pl.nstages; p.nraw = pl.nraw; p.w_static = 0; p.tma_epi = 0; p.solo = pl.mode; p.dbg = 0;
     p.g_off = off; p.g_tile_base = tile_base; p.g_perm = perm; p.n_expert = (int32_t)a.n_expert;
     static per_device_flag attr_set;
     if (!attr_set.test()) { B200_CUDA_TRY(cudaFuncSetAttribute(mmq_tc2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set.set(); }
