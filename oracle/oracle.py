@@ -42,8 +42,11 @@ IQ_TYPES = (IQ2_XXS, IQ3_XXS, IQ1_S, IQ2_XS, IQ2_S, IQ3_S, IQ1_M, TQ1_0, TQ2_0)
 
 def build(ref: bool = True) -> None:
     """(Re)build liboracle_quants.so and, where /root/reference exists, oracle/_ref."""
-    targets = ["oracle"] + (["ref"] if ref else [])
-    subprocess.run(["make", "-s", "-j8", "-C", str(HERE)] + targets, check=True)
+    subprocess.run(["make", "-s", "-j8", "-C", str(HERE), "oracle"] + (["ref"] if ref else []), check=True)
+    # the reference's programs linked against the plug-in (gpt-2-backend-b200, -dump variants, gpt2-compare): needed by
+    # tests/test_gpu_gpt2.py and bench.py's gpt-2 leg on the GPU box, so they are part of every build where the reference exists
+    if ref and (HERE.parent / "ggml_b200" / "libggml-b200.so").exists():
+        subprocess.run(["make", "-s", "-j8", "-C", str(HERE), "b200bins"], check=True)
 
 
 def _p(a: np.ndarray):
