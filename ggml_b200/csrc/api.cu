@@ -47,17 +47,27 @@ static int validate(const ggml_b200_mul_mat_args * a) {
     return GGML_B200_OK;
 }
 
+// the int8 mma.sync consume path (mmvq_mma.cu): default for 2 <= n <= 8; GGML_B200_MMA = 0 never, 2 also for n = 1; per call GGML_B200_MM_GEMV_MMA /
+// GGML_B200_MM_GEMV_DP4A select explicitly
+static bool mma_wanted(const ggml_b200_mul_mat_args & a) {
+    static const int env = getenv("GGML_B200_MMA") ? atoi(getenv("GGML_B200_MMA")) : 1;
+    if (a.flags & (GGML_B200_MM_GEMV_V1 | GGML_B200_MM_GEMV_DP4A)) return false;
+    if (!(a.flags & GGML_B200_MM_GEMV_MMA) && (env == 0 || (a.N < 2 && env != 2))) return false;
+    return mmvq_mma_eligible(a);
+}
+
 static int plan(const ggml_b200_mul_mat_args & a) {
     static const bool env_generic = getenv("GGML_B200_FORCE_GENERIC") && atoi(getenv("GGML_B200_FORCE_GENERIC")) != 0;   // debugging aid
     if (env_generic) return GGML_B200_MM_FORCE_GENERIC;
     if (a.flags & GGML_B200_MM_FORCE_GENERIC) return GGML_B200_MM_FORCE_GENERIC;
     if (a.flags & GGML_B200_MM_FORCE_GEMV) {
-        const bool ok = (a.flags & GGML_B200_MM_GEMV_V1) ? mmvq_tma_eligible(a) : (mmvq_sb_eligible(a) || mmvq_tma_eligible(a));
+        const bool ok = (a.flags & GGML_B200_MM_GEMV_V1) ? mmvq_tma_eligible(a) : (mma_wanted(a) || mmvq_sb_eligible(a) || mmvq_tma_eligible(a));
         return ok ? GGML_B200_MM_FORCE_GEMV : GGML_B200_EUNSUPPORTED;
     }
     if (a.flags & GGML_B200_MM_FORCE_GEMM) return (mmq_tc_eligible(a) || mmq_tc_eligible_small(a)) ? GGML_B200_MM_FORCE_GEMM : GGML_B200_EUNSUPPORTED;
     // 5..8 columns of very long rows: the superblock kernel would need two column-group launches (each re-streaming W, issue-bound); the
     // tensor-core kernel takes them in one pass (fp16-operand tolerance instead of the integer-exact dot: DESIGN.md section 3)
+    if (a.N <= 8 && mma_wanted(a)) return GGML_B200_MM_FORCE_GEMV;
     if (a.N >= 5 && a.N <= 8 && !mmvq_sb_eligible(a) && mmq_tc_eligible_small(a)) return GGML_B200_MM_FORCE_GEMM;
     if (a.N <= 8 && (mmvq_sb_eligible(a) || mmvq_tma_eligible(a))) return GGML_B200_MM_FORCE_GEMV;
     if (a.N > 8 && mmq_tc_eligible(a)) return GGML_B200_MM_FORCE_GEMM;
@@ -122,6 +132,7 @@ int ggml_b200_mul_mat(const ggml_b200_mul_mat_args * args, void * stream) {
         case GGML_B200_MM_FORCE_GEMV:
             // the superblock kernel (mmvq_sb.cu) for 1 <= n <= 8; the first-generation unit kernel (mmvq.cu) on request or as the last resort
             if (!(args->flags & GGML_B200_MM_GEMV_V1)) {
+                if (mma_wanted(*args)) return launch_mmvq_mma(*args, st);
                 if (mmvq_sb_eligible(*args)) return launch_mmvq_sb(*args, st);
                 // long rows x many columns: the activation records of all columns do not fit next to the weight stages.  Column groups of
                 // 4 / 2 / 1 on the same kernel re-stream W per group, which is far cheaper than leaving the bandwidth kernel

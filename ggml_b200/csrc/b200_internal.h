@@ -53,6 +53,10 @@ int    debug_read_trace(unsigned long long * out);
 int    prepare_device();   // allocate the per-device control block (never inside a stream capture)
 int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cudaStream_t st);
 
+// mmvq_mma.cu (bandwidth path, int8 mma.sync consume phase: 2 <= n <= 8, n = 1 on request)
+bool   mmvq_mma_eligible(const ggml_b200_mul_mat_args & a);
+int    launch_mmvq_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+
 // mmq_tc.cu (tcgen05 GEMM)
 bool   mmq_tc_eligible(const ggml_b200_mul_mat_args & a);
 size_t mmq_tc_workspace(const ggml_b200_mul_mat_args & a);

@@ -1,0 +1,222 @@
+// b200_sb_mma.cuh — small-batch consume path of the bandwidth mat-vec kernel on the int8 tensor-core instruction
+// `mma.sync.aligned.m16n8k32.s32.s8.s8.s32`: one warp multiplies a tile of 16 weight rows x 32 weights with 8 activation columns.
+//
+// Why (profiles/r02_vs_reference_cuda.md): with 2..8 activation columns the dp4a task dots of b200_sb_tasks.cuh are issue-bound — a
+// lane decodes its 256 weights once and then pays one dp4a per 4 weights per COLUMN, and every column's int8 record is re-read from
+// shared memory per row.  Here a warp's 32 lanes hold the 16 x 32 weight fragment and the 32 x 8 activation fragment of one
+// sub-block, so eight columns cost the instructions of one, the activations are read once per 16 rows, and the arithmetic stays the
+// reference's: integer dot products of the same int8 codes (ggml-cpu's quantize_row_q8_0 / q8_K), f32 scaling per block.
+//
+// Fragment layout (PTX ISA, m16n8k32 .s8): lane = 4 g + t.  A: a0 = row g, k-slots 4t..4t+3; a1 = row g+8, same slots; a2 / a3 = the
+// same rows, slots 16+4t..  B: b0 = column g, slots 4t..; b1 = slots 16+4t..  D: c0 = (row g, col 2t), c1 = (g, 2t+1), c2 = (g+8, 2t),
+// c3 = (g+8, 2t+1).  The sum over k is order-free, so slot s of lane t is mapped to weight / activation index 8t + (s & 3) + 4 (s >> 4)
+// of the sub-block: every lane then fetches its slots with ONE 8-byte load from the packed weights and one from the int8 activations.
+//
+// Pure per-thread code (plus the mma), compiled for the host by tests/hostemu (the mma becomes an exchange between 32 lockstep threads).
+#pragma once
+#include "b200_sb_tasks.cuh"
+
+namespace b200 {
+
+// ----------------------------------------------------------------------------- planar activation records (one per column)
+//   +0        q   : K int8 codes in natural order
+//   +off_h32  h32 : per 32-value block one int16 sum of its codes (16 bytes per 256-value task)
+//   +off_s16  s16 : (formats with 16-wide scale groups) per 16 values one int16 sum (32 bytes per task); absent otherwise
+//   +off_d    d   : Q8_K family: one float per task; Q8_0 family: one float per 32-value block (fp16-rounded)
+// col_bytes = 32 (mod 128): the eight columns' 8-byte fragment loads of a half-warp fall into distinct bank groups.
+struct mma_act {
+    int32_t ntask, off_h32, off_s16, off_d, col_bytes;
+};
+__host__ __device__ inline mma_act make_mma_act(int64_t K, bool kq, bool s16) {
+    mma_act A;
+    A.ntask = (int32_t)(K / 256);
+    A.off_h32 = (int32_t)K;
+    A.off_s16 = A.off_h32 + 16 * A.ntask;
+    A.off_d = A.off_s16 + (s16 ? 32 * A.ntask : 0);
+    int32_t bytes = A.off_d + (kq ? 4 : 32) * A.ntask;
+    bytes = (bytes + 31) & ~31;
+    while ((bytes & 127) != 32) bytes += 32;
+    A.col_bytes = bytes;
+    return A;
+}
+
+// half a warp quantizes act-task t of one column into the planar record at `col` (same arithmetic as sb_quantize_task_h)
+template <bool KQ, bool S16> __device__ __forceinline__ void mma_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * col, const mma_act & A, int t) {
+    const int l = threadIdx.x & 15;
+    const sb_qtask r = sb_quantize_core<KQ>(x, valid, t);
+    if (valid) {
+        *(int4 *)(col + 256 * t + 16 * l) = r.pk;
+        if constexpr (S16) *(int16_t *)(col + A.off_s16 + 32 * t + 2 * l) = (int16_t)r.s;
+        if ((l & 1) == 0) *(int16_t *)(col + A.off_h32 + 16 * t + 2 * (l >> 1)) = (int16_t)r.s2;
+        if constexpr (KQ) { if (l == 0) *(float *)(col + A.off_d + 4 * t) = r.d; }
+        else              { if ((l & 1) == 0) *(float *)(col + A.off_d + 32 * t + 4 * (l >> 1)) = r.d; }
+    }
+}
+
+// ----------------------------------------------------------------------------- the instruction
+#ifndef B200_HOST_EMU
+__device__ __forceinline__ void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+// 8 bytes at an address whose residue mod 8 is the compile-time constant R (block formats are only 2-byte aligned): aligned loads + funnel shifts
+template <int R> __device__ __forceinline__ uint2 lds8(const uint8_t * p) {
+    static_assert(R == 0 || R == 2 || R == 4 || R == 6, "two-byte aligned");
+    if constexpr (R == 0) return *(const uint2 *)p;
+    else if constexpr (R == 4) { uint2 v; v.x = *(const uint32_t *)p; v.y = *(const uint32_t *)(p + 4); return v; }
+    else if constexpr (R == 2) {
+        const uint2 lo = *(const uint2 *)(p - 2); const uint32_t hi = *(const uint32_t *)(p + 6);
+        uint2 v; v.x = __funnelshift_r(lo.x, lo.y, 16); v.y = __funnelshift_r(lo.y, hi, 16); return v;
+    } else {
+        const uint32_t lo = *(const uint32_t *)(p - 2); const uint2 hi = *(const uint2 *)(p + 2);
+        uint2 v; v.x = __funnelshift_r(lo, hi.x, 16); v.y = __funnelshift_r(hi.x, hi.y, 16); return v;
+    }
+}
+__device__ __forceinline__ uint32_t lds_u16(const uint8_t * p) { return *(const uint16_t *)p; }
+#else
+// host restatement: every lane publishes its fragments, then computes its four outputs from all lanes' fragments
+inline void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    static uint32_t fr[32][6];
+    const int lane = (int)(threadIdx.x & 31);
+    fr[lane][0] = a0; fr[lane][1] = a1; fr[lane][2] = a2; fr[lane][3] = a3; fr[lane][4] = b0; fr[lane][5] = b1;
+    pthread_barrier_wait(&warp_emu::barrier());
+    const int g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + 8 * (i >> 1), coln = 2 * t + (i & 1);
+        int sum = 0;
+        for (int tt = 0; tt < 4; ++tt) {
+            const uint32_t * A = fr[4 * (row & 7) + tt], * B = fr[4 * coln + tt];
+            const uint32_t alo = A[row >> 3], ahi = A[2 + (row >> 3)];
+            sum = __dp4a((int)alo, (int)B[4], sum);
+            sum = __dp4a((int)ahi, (int)B[5], sum);
+        }
+        c[i] = sum;
+    }
+    pthread_barrier_wait(&warp_emu::barrier());
+}
+template <int R> inline uint2 lds8(const uint8_t * p) { uint2 v; std::memcpy(&v, p, 8); return v; }
+inline uint32_t lds_u16(const uint8_t * p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
+#endif
+
+// what a lane needs of the activation columns for one task: its B column (fragment loads) and its two output columns (sums, scales)
+struct mma_cols {
+    const uint8_t * b;       // column g (clamped to the last real column): B fragments
+    const uint8_t * c0, * c1;   // columns 2t and 2t+1 (clamped): h32 / s16 / d of the outputs this lane accumulates
+};
+
+// bytes of a 256-weight task in the packed row
+template <int T> struct mmafmt;
+template <> struct mmafmt<T_Q4_K> { static constexpr int TASK_B = 144; static constexpr bool KQ = true,  S16 = false; };
+template <> struct mmafmt<T_Q5_K> { static constexpr int TASK_B = 176; static constexpr bool KQ = true,  S16 = false; };
+template <> struct mmafmt<T_Q4_0> { static constexpr int TASK_B = 144; static constexpr bool KQ = false, S16 = false; };
+template <> struct mmafmt<T_Q8_0> { static constexpr int TASK_B = 272; static constexpr bool KQ = false, S16 = false; };
+
+// One task (256 weights) of rows g (w0) and g+8 (w1) against the eight columns: facc[i] += the task's contribution to output i of the
+// D fragment.  `task` = index of the task in the row (selects the activation slice), t = lane & 3.
+template <int T> __device__ __forceinline__ void mma_task(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]);
+
+template <bool FIVE>
+__device__ __forceinline__ void mma_q45_task(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    const int4 hA = lds128(w0), hB = lds128(w1);                    // d | dmin | scales[12] of the two rows
+    // the 6-bit (scale, min) pairs of get_scale_min_k4, four sub-blocks per word (as q45_task)
+    const uint32_t scA[2] = { (uint32_t)hA.y & 0x3F3F3F3Fu, ((uint32_t)hA.w & 0x0F0F0F0Fu) | (((uint32_t)hA.y >> 2) & 0x30303030u) };
+    const uint32_t mnA[2] = { (uint32_t)hA.z & 0x3F3F3F3Fu, (((uint32_t)hA.w >> 4) & 0x0F0F0F0Fu) | (((uint32_t)hA.z >> 2) & 0x30303030u) };
+    const uint32_t scB[2] = { (uint32_t)hB.y & 0x3F3F3F3Fu, ((uint32_t)hB.w & 0x0F0F0F0Fu) | (((uint32_t)hB.y >> 2) & 0x30303030u) };
+    const uint32_t mnB[2] = { (uint32_t)hB.z & 0x3F3F3F3Fu, (((uint32_t)hB.w >> 4) & 0x0F0F0F0Fu) | (((uint32_t)hB.z >> 2) & 0x30303030u) };
+    uint2 qhA = { 0, 0 }, qhB = { 0, 0 };
+    if constexpr (FIVE) { qhA = *(const uint2 *)(w0 + 16 + 8 * t); qhB = *(const uint2 *)(w1 + 16 + 8 * t); }   // bit j of byte i = high bit of weight i of sub-block j
+    const uint8_t * qa = w0 + (FIVE ? 48 : 16) + 8 * t, * qb = w1 + (FIVE ? 48 : 16) + 8 * t;
+    const uint8_t * y = C.b + 256 * task + 8 * t;
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {                                   // 64 weights: sub-block 2p in the low nibbles, 2p+1 in the high ones
+        const uint2 wa = *(const uint2 *)(qa + 32 * p), wb = *(const uint2 *)(qb + 32 * p);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * p + h;
+            const uint2 yy = *(const uint2 *)(y + 32 * j);
+            uint32_t a0 = (wa.x >> (4 * h)) & 0x0F0F0F0Fu, a2 = (wa.y >> (4 * h)) & 0x0F0F0F0Fu;
+            uint32_t a1 = (wb.x >> (4 * h)) & 0x0F0F0F0Fu, a3 = (wb.y >> (4 * h)) & 0x0F0F0F0Fu;
+            if constexpr (FIVE) {
+                a0 |= ((qhA.x >> j) & 0x01010101u) << 4; a2 |= ((qhA.y >> j) & 0x01010101u) << 4;
+                a1 |= ((qhB.x >> j) & 0x01010101u) << 4; a3 |= ((qhB.y >> j) & 0x01010101u) << 4;
+            }
+            int c[4];
+            mma_s8_16x8x32(c, a0, a1, a2, a3, yy.x, yy.y);
+            const int sa = (j & 3) == 0 ? ubyte<0>(scA[j >> 2]) : (j & 3) == 1 ? ubyte<1>(scA[j >> 2]) : (j & 3) == 2 ? ubyte<2>(scA[j >> 2]) : ubyte<3>(scA[j >> 2]);
+            const int sb = (j & 3) == 0 ? ubyte<0>(scB[j >> 2]) : (j & 3) == 1 ? ubyte<1>(scB[j >> 2]) : (j & 3) == 2 ? ubyte<2>(scB[j >> 2]) : ubyte<3>(scB[j >> 2]);
+            acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+        }
+    }
+    // mins: sum_j min_j(row) * (sum of the 32 activations of sub-block j)(column), two sub-blocks per dp2a
+    const int4 s0 = lds128(C.c0 + A.off_h32 + 16 * task), s1 = lds128(C.c1 + A.off_h32 + 16 * task);
+    auto mins = [](const int4 & s, const uint32_t (&mn)[2]) {
+        int m = dp2a_lo_su(s.x, mn[0], 0);
+        m = dp2a_hi_su(s.y, mn[0], m);
+        m = dp2a_lo_su(s.z, mn[1], m);
+        return dp2a_hi_su(s.w, mn[1], m);
+    };
+    const float yd0 = *(const float *)(C.c0 + A.off_d + 4 * task), yd1 = *(const float *)(C.c1 + A.off_d + 4 * task);
+    const float dA = h2f((uint32_t)hA.x & 0xFFFF), mA = h2f((uint32_t)hA.x >> 16), dB = h2f((uint32_t)hB.x & 0xFFFF), mB = h2f((uint32_t)hB.x >> 16);
+    facc[0] += (dA * yd0) * (float)acc[0] - (mA * yd0) * (float)mins(s0, mnA);
+    facc[1] += (dA * yd1) * (float)acc[1] - (mA * yd1) * (float)mins(s1, mnA);
+    facc[2] += (dB * yd0) * (float)acc[2] - (mB * yd0) * (float)mins(s0, mnB);
+    facc[3] += (dB * yd1) * (float)acc[3] - (mB * yd1) * (float)mins(s1, mnB);
+}
+template <> __device__ __forceinline__ void mma_task<T_Q4_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_q45_task<false>(w0, w1, C, A, task, t, facc); }
+template <> __device__ __forceinline__ void mma_task<T_Q5_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_q45_task<true>(w0, w1, C, A, task, t, facc); }
+
+// 32-weight block formats (Q4_0: 18-byte blocks, weight i in the low nibble of byte i, weight i + 16 in the high one; Q8_0: 34-byte
+// blocks of int8): a task = eight blocks.  Block b starts at BLK * b from a 16-byte aligned task base, its codes 2 bytes later:
+// the residue of every 8-byte fragment load mod 8 is (2 b + 2) mod 8, a compile-time constant.
+template <int T, int B>
+__device__ __forceinline__ void mma_blk32(const uint8_t * w0, const uint8_t * w1, const uint8_t * y, const int4 & s0, const int4 & s1,
+                                         const float (&yd0)[8], const float (&yd1)[8], int t, float (&facc)[4]) {
+    constexpr bool NIB = T == T_Q4_0;
+    constexpr int BLK = NIB ? 18 : 34, R = (2 * B + 2) & 7;
+    const int off = BLK * B + 2 + (NIB ? 8 * (t & 1) : 8 * t);
+    const uint2 wa = lds8<R>(w0 + off), wb = lds8<R>(w1 + off);
+    const uint2 yy = *(const uint2 *)(y + 32 * B);
+    uint32_t a0 = wa.x, a2 = wa.y, a1 = wb.x, a3 = wb.y;
+    if constexpr (NIB) {                                            // lanes t = 0, 1 hold weights 0..15 (low nibbles), t = 2, 3 weights 16..31 (high nibbles)
+        const int sh = (t >> 1) * 4;
+        a0 = (a0 >> sh) & 0x0F0F0F0Fu; a2 = (a2 >> sh) & 0x0F0F0F0Fu; a1 = (a1 >> sh) & 0x0F0F0F0Fu; a3 = (a3 >> sh) & 0x0F0F0F0Fu;
+    }
+    int c[4];
+    mma_s8_16x8x32(c, a0, a1, a2, a3, yy.x, yy.y);
+    const float dA = h2f(lds_u16(w0 + BLK * B)), dB = h2f(lds_u16(w1 + BLK * B));
+    if constexpr (NIB) {                                            // codes are q - 8: subtract 8 x (sum of the block's activations)
+        const int * p0 = &s0.x, * p1 = &s1.x;
+        const int h0 = (B & 1) ? (p0[B >> 1] >> 16) : (int)(int16_t)(p0[B >> 1] & 0xFFFF);
+        const int h1 = (B & 1) ? (p1[B >> 1] >> 16) : (int)(int16_t)(p1[B >> 1] & 0xFFFF);
+        c[0] -= 8 * h0; c[1] -= 8 * h1; c[2] -= 8 * h0; c[3] -= 8 * h1;
+        facc[0] += (float)c[0] * dA * yd0[B]; facc[1] += (float)c[1] * dA * yd1[B];
+        facc[2] += (float)c[2] * dB * yd0[B]; facc[3] += (float)c[3] * dB * yd1[B];
+    } else {
+        facc[0] += (float)c[0] * (dA * yd0[B]); facc[1] += (float)c[1] * (dA * yd1[B]);
+        facc[2] += (float)c[2] * (dB * yd0[B]); facc[3] += (float)c[3] * (dB * yd1[B]);
+    }
+}
+template <int T>
+__device__ __forceinline__ void mma_blk32_task(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    const uint8_t * y = C.b + 256 * task + 8 * t;
+    int4 s0 = { 0, 0, 0, 0 }, s1 = { 0, 0, 0, 0 };
+    if constexpr (T == T_Q4_0) { s0 = lds128(C.c0 + A.off_h32 + 16 * task); s1 = lds128(C.c1 + A.off_h32 + 16 * task); }
+    float yd0[8], yd1[8];
+    {
+        const int4 a = lds128(C.c0 + A.off_d + 32 * task), b = lds128(C.c0 + A.off_d + 32 * task + 16);
+        const int4 c = lds128(C.c1 + A.off_d + 32 * task), d = lds128(C.c1 + A.off_d + 32 * task + 16);
+        yd0[0] = __int_as_float(a.x); yd0[1] = __int_as_float(a.y); yd0[2] = __int_as_float(a.z); yd0[3] = __int_as_float(a.w);
+        yd0[4] = __int_as_float(b.x); yd0[5] = __int_as_float(b.y); yd0[6] = __int_as_float(b.z); yd0[7] = __int_as_float(b.w);
+        yd1[0] = __int_as_float(c.x); yd1[1] = __int_as_float(c.y); yd1[2] = __int_as_float(c.z); yd1[3] = __int_as_float(c.w);
+        yd1[4] = __int_as_float(d.x); yd1[5] = __int_as_float(d.y); yd1[6] = __int_as_float(d.z); yd1[7] = __int_as_float(d.w);
+    }
+    mma_blk32<T, 0>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 1>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
+    mma_blk32<T, 2>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 3>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
+    mma_blk32<T, 4>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 5>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
+    mma_blk32<T, 6>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 7>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
+}
+template <> __device__ __forceinline__ void mma_task<T_Q4_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q4_0>(w0, w1, C, A, task, t, facc); }
+template <> __device__ __forceinline__ void mma_task<T_Q8_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q8_0>(w0, w1, C, A, task, t, facc); }
+
+} // namespace b200

@@ -62,7 +62,15 @@ __host__ __device__ inline sb_act make_sb_act(int64_t K) {
 // Numerics: exactly ggml-cpu's quantize_row_q8_K (KQ) / AVX2 quantize_row_q8_0 (see b200_quants.cuh).
 // Q81S (Q8_0 family only): the H32 slot receives block_q8_1.s = fp16(d_unrounded * sum of the block's codes) instead of the int16 sums
 // (weight formats with a minimum, Q4_1 / Q5_1).  Q81S = false is the code path of the hot-path formats, unchanged.
-template <bool KQ, bool Q81S = false> __device__ __forceinline__ void sb_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * rec, int t) {
+// The arithmetic is sb_quantize_core (shared with the planar records of the mma path, b200_sb_mma.cuh); the wrappers only differ in
+// where the results are stored.
+struct sb_qtask {
+    int4  pk;        // this lane's 16 codes, packed
+    int   s, s2;     // sum of the lane's 16 codes; sum of the 32-value block (lanes 2b, 2b+1)
+    float d;         // KQ: the task's scale 1 / iscale (0 for an all-zero task); else the block's fp16-rounded scale
+    float dun;       // Q8_0 family: the block's unrounded scale amax / 127
+};
+template <bool KQ> __device__ __forceinline__ sb_qtask sb_quantize_core(const float * __restrict__ x, bool valid, int t) {
     const int l = threadIdx.x & 15;
     float v[16];
     if (valid) {
@@ -72,9 +80,9 @@ template <bool KQ, bool Q81S = false> __device__ __forceinline__ void sb_quantiz
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.0f;
     }
-    uint8_t * rb = rec + (size_t)t * SB_REC;
+    sb_qtask r;
     int q[16];
-    float dun = 0.0f;                                            // Q8_0 family: the block's unrounded scale amax / 127
+    r.dun = 0.0f; r.d = 0.0f;
     if constexpr (KQ) {
         float amax = 0.0f, vmax = 0.0f; int imax = 0;
 #pragma unroll
@@ -85,17 +93,15 @@ template <bool KQ, bool Q81S = false> __device__ __forceinline__ void sb_quantiz
             const int   oi = __shfl_xor_sync(0xffffffffu, imax, o);
             if (oa > amax || (oa == amax && oi < imax)) { amax = oa; vmax = ov; imax = oi; }
         }
-        float d = 0.0f;
         if (amax != 0.0f) {
             const float iscale = __fdiv_rn(-127.0f, vmax);
 #pragma unroll
             for (int i = 0; i < 16; ++i) q[i] = min(127, __float2int_rn(iscale * v[i]));
-            d = __fdiv_rn(1.0f, iscale);
+            r.d = __fdiv_rn(1.0f, iscale);
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) q[i] = 0;
         }
-        if (l == 0 && valid) *(float *)(rb + SB_OFF_D) = d;
     } else {
         float amax = 0.0f;
 #pragma unroll
@@ -104,24 +110,34 @@ template <bool KQ, bool Q81S = false> __device__ __forceinline__ void sb_quantiz
         const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) q[i] = __float2int_rn(v[i] * id);
-        dun = __fdiv_rn(amax, 127.0f);
-        if ((l & 1) == 0 && valid) *(float *)(rb + SB_OFF_D + 4 * (l >> 1)) = __half2float(__float2half_rn(dun));
+        r.dun = __fdiv_rn(amax, 127.0f);
+        r.d = __half2float(__float2half_rn(r.dun));
     }
-    int4 pk; int s = 0;
-    int * pw = &pk.x;
+    int s = 0;
+    int * pw = &r.pk.x;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         pw[w] = (int)((uint32_t)(q[4 * w] & 0xFF) | ((uint32_t)(q[4 * w + 1] & 0xFF) << 8) | ((uint32_t)(q[4 * w + 2] & 0xFF) << 16) | ((uint32_t)(q[4 * w + 3] & 0xFF) << 24));
         s += q[4 * w] + q[4 * w + 1] + q[4 * w + 2] + q[4 * w + 3];
     }
-    const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);
+    r.s = s;
+    r.s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);
+    return r;
+}
+
+template <bool KQ, bool Q81S = false> __device__ __forceinline__ void sb_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * rec, int t) {
+    const int l = threadIdx.x & 15;
+    const sb_qtask r = sb_quantize_core<KQ>(x, valid, t);
+    uint8_t * rb = rec + (size_t)t * SB_REC;
     if (valid) {
-        *(int4 *)(rb + 16 * l) = pk;
-        *(int16_t *)(rb + SB_OFF_S16 + 2 * l) = (int16_t)s;
+        if constexpr (KQ) { if (l == 0) *(float *)(rb + SB_OFF_D) = r.d; }
+        else              { if ((l & 1) == 0) *(float *)(rb + SB_OFF_D + 4 * (l >> 1)) = r.d; }
+        *(int4 *)(rb + 16 * l) = r.pk;
+        *(int16_t *)(rb + SB_OFF_S16 + 2 * l) = (int16_t)r.s;
         if ((l & 1) == 0) {
-            *(int32_t *)(rb + SB_OFF_S32 + 4 * (l >> 1)) = s2;
-            if constexpr (!KQ && Q81S) *(__half *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = __float2half_rn(__fmul_rn(dun, (float)s2));
-            else                       *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)s2;   // |s2| <= 32 * 127
+            *(int32_t *)(rb + SB_OFF_S32 + 4 * (l >> 1)) = r.s2;
+            if constexpr (!KQ && Q81S) *(__half *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = __float2half_rn(__fmul_rn(r.dun, (float)r.s2));
+            else                       *(int16_t *)(rb + SB_OFF_H32 + 2 * (l >> 1)) = (int16_t)r.s2;   // |s2| <= 32 * 127
         }
     }
 }

@@ -1,0 +1,255 @@
+// mmvq_mma.cu — the bandwidth-path quantized mat-mul for small batches (2 <= n <= 8; n = 1 on request) on int8 mma.sync.
+//
+// Same streaming skeleton as mmvq_sb.cu (persistent CTAs, one TMA producer warp, a ring of bulk-copy stages with full / empty
+// mbarriers, chunks handed out by a self-resetting atomic slot, programmatic dependent launch, weights read once from HBM in the
+// reference's packed layout), different consume phase (b200_sb_mma.cuh):
+//   * a chunk is a TILE of 16 weight rows; the eight consumer warps split the tile's K range by 256-weight task (task i of a slice
+//     goes to warp i mod 8), each multiplying its 16 x 256 weights with all (<= 8) activation columns on the tensor cores
+//     (m16n8k32, int8 x int8 -> int32, exactly the integer block dots of ggml-cpu) and keeping 4 f32 partial outputs per lane;
+//   * rows too long for a ring of whole-row stages are streamed in K slices of KS tasks (consecutive stages of the same tile, the
+//     accumulators stay in registers across them);
+//   * every row of a stage is its own bulk copy into a padded pitch (= 32 mod 128 bytes), so that the 8-byte fragment loads of the
+//     four row groups of a half-warp fall into distinct bank groups;
+//   * at the end of a tile the eight partial fragments meet in shared memory (double-buffered, one named barrier per tile) and are
+//     summed in a fixed order: results are bitwise repeatable.
+// Activations: quantized once per CTA into planar per-column records (int8 codes + block sums + scales), as ggml-cpu quantizes them.
+#include "b200_internal.h"
+#include "b200_quants.cuh"
+#include "b200_sb_ptx.cuh"
+#include "b200_sb_mma.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace b200 {
+
+constexpr int MMA_MAX_STAGES = 8;
+constexpr int MMA_WARPS = 8;             // consumer warps
+constexpr int MMA_TILE = 16;             // rows per tile (the m of m16n8k32)
+
+struct mma_params {
+    const uint8_t * w; const float * x; float * y;
+    int64_t M, K;
+    int32_t row_bytes, ntiles, nslices, ks, ntask_row, pitch, stage_bytes, nstages;
+    unsigned int * counters;      // this launch's scheduling slot: [0] next tile, [1] finished producers
+    int32_t ncols; int64_t x_stride;
+    int32_t src1_static, src0_static;
+    int64_t l2_prefetch_bytes;
+    mma_act A;
+};
+
+template <int T>
+__global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const mma_params p) {
+    using F = mmafmt<T>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t * stages = smem;
+    uint8_t * rec    = stages + (size_t)p.nstages * p.stage_bytes;                  // ncols planar records
+    float * partial  = (float *)(rec + (size_t)p.ncols * p.A.col_bytes);            // [2][MMA_WARPS][128]
+    uint64_t * full  = (uint64_t *)(partial + 2 * MMA_WARPS * 128);
+    uint64_t * empty = full + MMA_MAX_STAGES;
+    int2 * unit_of   = (int2 *)(empty + MMA_MAX_STAGES);                            // (tile, slice) held by each stage; tile < 0 = end
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) { sb_mbar_init(&full[s], 1); sb_mbar_init(&empty[s], MMA_WARPS); }
+        sb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == MMA_WARPS) {
+        // ===== producer warp: lane r copies row r of the tile (slice) — sixteen bulk copies per stage, one barrier
+        if (!p.src0_static) pdl_wait();
+        int it = 0;
+        int tile = (int)blockIdx.x;
+        bool first = true;
+        while (true) {
+            const bool valid = tile < p.ntiles;
+            // the next tile index is fetched (one global atomic round trip) before this tile's stages are waited for
+            int next = 0;
+            if (valid && lane == 0) next = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
+            const int nsl = valid ? p.nslices : 1;
+            for (int sl = 0; sl < nsl; ++sl, ++it) {
+                const int s = it % p.nstages;
+                if (it >= p.nstages) sb_mbar_wait(&empty[s], (uint32_t)((it / p.nstages) - 1) & 1u);
+                if (valid) {
+                    const int64_t row0 = (int64_t)tile * MMA_TILE;
+                    const int rows = (int)min((int64_t)MMA_TILE, p.M - row0);
+                    const int nt = min(p.ks, p.ntask_row - sl * p.ks);
+                    const uint32_t seg = (uint32_t)nt * (uint32_t)F::TASK_B;
+                    if (lane == 0) { unit_of[s] = make_int2(tile, sl); sb_mbar_expect_tx(&full[s], (uint32_t)rows * seg); }
+                    __syncwarp();
+                    if (lane < rows)
+                        sb_tma_g2s(stages + (size_t)s * p.stage_bytes + (size_t)lane * p.pitch,
+                                   p.w + (size_t)(row0 + lane) * p.row_bytes + (size_t)sl * p.ks * F::TASK_B, seg, &full[s]);
+                } else if (lane == 0) {
+                    unit_of[s] = make_int2(-1, 0);
+                    sb_mbar_arrive(&full[s]);                       // publish the end marker
+                }
+            }
+            if (first && p.l2_prefetch_bytes > 0 && lane == 0) {
+                // a dependent launch cannot consume before its predecessor's output is visible, but HBM need not idle meanwhile:
+                // CTA b pulls slice b of the matrix into L2, the ring then streams from L2
+                const int64_t per = ((p.l2_prefetch_bytes + gridDim.x - 1) / gridDim.x + 15) & ~(int64_t)15;
+                const int64_t lo = (int64_t)blockIdx.x * per;
+                const int64_t hi = min(lo + per, p.l2_prefetch_bytes & ~(int64_t)15);
+                for (int64_t o = lo; o < hi; o += 32768) sb_prefetch_l2(p.w + o, (uint32_t)min((int64_t)32768, hi - o));
+            }
+            first = false;
+            if (!valid) break;
+            tile = __shfl_sync(0xffffffffu, next, 0);
+        }
+        if (lane == 0) {
+            // last CTA to finish its scheduling resets the counters for the next launch
+            __threadfence();
+            if (atomicAdd(&p.counters[1], 1u) == gridDim.x - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
+        }
+        return;
+    }
+
+    // ===== consumers: quantize the activation columns (needs the previous kernel's output), one act-task per half-warp per round
+    if (!p.src1_static) pdl_wait();
+    for (int i0 = 2 * warp; i0 < p.ncols * p.A.ntask; i0 += 2 * MMA_WARPS) {
+        const int i = i0 + (lane >> 4);
+        const bool ok = i < p.ncols * p.A.ntask;
+        const int c = ok ? i / p.A.ntask : 0, t = ok ? i % p.A.ntask : 0;
+        mma_quantize_task_h<F::KQ, F::S16>(p.x + (size_t)c * p.x_stride, ok, rec + (size_t)c * p.A.col_bytes, p.A, t);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");              // consumers only
+
+    const int g = lane >> 2, t = lane & 3;
+    mma_cols C;
+    C.b  = rec + (size_t)min(g, p.ncols - 1) * p.A.col_bytes;                       // columns beyond n repeat the last one (results discarded)
+    C.c0 = rec + (size_t)min(2 * t, p.ncols - 1) * p.A.col_bytes;
+    C.c1 = rec + (size_t)min(2 * t + 1, p.ncols - 1) * p.A.col_bytes;
+    float facc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    int buf = 0;
+    for (int it = 0;; ++it) {
+        const int s = it % p.nstages;
+        sb_mbar_wait(&full[s], (uint32_t)(it / p.nstages) & 1u);
+        const int2 unit = unit_of[s];
+        if (unit.x < 0) break;
+        const int nt = min(p.ks, p.ntask_row - unit.y * p.ks);
+        const uint8_t * st = stages + (size_t)s * p.stage_bytes + (size_t)g * p.pitch;
+        for (int i = warp; i < nt; i += MMA_WARPS)
+            mma_task<T>(st + (size_t)i * F::TASK_B, st + (size_t)i * F::TASK_B + (size_t)8 * p.pitch, C, p.A, unit.y * p.ks + i, t, facc);
+        __syncwarp();
+        if (lane == 0) sb_mbar_arrive(&empty[s]);
+        if (unit.y == p.nslices - 1) {
+            // tile finished: the eight warps' partial fragments meet in shared memory and are summed in warp order
+            float * part = partial + buf * (MMA_WARPS * 128);
+            *(float4 *)(part + warp * 128 + lane * 4) = make_float4(facc[0], facc[1], facc[2], facc[3]);
+            facc[0] = facc[1] = facc[2] = facc[3] = 0.0f;
+            asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");
+            if (tid < 128) {
+                // thread o writes (column o / 16, row o % 16): consecutive threads, consecutive rows of one column
+                const int col = tid >> 4, row = tid & 15;
+                const int src = ((row & 7) * 4 + (col >> 1)) * 4 + (row >> 3) * 2 + (col & 1);
+                float sum = part[src];
+#pragma unroll
+                for (int w = 1; w < MMA_WARPS; ++w) sum += part[w * 128 + src];
+                const int64_t grow = (int64_t)unit.x * MMA_TILE + row;
+                if (col < p.ncols && grow < p.M) p.y[(size_t)col * p.M + grow] = sum;
+            }
+            buf ^= 1;
+        }
+    }
+    // completion stays transitive along the stream: a launch whose consumers did not wait for the preceding grid does so before it retires
+    if (p.src1_static && tid == 0) pdl_wait();
+}
+
+struct mma_plan { mma_params p; int grid, smem; };
+
+template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma_plan & pl) {
+    using F = mmafmt<T>;
+    if (a.N < 1 || a.N > 8 || a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
+    if (a.N > 1 && ((a.nb11 & 3) != 0 || a.nb11 < (size_t)a.K * 4)) return false;
+    if (a.K % 256 != 0 || a.K < 2048 || a.M < MMA_TILE || a.K > 65536) return false;      // K >= 2048: every consumer warp has a task
+    const size_t rb = row_bytes(a.type, a.K);
+    if (a.nb01 != rb || (rb & 15) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 15) != 0 || (a.nb11 & 15) != 0) return false;
+    mma_params & p = pl.p;
+    p.w = (const uint8_t *)a.src0; p.x = a.src1; p.y = a.dst; p.M = a.M; p.K = a.K;
+    p.row_bytes = (int)rb;
+    p.ntiles = (int)((a.M + MMA_TILE - 1) / MMA_TILE);
+    p.ntask_row = (int)(a.K / 256);
+    p.A = make_mma_act(a.K, F::KQ, F::S16);
+    p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
+    p.counters = nullptr;
+    p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
+    p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
+    static const int e_l2_mb = getenv("GGML_B200_SB_L2_MB") ? atoi(getenv("GGML_B200_SB_L2_MB")) : 48;
+    p.l2_prefetch_bytes = (!p.src1_static && p.src0_static && e_l2_mb > 0) ? (int64_t)std::min<size_t>((size_t)a.M * rb, (size_t)e_l2_mb << 20) : 0;
+    // slices of KS tasks (a multiple of the warp count): whole rows when at least three such stages fit next to the records
+    static const int e_ks = getenv("GGML_B200_MMA_KS") ? atoi(getenv("GGML_B200_MMA_KS")) : 0;
+    static const int e_stages = getenv("GGML_B200_MMA_STAGES") ? atoi(getenv("GGML_B200_MMA_STAGES")) : 0;
+    const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * MMA_WARPS * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + MMA_MAX_STAGES * 8 + 128;
+    const size_t budget = 226 * 1024;
+    if (fixed + 2 * 8 * F::TASK_B * MMA_TILE > budget) return false;
+    auto geometry = [&](int ks) {
+        p.ks = ks;
+        p.nslices = (p.ntask_row + ks - 1) / ks;
+        int pitch = std::min(ks, p.ntask_row) * F::TASK_B;
+        pitch = (pitch + 31) & ~31;
+        while ((pitch & 127) != 32) pitch += 32;
+        p.pitch = pitch;
+        p.stage_bytes = (pitch * MMA_TILE + 127) & ~127;
+        return (int)std::min<size_t>((budget - fixed) / p.stage_bytes, MMA_MAX_STAGES);
+    };
+    int ks = e_ks > 0 ? e_ks : 16;                       // 16 tasks x 16 rows: 36 KB (Q4_K) .. 70 KB (Q8_0) per stage
+    if (ks > p.ntask_row) ks = p.ntask_row;
+    int nst = geometry(ks);
+    while (nst < 3 && ks > 8) { ks = std::max(8, ks / 2); nst = geometry(ks); }
+    if (nst < 2) return false;
+    if (e_stages >= 2 && e_stages <= nst) nst = e_stages;
+    // no deeper than the units a CTA can expect (+1): short launches should not pay for barrier set-up they never use
+    p.nstages = nst;
+    pl.smem = (int)(fixed + (size_t)p.nstages * p.stage_bytes);
+    pl.grid = std::min(sm_count(), p.ntiles);
+    return true;
+}
+
+template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+    mma_plan pl;
+    if (!make_mma_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the mma small-batch kernel"); return GGML_B200_EUNSUPPORTED; }
+    unsigned int * ctl = sb_control_block();
+    if (!ctl) return GGML_B200_ECUDA;
+    pl.p.counters = sb_next_slot(ctl);
+    static per_device_flag attr_set;
+    if (!attr_set.test()) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set.set();
+    }
+    static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((MMA_WARPS + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<T>, pl.p));
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
+bool mmvq_mma_eligible(const ggml_b200_mul_mat_args & a) {
+    mma_plan pl;
+    switch (a.type) {
+        case T_Q4_0: return make_mma_plan<T_Q4_0>(a, pl);
+        case T_Q8_0: return make_mma_plan<T_Q8_0>(a, pl);
+        case T_Q4_K: return make_mma_plan<T_Q4_K>(a, pl);
+        case T_Q5_K: return make_mma_plan<T_Q5_K>(a, pl);
+        default: return false;
+    }
+}
+
+int launch_mmvq_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+    switch (a.type) {
+        case T_Q4_0: return launch_mma<T_Q4_0>(a, st);
+        case T_Q8_0: return launch_mma<T_Q8_0>(a, st);
+        case T_Q4_K: return launch_mma<T_Q4_K>(a, st);
+        case T_Q5_K: return launch_mma<T_Q5_K>(a, st);
+        default: set_error("mul_mat: unsupported weight type %d for the mma kernel", a.type); return GGML_B200_EUNSUPPORTED;
+    }
+}
+
+} // namespace b200

@@ -24,6 +24,7 @@
 // (int8 activations quantized as ggml-cpu does, integer dots, f32 scaling); only the f32 summation order differs.
 #include "b200_internal.h"
 #include "b200_quants.cuh"
+#include "b200_sb_ptx.cuh"
 #include "b200_sb_tasks.cuh"   // dp4a_us, task geometry, activation-record layout, task dot products (also compiled for the host by tests/hostemu)
 
 #include <atomic>
@@ -31,42 +32,6 @@
 #include <mutex>
 
 namespace b200 {
-
-// ----------------------------------------------------------------------------- PTX helpers (as mmvq.cu)
-__device__ __forceinline__ uint32_t sb_smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sb_mbar_init(uint64_t * bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void sb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void sb_mbar_expect_tx(uint64_t * bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sb_mbar_arrive(uint64_t * bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sb_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void sb_mbar_wait(uint64_t * bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SB_DONE;\n"
-        "bra SB_WAIT;\n"
-        "SB_DONE:\n"
-        "}\n" ::"r"(sb_smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void sb_tma_g2s(void * dst_smem, const void * src_gmem, uint32_t bytes, uint64_t * bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sb_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(sb_smem_u32(bar)) : "memory");
-}
-// programmatic dependent launch: let the next kernel's prologue start / wait for the previous kernel's results
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// pull a byte range into L2 without occupying shared memory (bulk prefetch; 16-byte aligned address and size)
-__device__ __forceinline__ void sb_prefetch_l2(const void * src_gmem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // ----------------------------------------------------------------------------- kernel
 constexpr int SB_MAX_STAGES = 6;
@@ -328,6 +293,9 @@ static unsigned int * sb_counters() {
 }
 
 int prepare_device() { return sb_counters() ? GGML_B200_OK : GGML_B200_ECUDA; }
+unsigned int * sb_control_block() { return sb_counters(); }
+static std::atomic<unsigned> g_sb_slot_seq{0};
+unsigned int * sb_next_slot(unsigned int * ctl) { return ctl + 64 + (g_sb_slot_seq.fetch_add(1, std::memory_order_relaxed) % 64u) * 8; }
 
 template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_plan & pl) {
     using F = sbfmt<T>;
@@ -408,8 +376,7 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
 static int assign_sb_slot(sb_params & p) {
     p.ctl = sb_counters();
     if (!p.ctl) return GGML_B200_ECUDA;
-    static std::atomic<unsigned> seq{0};
-    p.counters = p.ctl + 64 + (seq.fetch_add(1, std::memory_order_relaxed) % 64u) * 8;
+    p.counters = sb_next_slot(p.ctl);
     static const bool env_dbg = getenv("GGML_B200_SB_DEBUG") && atoi(getenv("GGML_B200_SB_DEBUG")) != 0;
     static std::atomic<unsigned> dbg_seq{0};
     p.dbg = env_dbg ? (unsigned long long *)(p.ctl + 1024) + (dbg_seq.fetch_add(1, std::memory_order_relaxed) % 32u) * 8 : nullptr;

@@ -94,6 +94,8 @@ enum {
                                          independent mat-vecs overlap.  It still waits for them before it retires, so completion stays
                                          ordered along the stream.  NOT valid for "the kernel before the previous one produced src1". */
     GGML_B200_MM_GEMV_V1     = 8,     /* with FORCE_GEMV: the first-generation 64-weight-unit kernel (mmvq.cu) even for n = 1 */
+    GGML_B200_MM_GEMV_MMA    = 64,    /* bandwidth path: the int8 mma.sync consume kernel (mmvq_mma.cu; default for 2 <= n <= 8) also for n = 1 */
+    GGML_B200_MM_GEMV_DP4A   = 128,   /* bandwidth path: the dp4a task-dot kernel (mmvq_sb.cu; default for n = 1) also for 2 <= n <= 8 */
 };
 
 GGML_B200_API size_t ggml_b200_mul_mat_workspace_size(const ggml_b200_mul_mat_args * args);

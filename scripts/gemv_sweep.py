@@ -30,9 +30,9 @@ def time_mm(t, M, N, K, flags, reps=400):
     X = torch.rand(N * K, device="cuda") * 2 - 1
     Y = torch.empty((1, 1, N, M), device="cuda")
     Ys = [torch.empty((1, 1, N, M), device="cuda") for _ in range(nbuf)] if IND else [Y] * nbuf
-    if IND and flags == g.MM_GEMV:
+    if IND and (flags & g.MM_GEMV) and not (flags & g.MM_GEMV_V1):
         flags = flags | g.MM_SRC0_STATIC | g.MM_SRC1_STATIC
-    elif flags == g.MM_GEMV and not os.environ.get("SWEEP_NO_SRC0_STATIC"):
+    elif (flags & g.MM_GEMV) and not (flags & g.MM_GEMV_V1) and not os.environ.get("SWEEP_NO_SRC0_STATIC"):
         flags = flags | g.MM_SRC0_STATIC          # weights are graph leaves (what the backend passes)
     for i in range(nbuf):
         g.mul_mat(t, Ws[i], X, M, N, K, flags=flags, out=Ys[i])
@@ -65,6 +65,8 @@ def main():
     ap.add_argument("--v1", action="store_true")
     ap.add_argument("--independent", action="store_true", help="flag launches SRC0_STATIC|SRC1_STATIC and give each its own output")
     ap.add_argument("--both", action="store_true", help="time dependent and independent launches")
+    ap.add_argument("--dp4a", action="store_true", help="force the dp4a task-dot kernel (mmvq_sb.cu) also for n >= 2")
+    ap.add_argument("--mma", action="store_true", help="force the mma.sync kernel (mmvq_mma.cu) also for n = 1")
     a = ap.parse_args()
     global IND
     IND = a.independent
@@ -83,11 +85,13 @@ def run(a):
             M, K = (int(v) for v in sh.split("x"))
             K = K // 256 * 256
             for n in (int(v) for v in a.n.split(",")):
-                for flags in ([g.MM_GEMV] + ([g.MM_GEMV | g.MM_GEMV_V1] if a.v1 else []) + ([g.MM_GENERIC] if a.generic else [])):
-                    if flags != g.MM_GENERIC and g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
+                base = g.MM_GEMV | (g.MM_GEMV_DP4A if a.dp4a else 0) | (g.MM_GEMV_MMA if a.mma else 0)
+                for flags in ([base] + ([g.MM_GEMV | g.MM_GEMV_V1] if a.v1 else []) + ([g.MM_GENERIC] if a.generic else [])):
+                    if flags != g.MM_GENERIC and g.mul_mat_plan(t, M, n, K, flags) != g.MM_GEMV:
                         continue
                     us, wb = time_mm(t, M, n, K, flags)
-                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": {g.MM_GEMV: "gemv_ind" if IND else "gemv", g.MM_GEMV | g.MM_GEMV_V1: "gemv_v1"}.get(flags, "generic"),
+                    kname = ("dp4a" if a.dp4a else "mma" if (a.mma or n > 1) else "gemv") + ("_ind" if IND else "")
+                    print(json.dumps({"type": tn, "M": M, "K": K, "N": n, "kernel": {base: kname, g.MM_GEMV | g.MM_GEMV_V1: "gemv_v1"}.get(flags, "generic"),
                                       "us": round(us, 2), "GBps": round(wb / us / 1e3, 1), "tun": tun}), flush=True)
 
 

@@ -4,9 +4,11 @@
 // the PTX-level instructions (dp2a, prmt, tcgen05 ...) of the fast kernels — those are covered by the `-m gpu` parity tests.
 #define B200_HOST_EMU 1
 #include "cuda_shim.h"
+#include <vector>
 #include "../../ggml_b200/csrc/b200_dequant.cuh"
 #include "../../ggml_b200/csrc/b200_sb_tasks.cuh"
 #include "../../ggml_b200/csrc/b200_tc_dequant.cuh"
+#include "../../ggml_b200/csrc/b200_sb_mma.cuh"
 
 using namespace b200;
 
@@ -54,6 +56,34 @@ template <int T> static void sb_row_nc(const uint8_t * row, int64_t K, const uin
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int t = 0; t < (int)(K / sbfmt<T>::TASK_W); ++t) task_dot_nc<T, 8>(row + (size_t)t * sbfmt<T>::TASK_B, rec, rec_stride, t, ncols, acc);
     for (int c = 0; c < 8; ++c) out[c] = acc[c];
+}
+// ---- the mma small-batch consume path (b200_sb_mma.cuh): one emulated warp, a tile of 16 packed rows (row r at rows + r * pitch) against
+// ncols (<= 8) activation columns (column c at x + c * K): planar records by the kernel's quantizer, every task by mma_task; out[16][8]
+template <int T> static void mma_tile(const uint8_t * rows, int64_t pitch, int64_t K, const float * x, int ncols, float * out) {
+    using F = mmafmt<T>;
+    const mma_act A = make_mma_act(K, F::KQ, F::S16);
+    std::vector<uint8_t> rec((size_t)ncols * A.col_bytes + 64);
+    uint8_t * recp = rec.data();
+    warp_emu::run([&] {
+        const int lane = (int)(threadIdx.x & 31);
+        for (int i0 = 0; i0 < ncols * A.ntask; i0 += 2) {
+            const int i = i0 + (lane >> 4);
+            const bool ok = i < ncols * A.ntask;
+            const int c = ok ? i / A.ntask : 0, t = ok ? i % A.ntask : 0;
+            mma_quantize_task_h<F::KQ, F::S16>(x + (size_t)c * K, ok, recp + (size_t)c * A.col_bytes, A, t);
+        }
+        pthread_barrier_wait(&warp_emu::barrier());
+        const int g = lane >> 2, t = lane & 3;
+        mma_cols C;
+        C.b  = recp + (size_t)std::min(g, ncols - 1) * A.col_bytes;
+        C.c0 = recp + (size_t)std::min(2 * t, ncols - 1) * A.col_bytes;
+        C.c1 = recp + (size_t)std::min(2 * t + 1, ncols - 1) * A.col_bytes;
+        float facc[4] = { 0, 0, 0, 0 };
+        for (int task = 0; task < (int)(K / 256); ++task)
+            mma_task<T>(rows + (size_t)g * pitch + (size_t)task * F::TASK_B, rows + (size_t)(g + 8) * pitch + (size_t)task * F::TASK_B, C, A, task, t, facc);
+        out[(size_t)g * 8 + 2 * t] = facc[0]; out[(size_t)g * 8 + 2 * t + 1] = facc[1];
+        out[(size_t)(g + 8) * 8 + 2 * t] = facc[2]; out[(size_t)(g + 8) * 8 + 2 * t + 1] = facc[3];
+    });
 }
 extern "C" {
 
@@ -159,6 +189,16 @@ int emu_sb_row_dot_nc(int type, const uint8_t * row, int64_t K, const uint8_t * 
 #define X(T) case T: sb_row_nc<T>(row, K, rec, rec_stride, ncols, out); return 0;
         FOR_SB_TYPES(X)
 #undef X
+        default: return -1;
+    }
+}
+
+int emu_mma_tile(int type, const uint8_t * rows, int64_t pitch, int64_t K, const float * x, int ncols, float * out) {
+    switch (type) {
+        case T_Q4_0: mma_tile<T_Q4_0>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q8_0: mma_tile<T_Q8_0>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q4_K: mma_tile<T_Q4_K>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q5_K: mma_tile<T_Q5_K>(rows, pitch, K, x, ncols, out); return 0;
         default: return -1;
     }
 }

@@ -137,19 +137,54 @@ def test_gemv_vs_oracle(t, n, g, oracle):
 
 @pytest.mark.parametrize("t", TYPES, ids=IDS)
 def test_small_batch_columns_match_single_column(t, g, oracle):
-    """2 <= n <= 8 runs the same superblock kernel with the weights decoded once per task: every column must be bit-identical
-    to the n = 1 product with that column (same integer dots, same f32 operations in the same order)."""
+    """2 <= n <= 8 on the dp4a superblock kernel (GGML_B200_MM_GEMV_DP4A) decodes the weights once per task: every column must be
+    bit-identical to the n = 1 product with that column (same integer dots, same f32 operations in the same order)."""
     M, K = 1536, 4096
     W = dev(weights(oracle, t, M, K, seed=99))
     rng = np.random.default_rng(7)
+    F = g.MM_GEMV | g.MM_GEMV_DP4A
     for n in (2, 3, 4, 7, 8):
-        if g.mul_mat_plan(t, M, n, K, g.MM_GEMV) != g.MM_GEMV:
+        if g.mul_mat_plan(t, M, n, K, F) != g.MM_GEMV:
             continue
         X = rng.uniform(-1, 1, (n, K)).astype(np.float32)
-        Y = g.mul_mat(t, W, dev(X), M, n, K, flags=g.MM_GEMV).cpu().numpy()[0, 0]
+        Y = g.mul_mat(t, W, dev(X), M, n, K, flags=F).cpu().numpy()[0, 0]
         for c in range(n):
-            y1 = g.mul_mat(t, W, dev(X[c]), M, 1, K, flags=g.MM_GEMV).cpu().numpy()[0, 0, 0]
+            y1 = g.mul_mat(t, W, dev(X[c]), M, 1, K, flags=F).cpu().numpy()[0, 0, 0]
             assert np.array_equal(Y[c], y1), (n, c)
+
+
+MMA_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K]
+
+
+@pytest.mark.parametrize("t", MMA_TYPES, ids=[O.TYPE_NAMES[t] for t in MMA_TYPES])
+def test_small_batch_mma_kernel_vs_oracle(t, g, oracle):
+    """mmvq_mma.cu (int8 mma.sync consume path, the default for 2 <= n <= 8): against the oracle at whole-row stages (K = 2048, 4096),
+    K-sliced stages with a ragged last slice (K = 11008: 43 tasks), ragged M (last tile partly filled), every n in 1..8;
+    bitwise repeatable; column c of an n-column launch bit-identical to the kernel's own n = 1 result for that column."""
+    rng = np.random.default_rng(17)
+    for (M, K) in [(1536, 4096), (1000, 2048), (264, 11008), (4096 + 24, 4096)]:
+        W = weights(oracle, t, M, K, seed=M + K)
+        Wd = dev(W)
+        for n in ((1, 2, 3, 4, 5, 6, 7, 8) if M == 1536 else (2, 8, 5)):
+            F = g.MM_GEMV | g.MM_GEMV_MMA
+            assert g.mul_mat_plan(t, M, n, K, F) == g.MM_GEMV
+            X = rng.uniform(-1, 1, (n, K)).astype(np.float32)
+            Y = g.mul_mat(t, Wd, dev(X), M, n, K, flags=F).cpu().numpy()[0, 0]
+            assert np.isfinite(Y).all()
+            assert O.nmse(Y, oracle.mul_mat(t, W, X.reshape(-1), M, n, K)) < TOL, (M, K, n)
+            Y2 = g.mul_mat(t, Wd, dev(X), M, n, K, flags=F | g.MM_SRC0_STATIC).cpu().numpy()[0, 0]
+            assert np.array_equal(Y, Y2), (M, K, n, "not repeatable")
+            if M == 1536 and n in (3, 8):
+                for c in range(n):
+                    y1 = g.mul_mat(t, Wd, dev(X[c]), M, 1, K, flags=F).cpu().numpy()[0, 0, 0]
+                    assert np.array_equal(Y[c], y1), (n, c)
+    # AUTO picks the mma kernel for 2 <= n <= 8 and leaves n = 1 on the dp4a kernel (same tolerance either way)
+    M, K = 512, 4096
+    W = weights(oracle, t, M, K, seed=5)
+    X = rng.uniform(-1, 1, (4, K)).astype(np.float32)
+    Ya = g.mul_mat(t, dev(W), dev(X), M, 4, K).cpu().numpy()[0, 0]
+    Ym = g.mul_mat(t, dev(W), dev(X), M, 4, K, flags=g.MM_GEMV | g.MM_GEMV_MMA).cpu().numpy()[0, 0]
+    assert np.array_equal(Ya, Ym)
 
 
 @pytest.mark.parametrize("t", TYPES, ids=IDS)

@@ -20,7 +20,7 @@ def emu():
     out = EMU / "_build"
     out.mkdir(exist_ok=True)
     so = out / "libhostemu.so"
-    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh", "b200_tc_dequant.cuh", "b200_iq.cuh", "generated/iq_grids.h")]
+    srcs = [EMU / "hostemu.cpp", EMU / "shim" / "cuda_shim.h"] + [ROOT / "ggml_b200" / "csrc" / f for f in ("b200_quants.cuh", "b200_dequant.cuh", "b200_sb_tasks.cuh", "b200_tc_dequant.cuh", "b200_iq.cuh", "b200_sb_mma.cuh", "generated/iq_grids.h")]
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-mf16c", "-mavx", "-ffp-contract=off", "-Wno-unused-variable", "-Wno-unknown-pragmas",
                f"-I{EMU / 'shim'}", "-o", str(so), str(EMU / "hostemu.cpp")]
@@ -41,6 +41,7 @@ def emu():
     L.emu_sb_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.emu_sb_two_row_dot.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.emu_sb_row_dot_nc.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.emu_mma_tile.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     return L
 
 
@@ -253,3 +254,27 @@ def test_gemm_operand_dequantization_matches_oracle(t, emu, oracle):
         want = oracle.dequantize(t, w, K)
         blk = np.abs(want).reshape(-1, 32).max(1).repeat(32) + 1e-12
         assert np.all(np.abs(got - want) <= 1.5e-3 * blk), (trial, float(np.max(np.abs(got - want) / blk)))
+
+
+@pytest.mark.parametrize("ncols", [1, 2, 5, 8])
+@pytest.mark.parametrize("t", [O.Q4_K, O.Q5_K, O.Q4_0, O.Q8_0], ids=lambda t: O.TYPE_NAMES[t])
+def test_mma_small_batch_tile_matches_oracle(t, ncols, emu, oracle):
+    """b200_sb_mma.cuh (the int8 mma.sync consume path of mmvq_mma.cu) in an emulated warp — fragment loads from the packed rows at a
+    padded pitch, the m16n8k32 fragment layout, scale / min application, the planar activation records of the kernel's own quantizer —
+    against the oracle's mul_mat (same integer dots, f32 order differs)."""
+    rng = np.random.default_rng(1000 * t + ncols)
+    K = 1024
+    rb = oracle.row_size(t, K)
+    W = O.random_blocks(t, 16 * K // oracle.blck_size(t), rng)
+    pitch = rb + 32
+    rows = np.zeros(16 * pitch + 64, dtype=np.uint8)
+    base = (-rows.ctypes.data) % 32                      # 32-byte aligned tile, as a shared-memory stage
+    for r in range(16):
+        rows[base + r * pitch: base + r * pitch + rb] = W[r * rb:(r + 1) * rb]
+    X = rng.uniform(-1, 1, ncols * K).astype(np.float32)
+    X[3 * 256:4 * 256] = 0.0                             # an all-zero act-task of column 0
+    out = np.zeros((16, 8), dtype=np.float32)
+    assert emu.emu_mma_tile(t, C.c_void_p(rows.ctypes.data + base), pitch, K, _p(X), ncols, _p(out)) == 0
+    want = oracle.mul_mat(t, W, X, 16, ncols, K)          # [ncols, 16]
+    got = out[:, :ncols].T
+    assert O.nmse(got, want) < 1e-10, (O.nmse(got, want), got[:, :3], want[:, :3])
