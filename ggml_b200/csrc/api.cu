@@ -117,7 +117,7 @@ int ggml_b200_mul_mat_plan(const ggml_b200_mul_mat_args * args) {
 size_t ggml_b200_mul_mat_workspace_size(const ggml_b200_mul_mat_args * args) {
     if (validate(args) != GGML_B200_OK) return 0;
     switch (plan(*args)) {
-        case GGML_B200_MM_FORCE_GEMV: return 0;
+        case GGML_B200_MM_FORCE_GEMV: return mma_wanted(*args) ? mmvq_mma_workspace(*args) : 0;
         case GGML_B200_MM_FORCE_GEMM: return mmq_tc_workspace(*args);
         default: return mmvq_generic_workspace(*args);
     }

@@ -56,6 +56,7 @@ int    launch_gather_wait(const uint32_t * flags, int world, uint32_t epoch, cud
 // mmvq_mma.cu (bandwidth path, int8 mma.sync consume phase: 2 <= n <= 8, n = 1 on request)
 bool   mmvq_mma_eligible(const ggml_b200_mul_mat_args & a);
 int    launch_mmvq_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st);
+size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a);   // the quantized activation records (written by the pre-kernel)
 
 // mmq_tc.cu (tcgen05 GEMM)
 bool   mmq_tc_eligible(const ggml_b200_mul_mat_args & a);

@@ -496,15 +496,17 @@ static int tc2_raw_bytes(int type) {
 // shared-memory split: the operand ring only has to cover the dequantize -> MMA hand-over and the L2 latency of the activation tiles; what is
 // left goes to the raw W ring, which covers the HBM latency of the weight stream (profiles/r02_gemm_pair.md: with 2 raw units in flight the
 // dequantizers spent a quarter of their time waiting for the next unit)
-// MMA mode of a launch.  2 (quantized formats): cta_group::1, the two CTAs of a cluster work independently (each loads the whole activation tile):
-// the hand-over of a dequantized stage stays inside one CTA -- the only form that is both clean under tests/gpu_tc2_stress.py and at least as fast
-// as everything else measured (profiles/r02_gemm_pair_v2.md).  0 (fp16 A tiles): cta_group::2 pair MMAs, every operand arrives by TMA, so nothing
-// crosses a CTA boundary on the generic proxy; for quantized formats mode 0 needs the relayed hand-over (clean, 10-25 % slower).  1: cta_group::1
-// with the activation tile shared by TMA multicast -- loses rows under the stress test (not understood), kept only for study.
+// MMA mode of a launch (GGML_B200_TC2_SOLO overrides).  0 (default): cta_group::2 pair MMAs; quantized formats hand the non-leader's dequantized
+// half-stage over through the relay warp (cluster-scope release), fp16 A tiles arrive by TMA and need no relay.  It is the only mode that is clean both
+// under tests/gpu_tc2_stress.py (one matrix, repeated launches) and under scripts/gemm_bench_parity.py (the bench's pattern: many distinct matrices,
+// PDL-overlapped launches, every element checked).  1: cta_group::1 per CTA with the activation tile shared by TMA multicast; 2: cta_group::1, fully
+// independent CTAs.  Both are 10 % faster and both compute wrong rows as soon as consecutive launches overlap (mode 2 passes the stress test, then
+// fails every matrix of the bench pattern; with programmatic launch off it still loses single rows): kept for study only, never selected.
 static int tc2_mode_for(bool dense) {
     static const int env = getenv("GGML_B200_TC2_SOLO") ? atoi(getenv("GGML_B200_TC2_SOLO")) : -1;
     if (env >= 0 && env <= 2) return env;
-    return dense ? 0 : 2;
+    (void)dense;
+    return 0;
 }
 static bool tc2_smem_plan(int BN, int raw, int mode, int & nstages, int & nraw, int & smem) {
     static const int env_stages = getenv("GGML_B200_TC2_STAGES") ? atoi(getenv("GGML_B200_TC2_STAGES")) : 0;

@@ -12,7 +12,10 @@
 //     four row groups of a half-warp fall into distinct bank groups;
 //   * at the end of a tile the eight partial fragments meet in shared memory (double-buffered, one named barrier per tile) and are
 //     summed in a fixed order: results are bitwise repeatable.
-// Activations: quantized once per CTA into planar per-column records (int8 codes + block sums + scales), as ggml-cpu quantizes them.
+// Activations: quantized ONCE per launch by a small pre-kernel (mma_quantize_kernel, chained with programmatic dependent launch) into
+// planar per-column records (int8 codes + block sums + scales, as ggml-cpu quantizes them) in the workspace; every CTA of the main
+// kernel pulls them into shared memory with one bulk copy per column while its first weight stages are in flight.  (First version:
+// every CTA quantized all columns itself -- 3.4 us per column at K = 14336, on the critical path of every CTA.)
 #include "b200_internal.h"
 #include "b200_quants.cuh"
 #include "b200_sb_ptx.cuh"
@@ -35,8 +38,21 @@ struct mma_params {
     int32_t ncols; int64_t x_stride;
     int32_t src1_static, src0_static;
     int64_t l2_prefetch_bytes;
+    const uint8_t * rec_global;   // ncols planar records written by mma_quantize_kernel (workspace)
     mma_act A;
 };
+
+// one act-task (256 activations of one column) per half-warp.  Always waits for the preceding kernel: it may have produced x, and the
+// records live in the launch-shared workspace that the previous mat-mul's CTAs may still be reading.
+template <bool KQ, bool S16>
+__global__ void __launch_bounds__(256) mma_quantize_kernel(const float * __restrict__ x, int64_t x_stride, int ncols, const mma_act A, uint8_t * __restrict__ rec) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = (int)blockIdx.x * 16 + (int)(threadIdx.x >> 4);
+    const bool ok = i < ncols * A.ntask;
+    const int c = ok ? i / A.ntask : 0, t = ok ? i % A.ntask : 0;
+    mma_quantize_task_h<KQ, S16>(x + (size_t)c * x_stride, ok, rec + (size_t)c * A.col_bytes, A, t);
+}
 
 template <int T>
 __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const mma_params p) {
@@ -47,12 +63,14 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
     float * partial  = (float *)(rec + (size_t)p.ncols * p.A.col_bytes);            // [2][MMA_WARPS][128]
     uint64_t * full  = (uint64_t *)(partial + 2 * MMA_WARPS * 128);
     uint64_t * empty = full + MMA_MAX_STAGES;
-    int2 * unit_of   = (int2 *)(empty + MMA_MAX_STAGES);                            // (tile, slice) held by each stage; tile < 0 = end
+    uint64_t * rec_full = empty + MMA_MAX_STAGES;                                   // the activation records have landed
+    int2 * unit_of   = (int2 *)(rec_full + 2);                                      // (tile, slice) held by each stage; tile < 0 = end
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < p.nstages; ++s) { sb_mbar_init(&full[s], 1); sb_mbar_init(&empty[s], MMA_WARPS); }
+        sb_mbar_init(rec_full, 1);
         sb_fence_mbar_init();
     }
     __syncthreads();
@@ -107,15 +125,14 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
         return;
     }
 
-    // ===== consumers: quantize the activation columns (needs the previous kernel's output), one act-task per half-warp per round
-    if (!p.src1_static) pdl_wait();
-    for (int i0 = 2 * warp; i0 < p.ncols * p.A.ntask; i0 += 2 * MMA_WARPS) {
-        const int i = i0 + (lane >> 4);
-        const bool ok = i < p.ncols * p.A.ntask;
-        const int c = ok ? i / p.A.ntask : 0, t = ok ? i % p.A.ntask : 0;
-        mma_quantize_task_h<F::KQ, F::S16>(p.x + (size_t)c * p.x_stride, ok, rec + (size_t)c * p.A.col_bytes, p.A, t);
+    // ===== consumers: the quantized activation columns (written by the pre-kernel just before this one) -> shared memory
+    if (tid == 0) {
+        pdl_wait();
+        sb_mbar_expect_tx(rec_full, (uint32_t)p.ncols * (uint32_t)p.A.col_bytes);
+        for (int c = 0; c < p.ncols; ++c)
+            sb_tma_g2s(rec + (size_t)c * p.A.col_bytes, p.rec_global + (size_t)c * p.A.col_bytes, (uint32_t)p.A.col_bytes, rec_full);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");              // consumers only
+    sb_mbar_wait(rec_full, 0u);
 
     const int g = lane >> 2, t = lane & 3;
     mma_cols C;
@@ -154,8 +171,6 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
             buf ^= 1;
         }
     }
-    // completion stays transitive along the stream: a launch whose consumers did not wait for the preceding grid does so before it retires
-    if (p.src1_static && tid == 0) pdl_wait();
 }
 
 struct mma_plan { mma_params p; int grid, smem; };
@@ -174,15 +189,15 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     p.ntask_row = (int)(a.K / 256);
     p.A = make_mma_act(a.K, F::KQ, F::S16);
     p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
-    p.counters = nullptr;
+    p.counters = nullptr; p.rec_global = nullptr;
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
     static const int e_l2_mb = getenv("GGML_B200_SB_L2_MB") ? atoi(getenv("GGML_B200_SB_L2_MB")) : 48;
-    p.l2_prefetch_bytes = (!p.src1_static && p.src0_static && e_l2_mb > 0) ? (int64_t)std::min<size_t>((size_t)a.M * rb, (size_t)e_l2_mb << 20) : 0;
+    p.l2_prefetch_bytes = (p.src0_static && e_l2_mb > 0) ? (int64_t)std::min<size_t>((size_t)a.M * rb, (size_t)e_l2_mb << 20) : 0;
     // slices of KS tasks (a multiple of the warp count): whole rows when at least three such stages fit next to the records
     static const int e_ks = getenv("GGML_B200_MMA_KS") ? atoi(getenv("GGML_B200_MMA_KS")) : 0;
     static const int e_stages = getenv("GGML_B200_MMA_STAGES") ? atoi(getenv("GGML_B200_MMA_STAGES")) : 0;
-    const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * MMA_WARPS * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + MMA_MAX_STAGES * 8 + 128;
+    const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * MMA_WARPS * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + 16 + MMA_MAX_STAGES * 8 + 128;
     const size_t budget = 226 * 1024;
     if (fixed + 2 * 8 * F::TASK_B * MMA_TILE > budget) return false;
     auto geometry = [&](int ks) {
@@ -208,9 +223,16 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     return true;
 }
 
+static size_t mma_rec_bytes(const mma_plan & pl) { return (size_t)pl.p.ncols * pl.p.A.col_bytes; }
+
 template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
+    using F = mmafmt<T>;
     mma_plan pl;
     if (!make_mma_plan<T>(a, pl)) { set_error("mul_mat: shape not eligible for the mma small-batch kernel"); return GGML_B200_EUNSUPPORTED; }
+    const size_t need = mma_rec_bytes(pl) + 256;
+    if (!a.workspace || a.workspace_size < need) { set_error("mul_mat: workspace %zu < %zu", a.workspace_size, need); return GGML_B200_EWORKSPACE; }
+    uint8_t * rec = (uint8_t *)(((uintptr_t)a.workspace + 255) & ~(uintptr_t)255);
+    pl.p.rec_global = rec;
     unsigned int * ctl = sb_control_block();
     if (!ctl) return GGML_B200_ECUDA;
     pl.p.counters = sb_next_slot(ctl);
@@ -220,15 +242,35 @@ template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStr
         attr_set.set();
     }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((MMA_WARPS + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((pl.p.ncols * pl.p.A.ntask + 15) / 16)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+        B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_quantize_kernel<F::KQ, F::S16>, a.src1, pl.p.x_stride, (int)pl.p.ncols, pl.p.A, rec));
+        B200_LAUNCH_CHECK();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((MMA_WARPS + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
     B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<T>, pl.p));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
+}
+
+size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a) {
+    mma_plan pl;
+    bool ok = false;
+    switch (a.type) {
+        case T_Q4_0: ok = make_mma_plan<T_Q4_0>(a, pl); break;
+        case T_Q8_0: ok = make_mma_plan<T_Q8_0>(a, pl); break;
+        case T_Q4_K: ok = make_mma_plan<T_Q4_K>(a, pl); break;
+        case T_Q5_K: ok = make_mma_plan<T_Q5_K>(a, pl); break;
+        default: break;
+    }
+    return ok ? mma_rec_bytes(pl) + 256 : 0;
 }
 
 bool mmvq_mma_eligible(const ggml_b200_mul_mat_args & a) {
