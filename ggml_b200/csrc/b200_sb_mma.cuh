@@ -59,6 +59,11 @@ __device__ __forceinline__ void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                  : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
+// A bytes unsigned (0..255): high nibbles used in place (q & 0xF0 = 16 x the nibble; the result is an exact multiple of 16)
+__device__ __forceinline__ void mma_u8s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
 // 8 bytes at an address whose residue mod 8 is the compile-time constant R (block formats are only 2-byte aligned): aligned loads + funnel shifts
 template <int R> __device__ __forceinline__ uint2 lds8(const uint8_t * p) {
     static_assert(R == 0 || R == 2 || R == 4 || R == 6, "two-byte aligned");
@@ -75,7 +80,8 @@ template <int R> __device__ __forceinline__ uint2 lds8(const uint8_t * p) {
 __device__ __forceinline__ uint32_t lds_u16(const uint8_t * p) { return *(const uint16_t *)p; }
 #else
 // host restatement: every lane publishes its fragments, then computes its four outputs from all lanes' fragments
-inline void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+template <bool A_UNSIGNED>
+inline void mma_emu_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     static uint32_t fr[32][6];
     const int lane = (int)(threadIdx.x & 31);
     fr[lane][0] = a0; fr[lane][1] = a1; fr[lane][2] = a2; fr[lane][3] = a3; fr[lane][4] = b0; fr[lane][5] = b1;
@@ -87,13 +93,15 @@ inline void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, u
         for (int tt = 0; tt < 4; ++tt) {
             const uint32_t * A = fr[4 * (row & 7) + tt], * B = fr[4 * coln + tt];
             const uint32_t alo = A[row >> 3], ahi = A[2 + (row >> 3)];
-            sum = __dp4a((int)alo, (int)B[4], sum);
-            sum = __dp4a((int)ahi, (int)B[5], sum);
+            if (A_UNSIGNED) { sum = dp4a_us(alo, (int)B[4], sum); sum = dp4a_us(ahi, (int)B[5], sum); }
+            else            { sum = __dp4a((int)alo, (int)B[4], sum); sum = __dp4a((int)ahi, (int)B[5], sum); }
         }
         c[i] = sum;
     }
     pthread_barrier_wait(&warp_emu::barrier());
 }
+inline void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) { mma_emu_16x8x32<false>(c, a0, a1, a2, a3, b0, b1); }
+inline void mma_u8s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) { mma_emu_16x8x32<true>(c, a0, a1, a2, a3, b0, b1); }
 template <int R> inline uint2 lds8(const uint8_t * p) { uint2 v; std::memcpy(&v, p, 8); return v; }
 inline uint32_t lds_u16(const uint8_t * p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
 #endif
@@ -127,7 +135,7 @@ __device__ __forceinline__ void mma_q45_task(const uint8_t * w0, const uint8_t *
     if constexpr (FIVE) { qhA = *(const uint2 *)(w0 + 16 + 8 * t); qhB = *(const uint2 *)(w1 + 16 + 8 * t); }   // bit j of byte i = high bit of weight i of sub-block j
     const uint8_t * qa = w0 + (FIVE ? 48 : 16) + 8 * t, * qb = w1 + (FIVE ? 48 : 16) + 8 * t;
     const uint8_t * y = C.b + 256 * task + 8 * t;
-    int acc[4] = { 0, 0, 0, 0 };
+    int acc[4] = { 0, 0, 0, 0 }, acc16[4] = { 0, 0, 0, 0 };         // acc16: sums of the in-place high nibbles (16 x the nibble dot), Q4_K only
 #pragma unroll
     for (int p = 0; p < 4; ++p) {                                   // 64 weights: sub-block 2p in the low nibbles, 2p+1 in the high ones
         const uint2 wa = *(const uint2 *)(qa + 32 * p), wb = *(const uint2 *)(qb + 32 * p);
@@ -135,18 +143,28 @@ __device__ __forceinline__ void mma_q45_task(const uint8_t * w0, const uint8_t *
         for (int h = 0; h < 2; ++h) {
             const int j = 2 * p + h;
             const uint2 yy = *(const uint2 *)(y + 32 * j);
-            uint32_t a0 = (wa.x >> (4 * h)) & 0x0F0F0F0Fu, a2 = (wa.y >> (4 * h)) & 0x0F0F0F0Fu;
-            uint32_t a1 = (wb.x >> (4 * h)) & 0x0F0F0F0Fu, a3 = (wb.y >> (4 * h)) & 0x0F0F0F0Fu;
-            if constexpr (FIVE) {
-                a0 |= ((qhA.x >> j) & 0x01010101u) << 4; a2 |= ((qhA.y >> j) & 0x01010101u) << 4;
-                a1 |= ((qhB.x >> j) & 0x01010101u) << 4; a3 |= ((qhB.y >> j) & 0x01010101u) << 4;
-            }
-            int c[4];
-            mma_s8_16x8x32(c, a0, a1, a2, a3, yy.x, yy.y);
             const int sa = (j & 3) == 0 ? ubyte<0>(scA[j >> 2]) : (j & 3) == 1 ? ubyte<1>(scA[j >> 2]) : (j & 3) == 2 ? ubyte<2>(scA[j >> 2]) : ubyte<3>(scA[j >> 2]);
             const int sb = (j & 3) == 0 ? ubyte<0>(scB[j >> 2]) : (j & 3) == 1 ? ubyte<1>(scB[j >> 2]) : (j & 3) == 2 ? ubyte<2>(scB[j >> 2]) : ubyte<3>(scB[j >> 2]);
-            acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+            int c[4];
+            if constexpr (!FIVE) {
+                if (h == 0) {
+                    mma_s8_16x8x32(c, wa.x & 0x0F0F0F0Fu, wb.x & 0x0F0F0F0Fu, wa.y & 0x0F0F0F0Fu, wb.y & 0x0F0F0F0Fu, yy.x, yy.y);
+                    acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+                } else {
+                    mma_u8s8_16x8x32(c, wa.x & 0xF0F0F0F0u, wb.x & 0xF0F0F0F0u, wa.y & 0xF0F0F0F0u, wb.y & 0xF0F0F0F0u, yy.x, yy.y);
+                    acc16[0] += sa * c[0]; acc16[1] += sa * c[1]; acc16[2] += sb * c[2]; acc16[3] += sb * c[3];
+                }
+            } else {
+                const uint32_t a0 = ((wa.x >> (4 * h)) & 0x0F0F0F0Fu) | (((qhA.x >> j) & 0x01010101u) << 4), a2 = ((wa.y >> (4 * h)) & 0x0F0F0F0Fu) | (((qhA.y >> j) & 0x01010101u) << 4);
+                const uint32_t a1 = ((wb.x >> (4 * h)) & 0x0F0F0F0Fu) | (((qhB.x >> j) & 0x01010101u) << 4), a3 = ((wb.y >> (4 * h)) & 0x0F0F0F0Fu) | (((qhB.y >> j) & 0x01010101u) << 4);
+                mma_s8_16x8x32(c, a0, a1, a2, a3, yy.x, yy.y);
+                acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+            }
         }
+    }
+    if constexpr (!FIVE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += acc16[i] >> 4;        // exact: every term is a multiple of 16
     }
     // mins: sum_j min_j(row) * (sum of the 32 activations of sub-block j)(column), two sub-blocks per dp2a
     const int4 s0 = lds128(C.c0 + A.off_h32 + 16 * task), s1 = lds128(C.c1 + A.off_h32 + 16 * task);

@@ -3,14 +3,14 @@
 // Same streaming skeleton as mmvq_sb.cu (persistent CTAs, one TMA producer warp, a ring of bulk-copy stages with full / empty
 // mbarriers, chunks handed out by a self-resetting atomic slot, programmatic dependent launch, weights read once from HBM in the
 // reference's packed layout), different consume phase (b200_sb_mma.cuh):
-//   * a chunk is a TILE of 16 weight rows; the eight consumer warps split the tile's K range by 256-weight task (task i of a slice
-//     goes to warp i mod 8), each multiplying its 16 x 256 weights with all (<= 8) activation columns on the tensor cores
+//   * a chunk is a TILE of 16 weight rows; the NW (16) consumer warps split the tile's K range by 256-weight task (task i of a slice
+//     goes to warp i mod NW), each multiplying its 16 x 256 weights with all (<= 8) activation columns on the tensor cores
 //     (m16n8k32, int8 x int8 -> int32, exactly the integer block dots of ggml-cpu) and keeping 4 f32 partial outputs per lane;
 //   * rows too long for a ring of whole-row stages are streamed in K slices of KS tasks (consecutive stages of the same tile, the
 //     accumulators stay in registers across them);
 //   * every row of a stage is its own bulk copy into a padded pitch (= 32 mod 128 bytes), so that the 8-byte fragment loads of the
 //     four row groups of a half-warp fall into distinct bank groups;
-//   * at the end of a tile the eight partial fragments meet in shared memory (double-buffered, one named barrier per tile) and are
+//   * at the end of a tile the warps' partial fragments meet in shared memory (double-buffered, one named barrier per tile) and are
 //     summed in a fixed order: results are bitwise repeatable.
 // Activations: quantized ONCE per launch by a small pre-kernel (mma_quantize_kernel, chained with programmatic dependent launch) into
 // planar per-column records (int8 codes + block sums + scales, as ggml-cpu quantizes them) in the workspace; every CTA of the main
@@ -27,7 +27,6 @@
 namespace b200 {
 
 constexpr int MMA_MAX_STAGES = 8;
-constexpr int MMA_WARPS = 8;             // consumer warps
 constexpr int MMA_TILE = 16;             // rows per tile (the m of m16n8k32)
 
 struct mma_params {
@@ -54,9 +53,10 @@ __global__ void __launch_bounds__(256) mma_quantize_kernel(const float * __restr
     mma_quantize_task_h<KQ, S16>(x + (size_t)c * x_stride, ok, rec + (size_t)c * A.col_bytes, A, t);
 }
 
-template <int T>
-__global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const mma_params p) {
+template <int T, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_params p) {
     using F = mmafmt<T>;
+    constexpr int MMA_WARPS = NW;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t * stages = smem;
     uint8_t * rec    = stages + (size_t)p.nstages * p.stage_bytes;                  // ncols planar records
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
     if (warp == MMA_WARPS) {
         // ===== producer warp: lane r copies row r of the tile (slice) — sixteen bulk copies per stage, one barrier
         if (!p.src0_static) pdl_wait();
-        int it = 0;
+        int s = 0; uint32_t par = 0; bool wrapped = false;        // ring position: stage, parity of the round, past the first round
         int tile = (int)blockIdx.x;
         bool first = true;
         while (true) {
@@ -87,9 +87,8 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
             int next = 0;
             if (valid && lane == 0) next = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
             const int nsl = valid ? p.nslices : 1;
-            for (int sl = 0; sl < nsl; ++sl, ++it) {
-                const int s = it % p.nstages;
-                if (it >= p.nstages) sb_mbar_wait(&empty[s], (uint32_t)((it / p.nstages) - 1) & 1u);
+            for (int sl = 0; sl < nsl; ++sl) {
+                if (wrapped) sb_mbar_wait(&empty[s], par ^ 1u);
                 if (valid) {
                     const int64_t row0 = (int64_t)tile * MMA_TILE;
                     const int rows = (int)min((int64_t)MMA_TILE, p.M - row0);
@@ -104,6 +103,7 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
                     unit_of[s] = make_int2(-1, 0);
                     sb_mbar_arrive(&full[s]);                       // publish the end marker
                 }
+                if (++s == p.nstages) { s = 0; par ^= 1u; wrapped = true; }
             }
             if (first && p.l2_prefetch_bytes > 0 && lane == 0) {
                 // a dependent launch cannot consume before its predecessor's output is visible, but HBM need not idle meanwhile:
@@ -141,9 +141,9 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
     C.c1 = rec + (size_t)min(2 * t + 1, p.ncols - 1) * p.A.col_bytes;
     float facc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
     int buf = 0;
-    for (int it = 0;; ++it) {
-        const int s = it % p.nstages;
-        sb_mbar_wait(&full[s], (uint32_t)(it / p.nstages) & 1u);
+    int s = 0; uint32_t par = 0;                                                    // ring position: stage, parity of the round
+    for (;;) {
+        sb_mbar_wait(&full[s], par);
         const int2 unit = unit_of[s];
         if (unit.x < 0) break;
         const int nt = min(p.ks, p.ntask_row - unit.y * p.ks);
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
             mma_task<T>(st + (size_t)i * F::TASK_B, st + (size_t)i * F::TASK_B + (size_t)8 * p.pitch, C, p.A, unit.y * p.ks + i, t, facc);
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
+        if (++s == p.nstages) { s = 0; par ^= 1u; }
         if (unit.y == p.nslices - 1) {
             // tile finished: the eight warps' partial fragments meet in shared memory and are summed in warp order
             float * part = partial + buf * (MMA_WARPS * 128);
@@ -173,13 +174,13 @@ __global__ void __launch_bounds__((MMA_WARPS + 1) * 32, 1) mmvq_mma_kernel(const
     }
 }
 
-struct mma_plan { mma_params p; int grid, smem; };
+struct mma_plan { mma_params p; int grid, smem, nw; };
 
 template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma_plan & pl) {
     using F = mmafmt<T>;
     if (a.N < 1 || a.N > 8 || a.ne02 != 1 || a.ne03 != 1 || a.ne12 != 1 || a.ne13 != 1) return false;
     if (a.N > 1 && ((a.nb11 & 3) != 0 || a.nb11 < (size_t)a.K * 4)) return false;
-    if (a.K % 256 != 0 || a.K < 2048 || a.M < MMA_TILE || a.K > 65536) return false;      // K >= 2048: every consumer warp has a task
+    if (a.K % 256 != 0 || a.K < 2048 || a.M < MMA_TILE || a.K > 65536) return false;      // shorter rows leave most consumer warps without a task
     const size_t rb = row_bytes(a.type, a.K);
     if (a.nb01 != rb || (rb & 15) != 0 || ((uintptr_t)a.src0 & 15) != 0 || ((uintptr_t)a.src1 & 15) != 0 || (a.nb11 & 15) != 0) return false;
     mma_params & p = pl.p;
@@ -197,7 +198,10 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     // slices of KS tasks (a multiple of the warp count): whole rows when at least three such stages fit next to the records
     static const int e_ks = getenv("GGML_B200_MMA_KS") ? atoi(getenv("GGML_B200_MMA_KS")) : 0;
     static const int e_stages = getenv("GGML_B200_MMA_STAGES") ? atoi(getenv("GGML_B200_MMA_STAGES")) : 0;
-    const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * MMA_WARPS * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + 16 + MMA_MAX_STAGES * 8 + 128;
+    // consumer warps: 16 (four per scheduler) hide the latency of the load -> unpack -> mma -> scale chains; 8 measured 1.8x slower per tile
+    static const int e_warps = getenv("GGML_B200_MMA_WARPS") ? atoi(getenv("GGML_B200_MMA_WARPS")) : 16;
+    pl.nw = e_warps == 8 ? 8 : 16;
+    const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * (size_t)pl.nw * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + 16 + MMA_MAX_STAGES * 8 + 128;
     const size_t budget = 226 * 1024;
     if (fixed + 2 * 8 * F::TASK_B * MMA_TILE > budget) return false;
     auto geometry = [&](int ks) {
@@ -225,6 +229,20 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
 
 static size_t mma_rec_bytes(const mma_plan & pl) { return (size_t)pl.p.ncols * pl.p.A.col_bytes; }
 
+template <int T, int NW> static int launch_mma_nw(const mma_plan & pl, cudaStream_t st, const cudaLaunchAttribute * attr, int nattr) {
+    static per_device_flag attr_set;
+    if (!attr_set.test()) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set.set();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((NW + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cfg.attrs = const_cast<cudaLaunchAttribute *>(attr); cfg.numAttrs = nattr;
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<T, NW>, pl.p));
+    B200_LAUNCH_CHECK();
+    return GGML_B200_OK;
+}
+
 template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
     using F = mmafmt<T>;
     mma_plan pl;
@@ -236,11 +254,6 @@ template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStr
     unsigned int * ctl = sb_control_block();
     if (!ctl) return GGML_B200_ECUDA;
     pl.p.counters = sb_next_slot(ctl);
-    static per_device_flag attr_set;
-    if (!attr_set.test()) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set.set();
-    }
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -252,12 +265,7 @@ template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStr
         B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_quantize_kernel<F::KQ, F::S16>, a.src1, pl.p.x_stride, (int)pl.p.ncols, pl.p.A, rec));
         B200_LAUNCH_CHECK();
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((MMA_WARPS + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<T>, pl.p));
-    B200_LAUNCH_CHECK();
-    return GGML_B200_OK;
+    return pl.nw == 8 ? launch_mma_nw<T, 8>(pl, st, attr, use_pdl ? 1 : 0) : launch_mma_nw<T, 16>(pl, st, attr, use_pdl ? 1 : 0);
 }
 
 size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a) {

@@ -39,19 +39,39 @@ else:
     timer = bench.Timer(torch)
     s, reps = timer.time_graph(sweep, min_seconds=0.05)
     print(f"{s / nbuf * 1e6:.2f} us per mul_mat over {reps} replays of {nbuf} matrices", flush=True)
-bad = 0
 Xd = X.view(N, K).double()
-for i in range(nbuf):
-    Wf = g.dequantize(t, Ws[i], M * K).view(M, K).double()
-    exact = Xd @ Wf.T
-    scale = exact.abs().mean().item()
-    err = (Ys[i][0, 0].double() - exact).abs()
-    wrong = err > 6e-3 * scale
-    if wrong.any():
-        bad += 1
-        idx = wrong.nonzero()
-        cols, rows = idx[:, 0].cpu().numpy(), idx[:, 1].cpu().numpy()
-        print(f"  matrix {i}: {len(rows)} elements off by up to {err.max().item() / scale:.3f} x typical; rows {rows.min()}..{rows.max()}, distinct rows {len(set(rows.tolist()))}, "
-              f"rows % 128: {sorted(set((rows % 128).tolist()))[:12]}, cols {cols.min()}..{cols.max()} ({len(set(cols.tolist()))} distinct)", flush=True)
+
+
+def check(label, verbose=True):
+    bad, wrong_rows = 0, {}
+    for i in range(nbuf):
+        Wf = g.dequantize(t, Ws[i], M * K).view(M, K).double()
+        exact = Xd @ Wf.T
+        scale = exact.abs().mean().item()
+        err = (Ys[i][0, 0].double() - exact).abs()
+        wrong = err > 6e-3 * scale
+        if wrong.any():
+            bad += 1
+            idx = wrong.nonzero()
+            cols, rows = idx[:, 0].cpu().numpy(), idx[:, 1].cpu().numpy()
+            wrong_rows[i] = sorted(set(rows.tolist()))
+            if verbose and bad <= 3:
+                print(f"  [{label}] matrix {i}: {len(rows)} elements off by up to {err.max().item() / scale:.3f} x typical; distinct rows {len(wrong_rows[i])}: {wrong_rows[i][:10]}, "
+                      f"cols {cols.min()}..{cols.max()} ({len(set(cols.tolist()))} distinct)", flush=True)
+    return bad, wrong_rows
+
+
+bad, rows_a = check("overlapped")
+if "--serial" in sys.argv:
+    # the same launches again, one at a time with a device synchronisation after each: a race between overlapping launches disappears,
+    # a data-dependent decode error stays on the same rows
+    for Y in Ys:
+        Y.zero_()
+    for i in range(nbuf):
+        g.mul_mat(t, Ws[i], X, M, N, K, out=Ys[i], flags=F)
+        torch.cuda.synchronize()
+    bad_s, rows_s = check("serial")
+    same = sum(1 for i in rows_s if rows_a.get(i) == rows_s[i])
+    print(f"serial re-run: {bad_s} of {nbuf} matrices wrong ({same} with exactly the rows of the overlapped run)", flush=True)
 tun = {k: v for k, v in os.environ.items() if k.startswith("GGML_B200_")}
 print(("CLEAN" if bad == 0 else f"BAD ({bad} of {nbuf} matrices)"), g.TYPE_NAMES[t], M, N, K, sys.argv[5:], tun, flush=True)
