@@ -530,7 +530,10 @@ static bool tc2_smem_plan(int BN, int raw, int mode, int & nstages, int & nraw, 
 static bool make_tc2_plan(const ggml_b200_mul_mat_args & a, tc2_plan & pl) {
     static const int env_mode = getenv("GGML_B200_TC_PAIR") ? atoi(getenv("GGML_B200_TC_PAIR")) : 1;     // 0 = off (one-CTA kernel everywhere)
     if (env_mode == 0) return false;
-    static const bool env_q6k_off = getenv("GGML_B200_TC_Q6K") && atoi(getenv("GGML_B200_TC_Q6K")) == 0;
+    // Q6_K stays on the one-CTA kernel (mmq_tc.cu): on CTA pairs its variable-lead raw units lose rows 0..15 of a tile now and then even with
+    // one launch at a time (scripts/gemm_bench_parity.py q6_K 4096 512 4096 --serial: 4 of 19 matrices), the one-CTA kernel is clean on the same
+    // pattern and as fast (45 vs 48 us).  GGML_B200_TC2_Q6K=1 puts it back on the pair kernel for study.
+    static const bool env_q6k_off = !(getenv("GGML_B200_TC2_Q6K") && atoi(getenv("GGML_B200_TC2_Q6K")) != 0);
     const bool dense = a.type == T_F16;                            // fp16 A tiles (launch_mmq_dense / launch_mmq_f16w)
     switch (a.type) {
         case T_Q4_0: case T_Q8_0: case T_Q4_K: case T_Q5_K: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_IQ4_NL: case T_IQ4_XS: case T_Q2_K: case T_Q3_K: break;

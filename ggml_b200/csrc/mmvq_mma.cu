@@ -33,7 +33,7 @@ struct mma_params {
     const uint8_t * w; const float * x; float * y;
     int64_t M, K;
     int32_t row_bytes, ntiles, nslices, ks, ntask_row, pitch, stage_bytes, nstages;
-    unsigned int * counters;      // this launch's scheduling slot: [0] next tile, [1] finished producers
+    unsigned int * counters;      // null: tiles dealt round-robin; else this launch's scheduling slot: [0] next tile, [1] finished producers
     int32_t ncols; int64_t x_stride;
     int32_t src1_static, src0_static;
     int64_t l2_prefetch_bytes;
@@ -83,9 +83,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
         bool first = true;
         while (true) {
             const bool valid = tile < p.ntiles;
-            // the next tile index is fetched (one global atomic round trip) before this tile's stages are waited for
-            int next = 0;
-            if (valid && lane == 0) next = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
+            // Tiles are dealt round-robin (tile b, b + grid, ...) unless p.counters is set.  Dynamic hand-out (one global atomic per tile, as
+            // mmvq_sb.cu does per 36 KB chunk) starved the ring: the producer issued ONE stage per atomic round trip (~1 us), ncu showed the
+            // consumers waiting for `full` a third of the time at 22 % of the DRAM peak (profiles/r02_mma_small_batch.md).
+            int next = tile + (int)gridDim.x;
+            if (p.counters && valid && lane == 0) next = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
             const int nsl = valid ? p.nslices : 1;
             for (int sl = 0; sl < nsl; ++sl) {
                 if (wrapped) sb_mbar_wait(&empty[s], par ^ 1u);
@@ -115,9 +117,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
             }
             first = false;
             if (!valid) break;
-            tile = __shfl_sync(0xffffffffu, next, 0);
+            tile = p.counters ? __shfl_sync(0xffffffffu, next, 0) : next;
         }
-        if (lane == 0) {
+        if (p.counters && lane == 0) {
             // last CTA to finish its scheduling resets the counters for the next launch
             __threadfence();
             if (atomicAdd(&p.counters[1], 1u) == gridDim.x - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
@@ -253,7 +255,8 @@ template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStr
     pl.p.rec_global = rec;
     unsigned int * ctl = sb_control_block();
     if (!ctl) return GGML_B200_ECUDA;
-    pl.p.counters = sb_next_slot(ctl);
+    static const bool e_dynamic = getenv("GGML_B200_MMA_DYNAMIC") && atoi(getenv("GGML_B200_MMA_DYNAMIC")) != 0;
+    pl.p.counters = e_dynamic ? sb_next_slot(ctl) : nullptr;
     static const bool use_pdl = !(getenv("GGML_B200_NO_PDL") && atoi(getenv("GGML_B200_NO_PDL")) != 0);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

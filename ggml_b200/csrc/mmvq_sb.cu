@@ -45,6 +45,7 @@ struct sb_params {
     int32_t ncols; int64_t x_stride;   // activation columns (1..8) and the distance between them in floats; y is [ncols][M]
     int32_t src1_static;          // activations are not produced by the preceding kernel either: never wait for it (independent ops overlap)
     int32_t src0_static;          // weights are not produced by the preceding kernel: prefetch them before griddepcontrol.wait
+    int32_t static_chunks;        // chunks dealt round-robin instead of by the atomic counter
     int64_t l2_prefetch_bytes;    // dependent launches: bytes of W every CTA's share of which is pulled into L2 while the previous kernel still runs (0 = off)
     // row-sharded multi-GPU: every result is stored straight into each peer's full-length y over NVLink (world == 0: off)
     // fused epilogue (bias add and GELU of the following ggml nodes): y2 = y + bias, y3 = gelu(y2); null = off
@@ -119,6 +120,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, NC > 1 ? 1 : NW == 8 ? 2 : 4) m
             // latency overlaps the consumers' work instead of delaying the refill
             int it = 1;
             bool done = (int)blockIdx.x >= p.nchunks;
+            if (p.static_chunks) {
+                // chunks dealt round-robin (b, b + grid, ...): no atomic round trip (~1 us) between consecutive stages of this CTA's ring
+                while (!done) {
+                    const int s = it % p.nstages;
+                    const int chunk = (int)blockIdx.x + it * (int)gridDim.x;
+                    if (it >= p.nstages) sb_mbar_wait(&empty[s], (uint32_t)((it / p.nstages) - 1) & 1u);
+                    issue(s, chunk);
+                    done = chunk >= p.nchunks;
+                    ++it;
+                }
+                return;
+            }
             while (!done) {
                 const int s = it % p.nstages;
                 const int chunk = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
@@ -348,6 +361,9 @@ template <int T> static bool make_sb_plan(const ggml_b200_mul_mat_args & a, sb_p
     p.world = 0; p.rank = 0; p.row_offset = 0; p.epoch = 0;
     p.ep_bias = nullptr; p.ep_y2 = nullptr; p.ep_y3 = nullptr; p.ep_res = nullptr;
     p.src1_static = (a.flags & GGML_B200_MM_SRC1_STATIC) ? 1 : 0;
+    // GGML_B200_SB_STATIC: 0 = dynamic hand-out everywhere, 1 = round-robin everywhere, 2 = round-robin for dependent launches only
+    static const int e_static = getenv("GGML_B200_SB_STATIC") ? atoi(getenv("GGML_B200_SB_STATIC")) : 0;
+    p.static_chunks = (e_static == 1 || (e_static == 2 && !ind)) ? 1 : 0;
     p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
     for (int q = 0; q < 8; ++q) { p.y_peers[q] = nullptr; p.flag_peers[q] = nullptr; }
     auto smem_of = [&]() { return p.nstages * p.stage_bytes + nc * p.A.bytes + 2 * SB_MAX_STAGES * 8 + SB_MAX_STAGES * 4 + 64; };
