@@ -200,9 +200,11 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     // slices of KS tasks (a multiple of the warp count): whole rows when at least three such stages fit next to the records
     static const int e_ks = getenv("GGML_B200_MMA_KS") ? atoi(getenv("GGML_B200_MMA_KS")) : 0;
     static const int e_stages = getenv("GGML_B200_MMA_STAGES") ? atoi(getenv("GGML_B200_MMA_STAGES")) : 0;
-    // consumer warps: 16 (four per scheduler) hide the latency of the load -> unpack -> mma -> scale chains; 8 measured 1.8x slower per tile
-    static const int e_warps = getenv("GGML_B200_MMA_WARPS") ? atoi(getenv("GGML_B200_MMA_WARPS")) : 16;
-    pl.nw = e_warps == 8 ? 8 : 16;
+    // consumer warps: 8 (16 selectable: GGML_B200_MMA_WARPS).  Sixteen warps on one tile measured 5-10 % SLOWER: all warps of a CTA walk the
+    // load -> unpack -> mma -> scale phases of a tile in lock-step, so the LSU, the tensor pipe and the ALUs are used one after the other
+    // whatever the warp count, and the per-tile barrier and reduction grow (profiles/r02_mma_small_batch.md)
+    static const int e_warps = getenv("GGML_B200_MMA_WARPS") ? atoi(getenv("GGML_B200_MMA_WARPS")) : 8;
+    pl.nw = e_warps == 16 ? 16 : 8;
     const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * (size_t)pl.nw * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + 16 + MMA_MAX_STAGES * 8 + 128;
     const size_t budget = 226 * 1024;
     if (fixed + 2 * 8 * F::TASK_B * MMA_TILE > budget) return false;
