@@ -23,19 +23,20 @@ namespace b200 {
 //   +off_h32  h32 : per 32-value block one int16 sum of its codes (16 bytes per 256-value task)
 //   +off_s16  s16 : (formats with 16-wide scale groups) per 16 values one int16 sum (32 bytes per task); absent otherwise
 //   +off_d    d   : Q8_K family: one float per task; Q8_0 family: one float per 32-value block (fp16-rounded)
-// col_bytes = 32 (mod 128): the eight columns' 8-byte fragment loads of a half-warp fall into distinct bank groups.
+// col_bytes = 32 (mod 128): the eight columns' 8-byte fragment loads of a half-warp fall into distinct bank groups (formats whose lanes
+// load 4-byte fragments, Q6_K: 16 (mod 128), eight columns x 16 bytes = all 32 banks).
 struct mma_act {
     int32_t ntask, off_h32, off_s16, off_d, col_bytes;
 };
-__host__ __device__ inline mma_act make_mma_act(int64_t K, bool kq, bool s16) {
+__host__ __device__ inline mma_act make_mma_act(int64_t K, bool kq, bool s16, int residue = 32) {
     mma_act A;
     A.ntask = (int32_t)(K / 256);
     A.off_h32 = (int32_t)K;
     A.off_s16 = A.off_h32 + 16 * A.ntask;
     A.off_d = A.off_s16 + (s16 ? 32 * A.ntask : 0);
     int32_t bytes = A.off_d + (kq ? 4 : 32) * A.ntask;
-    bytes = (bytes + 31) & ~31;
-    while ((bytes & 127) != 32) bytes += 32;
+    bytes = (bytes + 15) & ~15;
+    while ((bytes & 127) != residue) bytes += 16;
     A.col_bytes = bytes;
     return A;
 }
@@ -78,6 +79,16 @@ template <int R> __device__ __forceinline__ uint2 lds8(const uint8_t * p) {
     }
 }
 __device__ __forceinline__ uint32_t lds_u16(const uint8_t * p) { return *(const uint16_t *)p; }
+// m16n8k16: lane 4g+t holds A (row g, k 4t..4t+3), (row g+8, same k) and B (k 4t..4t+3, column g); D as m16n8k32
+__device__ __forceinline__ void mma_s8_16x8x16(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a0), "r"(a1), "r"(b0), "r"(0));
+}
+// a 32-bit word at an address whose residue mod 4 is the compile-time constant R (0 or 2)
+template <int R> __device__ __forceinline__ uint32_t lds4(const uint8_t * p) {
+    if constexpr (R == 0) return *(const uint32_t *)p;
+    else return __funnelshift_r(*(const uint32_t *)(p - 2), *(const uint32_t *)(p + 2), 16);
+}
 #else
 // host restatement: every lane publishes its fragments, then computes its four outputs from all lanes' fragments
 template <bool A_UNSIGNED>
@@ -102,6 +113,21 @@ inline void mma_emu_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, 
 }
 inline void mma_s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) { mma_emu_16x8x32<false>(c, a0, a1, a2, a3, b0, b1); }
 inline void mma_u8s8_16x8x32(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) { mma_emu_16x8x32<true>(c, a0, a1, a2, a3, b0, b1); }
+inline void mma_s8_16x8x16(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    static uint32_t fr[32][3];
+    const int lane = (int)(threadIdx.x & 31);
+    fr[lane][0] = a0; fr[lane][1] = a1; fr[lane][2] = b0;
+    pthread_barrier_wait(&warp_emu::barrier());
+    const int g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + 8 * (i >> 1), coln = 2 * t + (i & 1);
+        int sum = 0;
+        for (int tt = 0; tt < 4; ++tt) sum = __dp4a((int)fr[4 * (row & 7) + tt][row >> 3], (int)fr[4 * coln + tt][2], sum);
+        c[i] = sum;
+    }
+    pthread_barrier_wait(&warp_emu::barrier());
+}
+template <int R> inline uint32_t lds4(const uint8_t * p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
 template <int R> inline uint2 lds8(const uint8_t * p) { uint2 v; std::memcpy(&v, p, 8); return v; }
 inline uint32_t lds_u16(const uint8_t * p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
 #endif
@@ -114,10 +140,12 @@ struct mma_cols {
 
 // bytes of a 256-weight task in the packed row
 template <int T> struct mmafmt;
-template <> struct mmafmt<T_Q4_K> { static constexpr int TASK_B = 144; static constexpr bool KQ = true,  S16 = false; };
-template <> struct mmafmt<T_Q5_K> { static constexpr int TASK_B = 176; static constexpr bool KQ = true,  S16 = false; };
-template <> struct mmafmt<T_Q4_0> { static constexpr int TASK_B = 144; static constexpr bool KQ = false, S16 = false; };
-template <> struct mmafmt<T_Q8_0> { static constexpr int TASK_B = 272; static constexpr bool KQ = false, S16 = false; };
+// RESIDUE: row pitch of the weight stage and column pitch of the records mod 128 (lanes load 8-byte fragments: 32; 4-byte fragments: 16)
+template <> struct mmafmt<T_Q4_K> { static constexpr int TASK_B = 144, RESIDUE = 32; static constexpr bool KQ = true,  S16 = false; };
+template <> struct mmafmt<T_Q5_K> { static constexpr int TASK_B = 176, RESIDUE = 32; static constexpr bool KQ = true,  S16 = false; };
+template <> struct mmafmt<T_Q4_0> { static constexpr int TASK_B = 144, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
+template <> struct mmafmt<T_Q8_0> { static constexpr int TASK_B = 272, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
+template <> struct mmafmt<T_Q6_K> { static constexpr int TASK_B = 210, RESIDUE = 16; static constexpr bool KQ = true,  S16 = true;  };
 
 // One task (256 weights) of rows g (w0) and g+8 (w1) against the eight columns: facc[i] += the task's contribution to output i of the
 // D fragment.  `task` = index of the task in the row (selects the activation slice), t = lane & 3.
@@ -236,5 +264,60 @@ __device__ __forceinline__ void mma_blk32_task(const uint8_t * w0, const uint8_t
 }
 template <> __device__ __forceinline__ void mma_task<T_Q4_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q4_0>(w0, w1, C, A, task, t, facc); }
 template <> __device__ __forceinline__ void mma_task<T_Q8_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q8_0>(w0, w1, C, A, task, t, facc); }
+
+// Q6_K: 210-byte superblocks (ql[128] | qh[64] | int8 scales[16] | d), sixteen 16-weight scale groups -> sixteen m16n8k16 products per task.
+// Group (half n, quarter q, sixteen is) = weights 128 n + 32 q + 16 is .. + 15: low nibbles (q < 2) or high nibbles (q >= 2) of
+// ql[64 n + 32 (q & 1) + 16 is ..], bits 2q, 2q+1 of qh[32 n + 16 is ..], scale index 8 n + 2 q + is = (first weight) / 16.  The "- 32" of
+// the codes is sum_ch scale_ch * (16-sum of the activations)_ch.  Superblocks are only 2-byte aligned: R = 2 for odd tasks of a row slice.
+template <int R>
+__device__ __forceinline__ void mma_q6_task(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    uint32_t scA[4], scB[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { scA[i] = lds4<R>(w0 + 192 + 4 * i); scB[i] = lds4<R>(w1 + 192 + 4 * i); }
+    const uint8_t * y = C.b + 256 * task + 4 * t;
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+#pragma unroll
+        for (int is = 0; is < 2; ++is) {
+            const int o = 16 * is + 4 * t;
+            const uint32_t la0 = lds4<R>(w0 + 64 * n + o), lb0 = lds4<R>(w0 + 64 * n + 32 + o), h0 = lds4<R>(w0 + 128 + 32 * n + o);
+            const uint32_t la1 = lds4<R>(w1 + 64 * n + o), lb1 = lds4<R>(w1 + 64 * n + 32 + o), h1 = lds4<R>(w1 + 128 + 32 * n + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t l0 = (q & 1) ? lb0 : la0, l1 = (q & 1) ? lb1 : la1;
+                const uint32_t a0 = ((q < 2 ? l0 : l0 >> 4) & 0x0F0F0F0Fu) | ((q == 0 ? h0 << 4 : q == 1 ? h0 << 2 : q == 2 ? h0 : h0 >> 2) & 0x30303030u);
+                const uint32_t a1 = ((q < 2 ? l1 : l1 >> 4) & 0x0F0F0F0Fu) | ((q == 0 ? h1 << 4 : q == 1 ? h1 << 2 : q == 2 ? h1 : h1 >> 2) & 0x30303030u);
+                const uint32_t b0 = *(const uint32_t *)(y + 128 * n + 32 * q + 16 * is);
+                int c[4];
+                mma_s8_16x8x16(c, a0, a1, b0);
+                const int ch = 8 * n + 2 * q + is;                      // scale index (compile time)
+                const int sa = (ch & 3) == 0 ? sbyte<0>(scA[ch >> 2]) : (ch & 3) == 1 ? sbyte<1>(scA[ch >> 2]) : (ch & 3) == 2 ? sbyte<2>(scA[ch >> 2]) : sbyte<3>(scA[ch >> 2]);
+                const int sb = (ch & 3) == 0 ? sbyte<0>(scB[ch >> 2]) : (ch & 3) == 1 ? sbyte<1>(scB[ch >> 2]) : (ch & 3) == 2 ? sbyte<2>(scB[ch >> 2]) : sbyte<3>(scB[ch >> 2]);
+                acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+            }
+        }
+    }
+    // offsets: sum over the sixteen groups of scale x (16-sum of the column's activations), two groups per dp2a
+    auto offs = [](const int4 & sa, const int4 & sb, const uint32_t (&sc)[4]) {
+        int o = dp2a_lo_ss(sa.x, sc[0], 0);
+        o = dp2a_hi_ss(sa.y, sc[0], o); o = dp2a_lo_ss(sa.z, sc[1], o); o = dp2a_hi_ss(sa.w, sc[1], o);
+        o = dp2a_lo_ss(sb.x, sc[2], o); o = dp2a_hi_ss(sb.y, sc[2], o); o = dp2a_lo_ss(sb.z, sc[3], o);
+        return dp2a_hi_ss(sb.w, sc[3], o);
+    };
+    const int4 s0a = lds128(C.c0 + A.off_s16 + 32 * task), s0b = lds128(C.c0 + A.off_s16 + 32 * task + 16);
+    const int4 s1a = lds128(C.c1 + A.off_s16 + 32 * task), s1b = lds128(C.c1 + A.off_s16 + 32 * task + 16);
+    const float yd0 = *(const float *)(C.c0 + A.off_d + 4 * task), yd1 = *(const float *)(C.c1 + A.off_d + 4 * task);
+    const float dA = h2f(lds_u16(w0 + 208)), dB = h2f(lds_u16(w1 + 208));
+    facc[0] += (dA * yd0) * (float)(acc[0] - 32 * offs(s0a, s0b, scA));
+    facc[1] += (dA * yd1) * (float)(acc[1] - 32 * offs(s1a, s1b, scA));
+    facc[2] += (dB * yd0) * (float)(acc[2] - 32 * offs(s0a, s0b, scB));
+    facc[3] += (dB * yd1) * (float)(acc[3] - 32 * offs(s1a, s1b, scB));
+}
+template <> __device__ __forceinline__ void mma_task<T_Q6_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    // (w0 and w1 are a multiple of the 16-byte aligned row pitch apart: same residue)
+    if (((uintptr_t)w0 & 2) != 0) mma_q6_task<2>(w0, w1, C, A, task, t, facc);
+    else                          mma_q6_task<0>(w0, w1, C, A, task, t, facc);
+}
 
 } // namespace b200

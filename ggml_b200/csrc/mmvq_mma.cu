@@ -3,8 +3,8 @@
 // Same streaming skeleton as mmvq_sb.cu (persistent CTAs, one TMA producer warp, a ring of bulk-copy stages with full / empty
 // mbarriers, chunks handed out by a self-resetting atomic slot, programmatic dependent launch, weights read once from HBM in the
 // reference's packed layout), different consume phase (b200_sb_mma.cuh):
-//   * a chunk is a TILE of 16 weight rows; the NW (16) consumer warps split the tile's K range by 256-weight task (task i of a slice
-//     goes to warp i mod NW), each multiplying its 16 x 256 weights with all (<= 8) activation columns on the tensor cores
+//   * a chunk is a TILE of 16 weight rows; the eight consumer warps of a group split the tile's K range by 256-weight task (task i of a
+//     slice goes to warp i mod 8), each multiplying its 16 x 256 weights with all (<= 8) activation columns on the tensor cores
 //     (m16n8k32, int8 x int8 -> int32, exactly the integer block dots of ggml-cpu) and keeping 4 f32 partial outputs per lane;
 //   * rows too long for a ring of whole-row stages are streamed in K slices of KS tasks (consecutive stages of the same tile, the
 //     accumulators stay in registers across them);
@@ -28,6 +28,7 @@ namespace b200 {
 
 constexpr int MMA_MAX_STAGES = 8;
 constexpr int MMA_TILE = 16;             // rows per tile (the m of m16n8k32)
+constexpr int MMA_GROUP_WARPS = 8;       // consumer warps per group
 
 struct mma_params {
     const uint8_t * w; const float * x; float * y;
@@ -53,41 +54,46 @@ __global__ void __launch_bounds__(256) mma_quantize_kernel(const float * __restr
     mma_quantize_task_h<KQ, S16>(x + (size_t)c * x_stride, ok, rec + (size_t)c * A.col_bytes, A, t);
 }
 
-template <int T, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_params p) {
+// NG consumer groups per CTA, each = 8 consumer warps + its own producer warp, stage ring, barriers and tile sequence (group v of the
+// NG * grid "virtual CTAs" takes tiles v, v + NG * grid, ...); the groups share the activation records.  Two groups drift out of phase, so one
+// group's fragment loads overlap the other's mma / scaling arithmetic, and a tile round costs a group-time instead of a CTA-time.
+template <int T, int NG>
+__global__ void __launch_bounds__(NG * (MMA_GROUP_WARPS + 1) * 32, 1) mmvq_mma_kernel(const mma_params p) {
     using F = mmafmt<T>;
-    constexpr int MMA_WARPS = NW;
+    constexpr int GW = MMA_GROUP_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t * stages = smem;
-    uint8_t * rec    = stages + (size_t)p.nstages * p.stage_bytes;                  // ncols planar records
-    float * partial  = (float *)(rec + (size_t)p.ncols * p.A.col_bytes);            // [2][MMA_WARPS][128]
-    uint64_t * full  = (uint64_t *)(partial + 2 * MMA_WARPS * 128);
-    uint64_t * empty = full + MMA_MAX_STAGES;
-    uint64_t * rec_full = empty + MMA_MAX_STAGES;                                   // the activation records have landed
-    int2 * unit_of   = (int2 *)(rec_full + 2);                                      // (tile, slice) held by each stage; tile < 0 = end
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / (GW + 1), wg = warp - grp * (GW + 1);                    // group, warp within the group (GW = the producer)
+    uint8_t * stages = smem + (size_t)grp * p.nstages * p.stage_bytes;              // this group's ring (p.nstages stages per group)
+    uint8_t * rec    = smem + (size_t)NG * p.nstages * p.stage_bytes;               // ncols planar records
+    float * partial  = (float *)(rec + (size_t)p.ncols * p.A.col_bytes) + grp * (2 * GW * 128);   // per group [2][GW][128]
+    uint64_t * bars  = (uint64_t *)((float *)(rec + (size_t)p.ncols * p.A.col_bytes) + NG * (2 * GW * 128));
+    uint64_t * full  = bars + grp * (2 * MMA_MAX_STAGES);
+    uint64_t * empty = full + MMA_MAX_STAGES;
+    uint64_t * rec_full = bars + NG * (2 * MMA_MAX_STAGES);                         // the activation records have landed
+    int2 * unit_of   = (int2 *)(rec_full + 2) + grp * MMA_MAX_STAGES;               // (tile, slice) held by each stage; tile < 0 = end
+
     pdl_launch_dependents();
-    if (tid == 0) {
-        for (int s = 0; s < p.nstages; ++s) { sb_mbar_init(&full[s], 1); sb_mbar_init(&empty[s], MMA_WARPS); }
-        sb_mbar_init(rec_full, 1);
+    if (wg == 0 && lane == 0) {
+        for (int s = 0; s < p.nstages; ++s) { sb_mbar_init(&full[s], 1); sb_mbar_init(&empty[s], GW); }
+        if (grp == 0) sb_mbar_init(rec_full, 1);
         sb_fence_mbar_init();
     }
     __syncthreads();
+    const int vcta = (int)blockIdx.x * NG + grp, vgrid = (int)gridDim.x * NG;
 
-    if (warp == MMA_WARPS) {
+    if (wg == GW) {
         // ===== producer warp: lane r copies row r of the tile (slice) — sixteen bulk copies per stage, one barrier
         if (!p.src0_static) pdl_wait();
         int s = 0; uint32_t par = 0; bool wrapped = false;        // ring position: stage, parity of the round, past the first round
-        int tile = (int)blockIdx.x;
+        int tile = vcta;
         bool first = true;
         while (true) {
             const bool valid = tile < p.ntiles;
-            // Tiles are dealt round-robin (tile b, b + grid, ...) unless p.counters is set.  Dynamic hand-out (one global atomic per tile, as
-            // mmvq_sb.cu does per 36 KB chunk) starved the ring: the producer issued ONE stage per atomic round trip (~1 us), ncu showed the
-            // consumers waiting for `full` a third of the time at 22 % of the DRAM peak (profiles/r02_mma_small_batch.md).
-            int next = tile + (int)gridDim.x;
-            if (p.counters && valid && lane == 0) next = (int)atomicAdd(&p.counters[0], 1u) + (int)gridDim.x;
+            // Tiles are dealt round-robin (v, v + vgrid, ...) unless p.counters is set.  Dynamic hand-out (one global atomic per tile) gained
+            // nothing here: with a few tiles per group the atomic's round trip sits between consecutive stages of the ring.
+            int next = tile + vgrid;
+            if (p.counters && valid && lane == 0) next = (int)atomicAdd(&p.counters[0], 1u) + vgrid;
             const int nsl = valid ? p.nslices : 1;
             for (int sl = 0; sl < nsl; ++sl) {
                 if (wrapped) sb_mbar_wait(&empty[s], par ^ 1u);
@@ -109,9 +115,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
             }
             if (first && p.l2_prefetch_bytes > 0 && lane == 0) {
                 // a dependent launch cannot consume before its predecessor's output is visible, but HBM need not idle meanwhile:
-                // CTA b pulls slice b of the matrix into L2, the ring then streams from L2
-                const int64_t per = ((p.l2_prefetch_bytes + gridDim.x - 1) / gridDim.x + 15) & ~(int64_t)15;
-                const int64_t lo = (int64_t)blockIdx.x * per;
+                // virtual CTA v pulls slice v of the matrix into L2, the rings then stream from L2
+                const int64_t per = ((p.l2_prefetch_bytes + vgrid - 1) / vgrid + 15) & ~(int64_t)15;
+                const int64_t lo = (int64_t)vcta * per;
                 const int64_t hi = min(lo + per, p.l2_prefetch_bytes & ~(int64_t)15);
                 for (int64_t o = lo; o < hi; o += 32768) sb_prefetch_l2(p.w + o, (uint32_t)min((int64_t)32768, hi - o));
             }
@@ -120,9 +126,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
             tile = p.counters ? __shfl_sync(0xffffffffu, next, 0) : next;
         }
         if (p.counters && lane == 0) {
-            // last CTA to finish its scheduling resets the counters for the next launch
+            // last producer to finish its scheduling resets the counters for the next launch
             __threadfence();
-            if (atomicAdd(&p.counters[1], 1u) == gridDim.x - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
+            if (atomicAdd(&p.counters[1], 1u) == (unsigned)vgrid - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
         }
         return;
     }
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
     sb_mbar_wait(rec_full, 0u);
 
     const int g = lane >> 2, t = lane & 3;
+    const int gtid = wg * 32 + lane;                                                // thread index within the group's consumers
     mma_cols C;
     C.b  = rec + (size_t)min(g, p.ncols - 1) * p.A.col_bytes;                       // columns beyond n repeat the last one (results discarded)
     C.c0 = rec + (size_t)min(2 * t, p.ncols - 1) * p.A.col_bytes;
@@ -150,24 +157,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
         if (unit.x < 0) break;
         const int nt = min(p.ks, p.ntask_row - unit.y * p.ks);
         const uint8_t * st = stages + (size_t)s * p.stage_bytes + (size_t)g * p.pitch;
-        for (int i = warp; i < nt; i += MMA_WARPS)
+        for (int i = wg; i < nt; i += GW)
             mma_task<T>(st + (size_t)i * F::TASK_B, st + (size_t)i * F::TASK_B + (size_t)8 * p.pitch, C, p.A, unit.y * p.ks + i, t, facc);
         __syncwarp();
         if (lane == 0) sb_mbar_arrive(&empty[s]);
         if (++s == p.nstages) { s = 0; par ^= 1u; }
         if (unit.y == p.nslices - 1) {
-            // tile finished: the eight warps' partial fragments meet in shared memory and are summed in warp order
-            float * part = partial + buf * (MMA_WARPS * 128);
-            *(float4 *)(part + warp * 128 + lane * 4) = make_float4(facc[0], facc[1], facc[2], facc[3]);
+            // tile finished: the group's eight partial fragments meet in shared memory and are summed in warp order
+            float * part = partial + buf * (GW * 128);
+            *(float4 *)(part + wg * 128 + lane * 4) = make_float4(facc[0], facc[1], facc[2], facc[3]);
             facc[0] = facc[1] = facc[2] = facc[3] = 0.0f;
-            asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");
-            if (tid < 128) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GW * 32) : "memory");   // this group's consumers only
+            if (gtid < 128) {
                 // thread o writes (column o / 16, row o % 16): consecutive threads, consecutive rows of one column
-                const int col = tid >> 4, row = tid & 15;
+                const int col = gtid >> 4, row = gtid & 15;
                 const int src = ((row & 7) * 4 + (col >> 1)) * 4 + (row >> 3) * 2 + (col & 1);
                 float sum = part[src];
 #pragma unroll
-                for (int w = 1; w < MMA_WARPS; ++w) sum += part[w * 128 + src];
+                for (int w = 1; w < GW; ++w) sum += part[w * 128 + src];
                 const int64_t grow = (int64_t)unit.x * MMA_TILE + row;
                 if (col < p.ncols && grow < p.M) p.y[(size_t)col * p.M + grow] = sum;
             }
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) mmvq_mma_kernel(const mma_pa
     }
 }
 
-struct mma_plan { mma_params p; int grid, smem, nw; };
+struct mma_plan { mma_params p; int grid, smem, ng; };
 
 template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma_plan & pl) {
     using F = mmafmt<T>;
@@ -190,7 +197,7 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     p.row_bytes = (int)rb;
     p.ntiles = (int)((a.M + MMA_TILE - 1) / MMA_TILE);
     p.ntask_row = (int)(a.K / 256);
-    p.A = make_mma_act(a.K, F::KQ, F::S16);
+    p.A = make_mma_act(a.K, F::KQ, F::S16, F::RESIDUE);
     p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
     p.counters = nullptr; p.rec_global = nullptr;
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
@@ -200,49 +207,51 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     // slices of KS tasks (a multiple of the warp count): whole rows when at least three such stages fit next to the records
     static const int e_ks = getenv("GGML_B200_MMA_KS") ? atoi(getenv("GGML_B200_MMA_KS")) : 0;
     static const int e_stages = getenv("GGML_B200_MMA_STAGES") ? atoi(getenv("GGML_B200_MMA_STAGES")) : 0;
-    // consumer warps: 8 (16 selectable: GGML_B200_MMA_WARPS).  Sixteen warps on one tile measured 5-10 % SLOWER: all warps of a CTA walk the
-    // load -> unpack -> mma -> scale phases of a tile in lock-step, so the LSU, the tensor pipe and the ALUs are used one after the other
-    // whatever the warp count, and the per-tile barrier and reduction grow (profiles/r02_mma_small_batch.md)
-    static const int e_warps = getenv("GGML_B200_MMA_WARPS") ? atoi(getenv("GGML_B200_MMA_WARPS")) : 8;
-    pl.nw = e_warps == 16 ? 16 : 8;
-    const size_t fixed = (size_t)p.ncols * p.A.col_bytes + 2 * (size_t)pl.nw * 128 * 4 + 2 * MMA_MAX_STAGES * 8 + 16 + MMA_MAX_STAGES * 8 + 128;
+    // consumer groups: 2 by default (GGML_B200_MMA_GROUPS = 1: one group).  (Sixteen warps on ONE tile were 5-10 % slower than eight: all warps
+    // of a tile walk the load -> unpack -> mma -> scale phases in lock-step; two independent groups do not.)
+    static const int e_groups = getenv("GGML_B200_MMA_GROUPS") ? atoi(getenv("GGML_B200_MMA_GROUPS")) : 2;
     const size_t budget = 226 * 1024;
-    if (fixed + 2 * 8 * F::TASK_B * MMA_TILE > budget) return false;
-    auto geometry = [&](int ks) {
-        p.ks = ks;
-        p.nslices = (p.ntask_row + ks - 1) / ks;
-        int pitch = std::min(ks, p.ntask_row) * F::TASK_B;
-        pitch = (pitch + 31) & ~31;
-        while ((pitch & 127) != 32) pitch += 32;
-        p.pitch = pitch;
-        p.stage_bytes = (pitch * MMA_TILE + 127) & ~127;
-        return (int)std::min<size_t>((budget - fixed) / p.stage_bytes, MMA_MAX_STAGES);
-    };
-    int ks = e_ks > 0 ? e_ks : 16;                       // 16 tasks x 16 rows: 36 KB (Q4_K) .. 70 KB (Q8_0) per stage
-    if (ks > p.ntask_row) ks = p.ntask_row;
-    int nst = geometry(ks);
-    while (nst < 3 && ks > 8) { ks = std::max(8, ks / 2); nst = geometry(ks); }
-    if (nst < 2) return false;
-    if (e_stages >= 2 && e_stages <= nst) nst = e_stages;
-    // no deeper than the units a CTA can expect (+1): short launches should not pay for barrier set-up they never use
-    p.nstages = nst;
-    pl.smem = (int)(fixed + (size_t)p.nstages * p.stage_bytes);
-    pl.grid = std::min(sm_count(), p.ntiles);
-    return true;
+    for (int ng = e_groups == 1 ? 1 : 2; ng >= 1; --ng) {            // two groups when each gets a ring of >= 2 stages next to the records
+        pl.ng = ng;
+        const size_t fixed = (size_t)p.ncols * p.A.col_bytes + (size_t)ng * 2 * MMA_GROUP_WARPS * 128 * 4 + (size_t)ng * 2 * MMA_MAX_STAGES * 8 + 16
+                           + (size_t)ng * MMA_MAX_STAGES * 8 + 128;
+        if (fixed + (size_t)ng * 2 * 8 * F::TASK_B * MMA_TILE > budget) continue;
+        auto geometry = [&](int ks) {
+            p.ks = ks;
+            p.nslices = (p.ntask_row + ks - 1) / ks;
+            int pitch = std::min(ks, p.ntask_row) * F::TASK_B;
+            pitch = (pitch + 15) & ~15;
+            while ((pitch & 127) != F::RESIDUE) pitch += 16;
+            p.pitch = pitch;
+            p.stage_bytes = (pitch * MMA_TILE + 127) & ~127;
+            return (int)std::min<size_t>((budget - fixed) / p.stage_bytes / ng, MMA_MAX_STAGES);   // stages per group
+        };
+        int ks = e_ks > 0 ? e_ks : 16;                   // 16 tasks x 16 rows: 36 KB (Q4_K) .. 70 KB (Q8_0) per stage
+        if (ks > p.ntask_row) ks = p.ntask_row;
+        int nst = geometry(ks);
+        while (nst < (ng == 1 ? 3 : 2) && ks > 8) { ks = std::max(8, ks / 2); nst = geometry(ks); }
+        if (nst < 2) continue;
+        if (e_stages >= 2 && e_stages <= nst) nst = e_stages;
+        p.nstages = nst;
+        pl.smem = (int)(fixed + (size_t)ng * p.nstages * p.stage_bytes);
+        pl.grid = std::min(sm_count(), (p.ntiles + ng - 1) / ng);
+        return true;
+    }
+    return false;
 }
 
 static size_t mma_rec_bytes(const mma_plan & pl) { return (size_t)pl.p.ncols * pl.p.A.col_bytes; }
 
-template <int T, int NW> static int launch_mma_nw(const mma_plan & pl, cudaStream_t st, const cudaLaunchAttribute * attr, int nattr) {
+template <int T, int NG> static int launch_mma_ng(const mma_plan & pl, cudaStream_t st, const cudaLaunchAttribute * attr, int nattr) {
     static per_device_flag attr_set;
     if (!attr_set.test()) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set.set();
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3((NW + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(NG * (MMA_GROUP_WARPS + 1) * 32); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
     cfg.attrs = const_cast<cudaLaunchAttribute *>(attr); cfg.numAttrs = nattr;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<T, NW>, pl.p));
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<T, NG>, pl.p));
     B200_LAUNCH_CHECK();
     return GGML_B200_OK;
 }
@@ -270,7 +279,7 @@ template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStr
         B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_quantize_kernel<F::KQ, F::S16>, a.src1, pl.p.x_stride, (int)pl.p.ncols, pl.p.A, rec));
         B200_LAUNCH_CHECK();
     }
-    return pl.nw == 8 ? launch_mma_nw<T, 8>(pl, st, attr, use_pdl ? 1 : 0) : launch_mma_nw<T, 16>(pl, st, attr, use_pdl ? 1 : 0);
+    return pl.ng == 1 ? launch_mma_ng<T, 1>(pl, st, attr, use_pdl ? 1 : 0) : launch_mma_ng<T, 2>(pl, st, attr, use_pdl ? 1 : 0);
 }
 
 size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a) {
@@ -281,6 +290,7 @@ size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a) {
         case T_Q8_0: ok = make_mma_plan<T_Q8_0>(a, pl); break;
         case T_Q4_K: ok = make_mma_plan<T_Q4_K>(a, pl); break;
         case T_Q5_K: ok = make_mma_plan<T_Q5_K>(a, pl); break;
+        case T_Q6_K: ok = make_mma_plan<T_Q6_K>(a, pl); break;
         default: break;
     }
     return ok ? mma_rec_bytes(pl) + 256 : 0;
@@ -293,6 +303,7 @@ bool mmvq_mma_eligible(const ggml_b200_mul_mat_args & a) {
         case T_Q8_0: return make_mma_plan<T_Q8_0>(a, pl);
         case T_Q4_K: return make_mma_plan<T_Q4_K>(a, pl);
         case T_Q5_K: return make_mma_plan<T_Q5_K>(a, pl);
+        case T_Q6_K: return make_mma_plan<T_Q6_K>(a, pl);
         default: return false;
     }
 }
@@ -303,6 +314,7 @@ int launch_mmvq_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q8_0: return launch_mma<T_Q8_0>(a, st);
         case T_Q4_K: return launch_mma<T_Q4_K>(a, st);
         case T_Q5_K: return launch_mma<T_Q5_K>(a, st);
+        case T_Q6_K: return launch_mma<T_Q6_K>(a, st);
         default: set_error("mul_mat: unsupported weight type %d for the mma kernel", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }

@@ -61,7 +61,7 @@ template <int T> static void sb_row_nc(const uint8_t * row, int64_t K, const uin
 // ncols (<= 8) activation columns (column c at x + c * K): planar records by the kernel's quantizer, every task by mma_task; out[16][8]
 template <int T> static void mma_tile(const uint8_t * rows, int64_t pitch, int64_t K, const float * x, int ncols, float * out) {
     using F = mmafmt<T>;
-    const mma_act A = make_mma_act(K, F::KQ, F::S16);
+    const mma_act A = make_mma_act(K, F::KQ, F::S16, F::RESIDUE);
     std::vector<uint8_t> rec((size_t)ncols * A.col_bytes + 64);
     uint8_t * recp = rec.data();
     warp_emu::run([&] {
@@ -199,6 +199,7 @@ int emu_mma_tile(int type, const uint8_t * rows, int64_t pitch, int64_t K, const
         case T_Q8_0: mma_tile<T_Q8_0>(rows, pitch, K, x, ncols, out); return 0;
         case T_Q4_K: mma_tile<T_Q4_K>(rows, pitch, K, x, ncols, out); return 0;
         case T_Q5_K: mma_tile<T_Q5_K>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q6_K: mma_tile<T_Q6_K>(rows, pitch, K, x, ncols, out); return 0;
         default: return -1;
     }
 }
