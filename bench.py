@@ -714,7 +714,12 @@ def main():
                 ("q8_0_4096x32000_n1", lambda: extra_matvec(torch, g, timer, 8, 32000, 4096, peaks, dependent_too=False)),
                 ("q4_K_4096x32000_n512_tcgen05", lambda: extra_gemm(torch, g, timer, 12, 32000, 512, 4096, peaks)),
                 ("q8_0_4096x32000_n512_tcgen05", lambda: extra_gemm(torch, g, timer, 8, 32000, 512, 4096, peaks)),
-                ("q4_K_4096x11008_n8", lambda: extra_small_batch(torch, g, timer, 12, 11008, 8, 4096, peaks))]
+                ("q4_K_4096x11008_n8", lambda: extra_small_batch(torch, g, timer, 12, 11008, 8, 4096, peaks)),
+                # the reference harness' own perf shape (tests/test-backend-ops.cpp:4340-4346: m = 4096, k = 14336) at n = 8, and n = 2
+                ("q4_K_14336x4096_n8", lambda: extra_small_batch(torch, g, timer, 12, 4096, 8, 14336, peaks)),
+                ("q8_0_14336x4096_n8", lambda: extra_small_batch(torch, g, timer, 8, 4096, 8, 14336, peaks)),
+                ("q6_K_14336x4096_n8", lambda: extra_small_batch(torch, g, timer, 14, 4096, 8, 14336, peaks)),
+                ("q4_K_14336x4096_n2", lambda: extra_small_batch(torch, g, timer, 12, 4096, 2, 14336, peaks))]
         for name, job in jobs:
             try:
                 extra[name] = job()
@@ -793,7 +798,7 @@ def main():
 
 
 def extra_small_batch(torch, g, timer, t, M, n, K, peaks, seed=13):
-    """2 <= n <= 8 on the superblock mat-vec kernel"""
+    """2 <= n <= 8 on the bandwidth path (mmvq_mma.cu: int8 mma.sync consume phase; dependent launches, weights streaming from HBM)"""
     wb = weight_bytes(K, M, t)
     nbuf = max(3, math.ceil(300e6 / wb))
     Ws = make_weights(torch, t, nbuf, K, M, seed)
@@ -810,7 +815,8 @@ def extra_small_batch(torch, g, timer, t, M, n, K, peaks, seed=13):
     nm = max(parity_rows(t, Ws[i], X.cpu().numpy(), Ys[i], M, n, K, nrows=32, seed=i) for i in range(nbuf))
     assert nm <= 1e-10, f"parity failure small batch: {nm}"
     ab = algorithmic_bytes(K, M, n, t)
-    return {"shape": f"{TNAME[t]} {K}x{M} n={n}", "us_per_mul_mat": us, "GBps": wb / us / 1e3, "parity_nmse": nm,
+    return {"shape": f"{TNAME[t]} {K}x{M} n={n}", "us_per_mul_mat": us, "GBps": wb / us / 1e3, "parity_nmse": nm, "launches_per_mul_mat": 2,
+            "kernels": "mma_quantize_kernel (activations -> int8 records, once per launch) + mmvq_mma_kernel",
             "roofline": {"bound": "hbm", "achieved": ab / us / 1e3, "peak": peaks["hbm"], "unit": "GB/s", "frac": ab / us / 1e3 / peaks["hbm"]}}
 
 

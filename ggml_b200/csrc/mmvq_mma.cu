@@ -207,11 +207,12 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     // slices of KS tasks (a multiple of the warp count): whole rows when at least three such stages fit next to the records
     static const int e_ks = getenv("GGML_B200_MMA_KS") ? atoi(getenv("GGML_B200_MMA_KS")) : 0;
     static const int e_stages = getenv("GGML_B200_MMA_STAGES") ? atoi(getenv("GGML_B200_MMA_STAGES")) : 0;
-    // consumer groups: 2 by default (GGML_B200_MMA_GROUPS = 1: one group).  (Sixteen warps on ONE tile were 5-10 % slower than eight: all warps
-    // of a tile walk the load -> unpack -> mma -> scale phases in lock-step; two independent groups do not.)
-    static const int e_groups = getenv("GGML_B200_MMA_GROUPS") ? atoi(getenv("GGML_B200_MMA_GROUPS")) : 2;
+    // consumer groups per CTA: 1 by default, GGML_B200_MMA_GROUPS = 2 for two independent groups.  Measured (profiles/r02_mma_small_batch.md):
+    // 16 warps on ONE tile 5-10 % slower than 8; two groups of 8 within +-8 % of one group (faster on long rows, slower on short ones) --
+    // the time per tile does not follow the warp count, i.e. the consume phase is bound by a per-SM rate, not by latency.
+    static const int e_groups = getenv("GGML_B200_MMA_GROUPS") ? atoi(getenv("GGML_B200_MMA_GROUPS")) : 1;
     const size_t budget = 226 * 1024;
-    for (int ng = e_groups == 1 ? 1 : 2; ng >= 1; --ng) {            // two groups when each gets a ring of >= 2 stages next to the records
+    for (int ng = e_groups == 2 ? 2 : 1; ng >= 1; --ng) {            // two groups when each gets a ring of >= 2 stages next to the records
         pl.ng = ng;
         const size_t fixed = (size_t)p.ncols * p.A.col_bytes + (size_t)ng * 2 * MMA_GROUP_WARPS * 128 * 4 + (size_t)ng * 2 * MMA_MAX_STAGES * 8 + 16
                            + (size_t)ng * MMA_MAX_STAGES * 8 + 128;
