@@ -87,7 +87,7 @@ def test_split_buffer_mul_mat(plugin):
     (src/ggml-cuda/ggml-cuda.cu:1000, 3374-3380), rows sharded over every visible device, MUL_MAT through the vtable.  With one GPU
     the split is trivial (plumbing check: init_tensor / scatter set_tensor / gather get_tensor / compute); with more it is the
     single-process multi-device path (peer stores into the main device's dst over NVLink for n = 1, staged peer copies for batches).
-    The result must equal the 1-device result (bit-identical for the mat-vec: same kernel, rows are independent) and the oracle."""
+    The result must equal the 1-device result (bit-identical wherever both run the same kernel: rows are independent) and the oracle."""
     import torch
     ref = O.Ref()
     assert ref.load_backend(plugin)
@@ -102,8 +102,12 @@ def test_split_buffer_mul_mat(plugin):
         Y1, _ = ref.mul_mat(t, W, X, M, N, K, dev="B2000")
         for ts in splits:
             Ys, _ = ref.mul_mat_split(t, W, X, M, N, K, dev="B2000", main_device=0, tensor_split=ts)
-            if N <= 8:
+            if N <= 8 and not (N == 1 and K >= 8192):
                 assert np.array_equal(Ys, Y1[0, 0]), (O.TYPE_NAMES[t], M, N, K, ts)
+            elif N == 1:
+                # long rows: one device runs the mma kernel (api.cu::mma_wanted), the split path the fused-gather dp4a kernel: same integer
+                # dots, different f32 summation order
+                assert O.nmse(Ys, Y1[0, 0]) < 1e-12, (O.TYPE_NAMES[t], M, N, K, ts)
             else:
                 assert O.nmse(Ys, Y1[0, 0]) < 1e-6, (O.TYPE_NAMES[t], M, N, K, ts)       # tile / split-K grouping differs per shard
         rows = rng.choice(M, 64, replace=False)
