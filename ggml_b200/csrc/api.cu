@@ -47,13 +47,14 @@ static int validate(const ggml_b200_mul_mat_args * a) {
     return GGML_B200_OK;
 }
 
-// the int8 mma.sync consume path (mmvq_mma.cu): default for 2 <= n <= 8, and for n = 1 when the rows are long (K >= 8192: the dp4a kernel's
-// activation record leaves room for two stages only; measured at K = 14336: Q6_K 21.0 -> 13.5 us, Q4_K 12.2 -> 10.3, Q8_0 18.8 -> 14.6).
+// the int8 mma.sync consume path (mmvq_mma.cu): default for 2 <= n <= 8, and for n = 1 when the rows are very long (K >= 12288: the dp4a kernel's
+// chunks shrink to a few rows there; measured at K = 14336: Q6_K 21.0 -> 13.5 us, Q4_K 12.2 -> 10.3, Q8_0 18.8 -> 14.6; at K = 8192 the dp4a
+// kernel is still the faster one: Q4_K 8192 x 28672 24.0 vs 31.4 us).
 // GGML_B200_MMA = 0 never, 2 always; per call GGML_B200_MM_GEMV_MMA / GGML_B200_MM_GEMV_DP4A select explicitly
 static bool mma_wanted(const ggml_b200_mul_mat_args & a) {
     static const int env = getenv("GGML_B200_MMA") ? atoi(getenv("GGML_B200_MMA")) : 1;
     if (a.flags & (GGML_B200_MM_GEMV_V1 | GGML_B200_MM_GEMV_DP4A)) return false;
-    if (!(a.flags & GGML_B200_MM_GEMV_MMA) && (env == 0 || (a.N < 2 && env != 2 && a.K < 8192))) return false;
+    if (!(a.flags & GGML_B200_MM_GEMV_MMA) && (env == 0 || (a.N < 2 && env != 2 && a.K < 12288))) return false;
     return mmvq_mma_eligible(a);
 }
 
