@@ -23,18 +23,20 @@ namespace b200 {
 //   +off_h32  h32 : per 32-value block one int16 sum of its codes (16 bytes per 256-value task)
 //   +off_s16  s16 : (formats with 16-wide scale groups) per 16 values one int16 sum (32 bytes per task); absent otherwise
 //   +off_d    d   : Q8_K family: one float per task; Q8_0 family: one float per 32-value block (fp16-rounded)
+//   +off_s    s   : (weight formats with a minimum, Q4_1 / Q5_1) block_q8_1.s = fp16(d_unrounded * sum of the block's codes), as a float per block
 // col_bytes = 32 (mod 128): the eight columns' 8-byte fragment loads of a half-warp fall into distinct bank groups (formats whose lanes
 // load 4-byte fragments, Q6_K: 16 (mod 128), eight columns x 16 bytes = all 32 banks).
 struct mma_act {
-    int32_t ntask, off_h32, off_s16, off_d, col_bytes;
+    int32_t ntask, off_h32, off_s16, off_d, off_s, col_bytes;
 };
-__host__ __device__ inline mma_act make_mma_act(int64_t K, bool kq, bool s16, int residue = 32) {
+__host__ __device__ inline mma_act make_mma_act(int64_t K, bool kq, bool s16, int residue = 32, bool s81 = false) {
     mma_act A;
     A.ntask = (int32_t)(K / 256);
     A.off_h32 = (int32_t)K;
     A.off_s16 = A.off_h32 + 16 * A.ntask;
     A.off_d = A.off_s16 + (s16 ? 32 * A.ntask : 0);
-    int32_t bytes = A.off_d + (kq ? 4 : 32) * A.ntask;
+    A.off_s = A.off_d + (kq ? 4 : 32) * A.ntask;
+    int32_t bytes = A.off_s + (s81 ? 32 * A.ntask : 0);
     bytes = (bytes + 15) & ~15;
     while ((bytes & 127) != residue) bytes += 16;
     A.col_bytes = bytes;
@@ -42,7 +44,7 @@ __host__ __device__ inline mma_act make_mma_act(int64_t K, bool kq, bool s16, in
 }
 
 // half a warp quantizes act-task t of one column into the planar record at `col` (same arithmetic as sb_quantize_task_h)
-template <bool KQ, bool S16> __device__ __forceinline__ void mma_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * col, const mma_act & A, int t) {
+template <bool KQ, bool S16, bool S81 = false> __device__ __forceinline__ void mma_quantize_task_h(const float * __restrict__ x, bool valid, uint8_t * col, const mma_act & A, int t) {
     const int l = threadIdx.x & 15;
     const sb_qtask r = sb_quantize_core<KQ>(x, valid, t);
     if (valid) {
@@ -51,6 +53,7 @@ template <bool KQ, bool S16> __device__ __forceinline__ void mma_quantize_task_h
         if ((l & 1) == 0) *(int16_t *)(col + A.off_h32 + 16 * t + 2 * (l >> 1)) = (int16_t)r.s2;
         if constexpr (KQ) { if (l == 0) *(float *)(col + A.off_d + 4 * t) = r.d; }
         else              { if ((l & 1) == 0) *(float *)(col + A.off_d + 32 * t + 4 * (l >> 1)) = r.d; }
+        if constexpr (!KQ && S81) { if ((l & 1) == 0) *(float *)(col + A.off_s + 32 * t + 4 * (l >> 1)) = __half2float(__float2half_rn(__fmul_rn(r.dun, (float)r.s2))); }
     }
 }
 
@@ -132,6 +135,13 @@ template <int R> inline uint2 lds8(const uint8_t * p) { uint2 v; std::memcpy(&v,
 inline uint32_t lds_u16(const uint8_t * p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
 #endif
 
+// sixteen bytes at a 4-byte aligned address
+__device__ __forceinline__ int4 lds128w(const uint8_t * p) {
+    const uint32_t * q = (const uint32_t *)p;
+    int4 v; v.x = (int)q[0]; v.y = (int)q[1]; v.z = (int)q[2]; v.w = (int)q[3];
+    return v;
+}
+
 // what a lane needs of the activation columns for one task: its B column (fragment loads) and its two output columns (sums, scales)
 struct mma_cols {
     const uint8_t * b;       // column g (clamped to the last real column): B fragments
@@ -146,6 +156,15 @@ template <> struct mmafmt<T_Q5_K> { static constexpr int TASK_B = 176, RESIDUE =
 template <> struct mmafmt<T_Q4_0> { static constexpr int TASK_B = 144, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
 template <> struct mmafmt<T_Q8_0> { static constexpr int TASK_B = 272, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
 template <> struct mmafmt<T_Q6_K> { static constexpr int TASK_B = 210, RESIDUE = 16; static constexpr bool KQ = true,  S16 = true;  };
+template <> struct mmafmt<T_Q5_0>   { static constexpr int TASK_B = 176, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
+template <> struct mmafmt<T_Q4_1>   { static constexpr int TASK_B = 160, RESIDUE = 32; static constexpr bool KQ = false, S16 = false, S81 = true; };
+template <> struct mmafmt<T_Q5_1>   { static constexpr int TASK_B = 192, RESIDUE = 32; static constexpr bool KQ = false, S16 = false, S81 = true; };
+template <> struct mmafmt<T_IQ4_NL> { static constexpr int TASK_B = 144, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
+template <> struct mmafmt<T_IQ4_XS> { static constexpr int TASK_B = 136, RESIDUE = 32; static constexpr bool KQ = true,  S16 = false; };
+template <> struct mmafmt<T_Q2_K>   { static constexpr int TASK_B = 84,  RESIDUE = 16; static constexpr bool KQ = true,  S16 = true;  };
+// (formats without a minimum: no Q8_1 s region)
+template <int T, typename = void> struct mma_s81 { static constexpr bool value = false; };
+template <int T> struct mma_s81<T, decltype((void)mmafmt<T>::S81)> { static constexpr bool value = mmafmt<T>::S81; };
 
 // One task (256 weights) of rows g (w0) and g+8 (w1) against the eight columns: facc[i] += the task's contribution to output i of the
 // D fragment.  `task` = index of the task in the row (selects the activation slice), t = lane & 3.
@@ -212,58 +231,152 @@ __device__ __forceinline__ void mma_q45_task(const uint8_t * w0, const uint8_t *
 template <> __device__ __forceinline__ void mma_task<T_Q4_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_q45_task<false>(w0, w1, C, A, task, t, facc); }
 template <> __device__ __forceinline__ void mma_task<T_Q5_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_q45_task<true>(w0, w1, C, A, task, t, facc); }
 
-// 32-weight block formats (Q4_0: 18-byte blocks, weight i in the low nibble of byte i, weight i + 16 in the high one; Q8_0: 34-byte
-// blocks of int8): a task = eight blocks.  Block b starts at BLK * b from a 16-byte aligned task base, its codes 2 bytes later:
-// the residue of every 8-byte fragment load mod 8 is (2 b + 2) mod 8, a compile-time constant.
+// 32-weight block formats: a task = eight blocks.  Block layouts (bytes): Q4_0 / IQ4_NL d | qs[16]; Q5_0 d | qh[4] | qs[16]; Q4_1 d | m | qs[16];
+// Q5_1 d | m | qh[4] | qs[16]; Q8_0 d | int8[32].  4-bit formats: weight i in the low nibble of qs[i], weight i + 16 in the high one, fifth bit i of qh.
+// Block b starts at BLK * b from a 16-byte aligned task base: the residue of every fragment load mod 8 (mod 4) is a compile-time constant.
+template <int T> struct blk32fmt;
+template <> struct blk32fmt<T_Q4_0>   { static constexpr int BLK = 18, QS = 2, QH = -1, OFF = 8;  static constexpr bool NIB = true,  MIN = false, LUT = false; };
+template <> struct blk32fmt<T_IQ4_NL> { static constexpr int BLK = 18, QS = 2, QH = -1, OFF = 0;  static constexpr bool NIB = true,  MIN = false, LUT = true;  };
+template <> struct blk32fmt<T_Q5_0>   { static constexpr int BLK = 22, QS = 6, QH = 2,  OFF = 16; static constexpr bool NIB = true,  MIN = false, LUT = false; };
+template <> struct blk32fmt<T_Q4_1>   { static constexpr int BLK = 20, QS = 4, QH = -1, OFF = 0;  static constexpr bool NIB = true,  MIN = true,  LUT = false; };
+template <> struct blk32fmt<T_Q5_1>   { static constexpr int BLK = 24, QS = 8, QH = 4,  OFF = 0;  static constexpr bool NIB = true,  MIN = true,  LUT = false; };
+template <> struct blk32fmt<T_Q8_0>   { static constexpr int BLK = 34, QS = 2, QH = -1, OFF = 0;  static constexpr bool NIB = false, MIN = false, LUT = false; };
+
 template <int T, int B>
 __device__ __forceinline__ void mma_blk32(const uint8_t * w0, const uint8_t * w1, const uint8_t * y, const int4 & s0, const int4 & s1,
-                                         const float (&yd0)[8], const float (&yd1)[8], int t, float (&facc)[4]) {
-    constexpr bool NIB = T == T_Q4_0;
-    constexpr int BLK = NIB ? 18 : 34, R = (2 * B + 2) & 7;
-    const int off = BLK * B + 2 + (NIB ? 8 * (t & 1) : 8 * t);
+                                         const float (&yd0)[8], const float (&yd1)[8], const float (&ys0)[8], const float (&ys1)[8], int t, float (&facc)[4]) {
+    using F = blk32fmt<T>;
+    constexpr int BLK = F::BLK, R = (BLK * B + F::QS) & 7;
+    const int off = BLK * B + F::QS + (F::NIB ? 8 * (t & 1) : 8 * t);
     const uint2 wa = lds8<R>(w0 + off), wb = lds8<R>(w1 + off);
     const uint2 yy = *(const uint2 *)(y + 32 * B);
     uint32_t a0 = wa.x, a2 = wa.y, a1 = wb.x, a3 = wb.y;
-    if constexpr (NIB) {                                            // lanes t = 0, 1 hold weights 0..15 (low nibbles), t = 2, 3 weights 16..31 (high nibbles)
+    if constexpr (F::NIB) {                                         // lanes t = 0, 1 hold weights 0..15 (low nibbles), t = 2, 3 weights 16..31 (high nibbles)
         const int sh = (t >> 1) * 4;
         a0 = (a0 >> sh) & 0x0F0F0F0Fu; a2 = (a2 >> sh) & 0x0F0F0F0Fu; a1 = (a1 >> sh) & 0x0F0F0F0Fu; a3 = (a3 >> sh) & 0x0F0F0F0Fu;
     }
+    if constexpr (F::QH >= 0) {                                     // fifth bits 8t .. 8t+7 of the block's 32
+        constexpr int RH = (BLK * B + F::QH) & 3;
+        const uint32_t ha = (lds4<RH>(w0 + BLK * B + F::QH) >> (8 * t)) & 0xFFu, hb = (lds4<RH>(w1 + BLK * B + F::QH) >> (8 * t)) & 0xFFu;
+        a0 |= spread4_to_bit4(ha); a2 |= spread4_to_bit4(ha >> 4); a1 |= spread4_to_bit4(hb); a3 |= spread4_to_bit4(hb >> 4);
+    }
+    if constexpr (F::LUT) { a0 = iq4nl_lookup4(a0); a1 = iq4nl_lookup4(a1); a2 = iq4nl_lookup4(a2); a3 = iq4nl_lookup4(a3); }
     int c[4];
     mma_s8_16x8x32(c, a0, a1, a2, a3, yy.x, yy.y);
     const float dA = h2f(lds_u16(w0 + BLK * B)), dB = h2f(lds_u16(w1 + BLK * B));
-    if constexpr (NIB) {                                            // codes are q - 8: subtract 8 x (sum of the block's activations)
+    if constexpr (F::OFF != 0) {                                    // codes are q - OFF: subtract OFF x (sum of the block's activations)
         const int * p0 = &s0.x, * p1 = &s1.x;
         const int h0 = (B & 1) ? (p0[B >> 1] >> 16) : (int)(int16_t)(p0[B >> 1] & 0xFFFF);
         const int h1 = (B & 1) ? (p1[B >> 1] >> 16) : (int)(int16_t)(p1[B >> 1] & 0xFFFF);
-        c[0] -= 8 * h0; c[1] -= 8 * h1; c[2] -= 8 * h0; c[3] -= 8 * h1;
+        c[0] -= F::OFF * h0; c[1] -= F::OFF * h1; c[2] -= F::OFF * h0; c[3] -= F::OFF * h1;
+    }
+    if constexpr (T == T_Q4_0) {
         facc[0] += (float)c[0] * dA * yd0[B]; facc[1] += (float)c[1] * dA * yd1[B];
         facc[2] += (float)c[2] * dB * yd0[B]; facc[3] += (float)c[3] * dB * yd1[B];
-    } else {
+    } else if constexpr (T == T_Q8_0) {
         facc[0] += (float)c[0] * (dA * yd0[B]); facc[1] += (float)c[1] * (dA * yd1[B]);
         facc[2] += (float)c[2] * (dB * yd0[B]); facc[3] += (float)c[3] * (dB * yd1[B]);
+    } else if constexpr (F::MIN) {
+        const float mA = h2f(lds_u16(w0 + BLK * B + 2)), mB = h2f(lds_u16(w1 + BLK * B + 2));
+        facc[0] += (dA * yd0[B]) * (float)c[0] + mA * ys0[B]; facc[1] += (dA * yd1[B]) * (float)c[1] + mA * ys1[B];
+        facc[2] += (dB * yd0[B]) * (float)c[2] + mB * ys0[B]; facc[3] += (dB * yd1[B]) * (float)c[3] + mB * ys1[B];
+    } else {
+        facc[0] += (dA * yd0[B]) * (float)c[0]; facc[1] += (dA * yd1[B]) * (float)c[1];
+        facc[2] += (dB * yd0[B]) * (float)c[2]; facc[3] += (dB * yd1[B]) * (float)c[3];
     }
+}
+__device__ __forceinline__ void mma_load8f(const uint8_t * p, float (&v)[8]) {
+    const int4 a = lds128(p), b = lds128(p + 16);
+    v[0] = __int_as_float(a.x); v[1] = __int_as_float(a.y); v[2] = __int_as_float(a.z); v[3] = __int_as_float(a.w);
+    v[4] = __int_as_float(b.x); v[5] = __int_as_float(b.y); v[6] = __int_as_float(b.z); v[7] = __int_as_float(b.w);
 }
 template <int T>
 __device__ __forceinline__ void mma_blk32_task(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    using F = blk32fmt<T>;
     const uint8_t * y = C.b + 256 * task + 8 * t;
     int4 s0 = { 0, 0, 0, 0 }, s1 = { 0, 0, 0, 0 };
-    if constexpr (T == T_Q4_0) { s0 = lds128(C.c0 + A.off_h32 + 16 * task); s1 = lds128(C.c1 + A.off_h32 + 16 * task); }
-    float yd0[8], yd1[8];
-    {
-        const int4 a = lds128(C.c0 + A.off_d + 32 * task), b = lds128(C.c0 + A.off_d + 32 * task + 16);
-        const int4 c = lds128(C.c1 + A.off_d + 32 * task), d = lds128(C.c1 + A.off_d + 32 * task + 16);
-        yd0[0] = __int_as_float(a.x); yd0[1] = __int_as_float(a.y); yd0[2] = __int_as_float(a.z); yd0[3] = __int_as_float(a.w);
-        yd0[4] = __int_as_float(b.x); yd0[5] = __int_as_float(b.y); yd0[6] = __int_as_float(b.z); yd0[7] = __int_as_float(b.w);
-        yd1[0] = __int_as_float(c.x); yd1[1] = __int_as_float(c.y); yd1[2] = __int_as_float(c.z); yd1[3] = __int_as_float(c.w);
-        yd1[4] = __int_as_float(d.x); yd1[5] = __int_as_float(d.y); yd1[6] = __int_as_float(d.z); yd1[7] = __int_as_float(d.w);
-    }
-    mma_blk32<T, 0>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 1>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
-    mma_blk32<T, 2>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 3>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
-    mma_blk32<T, 4>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 5>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
-    mma_blk32<T, 6>(w0, w1, y, s0, s1, yd0, yd1, t, facc); mma_blk32<T, 7>(w0, w1, y, s0, s1, yd0, yd1, t, facc);
+    if constexpr (F::OFF != 0) { s0 = lds128(C.c0 + A.off_h32 + 16 * task); s1 = lds128(C.c1 + A.off_h32 + 16 * task); }
+    float yd0[8], yd1[8], ys0[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ys1[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    mma_load8f(C.c0 + A.off_d + 32 * task, yd0); mma_load8f(C.c1 + A.off_d + 32 * task, yd1);
+    if constexpr (F::MIN) { mma_load8f(C.c0 + A.off_s + 32 * task, ys0); mma_load8f(C.c1 + A.off_s + 32 * task, ys1); }
+    mma_blk32<T, 0>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc); mma_blk32<T, 1>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc);
+    mma_blk32<T, 2>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc); mma_blk32<T, 3>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc);
+    mma_blk32<T, 4>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc); mma_blk32<T, 5>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc);
+    mma_blk32<T, 6>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc); mma_blk32<T, 7>(w0, w1, y, s0, s1, yd0, yd1, ys0, ys1, t, facc);
 }
 template <> __device__ __forceinline__ void mma_task<T_Q4_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q4_0>(w0, w1, C, A, task, t, facc); }
 template <> __device__ __forceinline__ void mma_task<T_Q8_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q8_0>(w0, w1, C, A, task, t, facc); }
+template <> __device__ __forceinline__ void mma_task<T_Q5_0>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q5_0>(w0, w1, C, A, task, t, facc); }
+template <> __device__ __forceinline__ void mma_task<T_Q4_1>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q4_1>(w0, w1, C, A, task, t, facc); }
+template <> __device__ __forceinline__ void mma_task<T_Q5_1>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_Q5_1>(w0, w1, C, A, task, t, facc); }
+template <> __device__ __forceinline__ void mma_task<T_IQ4_NL>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) { mma_blk32_task<T_IQ4_NL>(w0, w1, C, A, task, t, facc); }
+
+// IQ4_XS: 136-byte superblocks (d | scales_h | scales_l[4] | qs[128]), eight 32-weight sub-blocks laid out as Q4_0 blocks (weight i in the low nibble
+// of qs[16 ib + i], weight i + 16 in the high one), nibbles mapped through the IQ4_NL codebook, 6-bit sub-block scales (value - 32), Q8_K activations.
+template <> __device__ __forceinline__ void mma_task<T_IQ4_XS>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    const uint2 hA = *(const uint2 *)w0, hB = *(const uint2 *)w1;
+    const uint8_t * y = C.b + 256 * task + 8 * t;
+    const int sh = (t >> 1) * 4;
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) {
+        const uint2 wa = *(const uint2 *)(w0 + 8 + 16 * ib + 8 * (t & 1)), wb = *(const uint2 *)(w1 + 8 + 16 * ib + 8 * (t & 1));
+        const uint2 yy = *(const uint2 *)(y + 32 * ib);
+        int c[4];
+        mma_s8_16x8x32(c, iq4nl_lookup4((wa.x >> sh) & 0x0F0F0F0Fu), iq4nl_lookup4((wb.x >> sh) & 0x0F0F0F0Fu),
+                          iq4nl_lookup4((wa.y >> sh) & 0x0F0F0F0Fu), iq4nl_lookup4((wb.y >> sh) & 0x0F0F0F0Fu), yy.x, yy.y);
+        const int sa = iq4xs_scale(hA.x, hA.y, ib), sb = iq4xs_scale(hB.x, hB.y, ib);
+        acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+    }
+    const float yd0 = *(const float *)(C.c0 + A.off_d + 4 * task), yd1 = *(const float *)(C.c1 + A.off_d + 4 * task);
+    const float dA = h2f(hA.x & 0xFFFF), dB = h2f(hB.x & 0xFFFF);
+    facc[0] += (dA * yd0) * (float)acc[0]; facc[1] += (dA * yd1) * (float)acc[1];
+    facc[2] += (dB * yd0) * (float)acc[2]; facc[3] += (dB * yd1) * (float)acc[3];
+}
+
+// Q2_K: 84-byte superblocks (scales[16]: 4-bit scale | 4-bit min << 4, qs[64], d | dmin), sixteen 16-weight groups -> sixteen m16n8k16 products.
+// Group g = 8 h + 2 jj + half: weights 16 g .. 16 g + 15 = bits 2 jj, 2 jj + 1 of qs[32 h + 16 half .. + 15].
+template <> __device__ __forceinline__ void mma_task<T_Q2_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    const int4 sA = lds128w(w0), sB = lds128w(w1);                  // the sixteen scale bytes of the two rows (4-byte aligned superblocks: four word loads)
+    const uint32_t scA[4] = { (uint32_t)sA.x, (uint32_t)sA.y, (uint32_t)sA.z, (uint32_t)sA.w }, scB[4] = { (uint32_t)sB.x, (uint32_t)sB.y, (uint32_t)sB.z, (uint32_t)sB.w };
+    const uint8_t * y = C.b + 256 * task + 4 * t;
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t qa = *(const uint32_t *)(w0 + 16 + 32 * h + 16 * half + 4 * t), qb = *(const uint32_t *)(w1 + 16 + 32 * h + 16 * half + 4 * t);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int g = 8 * h + 2 * jj + half;                // compile time
+                const uint32_t b0 = *(const uint32_t *)(y + 16 * g);
+                int c[4];
+                mma_s8_16x8x16(c, (qa >> (2 * jj)) & 0x03030303u, (qb >> (2 * jj)) & 0x03030303u, b0);
+                const uint32_t wa = scA[g >> 2] & 0x0F0F0F0Fu, wb = scB[g >> 2] & 0x0F0F0F0Fu;
+                const int sa = (g & 3) == 0 ? ubyte<0>(wa) : (g & 3) == 1 ? ubyte<1>(wa) : (g & 3) == 2 ? ubyte<2>(wa) : ubyte<3>(wa);
+                const int sb = (g & 3) == 0 ? ubyte<0>(wb) : (g & 3) == 1 ? ubyte<1>(wb) : (g & 3) == 2 ? ubyte<2>(wb) : ubyte<3>(wb);
+                acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+            }
+        }
+    }
+    // mins: sum over the sixteen groups of min_g x (16-sum of the column's activations)
+    auto mins = [](const int4 & sa, const int4 & sb, const uint32_t (&sc)[4]) {
+        const uint32_t m0 = (sc[0] >> 4) & 0x0F0F0F0Fu, m1 = (sc[1] >> 4) & 0x0F0F0F0Fu, m2 = (sc[2] >> 4) & 0x0F0F0F0Fu, m3 = (sc[3] >> 4) & 0x0F0F0F0Fu;
+        int m = dp2a_lo_su(sa.x, m0, 0);
+        m = dp2a_hi_su(sa.y, m0, m); m = dp2a_lo_su(sa.z, m1, m); m = dp2a_hi_su(sa.w, m1, m);
+        m = dp2a_lo_su(sb.x, m2, m); m = dp2a_hi_su(sb.y, m2, m); m = dp2a_lo_su(sb.z, m3, m);
+        return dp2a_hi_su(sb.w, m3, m);
+    };
+    const int4 s0a = lds128(C.c0 + A.off_s16 + 32 * task), s0b = lds128(C.c0 + A.off_s16 + 32 * task + 16);
+    const int4 s1a = lds128(C.c1 + A.off_s16 + 32 * task), s1b = lds128(C.c1 + A.off_s16 + 32 * task + 16);
+    const float yd0 = *(const float *)(C.c0 + A.off_d + 4 * task), yd1 = *(const float *)(C.c1 + A.off_d + 4 * task);
+    const uint32_t ddA = *(const uint32_t *)(w0 + 80), ddB = *(const uint32_t *)(w1 + 80);
+    const float dA = h2f(ddA & 0xFFFF), mA = h2f(ddA >> 16), dB = h2f(ddB & 0xFFFF), mB = h2f(ddB >> 16);
+    facc[0] += (yd0 * dA) * (float)acc[0] - (yd0 * mA) * (float)mins(s0a, s0b, scA);
+    facc[1] += (yd1 * dA) * (float)acc[1] - (yd1 * mA) * (float)mins(s1a, s1b, scA);
+    facc[2] += (yd0 * dB) * (float)acc[2] - (yd0 * mB) * (float)mins(s0a, s0b, scB);
+    facc[3] += (yd1 * dB) * (float)acc[3] - (yd1 * mB) * (float)mins(s1a, s1b, scB);
+}
 
 // Q6_K: 210-byte superblocks (ql[128] | qh[64] | int8 scales[16] | d), sixteen 16-weight scale groups -> sixteen m16n8k16 products per task.
 // Group (half n, quarter q, sixteen is) = weights 128 n + 32 q + 16 is .. + 15: low nibbles (q < 2) or high nibbles (q >= 2) of

@@ -44,14 +44,14 @@ struct mma_params {
 
 // one act-task (256 activations of one column) per half-warp.  Always waits for the preceding kernel: it may have produced x, and the
 // records live in the launch-shared workspace that the previous mat-mul's CTAs may still be reading.
-template <bool KQ, bool S16>
+template <bool KQ, bool S16, bool S81>
 __global__ void __launch_bounds__(256) mma_quantize_kernel(const float * __restrict__ x, int64_t x_stride, int ncols, const mma_act A, uint8_t * __restrict__ rec) {
     pdl_launch_dependents();
     pdl_wait();
     const int i = (int)blockIdx.x * 16 + (int)(threadIdx.x >> 4);
     const bool ok = i < ncols * A.ntask;
     const int c = ok ? i / A.ntask : 0, t = ok ? i % A.ntask : 0;
-    mma_quantize_task_h<KQ, S16>(x + (size_t)c * x_stride, ok, rec + (size_t)c * A.col_bytes, A, t);
+    mma_quantize_task_h<KQ, S16, S81>(x + (size_t)c * x_stride, ok, rec + (size_t)c * A.col_bytes, A, t);
 }
 
 // NG consumer groups per CTA, each = 8 consumer warps + its own producer warp, stage ring, barriers and tile sequence (group v of the
@@ -197,7 +197,7 @@ template <int T> static bool make_mma_plan(const ggml_b200_mul_mat_args & a, mma
     p.row_bytes = (int)rb;
     p.ntiles = (int)((a.M + MMA_TILE - 1) / MMA_TILE);
     p.ntask_row = (int)(a.K / 256);
-    p.A = make_mma_act(a.K, F::KQ, F::S16, F::RESIDUE);
+    p.A = make_mma_act(a.K, F::KQ, F::S16, F::RESIDUE, mma_s81<T>::value);
     p.ncols = (int32_t)a.N; p.x_stride = a.N > 1 ? (int64_t)(a.nb11 / 4) : 0;
     p.counters = nullptr; p.rec_global = nullptr;
     p.src0_static = (a.flags & GGML_B200_MM_SRC0_STATIC) ? 1 : 0;
@@ -277,7 +277,7 @@ template <int T> static int launch_mma(const ggml_b200_mul_mat_args & a, cudaStr
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)((pl.p.ncols * pl.p.A.ntask + 15) / 16)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-        B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_quantize_kernel<F::KQ, F::S16>, a.src1, pl.p.x_stride, (int)pl.p.ncols, pl.p.A, rec));
+        B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_quantize_kernel<F::KQ, F::S16, mma_s81<T>::value>, a.src1, pl.p.x_stride, (int)pl.p.ncols, pl.p.A, rec));
         B200_LAUNCH_CHECK();
     }
     return pl.ng == 1 ? launch_mma_ng<T, 1>(pl, st, attr, use_pdl ? 1 : 0) : launch_mma_ng<T, 2>(pl, st, attr, use_pdl ? 1 : 0);
@@ -292,6 +292,12 @@ size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a) {
         case T_Q4_K: ok = make_mma_plan<T_Q4_K>(a, pl); break;
         case T_Q5_K: ok = make_mma_plan<T_Q5_K>(a, pl); break;
         case T_Q6_K: ok = make_mma_plan<T_Q6_K>(a, pl); break;
+        case T_Q5_0: ok = make_mma_plan<T_Q5_0>(a, pl); break;
+        case T_Q4_1: ok = make_mma_plan<T_Q4_1>(a, pl); break;
+        case T_Q5_1: ok = make_mma_plan<T_Q5_1>(a, pl); break;
+        case T_IQ4_NL: ok = make_mma_plan<T_IQ4_NL>(a, pl); break;
+        case T_IQ4_XS: ok = make_mma_plan<T_IQ4_XS>(a, pl); break;
+        case T_Q2_K: ok = make_mma_plan<T_Q2_K>(a, pl); break;
         default: break;
     }
     return ok ? mma_rec_bytes(pl) + 256 : 0;
@@ -305,6 +311,12 @@ bool mmvq_mma_eligible(const ggml_b200_mul_mat_args & a) {
         case T_Q4_K: return make_mma_plan<T_Q4_K>(a, pl);
         case T_Q5_K: return make_mma_plan<T_Q5_K>(a, pl);
         case T_Q6_K: return make_mma_plan<T_Q6_K>(a, pl);
+        case T_Q5_0: return make_mma_plan<T_Q5_0>(a, pl);
+        case T_Q4_1: return make_mma_plan<T_Q4_1>(a, pl);
+        case T_Q5_1: return make_mma_plan<T_Q5_1>(a, pl);
+        case T_IQ4_NL: return make_mma_plan<T_IQ4_NL>(a, pl);
+        case T_IQ4_XS: return make_mma_plan<T_IQ4_XS>(a, pl);
+        case T_Q2_K: return make_mma_plan<T_Q2_K>(a, pl);
         default: return false;
     }
 }
@@ -316,6 +328,12 @@ int launch_mmvq_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_Q4_K: return launch_mma<T_Q4_K>(a, st);
         case T_Q5_K: return launch_mma<T_Q5_K>(a, st);
         case T_Q6_K: return launch_mma<T_Q6_K>(a, st);
+        case T_Q5_0: return launch_mma<T_Q5_0>(a, st);
+        case T_Q4_1: return launch_mma<T_Q4_1>(a, st);
+        case T_Q5_1: return launch_mma<T_Q5_1>(a, st);
+        case T_IQ4_NL: return launch_mma<T_IQ4_NL>(a, st);
+        case T_IQ4_XS: return launch_mma<T_IQ4_XS>(a, st);
+        case T_Q2_K: return launch_mma<T_Q2_K>(a, st);
         default: set_error("mul_mat: unsupported weight type %d for the mma kernel", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }

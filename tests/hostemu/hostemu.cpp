@@ -61,7 +61,7 @@ template <int T> static void sb_row_nc(const uint8_t * row, int64_t K, const uin
 // ncols (<= 8) activation columns (column c at x + c * K): planar records by the kernel's quantizer, every task by mma_task; out[16][8]
 template <int T> static void mma_tile(const uint8_t * rows, int64_t pitch, int64_t K, const float * x, int ncols, float * out) {
     using F = mmafmt<T>;
-    const mma_act A = make_mma_act(K, F::KQ, F::S16, F::RESIDUE);
+    const mma_act A = make_mma_act(K, F::KQ, F::S16, F::RESIDUE, mma_s81<T>::value);
     std::vector<uint8_t> rec((size_t)ncols * A.col_bytes + 64);
     uint8_t * recp = rec.data();
     warp_emu::run([&] {
@@ -70,7 +70,7 @@ template <int T> static void mma_tile(const uint8_t * rows, int64_t pitch, int64
             const int i = i0 + (lane >> 4);
             const bool ok = i < ncols * A.ntask;
             const int c = ok ? i / A.ntask : 0, t = ok ? i % A.ntask : 0;
-            mma_quantize_task_h<F::KQ, F::S16>(x + (size_t)c * K, ok, recp + (size_t)c * A.col_bytes, A, t);
+            mma_quantize_task_h<F::KQ, F::S16, mma_s81<T>::value>(x + (size_t)c * K, ok, recp + (size_t)c * A.col_bytes, A, t);
         }
         pthread_barrier_wait(&warp_emu::barrier());
         const int g = lane >> 2, t = lane & 3;
@@ -200,6 +200,12 @@ int emu_mma_tile(int type, const uint8_t * rows, int64_t pitch, int64_t K, const
         case T_Q4_K: mma_tile<T_Q4_K>(rows, pitch, K, x, ncols, out); return 0;
         case T_Q5_K: mma_tile<T_Q5_K>(rows, pitch, K, x, ncols, out); return 0;
         case T_Q6_K: mma_tile<T_Q6_K>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q5_0: mma_tile<T_Q5_0>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q4_1: mma_tile<T_Q4_1>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q5_1: mma_tile<T_Q5_1>(rows, pitch, K, x, ncols, out); return 0;
+        case T_IQ4_NL: mma_tile<T_IQ4_NL>(rows, pitch, K, x, ncols, out); return 0;
+        case T_IQ4_XS: mma_tile<T_IQ4_XS>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q2_K: mma_tile<T_Q2_K>(rows, pitch, K, x, ncols, out); return 0;
         default: return -1;
     }
 }

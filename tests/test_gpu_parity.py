@@ -153,7 +153,7 @@ def test_small_batch_columns_match_single_column(t, g, oracle):
             assert np.array_equal(Y[c], y1), (n, c)
 
 
-MMA_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K]
+MMA_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K, O.Q5_0, O.Q4_1, O.Q5_1, O.IQ4_NL, O.IQ4_XS, O.Q2_K]
 
 
 @pytest.mark.parametrize("t", MMA_TYPES, ids=[O.TYPE_NAMES[t] for t in MMA_TYPES])
