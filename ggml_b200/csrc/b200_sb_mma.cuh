@@ -162,6 +162,7 @@ template <> struct mmafmt<T_Q5_1>   { static constexpr int TASK_B = 192, RESIDUE
 template <> struct mmafmt<T_IQ4_NL> { static constexpr int TASK_B = 144, RESIDUE = 32; static constexpr bool KQ = false, S16 = false; };
 template <> struct mmafmt<T_IQ4_XS> { static constexpr int TASK_B = 136, RESIDUE = 32; static constexpr bool KQ = true,  S16 = false; };
 template <> struct mmafmt<T_Q2_K>   { static constexpr int TASK_B = 84,  RESIDUE = 16; static constexpr bool KQ = true,  S16 = true;  };
+template <> struct mmafmt<T_Q3_K>   { static constexpr int TASK_B = 110, RESIDUE = 16; static constexpr bool KQ = true,  S16 = true;  };
 // (formats without a minimum: no Q8_1 s region)
 template <int T, typename = void> struct mma_s81 { static constexpr bool value = false; };
 template <int T> struct mma_s81<T, decltype((void)mmafmt<T>::S81)> { static constexpr bool value = mmafmt<T>::S81; };
@@ -376,6 +377,65 @@ template <> __device__ __forceinline__ void mma_task<T_Q2_K>(const uint8_t * w0,
     facc[1] += (yd1 * dA) * (float)acc[1] - (yd1 * mA) * (float)mins(s1a, s1b, scA);
     facc[2] += (yd0 * dB) * (float)acc[2] - (yd0 * mB) * (float)mins(s0a, s0b, scB);
     facc[3] += (yd1 * dB) * (float)acc[3] - (yd1 * mB) * (float)mins(s1a, s1b, scB);
+}
+
+// Q3_K: 110-byte superblocks (hmask[32] | qs[64] | scales[12] | d), 2-byte aligned like Q6_K; sixteen 16-weight groups -> sixteen m16n8k16 products.
+// Group g = 8 h + 2 jj + half: bits 2 jj, 2 jj + 1 of qs[32 h + 16 half .. + 15] plus bit (4 h + jj) of hmask[16 half .. + 15] as bit 2; value = code - 4
+// (the "- 4" is sum_g scale_g * 4 * (16-sum of the activations)_g); scales are 6 bits (value - 32), low nibbles in bytes 0..7, high bits in bytes 8..11.
+template <int R>
+__device__ __forceinline__ void mma_q3_task(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    auto scales = [](const uint8_t * w, uint32_t (&sc)[4]) {
+        const uint32_t s0 = lds4<R>(w + 96), s1 = lds4<R>(w + 100), s2 = lds4<R>(w + 104);
+        const uint32_t aux[4] = { ( s0       & 0x0F0F0F0Fu) | (( s2       & 0x03030303u) << 4), ( s1       & 0x0F0F0F0Fu) | (((s2 >> 2) & 0x03030303u) << 4),
+                                  ((s0 >> 4) & 0x0F0F0F0Fu) | (((s2 >> 4) & 0x03030303u) << 4), ((s1 >> 4) & 0x0F0F0F0Fu) | (((s2 >> 6) & 0x03030303u) << 4) };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                               // 6-bit x -> int8 (x - 32): flip bit 5, then replicate it into bits 6 and 7
+            const uint32_t y = aux[i] ^ 0x20202020u, m = y & 0x20202020u;
+            sc[i] = y | (m << 1) | (m << 2);
+        }
+    };
+    uint32_t scA[4], scB[4];
+    scales(w0, scA); scales(w1, scB);
+    const uint8_t * y = C.b + 256 * task + 4 * t;
+    int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t hmA = lds4<R>(w0 + 16 * half + 4 * t), hmB = lds4<R>(w1 + 16 * half + 4 * t);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t qa = lds4<R>(w0 + 32 + 32 * h + 16 * half + 4 * t), qb = lds4<R>(w1 + 32 + 32 * h + 16 * half + 4 * t);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int g = 8 * h + 2 * jj + half, bit = 4 * h + jj;   // compile time
+                const uint32_t a0 = ((qa >> (2 * jj)) & 0x03030303u) | (((hmA >> bit) & 0x01010101u) << 2);
+                const uint32_t a1 = ((qb >> (2 * jj)) & 0x03030303u) | (((hmB >> bit) & 0x01010101u) << 2);
+                const uint32_t b0 = *(const uint32_t *)(y + 16 * g);
+                int c[4];
+                mma_s8_16x8x16(c, a0, a1, b0);
+                const int sa = (g & 3) == 0 ? sbyte<0>(scA[g >> 2]) : (g & 3) == 1 ? sbyte<1>(scA[g >> 2]) : (g & 3) == 2 ? sbyte<2>(scA[g >> 2]) : sbyte<3>(scA[g >> 2]);
+                const int sb = (g & 3) == 0 ? sbyte<0>(scB[g >> 2]) : (g & 3) == 1 ? sbyte<1>(scB[g >> 2]) : (g & 3) == 2 ? sbyte<2>(scB[g >> 2]) : sbyte<3>(scB[g >> 2]);
+                acc[0] += sa * c[0]; acc[1] += sa * c[1]; acc[2] += sb * c[2]; acc[3] += sb * c[3];
+            }
+        }
+    }
+    auto offs = [](const int4 & sa, const int4 & sb, const uint32_t (&sc)[4]) {
+        int o = dp2a_lo_ss(sa.x, sc[0], 0);
+        o = dp2a_hi_ss(sa.y, sc[0], o); o = dp2a_lo_ss(sa.z, sc[1], o); o = dp2a_hi_ss(sa.w, sc[1], o);
+        o = dp2a_lo_ss(sb.x, sc[2], o); o = dp2a_hi_ss(sb.y, sc[2], o); o = dp2a_lo_ss(sb.z, sc[3], o);
+        return dp2a_hi_ss(sb.w, sc[3], o);
+    };
+    const int4 s0a = lds128(C.c0 + A.off_s16 + 32 * task), s0b = lds128(C.c0 + A.off_s16 + 32 * task + 16);
+    const int4 s1a = lds128(C.c1 + A.off_s16 + 32 * task), s1b = lds128(C.c1 + A.off_s16 + 32 * task + 16);
+    const float yd0 = *(const float *)(C.c0 + A.off_d + 4 * task), yd1 = *(const float *)(C.c1 + A.off_d + 4 * task);
+    const float dA = h2f(lds_u16(w0 + 108)), dB = h2f(lds_u16(w1 + 108));
+    facc[0] += (dA * yd0) * (float)(acc[0] - 4 * offs(s0a, s0b, scA));
+    facc[1] += (dA * yd1) * (float)(acc[1] - 4 * offs(s1a, s1b, scA));
+    facc[2] += (dB * yd0) * (float)(acc[2] - 4 * offs(s0a, s0b, scB));
+    facc[3] += (dB * yd1) * (float)(acc[3] - 4 * offs(s1a, s1b, scB));
+}
+template <> __device__ __forceinline__ void mma_task<T_Q3_K>(const uint8_t * w0, const uint8_t * w1, const mma_cols & C, const mma_act & A, int task, int t, float (&facc)[4]) {
+    if (((uintptr_t)w0 & 2) != 0) mma_q3_task<2>(w0, w1, C, A, task, t, facc);
+    else                          mma_q3_task<0>(w0, w1, C, A, task, t, facc);
 }
 
 // Q6_K: 210-byte superblocks (ql[128] | qh[64] | int8 scales[16] | d), sixteen 16-weight scale groups -> sixteen m16n8k16 products per task.

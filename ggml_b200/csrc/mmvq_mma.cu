@@ -298,6 +298,7 @@ size_t mmvq_mma_workspace(const ggml_b200_mul_mat_args & a) {
         case T_IQ4_NL: ok = make_mma_plan<T_IQ4_NL>(a, pl); break;
         case T_IQ4_XS: ok = make_mma_plan<T_IQ4_XS>(a, pl); break;
         case T_Q2_K: ok = make_mma_plan<T_Q2_K>(a, pl); break;
+        case T_Q3_K: ok = make_mma_plan<T_Q3_K>(a, pl); break;
         default: break;
     }
     return ok ? mma_rec_bytes(pl) + 256 : 0;
@@ -317,6 +318,7 @@ bool mmvq_mma_eligible(const ggml_b200_mul_mat_args & a) {
         case T_IQ4_NL: return make_mma_plan<T_IQ4_NL>(a, pl);
         case T_IQ4_XS: return make_mma_plan<T_IQ4_XS>(a, pl);
         case T_Q2_K: return make_mma_plan<T_Q2_K>(a, pl);
+        case T_Q3_K: return make_mma_plan<T_Q3_K>(a, pl);
         default: return false;
     }
 }
@@ -334,6 +336,7 @@ int launch_mmvq_mma(const ggml_b200_mul_mat_args & a, cudaStream_t st) {
         case T_IQ4_NL: return launch_mma<T_IQ4_NL>(a, st);
         case T_IQ4_XS: return launch_mma<T_IQ4_XS>(a, st);
         case T_Q2_K: return launch_mma<T_Q2_K>(a, st);
+        case T_Q3_K: return launch_mma<T_Q3_K>(a, st);
         default: set_error("mul_mat: unsupported weight type %d for the mma kernel", a.type); return GGML_B200_EUNSUPPORTED;
     }
 }

@@ -206,6 +206,7 @@ int emu_mma_tile(int type, const uint8_t * rows, int64_t pitch, int64_t K, const
         case T_IQ4_NL: mma_tile<T_IQ4_NL>(rows, pitch, K, x, ncols, out); return 0;
         case T_IQ4_XS: mma_tile<T_IQ4_XS>(rows, pitch, K, x, ncols, out); return 0;
         case T_Q2_K: mma_tile<T_Q2_K>(rows, pitch, K, x, ncols, out); return 0;
+        case T_Q3_K: mma_tile<T_Q3_K>(rows, pitch, K, x, ncols, out); return 0;
         default: return -1;
     }
 }

@@ -153,7 +153,7 @@ def test_small_batch_columns_match_single_column(t, g, oracle):
             assert np.array_equal(Y[c], y1), (n, c)
 
 
-MMA_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K, O.Q5_0, O.Q4_1, O.Q5_1, O.IQ4_NL, O.IQ4_XS, O.Q2_K]
+MMA_TYPES = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K, O.Q5_0, O.Q4_1, O.Q5_1, O.IQ4_NL, O.IQ4_XS, O.Q2_K, O.Q3_K]
 
 
 @pytest.mark.parametrize("t", MMA_TYPES, ids=[O.TYPE_NAMES[t] for t in MMA_TYPES])
@@ -162,7 +162,8 @@ def test_small_batch_mma_kernel_vs_oracle(t, g, oracle):
     K-sliced stages with a ragged last slice (K = 11008: 43 tasks), ragged M (last tile partly filled), every n in 1..8;
     bitwise repeatable; column c of an n-column launch bit-identical to the kernel's own n = 1 result for that column."""
     rng = np.random.default_rng(17)
-    for (M, K) in [(1536, 4096), (1000, 2048), (264, 11008 if t != O.Q6_K else 14336), (4096 + 24, 4096)]:   # (Q6_K rows must be 16-byte multiples)
+    k_sliced = 11008 if oracle.row_size(t, 11008) % 16 == 0 else 14336        # rows must be 16-byte multiples (bulk copies)
+    for (M, K) in [(1536, 4096), (1000, 2048), (264, k_sliced), (4096 + 24, 4096)]:
         W = weights(oracle, t, M, K, seed=M + K)
         Wd = dev(W)
         for n in ((1, 2, 3, 4, 5, 6, 7, 8) if M == 1536 else (2, 8, 5)):

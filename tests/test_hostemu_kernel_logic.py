@@ -257,7 +257,7 @@ def test_gemm_operand_dequantization_matches_oracle(t, emu, oracle):
 
 
 @pytest.mark.parametrize("ncols", [1, 2, 5, 8])
-@pytest.mark.parametrize("t", [O.Q4_K, O.Q5_K, O.Q6_K, O.Q4_0, O.Q8_0, O.Q5_0, O.Q4_1, O.Q5_1, O.IQ4_NL, O.IQ4_XS, O.Q2_K], ids=lambda t: O.TYPE_NAMES[t])
+@pytest.mark.parametrize("t", [O.Q4_K, O.Q5_K, O.Q6_K, O.Q4_0, O.Q8_0, O.Q5_0, O.Q4_1, O.Q5_1, O.IQ4_NL, O.IQ4_XS, O.Q2_K, O.Q3_K], ids=lambda t: O.TYPE_NAMES[t])
 def test_mma_small_batch_tile_matches_oracle(t, ncols, emu, oracle):
     """b200_sb_mma.cuh (the int8 mma.sync consume path of mmvq_mma.cu) in an emulated warp — fragment loads from the packed rows at a
     padded pitch, the m16n8k32 fragment layout, scale / min application, the planar activation records of the kernel's own quantizer —
@@ -266,7 +266,7 @@ def test_mma_small_batch_tile_matches_oracle(t, ncols, emu, oracle):
     K = 1024
     rb = oracle.row_size(t, K)
     W = O.random_blocks(t, 16 * K // oracle.blck_size(t), rng)
-    pitch = rb + (16 if t in (O.Q6_K, O.Q2_K) else 32)
+    pitch = rb + (16 if t in (O.Q6_K, O.Q2_K, O.Q3_K) else 32)
     rows = np.zeros(16 * pitch + 64, dtype=np.uint8)
     base = (-rows.ctypes.data) % 32                      # 32-byte aligned tile, as a shared-memory stage
     for r in range(16):
