@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(256) mmid_x_to_f16_kernel(const uint8_t * __re
 struct mmid_g_plan { int BN, m_tiles, max_tiles, chunks, nstages, nraw, smem, mode; size_t xb_bytes, scale_bytes, tab_bytes, perm_bytes; int64_t n_pairs; };
 
 static bool make_mmid_g_plan(const ggml_b200_mul_mat_id_args & a, mmid_g_plan & pl) {
-    static const int env_on = getenv("GGML_B200_MMID_GROUPED") ? atoi(getenv("GGML_B200_MMID_GROUPED")) : 0;      // opt-in until validated on a B200
+    static const int env_on = getenv("GGML_B200_MMID_GROUPED") ? atoi(getenv("GGML_B200_MMID_GROUPED")) : 0;      // passes tests/gpu_mmid_grouped_check.py on a B200; opt-in until the reference's whole MUL_MAT_ID sweep has run with it
     if (!env_on) return false;
     switch (a.type) {
         case T_Q4_0: case T_Q8_0: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_IQ4_NL: case T_IQ4_XS: case T_Q2_K: case T_Q3_K: break;
