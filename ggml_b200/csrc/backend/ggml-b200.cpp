@@ -105,6 +105,10 @@ struct backend_ctx {
     void * scratch(size_t need) {
         if (need <= workspace_size) return workspace;
         GGML_ASSERT(!capturing && "scratch must be sized before stream capture");
+        // the kernels of every cached executable graph hold the old pool address (it is not part of the node signature): a later replay
+        // would write through a freed pointer.  Graphs still in flight finish first (cudaGraphExecDestroy defers, cudaFreeAsync is stream-ordered).
+        for (auto & g : graphs) if (g.exec) CUDA_OK(cudaGraphExecDestroy(g.exec));
+        graphs.clear();
         if (workspace) CUDA_OK(cudaFreeAsync(workspace, stream));
         size_t sz = need + need / 4;
         sz = (sz + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
