@@ -260,7 +260,9 @@ ggml_backend_buffer_t host_buft_alloc_buffer(ggml_backend_buffer_type_t buft, si
 size_t host_buft_get_alignment(ggml_backend_buffer_type_t) { return 64; }
 bool   host_buft_is_host(ggml_backend_buffer_type_t) { return true; }
 
+int registry_device_count();
 ggml_backend_buffer_type_t host_buffer_type() {
+    if (registry_device_count() == 0) return nullptr;        // no B200 visible: there is no device to hang the buffer type on (reg_get_device would assert)
     static ggml_backend_buffer_type buft = {
         /* .iface   = */ { host_buft_get_name, host_buft_alloc_buffer, host_buft_get_alignment, nullptr, nullptr, host_buft_is_host },
         /* .device  = */ ggml_backend_reg_dev_get(b200_reg(), 0),

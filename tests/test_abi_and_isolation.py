@@ -47,6 +47,44 @@ def test_backend_plugin_exports_entry_points():
     assert not missing, missing
 
 
+def test_plugin_without_a_device_reports_nothing_instead_of_aborting():
+    """No B200 visible (this suite runs without a GPU; skipped where one exists): the plug-in must load, score 0 so that ggml's loader passes it
+    over (src/ggml-backend-reg.cpp:220-263), enumerate no device and hand out no backend / buffer type -- in a child process, because the
+    reference's own answer to misuse is GGML_ABORT."""
+    import ggml_b200
+    ref = ROOT / "oracle" / "_ref"
+    if not (ref / "libggml-base.so").exists():
+        pytest.skip("needs ggml-base (oracle/_ref) to resolve the plug-in's ggml symbols")
+    code = f"""
+import ctypes as C
+C.CDLL(r"{ref / 'libggml-base.so'}", mode=C.RTLD_GLOBAL)
+try:
+    C.CDLL(r"{ref / 'libggml-cpu.so'}", mode=C.RTLD_GLOBAL)
+except OSError:
+    pass
+B = C.CDLL(r"{ggml_b200.BACKEND_SO}")
+for f in ("ggml_backend_b200_host_buffer_type", "ggml_backend_b200_init", "ggml_backend_b200_buffer_type", "ggml_backend_b200_split_buffer_type", "ggml_backend_init"):
+    getattr(B, f).restype = C.c_void_p
+B.ggml_backend_b200_split_buffer_type.argtypes = [C.c_int, C.c_void_p]
+n = B.ggml_backend_b200_get_device_count()
+if n > 0:
+    print("HAS_GPU")
+else:
+    assert B.ggml_backend_score() == 0
+    assert B.ggml_backend_init() is not None                      # the registry entry itself exists, with zero devices
+    assert B.ggml_backend_b200_host_buffer_type() is None
+    assert B.ggml_backend_b200_buffer_type(0) is None
+    assert B.ggml_backend_b200_split_buffer_type(0, None) is None
+    assert B.ggml_backend_b200_init(0) is None
+    print("OK")
+"""
+    p = subprocess.run([__import__("sys").executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    if "HAS_GPU" in p.stdout:
+        pytest.skip("a B200 is visible")
+    assert "OK" in p.stdout
+
+
 def test_shim_validates_arguments_without_a_device():
     import ggml_b200 as g
     L = g.lib()
