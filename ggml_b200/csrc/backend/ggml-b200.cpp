@@ -107,9 +107,11 @@ struct backend_ctx {
         GGML_ASSERT(!capturing && "scratch must be sized before stream capture");
         // the kernels of every cached executable graph hold the old pool address (it is not part of the node signature): a later replay
         // would write through a freed pointer.  Graphs still in flight finish first (cudaGraphExecDestroy defers, cudaFreeAsync is stream-ordered).
-        for (auto & g : graphs) if (g.exec) CUDA_OK(cudaGraphExecDestroy(g.exec));
-        graphs.clear();
-        if (workspace) CUDA_OK(cudaFreeAsync(workspace, stream));
+        if (workspace) {
+            for (auto & g : graphs) if (g.exec) CUDA_OK(cudaGraphExecDestroy(g.exec));
+            graphs.clear();
+            CUDA_OK(cudaFreeAsync(workspace, stream));
+        }
         size_t sz = need + need / 4;
         sz = (sz + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
         CUDA_OK(cudaMallocAsync(&workspace, sz, stream));
